@@ -1,0 +1,199 @@
+"""ctypes binding of ``libdsfuse.so`` (C ABI declared in ``include/dsfuse.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C deepsense6g_tii_b200/csrc``.
+There is NO fallback: if the shared object is missing or a call fails, a ``RuntimeError`` is raised.
+PyTorch is used only for device memory and streams; every pointer handed to the library is a
+``tensor.data_ptr()`` and every call runs on ``torch.cuda.current_stream()``.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdsfuse.so")
+
+DSF_F32, DSF_BF16 = 0, 1
+DSF_NCHW, DSF_NHWC = 0, 1
+EPI_BIAS, EPI_RELU, EPI_RESIDUAL, EPI_ACCUM = 1, 2, 4, 8
+
+# every symbol include/dsfuse.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "dsf_version", "dsf_last_error", "dsf_check_device", "dsf_tokens_fwd", "dsf_tokens_bwd",
+    "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_f32",
+    "dsf_colsum", "dsf_relu_bwd", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd",
+    "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16",
+]
+
+
+class Geom(ctypes.Structure):
+    """``dsf_geom`` (include/dsfuse.h)."""
+    _fields_ = [(n, c_int32) for n in ("B", "S", "V", "A_h", "A_w", "C", "H", "W", "feat_dtype", "layout")]
+
+
+class GemmF32Desc(ctypes.Structure):
+    """``dsf_gemm_f32_desc`` (include/dsfuse.h)."""
+    _fields_ = ([(n, c_int32) for n in ("M", "N", "K", "nb1", "nb2")] +
+                [(n, c_int64) for n in ("a_b1", "a_b2", "a_m", "a_k", "b_b1", "b_b2", "b_n", "b_k",
+                                        "c_b1", "c_b2", "c_m", "c_n")] +
+                [("alpha", c_float), ("epi_flags", c_int32)])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                "libdsfuse.so not found at %s — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU / PyTorch fallback for the fusion stage)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.dsf_last_error.restype = c_char_p
+        L.dsf_version.restype = c_int32
+        P = c_void_p
+        sig = {
+            "dsf_check_device": [],
+            "dsf_tokens_fwd": [POINTER(Geom), P, P, P, P, P, P, P],
+            "dsf_tokens_bwd": [POINTER(Geom), P, P, P, P, P, P, P, P, P, P],
+            "dsf_layernorm_fwd": [P, P, P, P, c_int32, P, P, c_int32, c_int32, c_float, P],
+            "dsf_layernorm_bwd": [P, c_int32, P, P, P, P, P, P, P, P, c_int32, c_int32, P],
+            "dsf_gemm_bf16_nt": [P, c_int32, P, c_int32, P, c_int32, c_int32, P, P, c_int32, c_int32, c_int32, c_int32, P],
+            "dsf_gemm_bf16_tn": [P, c_int32, P, c_int32, P, c_int32, c_int32, c_int32, c_int32, P],
+            "dsf_gemm_f32": [POINTER(GemmF32Desc), P, P, P, P, P, P],
+            "dsf_colsum": [P, c_int32, c_int32, P, c_int32, c_int32, P],
+            "dsf_relu_bwd": [P, P, c_int32, c_int64, P],
+            "dsf_softmax_fwd": [P, c_int64, c_int32, P],
+            "dsf_softmax_bwd": [P, P, c_int64, c_int32, P],
+            "dsf_attn_fwd": [P, P, P, c_int32, c_int32, c_int32, c_int32, P],
+            "dsf_attn_bwd": [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P],
+            "dsf_upsample_add_fwd": [POINTER(Geom), P, P, P, P, P, P, P, P],
+            "dsf_upsample_add_bwd": [POINTER(Geom), P, P, P, P, P, P],
+            "dsf_cast_f32_bf16": [P, P, c_int64, P],
+        }
+        for name, argtypes in sig.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = c_int32
+        _lib = L
+    return _lib
+
+
+def _chk(code, what):
+    if code != 0:
+        raise RuntimeError("%s failed (code %d): %s" % (what, code, lib().dsf_last_error().decode()))
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return DSF_F32
+    if t.dtype == torch.bfloat16:
+        return DSF_BF16
+    raise RuntimeError("dsfuse supports float32 and bfloat16 tensors only, got %s" % t.dtype)
+
+
+def _req(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (the fusion stage has no CPU path)" % name)
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+def check_device():
+    _chk(lib().dsf_check_device(), "dsf_check_device")
+
+
+def make_geom(B, S, V, A_h, A_w, C, H, W, feat_dtype, layout=DSF_NCHW):
+    return Geom(B, S, V, A_h, A_w, C, H, W, feat_dtype, layout)
+
+
+# ------------------------------------------------------------------------------------------ wrappers
+def tokens_fwd(g, img, lidar, radar, gps, pos_emb, x):
+    _chk(lib().dsf_tokens_fwd(ctypes.byref(g), _p(img), _p(lidar), _p(radar), _p(gps), _p(pos_emb), _p(x), _stream()), "dsf_tokens_fwd")
+
+
+def tokens_bwd(g, dx, dres, douts, dgps, dpos_emb):
+    dres = dres or (None, None, None)
+    _chk(lib().dsf_tokens_bwd(ctypes.byref(g), _p(dx), _p(dres[0]), _p(dres[1]), _p(dres[2]), _p(douts[0]), _p(douts[1]),
+                              _p(douts[2]), _p(dgps), _p(dpos_emb), _stream()), "dsf_tokens_bwd")
+
+
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-5):
+    M, C = x.shape
+    _chk(lib().dsf_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _dt(y), _p(mean), _p(rstd), M, C, eps, _stream()), "dsf_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta):
+    M, C = x.shape
+    _chk(lib().dsf_layernorm_bwd(_p(dy), _dt(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx_add), _p(dx_out), _p(dgamma),
+                                 _p(dbeta), M, C, _stream()), "dsf_layernorm_bwd")
+
+
+def gemm_bf16_nt(A, B, C, bias=None, residual=None, relu=False):
+    """C[M,N] = A[M,K] @ B[N,K]^T (+bias)(relu)(+residual fp32).  A, B bf16 2-D contiguous; C bf16 or fp32."""
+    M, K = A.shape
+    N = B.shape[0]
+    flags = (EPI_BIAS if bias is not None else 0) | (EPI_RELU if relu else 0) | (EPI_RESIDUAL if residual is not None else 0)
+    _chk(lib().dsf_gemm_bf16_nt(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), _dt(C), _p(bias), _p(residual),
+                                M, N, K, flags, _stream()), "dsf_gemm_bf16_nt")
+
+
+def gemm_bf16_tn(A, B, C):
+    """C[N',K'] += A[M,N']^T @ B[M,K'] (fp32 atomics; C must be pre-zeroed or hold a running sum)."""
+    M, Nout = A.shape
+    Kout = B.shape[1]
+    _chk(lib().dsf_gemm_bf16_tn(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, Nout, Kout, _stream()), "dsf_gemm_bf16_tn")
+
+
+def gemm_f32(desc, A, B, C, bias=None, residual=None):
+    _chk(lib().dsf_gemm_f32(ctypes.byref(desc), _p(A), _p(B), _p(C), _p(bias), _p(residual), _stream()), "dsf_gemm_f32")
+
+
+def colsum(X, out):
+    M, N = X.shape
+    _chk(lib().dsf_colsum(_p(X), _dt(X), X.stride(0), _p(out), M, N, _stream()), "dsf_colsum")
+
+
+def relu_bwd(dy, h):
+    _chk(lib().dsf_relu_bwd(_p(dy), _p(h), _dt(dy), dy.numel(), _stream()), "dsf_relu_bwd")
+
+
+def softmax_fwd(s, rows, T):
+    _chk(lib().dsf_softmax_fwd(_p(s), rows, T, _stream()), "dsf_softmax_fwd")
+
+
+def softmax_bwd(dp, p, rows, T):
+    _chk(lib().dsf_softmax_bwd(_p(dp), _p(p), rows, T, _stream()), "dsf_softmax_bwd")
+
+
+def attn_fwd(qkv, y, lse, B, T, C, nh):
+    _chk(lib().dsf_attn_fwd(_p(qkv), _p(y), _p(lse), B, T, C, nh, _stream()), "dsf_attn_fwd")
+
+
+def attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh):
+    _chk(lib().dsf_attn_bwd(_p(qkv), _p(y), _p(dy), _p(lse), _p(delta), _p(dqkv), B, T, C, nh, _stream()), "dsf_attn_bwd")
+
+
+def upsample_add_fwd(g, y, feats, outs):
+    _chk(lib().dsf_upsample_add_fwd(ctypes.byref(g), _p(y), _p(feats[0]), _p(feats[1]), _p(feats[2]), _p(outs[0]), _p(outs[1]),
+                                    _p(outs[2]), _stream()), "dsf_upsample_add_fwd")
+
+
+def upsample_add_bwd(g, douts, dgps_out, dy):
+    _chk(lib().dsf_upsample_add_bwd(ctypes.byref(g), _p(douts[0]), _p(douts[1]), _p(douts[2]), _p(dgps_out), _p(dy), _stream()), "dsf_upsample_add_bwd")
+
+
+def cast_f32_bf16(src, dst):
+    _chk(lib().dsf_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()), "dsf_cast_f32_bf16")

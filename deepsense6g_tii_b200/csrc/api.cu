@@ -1,0 +1,55 @@
+// Library-level entry points: version, error string, device check.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace dsf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA error: %s", what, cudaGetErrorString(e));
+    return DSF_ELAUNCH;
+  }
+  return DSF_OK;
+}
+
+int num_sms() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+    if (cached <= 0) cached = 148;
+  }
+  return cached;
+}
+
+}  // namespace dsf
+
+extern "C" int dsf_version(void) { return DSF_VERSION; }
+extern "C" const char* dsf_last_error(void) { return dsf::g_err; }
+
+extern "C" int dsf_check_device(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    dsf::set_error("no CUDA device");
+    return DSF_EARCH;
+  }
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) {
+    dsf::set_error("libdsfuse is built for sm_100a only; device has compute capability %d.x", major);
+    return DSF_EARCH;
+  }
+  return DSF_OK;
+}

@@ -1,0 +1,331 @@
+"""Autograd wiring of one GPT fusion stage onto the dsfuse C ABI.
+
+``fusion_stage(...)`` computes, for one ResNet stage, exactly what ``Encoder.forward`` does at
+model2_seq.py:515-526 (and :533-544, :552-563, :571-579):
+
+    pooled_m = AdaptiveAvgPool2d((A, A))(feat_m)                      m in {image, lidar, radar}
+    tok_m, gps_out = GPT(pooled_image, pooled_lidar, pooled_radar, gps_emb)
+    feat_m' = feat_m + bilinear_upsample(tok_m)
+
+as ONE ``torch.autograd.Function`` whose forward and backward are sequences of hand-written CUDA
+kernels (no ATen math on the path).  Two compute modes:
+
+  * ``torch.bfloat16`` (performance mode): tcgen05/TMEM GEMMs + flash attention, fp32 residual
+    stream and LayerNorm statistics, bf16 activations / weight shadows.  Needs C % 64 == 0 and
+    head size in {16, 32, 64, 128}.
+  * ``torch.float32`` (parity mode, <= 1e-3 of the reference): FFMA GEMMs and materialised
+    softmax attention, everything fp32.
+
+Dropout (model2_seq.py:104,109,125,272) is NOT implemented yet; non-zero probabilities raise.
+"""
+import math
+
+import torch
+
+from . import _capi as K
+from ._capi import EPI_ACCUM, EPI_BIAS, EPI_RELU, EPI_RESIDUAL, GemmF32Desc
+
+PER_BLOCK = ("ln1.weight", "ln1.bias", "ln2.weight", "ln2.bias",
+             "attn.key.weight", "attn.key.bias", "attn.query.weight", "attn.query.bias",
+             "attn.value.weight", "attn.value.bias", "attn.proj.weight", "attn.proj.bias",
+             "mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias")
+
+
+def param_names(n_layer):
+    """Flat parameter order used by ``FusionStageFn`` (names are the reference state-dict names)."""
+    names = ["pos_emb"]
+    for i in range(n_layer):
+        names += ["blocks.%d.%s" % (i, n) for n in PER_BLOCK]
+    return names + ["ln_f.weight", "ln_f.bias"]
+
+
+def _f32_linear_desc(M, N, Kd, flags, trans=None):
+    """Descriptors for y = x W^T (+...), x (M,K) row-major, W (N,K) row-major, fp32 SIMT path."""
+    return GemmF32Desc(M, N, Kd, 1, 1, 0, 0, Kd, 1, 0, 0, Kd, 1, 0, 0, N, 1, 1.0, flags)
+
+
+class _Ctx:
+    pass
+
+
+class _Runner:
+    """Holds shapes + mode and implements forward / backward over raw tensors."""
+
+    def __init__(self, B, S, V, A_h, A_w, C, H, W, n_head, n_layer, feat_dtype, compute_dtype, layout):
+        self.B, self.S, self.V, self.A_h, self.A_w, self.C, self.H, self.W = B, S, V, A_h, A_w, C, H, W
+        self.nh, self.L = n_head, n_layer
+        self.hs = C // n_head
+        self.Tm = (V + 2) * S * A_h * A_w
+        self.T = self.Tm + 2
+        self.M = B * self.T
+        self.bf16 = compute_dtype == torch.bfloat16
+        self.act = torch.bfloat16 if self.bf16 else torch.float32
+        if self.bf16:
+            if C % 64 != 0 or self.hs not in (16, 32, 64, 128):
+                raise RuntimeError("bf16 tensor-core mode needs n_embd %% 64 == 0 and head size in {16,32,64,128}; "
+                                   "got n_embd=%d n_head=%d" % (C, n_head))
+        self.geom = K.make_geom(B, S, V, A_h, A_w, C, H, W, K.DSF_BF16 if feat_dtype == torch.bfloat16 else K.DSF_F32, layout)
+
+    # ------------------------------------------------------------------ linear layers
+    def _linear_fwd(self, x, w, b, out_dtype, relu=False, residual=None, w_shadow=None):
+        M, Kd = x.shape
+        N = w.shape[0]
+        out = torch.empty(M, N, device=x.device, dtype=out_dtype)
+        if self.bf16:
+            K.gemm_bf16_nt(x, w_shadow, out, bias=b, residual=residual, relu=relu)
+        else:
+            flags = EPI_BIAS | (EPI_RELU if relu else 0) | (EPI_RESIDUAL if residual is not None else 0)
+            K.gemm_f32(_f32_linear_desc(M, N, Kd, flags), x, w, out, bias=b, residual=residual)
+        return out
+
+    def _linear_bwd(self, dy, x, w, w_t_shadow, need_dx=True, db_src=None):
+        """dy (M,N) act dtype, x (M,K) act dtype, w (N,K) fp32.  Returns dx (act dtype), dw fp32, db fp32.
+        db_src: optional fp32 copy of dy to take the bias gradient from (avoids bf16 rounding)."""
+        M, N = dy.shape
+        Kd = x.shape[1]
+        dev = dy.device
+        dw = torch.zeros(N, Kd, device=dev, dtype=torch.float32)
+        db = torch.zeros(N, device=dev, dtype=torch.float32)
+        K.colsum(dy if db_src is None else db_src, db)
+        dx = None
+        if self.bf16:
+            K.gemm_bf16_tn(dy, x, dw)
+            if need_dx:
+                dx = torch.empty(M, Kd, device=dev, dtype=torch.bfloat16)
+                K.gemm_bf16_nt(dy, w_t_shadow, dx)
+        else:
+            # dW[n,k] = sum_m dy[m,n] x[m,k]
+            K.gemm_f32(GemmF32Desc(N, Kd, M, 1, 1, 0, 0, 1, N, 0, 0, 1, Kd, 0, 0, Kd, 1, 1.0, 0), dy, x, dw)
+            if need_dx:
+                dx = torch.empty(M, Kd, device=dev, dtype=torch.float32)
+                # dx[m,k] = sum_n dy[m,n] w[n,k]
+                K.gemm_f32(GemmF32Desc(M, Kd, N, 1, 1, 0, 0, N, 1, 0, 0, 1, Kd, 0, 0, Kd, 1, 1.0, 0), dy, w, dx)
+        return dx, dw, db
+
+    # ------------------------------------------------------------------ attention
+    def _attn_fwd(self, qkv, st):
+        B, T, C, nh, hs = self.B, self.T, self.C, self.nh, self.hs
+        dev = qkv.device
+        y = torch.empty(self.M, C, device=dev, dtype=self.act)
+        if self.bf16:
+            st.lse = torch.empty(B, nh, T, device=dev, dtype=torch.float32)
+            K.attn_fwd(qkv, y, st.lse, B, T, C, nh)
+            return y
+        # fp32 parity mode: materialised scores (model2_seq.py:102-105)
+        P = torch.empty(B, nh, T, T, device=dev, dtype=torch.float32)
+        q, k, v = qkv, qkv[:, C:], qkv[:, 2 * C:]
+        ld = 3 * C
+        K.gemm_f32(GemmF32Desc(T, T, hs, B, nh, T * ld, hs, ld, 1, T * ld, hs, ld, 1, nh * T * T, T * T, T, 1,
+                               1.0 / math.sqrt(hs), 0), q, k, P)
+        K.softmax_fwd(P, B * nh * T, T)
+        # y[b,t,h*hs+d] = sum_j P[b,h,t,j] v[b,j,h,d]
+        K.gemm_f32(GemmF32Desc(T, hs, T, B, nh, nh * T * T, T * T, T, 1, T * ld, hs, 1, ld, T * C, hs, C, 1, 1.0, 0), P, v, y)
+        st.P = P
+        return y
+
+    def _attn_bwd(self, dy, qkv, y, st):
+        B, T, C, nh, hs = self.B, self.T, self.C, self.nh, self.hs
+        dev = dy.device
+        dqkv = torch.empty(self.M, 3 * C, device=dev, dtype=self.act)
+        if self.bf16:
+            delta = torch.empty(B, nh, T, device=dev, dtype=torch.float32)
+            K.attn_bwd(qkv, y, dy, st.lse, delta, dqkv, B, T, C, nh)
+            return dqkv
+        P = st.P
+        q, k, v = qkv, qkv[:, C:], qkv[:, 2 * C:]
+        dq, dk, dv = dqkv, dqkv[:, C:], dqkv[:, 2 * C:]
+        ld = 3 * C
+        sc = 1.0 / math.sqrt(hs)
+        dP = torch.empty_like(P)
+        # dP[b,h,t,j] = sum_d dy[b,t,h,d] v[b,j,h,d]
+        K.gemm_f32(GemmF32Desc(T, T, hs, B, nh, T * C, hs, C, 1, T * ld, hs, ld, 1, nh * T * T, T * T, T, 1, 1.0, 0), dy, v, dP)
+        # dv[b,j,h,d] = sum_t P[b,h,t,j] dy[b,t,h,d]
+        K.gemm_f32(GemmF32Desc(T, hs, T, B, nh, nh * T * T, T * T, 1, T, T * C, hs, 1, C, T * ld, hs, ld, 1, 1.0, 0), P, dy, dv)
+        K.softmax_bwd(dP, P, B * nh * T, T)  # dP <- dS
+        # dq[b,t,h,d] = sc * sum_j dS[t,j] k[j,d]
+        K.gemm_f32(GemmF32Desc(T, hs, T, B, nh, nh * T * T, T * T, T, 1, T * ld, hs, 1, ld, T * ld, hs, ld, 1, sc, 0), dP, k, dq)
+        # dk[b,j,h,d] = sc * sum_t dS[t,j] q[t,d]
+        K.gemm_f32(GemmF32Desc(T, hs, T, B, nh, nh * T * T, T * T, 1, T, T * ld, hs, 1, ld, T * ld, hs, ld, 1, sc, 0), dP, q, dk)
+        return dqkv
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, feats, gps_emb, params, residual=True):
+        """feats: 3 tensors (N, C, H, W) [or NHWC storage]; gps_emb (B, 2, C) fp32; params: flat list.
+        residual=False returns the upsampled token maps alone (plain ``GPT.forward`` semantics)."""
+        dev = gps_emb.device
+        M, C, L = self.M, self.C, self.L
+        f32 = torch.float32
+        saved = _Ctx()
+        saved.layers = []
+        x = torch.empty(M, C, device=dev, dtype=f32)
+        K.tokens_fwd(self.geom, feats[0], feats[1], feats[2], gps_emb, params[0], x)
+        saved.shadows = []
+        for i in range(L):
+            (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[1 + 16 * i: 17 + 16 * i]
+            st = _Ctx()
+            # fused QKV weight [3C, C] in the order [query | key | value]
+            wqkv = torch.cat([qw, kw, vw], dim=0)
+            bqkv = torch.cat([qb, kb, vb], dim=0)
+            if self.bf16:
+                sh = _Ctx()
+                sh.wqkv = torch.empty(3 * C, C, device=dev, dtype=torch.bfloat16)
+                K.cast_f32_bf16(wqkv, sh.wqkv)
+                sh.wp = torch.empty_like(pw, dtype=torch.bfloat16)
+                K.cast_f32_bf16(pw, sh.wp)
+                sh.w1 = torch.empty_like(w1, dtype=torch.bfloat16)
+                K.cast_f32_bf16(w1, sh.w1)
+                sh.w2 = torch.empty_like(w2, dtype=torch.bfloat16)
+                K.cast_f32_bf16(w2, sh.w2)
+            else:
+                sh = _Ctx()
+                sh.wqkv = sh.wp = sh.w1 = sh.w2 = None
+            st.wqkv = wqkv
+            st.x_in = x
+            st.mean1 = torch.empty(M, device=dev, dtype=f32)
+            st.rstd1 = torch.empty(M, device=dev, dtype=f32)
+            st.h1 = torch.empty(M, C, device=dev, dtype=self.act)
+            K.layernorm_fwd(x, ln1w, ln1b, st.h1, st.mean1, st.rstd1)
+            st.qkv = self._linear_fwd(st.h1, wqkv, bqkv, self.act, w_shadow=sh.wqkv)
+            st.y = self._attn_fwd(st.qkv, st)
+            x_mid = self._linear_fwd(st.y, pw, pb, f32, residual=x, w_shadow=sh.wp)
+            st.x_mid = x_mid
+            st.mean2 = torch.empty(M, device=dev, dtype=f32)
+            st.rstd2 = torch.empty(M, device=dev, dtype=f32)
+            st.h2 = torch.empty(M, C, device=dev, dtype=self.act)
+            K.layernorm_fwd(x_mid, ln2w, ln2b, st.h2, st.mean2, st.rstd2)
+            st.a = self._linear_fwd(st.h2, w1, b1, self.act, relu=True, w_shadow=sh.w1)
+            x = self._linear_fwd(st.a, w2, b2, f32, residual=x_mid, w_shadow=sh.w2)
+            saved.layers.append(st)
+        saved.x_last = x
+        saved.mean_f = torch.empty(M, device=dev, dtype=f32)
+        saved.rstd_f = torch.empty(M, device=dev, dtype=f32)
+        yf = torch.empty(M, C, device=dev, dtype=f32)
+        K.layernorm_fwd(x, params[-2], params[-1], yf, saved.mean_f, saved.rstd_f)
+        outs = [torch.empty_like(f) for f in feats]
+        K.upsample_add_fwd(self.geom, yf, feats if residual else [torch.zeros_like(f) for f in feats], outs)
+        gps_out = yf.view(self.B, self.T, C)[:, self.Tm:, :].contiguous()
+        return outs, gps_out, saved
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, saved, params, douts, dgps_out, residual=True):
+        dev = douts[0].device
+        M, C, L = self.M, self.C, self.L
+        f32 = torch.float32
+        grads = [None] * len(params)
+        dyf = torch.empty(M, C, device=dev, dtype=f32)
+        K.upsample_add_bwd(self.geom, douts, dgps_out, dyf)
+        dg = torch.zeros(C, device=dev, dtype=f32)
+        db = torch.zeros(C, device=dev, dtype=f32)
+        dx = torch.empty(M, C, device=dev, dtype=f32)
+        K.layernorm_bwd(dyf, saved.x_last, params[-2], saved.mean_f, saved.rstd_f, None, dx, dg, db)
+        grads[-2], grads[-1] = dg, db
+        for i in reversed(range(L)):
+            base = 1 + 16 * i
+            (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[base: base + 16]
+            st = saved.layers[i]
+            if self.bf16:
+                # transposed bf16 shadows for the data-gradient GEMMs (NT kernel wants K-major B)
+                w2_t = w2.t().contiguous().to(torch.bfloat16)      # (4C, C)
+                w1_t = w1.t().contiguous().to(torch.bfloat16)      # (C, 4C)
+                wp_t = pw.t().contiguous().to(torch.bfloat16)      # (C, C)
+                wqkv_t = st.wqkv.t().contiguous().to(torch.bfloat16)  # (C, 3C)
+                dxa = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+                K.cast_f32_bf16(dx, dxa)
+            else:
+                w2_t = w1_t = wp_t = wqkv_t = None
+                dxa = dx
+            # ---- MLP:  x_out = x_mid + relu(h2 W1^T + b1) W2^T + b2     (model2_seq.py:121-126,132)
+            da, dw2, db2 = self._linear_bwd(dxa, st.a, w2, w2_t, db_src=dx)
+            K.relu_bwd(da, st.a)
+            dh2, dw1, db1 = self._linear_bwd(da, st.h2, w1, w1_t)
+            dg2 = torch.zeros(C, device=dev, dtype=f32)
+            dbt2 = torch.zeros(C, device=dev, dtype=f32)
+            dx_mid = torch.empty(M, C, device=dev, dtype=f32)
+            K.layernorm_bwd(dh2, st.x_mid, ln2w, st.mean2, st.rstd2, dx, dx_mid, dg2, dbt2)
+            # ---- attention:  x_mid = x_in + proj(attn(qkv(ln1(x_in))))   (model2_seq.py:94-110,131)
+            if self.bf16:
+                dxm = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+                K.cast_f32_bf16(dx_mid, dxm)
+            else:
+                dxm = dx_mid
+            dy, dwp, dbp = self._linear_bwd(dxm, st.y, pw, wp_t, db_src=dx_mid)
+            dqkv = self._attn_bwd(dy, st.qkv, st.y, st)
+            dh1, dwqkv, dbqkv = self._linear_bwd(dqkv, st.h1, st.wqkv, wqkv_t)
+            dg1 = torch.zeros(C, device=dev, dtype=f32)
+            dbt1 = torch.zeros(C, device=dev, dtype=f32)
+            dx = torch.empty(M, C, device=dev, dtype=f32)
+            K.layernorm_bwd(dh1, st.x_in, ln1w, st.mean1, st.rstd1, dx_mid, dx, dg1, dbt1)
+            grads[base: base + 16] = [dg1, dbt1, dg2, dbt2,
+                                      dwqkv[C:2 * C], dbqkv[C:2 * C], dwqkv[:C], dbqkv[:C], dwqkv[2 * C:], dbqkv[2 * C:],
+                                      dwp, dbp, dw1, db1, dw2, db2]
+            saved.layers[i] = None  # release this layer's activations early
+        dfeats = [torch.empty_like(d) for d in douts]
+        dgps = torch.empty(self.B, 2, C, device=dev, dtype=f32)
+        dpos = torch.empty(1, self.T, C, device=dev, dtype=f32)
+        K.tokens_bwd(self.geom, dx, douts if residual else None, dfeats, dgps, dpos)
+        grads[0] = dpos
+        return dfeats, dgps, grads
+
+
+def _layout_of(t):
+    """NCHW-contiguous -> DSF_NCHW; channels_last storage -> DSF_NHWC."""
+    if t.is_contiguous():
+        return K.DSF_NCHW
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return K.DSF_NHWC
+    raise RuntimeError("feature maps must be contiguous or channels_last")
+
+
+class FusionStageFn(torch.autograd.Function):
+    """(image, lidar, radar feature maps, gps_emb, *GPT params) -> (image', lidar', radar', gps_out)."""
+
+    @staticmethod
+    def forward(ctx, cfg, img, lidar, radar, gps_emb, *params):
+        K.check_device()
+        for t, n in ((img, "image features"), (lidar, "lidar features"), (radar, "radar features")):
+            if not t.is_cuda:
+                raise RuntimeError("%s must be CUDA tensors (the fusion stage has no CPU path)" % n)
+        layout = _layout_of(img)
+        if _layout_of(lidar) != layout or _layout_of(radar) != layout:
+            lidar = lidar.contiguous(memory_format=torch.channels_last if layout == K.DSF_NHWC else torch.contiguous_format)
+            radar = radar.contiguous(memory_format=torch.channels_last if layout == K.DSF_NHWC else torch.contiguous_format)
+        if img.dtype not in (torch.float32, torch.bfloat16) or lidar.dtype != img.dtype or radar.dtype != img.dtype:
+            raise RuntimeError("feature maps must share one dtype (float32 or bfloat16)")
+        S, V = cfg["seq_len"], cfg["n_views"]
+        N, C, H, W = lidar.shape
+        B = N // S
+        if img.shape[0] != B * V * S or radar.shape[0] != B * S:
+            raise RuntimeError("inconsistent frame counts: image %d lidar %d radar %d (seq_len %d, n_views %d)"
+                               % (img.shape[0], N, radar.shape[0], S, V))
+        r = _Runner(B, S, V, cfg["vert_anchors"], cfg["horz_anchors"], C, H, W, cfg["n_head"], cfg["n_layer"],
+                    img.dtype, cfg["compute_dtype"], layout)
+        if params[0].shape[1] != r.T:
+            raise RuntimeError("pos_emb has %d tokens, inputs imply %d" % (params[0].shape[1], r.T))
+        gps_emb = gps_emb.contiguous().float()
+        plist = [p.detach().contiguous().float() for p in params]
+        residual = bool(cfg.get("residual", True))
+        outs, gps_out, saved = r.forward([img.detach(), lidar.detach(), radar.detach()], gps_emb.detach(), plist, residual)
+        ctx.runner, ctx.saved_state, ctx.plist, ctx.residual = r, saved, plist, residual
+        ctx.feat_mf = torch.channels_last if layout == K.DSF_NHWC else torch.contiguous_format
+        ctx.gps_dtype = gps_emb.dtype
+        return outs[0], outs[1], outs[2], gps_out
+
+    @staticmethod
+    def backward(ctx, d_img, d_lidar, d_radar, d_gps):
+        r = ctx.runner
+        mf = ctx.feat_mf
+
+        def prep(d, like_dtype):
+            return d.contiguous(memory_format=mf).to(like_dtype)
+
+        fdt = torch.bfloat16 if r.geom.feat_dtype == K.DSF_BF16 else torch.float32
+        douts = [prep(d_img, fdt), prep(d_lidar, fdt), prep(d_radar, fdt)]
+        dgps_out = None if d_gps is None else d_gps.contiguous().float()
+        dfeats, dgps, grads = r.backward(ctx.saved_state, ctx.plist, douts, dgps_out, ctx.residual)
+        ctx.saved_state = None
+        return (None, dfeats[0], dfeats[1], dfeats[2], dgps) + tuple(grads)
+
+
+def fusion_stage(cfg, img, lidar, radar, gps_emb, params):
+    """cfg: dict(seq_len, n_views, vert_anchors, horz_anchors, n_head, n_layer, compute_dtype[, residual])."""
+    return FusionStageFn.apply(cfg, img, lidar, radar, gps_emb, *params)

@@ -1,0 +1,276 @@
+"""Drop-in modules for the reference's GPT fusion path (model2_seq.py).
+
+Same constructors, ``forward`` signatures, attribute names and ``state_dict`` keys as the reference
+classes, so reference checkpoints load with ``strict=True`` (including the ``module.`` DataParallel
+prefix handled by the caller, my_test.py:11):
+
+  * ``SelfAttention`` / ``Block``   model2_seq.py:74-134   (parameter containers; math is fused)
+  * ``GPT``                         model2_seq.py:175-287
+  * ``ImageCNN`` / ``LidarEncoder`` model2_seq.py:12-72    (stock torchvision ResNets, out of scope)
+  * ``Encoder``                     model2_seq.py:406-597
+  * ``TransFuser``                  model2_seq.py:850-894  (wired to the GPT ``Encoder``)
+
+The fusion stage itself (pool -> tokens -> 8 blocks -> ln_f -> upsample -> residual add, forward and
+backward) runs in ``functional.FusionStageFn`` on the hand-written sm_100a kernels.  There is no
+PyTorch fallback: on a CPU tensor or without ``libdsfuse.so`` the modules raise.
+
+Extra, optional config attributes (duck-typed ``config`` object, config_seq.py:3-45):
+  ``fusion_dtype``            torch.bfloat16 (default, tensor-core mode) or torch.float32 (parity mode)
+  ``modality_missing``        None | 'image' | 'lidar' | 'radar' | 'lidar_radar'  (mambafuser_seq.py:361-391)
+  ``modality_missing_type``   'zerolike' | 'randlike'
+  ``pretrained``              bool; torchvision ImageNet weights for the trunks (needs a local cache)
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .functional import fusion_stage, param_names
+
+
+class SelfAttention(nn.Module):
+    """Parameter container with the reference layout (model2_seq.py:79-91)."""
+
+    def __init__(self, n_embd, n_head, attn_pdrop, resid_pdrop):
+        super().__init__()
+        if n_embd % n_head != 0:
+            raise AssertionError("n_embd must be divisible by n_head")
+        self.key = nn.Linear(n_embd, n_embd)
+        self.query = nn.Linear(n_embd, n_embd)
+        self.value = nn.Linear(n_embd, n_embd)
+        self.attn_drop = nn.Dropout(attn_pdrop)
+        self.resid_drop = nn.Dropout(resid_pdrop)
+        self.proj = nn.Linear(n_embd, n_embd)
+        self.n_head = n_head
+
+
+class Block(nn.Module):
+    """Parameter container with the reference layout (model2_seq.py:116-126)."""
+
+    def __init__(self, n_embd, n_head, block_exp, attn_pdrop, resid_pdrop):
+        super().__init__()
+        self.ln1 = nn.LayerNorm(n_embd)
+        self.ln2 = nn.LayerNorm(n_embd)
+        self.attn = SelfAttention(n_embd, n_head, attn_pdrop, resid_pdrop)
+        self.mlp = nn.Sequential(
+            nn.Linear(n_embd, block_exp * n_embd),
+            nn.ReLU(True),
+            nn.Linear(block_exp * n_embd, n_embd),
+            nn.Dropout(resid_pdrop),
+        )
+
+
+class GPT(nn.Module):
+    """B200-native replacement of ``model2_seq.GPT`` (same ctor / forward / state_dict)."""
+
+    def __init__(self, n_embd, n_head, block_exp, n_layer, vert_anchors, horz_anchors, seq_len,
+                 embd_pdrop, attn_pdrop, resid_pdrop, config):
+        super().__init__()
+        self.n_embd = n_embd
+        self.n_head = n_head
+        self.n_layer = n_layer
+        self.seq_len = seq_len
+        self.vert_anchors = vert_anchors
+        self.horz_anchors = horz_anchors
+        self.config = config
+        n_tok = (config.n_views + 2) * seq_len * vert_anchors * horz_anchors + 2
+        self.pos_emb = nn.Parameter(torch.zeros(1, n_tok, n_embd))
+        self.drop = nn.Dropout(embd_pdrop)
+        self.blocks = nn.Sequential(*[Block(n_embd, n_head, block_exp, attn_pdrop, resid_pdrop) for _ in range(n_layer)])
+        self.ln_f = nn.LayerNorm(n_embd)
+        self.block_size = seq_len
+        self._pdrop = (float(embd_pdrop), float(attn_pdrop), float(resid_pdrop))
+        self.apply(self._init_weights)
+        self._names = param_names(n_layer)
+
+    def get_block_size(self):
+        return self.block_size
+
+    def _init_weights(self, module):
+        # reference init law, model2_seq.py:207-214
+        if isinstance(module, nn.Linear):
+            module.weight.data.normal_(mean=0.0, std=0.02)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+
+    def _flat_params(self):
+        table = dict(self.named_parameters())
+        return [table[n] for n in self._names]
+
+    def _stage_cfg(self, residual):
+        if self.training and any(p > 0.0 for p in self._pdrop):
+            raise NotImplementedError(
+                "dropout > 0 in training mode is not implemented in the B200 fusion path yet; build the config with "
+                "embd_pdrop=attn_pdrop=resid_pdrop=0 (GlobalConfig(**kwargs), config_seq.py:43-45) or call .eval()")
+        return dict(seq_len=self.seq_len, n_views=self.config.n_views, vert_anchors=self.vert_anchors,
+                    horz_anchors=self.horz_anchors, n_head=self.n_head, n_layer=self.n_layer,
+                    compute_dtype=getattr(self.config, "fusion_dtype", torch.bfloat16), residual=residual)
+
+    def forward(self, image_tensor, lidar_tensor, radar_tensor, gps):
+        """Reference semantics (model2_seq.py:248-287): inputs are already pooled to the anchor grid,
+        outputs are the un-tokenised anchor maps + the two GPS tokens."""
+        return fusion_stage(self._stage_cfg(False), image_tensor, lidar_tensor, radar_tensor, gps, self._flat_params())
+
+    def fuse(self, image_features, lidar_features, radar_features, gps_embd):
+        """Whole stage on full-resolution trunk features (model2_seq.py:515-526): returns
+        (image', lidar', radar', gps_out) with feat' = feat + upsample(GPT(pool(feat)))."""
+        return fusion_stage(self._stage_cfg(True), image_features, lidar_features, radar_features, gps_embd, self._flat_params())
+
+
+# --------------------------------------------------------------------------------------------- trunks
+def normalize_imagenet(x):
+    """ImageNet mean/std on 0-255 input (model2_seq.py:36-45)."""
+    mean = x.new_tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = x.new_tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    return (x / 255.0 - mean) / std
+
+
+def _resnet(kind, pretrained):
+    from torchvision import models
+    ctor = getattr(models, kind)
+    if pretrained:
+        return ctor(weights="DEFAULT")
+    return ctor(weights=None)
+
+
+class ImageCNN(nn.Module):
+    """ResNet-34 image trunk, fc removed (model2_seq.py:12-34)."""
+
+    def __init__(self, c_dim, normalize=True, pretrained=False):
+        super().__init__()
+        self.normalize = normalize
+        self.features = _resnet("resnet34", pretrained)
+        self.features.fc = nn.Sequential()
+
+    def forward(self, inputs):
+        c = 0
+        for x in inputs:
+            if self.normalize:
+                x = normalize_imagenet(x)
+            c = c + self.features(x)
+        return c
+
+
+class LidarEncoder(nn.Module):
+    """ResNet-18 trunk with an ``in_channels`` stem, fc removed (model2_seq.py:48-72)."""
+
+    def __init__(self, num_classes=512, in_channels=2, pretrained=False):
+        super().__init__()
+        self._model = _resnet("resnet18", pretrained)
+        self._model.fc = nn.Sequential()
+        old = self._model.conv1
+        self._model.conv1 = nn.Conv2d(in_channels, out_channels=old.out_channels, kernel_size=old.kernel_size,
+                                      stride=old.stride, padding=old.padding, bias=old.bias)
+
+    def forward(self, inputs):
+        feats = 0
+        for x in inputs:
+            feats = feats + self._model(x)
+        return feats
+
+
+def _missing(cfg, name):
+    mm = getattr(cfg, "modality_missing", None)
+    return mm == name or (mm == "lidar_radar" and name in ("lidar", "radar"))
+
+
+class Encoder(nn.Module):
+    """Multi-scale fusion encoder (model2_seq.py:406-597) with the four GPT stages on dsfuse kernels."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        pre = bool(getattr(config, "pretrained", False))
+        self.avgpool = nn.AdaptiveAvgPool2d((config.vert_anchors, config.horz_anchors))  # kept for state/attr parity; fused
+        self.image_encoder = ImageCNN(512, normalize=True, pretrained=pre)
+        self.lidar_encoder = LidarEncoder(num_classes=512, in_channels=1, pretrained=pre)
+        self.radar_encoder = LidarEncoder(num_classes=512, in_channels=2 if getattr(config, "add_velocity", 0) else 1,
+                                          pretrained=pre)
+        self.vel_emb1 = nn.Linear(2, 64)
+        self.vel_emb2 = nn.Linear(64, 128)
+        self.vel_emb3 = nn.Linear(128, 256)
+        self.vel_emb4 = nn.Linear(256, 512)
+
+        def gpt(c):
+            return GPT(n_embd=c, n_head=config.n_head, block_exp=config.block_exp, n_layer=config.n_layer,
+                       vert_anchors=config.vert_anchors, horz_anchors=config.horz_anchors, seq_len=config.seq_len,
+                       embd_pdrop=config.embd_pdrop, attn_pdrop=config.attn_pdrop, resid_pdrop=config.resid_pdrop,
+                       config=config)
+
+        self.transformer1 = gpt(64)
+        self.transformer2 = gpt(128)
+        self.transformer3 = gpt(256)
+        self.transformer4 = gpt(512)
+
+    def _apply_missing(self, name, t):
+        # semantics of mambafuser_seq.py:361-391, 418-420: replace the stacked input ahead of conv1
+        if not _missing(self.config, name):
+            return t
+        if getattr(self.config, "modality_missing_type", "zerolike") == "randlike":
+            return torch.rand_like(t)
+        return torch.zeros_like(t)
+
+    def forward(self, image_list, lidar_list, radar_list, gps, velocity=None, rebuild_modality_feat_list=None):
+        cfg = self.config
+        if self.image_encoder.normalize:
+            image_list = [normalize_imagenet(t) for t in image_list]
+        bz, _, h, w = lidar_list[0].shape
+        cfg.n_views = len(image_list) // cfg.seq_len  # the reference mutates the shared config too (:489)
+        S, V = cfg.seq_len, cfg.n_views
+        img = torch.stack(image_list, dim=1).view(bz * V * S, image_list[0].shape[1], h, w)
+        lid = torch.stack(lidar_list, dim=1).view(bz * S, lidar_list[0].shape[1], h, w)
+        rad = torch.stack(radar_list, dim=1).view(bz * S, radar_list[0].shape[1], h, w)
+        img, lid, rad = self._apply_missing("image", img), self._apply_missing("lidar", lid), self._apply_missing("radar", rad)
+
+        ie, le, re_ = self.image_encoder.features, self.lidar_encoder._model, self.radar_encoder._model
+
+        def stem(m, x):
+            return m.layer1(m.maxpool(m.relu(m.bn1(m.conv1(x)))))
+
+        f_img, f_lid, f_rad = stem(ie, img), stem(le, lid), stem(re_, rad)
+        g = self.vel_emb1(gps)
+        f_img, f_lid, f_rad, g = self.transformer1.fuse(f_img, f_lid, f_rad, g)
+        f_img, f_lid, f_rad = ie.layer2(f_img), le.layer2(f_lid), re_.layer2(f_rad)
+        g = self.vel_emb2(g)
+        f_img, f_lid, f_rad, g = self.transformer2.fuse(f_img, f_lid, f_rad, g)
+        f_img, f_lid, f_rad = ie.layer3(f_img), le.layer3(f_lid), re_.layer3(f_rad)
+        g = self.vel_emb3(g)
+        f_img, f_lid, f_rad, g = self.transformer3.fuse(f_img, f_lid, f_rad, g)
+        f_img, f_lid, f_rad = ie.layer4(f_img), le.layer4(f_lid), re_.layer4(f_rad)
+        g = self.vel_emb4(g)
+        f_img, f_lid, f_rad, g = self.transformer4.fuse(f_img, f_lid, f_rad, g)
+
+        p_img = torch.flatten(ie.avgpool(f_img), 1).view(bz, V * S, -1)
+        p_lid = torch.flatten(le.avgpool(f_lid), 1).view(bz, S, -1)
+        p_rad = torch.flatten(re_.avgpool(f_rad), 1).view(bz, S, -1)
+        fused = torch.cat([p_img, p_lid, p_rad, g.to(p_img.dtype)], dim=1)  # (B, (V+2)S + 2, 512)
+        return torch.sum(fused, dim=1)
+
+
+class TransFuser(nn.Module):
+    """``model2_seq.TransFuser`` (model2_seq.py:850-894) with the GPT ``Encoder`` wired in."""
+
+    def __init__(self, config, device, pretrain_weight=False):
+        super().__init__()
+        self.device = device
+        self.config = config
+        self.pred_len = config.pred_len
+        self.encoder = Encoder(config).to(self.device)
+        self.join = nn.Sequential(
+            nn.Linear(512, 256),
+            nn.ReLU(inplace=True),
+            nn.Linear(256, 128),
+            nn.ReLU(inplace=True),
+            nn.Linear(128, 64),
+        ).to(self.device)
+        if pretrain_weight:
+            self.load_pretrained_weight()
+
+    def load_pretrained_weight(self, path="mamba_fusion.pth"):
+        self.load_state_dict(torch.load(path, map_location=self.device))
+
+    def forward(self, image_list, lidar_list, radar_list, gps, rebuild_modality_feat_list=None, velocity=None):
+        fused = self.encoder(image_list, lidar_list, radar_list, gps)
+        return self.join(fused)

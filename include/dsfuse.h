@@ -1,0 +1,159 @@
+/*
+ * dsfuse.h — C ABI of the B200-native multimodal fusion stage (libdsfuse.so, sm_100a only).
+ *
+ * The reference (szy4017/DeepSense6G_TII) is 100 % Python and has no FFI of its own: the boundary it
+ * exposes for this path is the Python class API of model2_seq.py (GPT :175-287, Encoder :406-597,
+ * TransFuser :850-894).  The drop-in Python modules in deepsense6g_tii_b200/modules.py keep that class
+ * API; underneath they call the entry points declared here through ctypes.  Each entry point names
+ * the reference lines whose ATen/cuBLAS kernels it replaces.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller (PyTorch); the library never allocates,
+ *     frees or retains device memory.  Pointers must be 16-byte aligned.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream and
+ *     touches only the current device.  Calls are re-entrant.
+ *   - Return value: 0 on success, a DSF_E* code otherwise.  Never throws, never exits.
+ *     dsf_last_error() returns a thread-local message for the last failing call.
+ *   - dtype codes: DSF_F32 = 0, DSF_BF16 = 1.  layout codes: DSF_NCHW = 0, DSF_NHWC = 1.
+ *   - "tokens" are (B, T, C) row-major fp32 with T = n_slots*S*A*A + 2; the token order is the
+ *     reference's: ((slot*S + t)*A + y)*A + x, slots = V image views, lidar, radar; the last two
+ *     tokens are the GPS tokens (model2_seq.py:261-270).
+ */
+#ifndef DSFUSE_H_
+#define DSFUSE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSF_VERSION 100
+
+enum { DSF_F32 = 0, DSF_BF16 = 1 };
+enum { DSF_NCHW = 0, DSF_NHWC = 1 };
+enum {
+  DSF_OK = 0,
+  DSF_EINVAL = 1,   /* bad shape / dtype / alignment */
+  DSF_ELAUNCH = 2,  /* CUDA launch or runtime error */
+  DSF_EARCH = 3,    /* device is not sm_100 */
+  DSF_EUNSUPPORTED = 4
+};
+
+/* GEMM epilogue flags (bit mask) */
+enum {
+  DSF_EPI_BIAS = 1,      /* + bias[n]                      (nn.Linear bias, model2_seq.py:83-90,122,124) */
+  DSF_EPI_RELU = 2,      /* max(.,0)                       (nn.ReLU(True), :123) */
+  DSF_EPI_RESIDUAL = 4,  /* + residual[m,n] (fp32)          (x + attn / x + mlp, :131-132) */
+  DSF_EPI_ACCUM = 8      /* C += result (fp32 outputs only; used by weight-grad accumulation) */
+};
+
+int dsf_version(void);
+const char* dsf_last_error(void);
+/* 0 if the current device is sm_100 and the kernels can run on it, DSF_EARCH otherwise. */
+int dsf_check_device(void);
+
+/* Geometry shared by the token kernels. */
+typedef struct {
+  int32_t B;        /* samples */
+  int32_t S;        /* seq_len (frames per modality slot) */
+  int32_t V;        /* camera views (config.n_views) */
+  int32_t A_h, A_w; /* vert_anchors, horz_anchors */
+  int32_t C;        /* n_embd */
+  int32_t H, W;     /* feature-map size; H % A_h == 0 and W % A_w == 0 */
+  int32_t feat_dtype; /* DSF_F32 / DSF_BF16: dtype of the feature maps */
+  int32_t layout;     /* DSF_NCHW / DSF_NHWC: physical layout of the feature maps */
+} dsf_geom;
+
+/* K1 forward. Replaces nn.AdaptiveAvgPool2d x3 (model2_seq.py:515-517, 533-535, 552-554, 571-573) +
+ * view/cat/permute/contiguous/cat(gps) + pos_emb add (model2_seq.py:256-272).
+ *   img   (B*V*S, C, H, W), lidar/radar (B*S, C, H, W)  [feat_dtype, layout]
+ *   gps   (B, 2, C) fp32, pos_emb (T, C) fp32  ->  x (B, T, C) fp32                                */
+int dsf_tokens_fwd(const dsf_geom* g, const void* img, const void* lidar, const void* radar,
+                   const float* gps, const float* pos_emb, float* x, void* stream);
+
+/* K1 backward (autograd of the above, train2_seq.py:127).
+ *   dx (B,T,C) fp32 -> dimg/dlidar/dradar = [dres_* +] pool-broadcast(dx)/(kh*kw)  [feat_dtype]
+ *                      dgps (B,2,C) fp32, dpos_emb (T,C) fp32 (= sum_b dx, overwritten)
+ * dres_* may be NULL; when given it is the gradient that reaches the same feature map through the
+ * residual branch (feat + up, model2_seq.py:524-526) and is added in the same pass.               */
+int dsf_tokens_bwd(const dsf_geom* g, const float* dx, const void* dres_img, const void* dres_lidar,
+                   const void* dres_radar, void* dimg, void* dlidar, void* dradar, float* dgps,
+                   float* dpos_emb, void* stream);
+
+/* K2. nn.LayerNorm(C), eps 1e-5 (model2_seq.py:118-119,199; used :131-132,274).
+ *   x (M,C) fp32 -> y (M,C) y_dtype; mean, rstd (M) fp32 saved for backward.                        */
+int dsf_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int32_t y_dtype,
+                      float* mean, float* rstd, int32_t M, int32_t C, float eps, void* stream);
+/*   dy (M,C) dy_dtype; dx_out = (dx_add ? dx_add : 0) + LN'(dy); dgamma/dbeta (C) fp32 are
+ *   ACCUMULATED into (caller zeroes or passes .grad).                                              */
+int dsf_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* gamma,
+                      const float* mean, const float* rstd, const float* dx_add, float* dx_out,
+                      float* dgamma, float* dbeta, int32_t M, int32_t C, void* stream);
+
+/* K3/K5/K6 (bf16 tensor-core path, tcgen05 + TMEM + TMA).  Replaces nn.Linear (model2_seq.py:83-90,
+ * 97-99,109,122,124) and its autograd.
+ *   NT:  C[M,N] = A[M,K] . B[N,K]^T  (+bias)(relu)(+residual)      A, B bf16 row-major (K contiguous)
+ *        C is c_dtype (bf16 or fp32) with leading dimension ldc; residual is fp32 with ldc.
+ *   TN:  C[N',K'] (+)= A[M,N']^T . B[M,K']   (weight gradient; contraction over the M rows)
+ *        A, B bf16 row-major; C fp32.  With DSF_EPI_ACCUM the result is atomically added to C
+ *        (split over M across CTAs); without it C must be zero-filled by the caller.              */
+int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32_t ldb, void* C, int32_t ldc,
+                     int32_t c_dtype, const float* bias, const float* residual, int32_t M, int32_t N,
+                     int32_t K, int32_t epi_flags, void* stream);
+int dsf_gemm_bf16_tn(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc,
+                     int32_t M, int32_t Nout, int32_t Kout, void* stream);
+
+/* fp32 parity path: generic strided, two-level batched SIMT GEMM (FFMA).
+ *   C[b1,b2][m,n] = alpha * sum_k A[b1,b2][m,k] * B[b1,b2][n,k]  (+bias)(relu)(+residual)(+C)      */
+typedef struct {
+  int32_t M, N, K;
+  int32_t nb1, nb2;                  /* batch extents (1,1 for a plain GEMM) */
+  int64_t a_b1, a_b2, a_m, a_k;      /* element strides */
+  int64_t b_b1, b_b2, b_n, b_k;
+  int64_t c_b1, c_b2, c_m, c_n;
+  float alpha;
+  int32_t epi_flags;
+} dsf_gemm_f32_desc;
+int dsf_gemm_f32(const dsf_gemm_f32_desc* d, const float* A, const float* B, float* C,
+                 const float* bias, const float* residual, void* stream);
+
+/* Column sums: out[n] (+)= sum_m X[m,n]  (bias gradients).  X dtype x_dtype, out fp32 accumulated. */
+int dsf_colsum(const void* X, int32_t x_dtype, int32_t ldx, float* out, int32_t M, int32_t N,
+               void* stream);
+/* dst = relu-mask: dy * (h > 0), elementwise in place on dy (bf16 or fp32), n elements.           */
+int dsf_relu_bwd(void* dy, const void* h, int32_t dtype, int64_t n, void* stream);
+
+/* fp32 parity path softmax over the last dim of (rows, T), in place (model2_seq.py:103) and its
+ * backward dS = P * (dP - sum(dP*P)), in place on dP.                                             */
+int dsf_softmax_fwd(float* s, int64_t rows, int32_t T, void* stream);
+int dsf_softmax_bwd(float* dp, const float* p, int64_t rows, int32_t T, void* stream);
+
+/* K4 (bf16 tensor-core path): fused flash-style attention, no mask (model2_seq.py:102-106).
+ *   qkv (B, T, 3C) bf16 = [q | k | v] per token, head h at columns h*hs within each third
+ *   -> y (B, T, C) bf16 (heads re-assembled side by side), lse (B, nh, T) fp32 (natural log units
+ *   of the scaled scores).  hs = C/nh in {16, 32, 64, 128}.                                        */
+int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int32_t T, int32_t C, int32_t nh,
+                 void* stream);
+/*   dy (B,T,C) bf16 -> dqkv (B,T,3C) bf16.  delta (B,nh,T) fp32 is scratch (rowsum(dy*y)).         */
+int dsf_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* delta,
+                 void* dqkv, int32_t B, int32_t T, int32_t C, int32_t nh, void* stream);
+
+/* K7 forward.  Replaces slice/view/permute/contiguous (model2_seq.py:275-286) + F.interpolate
+ * (bilinear, align_corners=False; :521-523, 539-541, 558-560) + residual add (:524-526 ...).
+ *   y (B,T,C) fp32 (ln_f output), feat_* in -> out_* = feat_* + up(untokenise(y))   [feat_dtype]   */
+int dsf_upsample_add_fwd(const dsf_geom* g, const float* y, const void* img, const void* lidar,
+                         const void* radar, void* out_img, void* out_lidar, void* out_radar,
+                         void* stream);
+/* K7 backward: dout_* (N,C,H,W) -> dy (B,T,C) fp32 for the n_slots*S*A*A map tokens; the two GPS
+ * rows are copied from dgps_out (B,2,C) (zero when NULL).                                          */
+int dsf_upsample_add_bwd(const dsf_geom* g, const void* dout_img, const void* dout_lidar,
+                         const void* dout_radar, const float* dgps_out, float* dy, void* stream);
+
+/* fp32 -> bf16 conversion (weight shadow refresh), n elements. */
+int dsf_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSFUSE_H_ */

@@ -1,0 +1,291 @@
+"""Per-kernel GPU parity tests: every C-ABI entry point against the oracle restatement
+(oracle/fusion_ref.py) or a plain fp32 torch expression of the same reference lines, on the same
+seeded inputs.  All calls go through the C ABI (deepsense6g_tii_b200/_capi.py -> libdsfuse.so).
+
+Tolerances: fp32 kernels 1e-5..1e-4 relative (summation order only); bf16 tensor-core kernels are
+compared against an fp32 evaluation of the *same bf16-rounded inputs*, 1e-2 relative (north_star
+allows 2e-2 end to end).
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import assert_close
+from oracle import fusion_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K(cuda_dev):
+    from deepsense6g_tii_b200 import _capi
+    _capi.check_device()
+    return _capi
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _feat(n, c, h, w, g, dev, dtype=torch.float32, nhwc=False):
+    t = torch.randn(n, c, h, w, generator=g).to(dev).to(dtype)
+    if nhwc:
+        t = t.contiguous(memory_format=torch.channels_last)
+    return t
+
+
+STAGE_SHAPES = [  # (B, S, A, C, H)  H = A * scale
+    (2, 5, 8, 64, 64), (2, 5, 8, 128, 32), (1, 5, 8, 256, 16), (2, 5, 8, 512, 8),
+    (1, 2, 16, 64, 32),  # scaled config: 16x16 anchors
+    (1, 3, 4, 8, 24),    # odd scale 6, tiny C
+]
+
+
+@pytest.mark.parametrize("shape", STAGE_SHAPES)
+@pytest.mark.parametrize("variant", ["nchw_f32", "nchw_bf16", "nhwc_f32", "nhwc_bf16"])
+def test_tokens_fwd_bwd(K, cuda_dev, shape, variant):
+    B, S, A, C, H = shape
+    nhwc = variant.startswith("nhwc")
+    dt = torch.bfloat16 if variant.endswith("bf16") else torch.float32
+    g = _gen(1)
+    T = 3 * S * A * A + 2
+    feats = [_feat(B * S, C, H, H, g, cuda_dev, dt, nhwc) for _ in range(3)]
+    gps = torch.randn(B, 2, C, generator=g).to(cuda_dev)
+    pos = torch.randn(1, T, C, generator=g).to(cuda_dev)
+    geom = K.make_geom(B, S, 1, A, A, C, H, H, K.DSF_BF16 if dt == torch.bfloat16 else K.DSF_F32, K.DSF_NHWC if nhwc else K.DSF_NCHW)
+    x = torch.empty(B * T, C, device=cuda_dev)
+    K.tokens_fwd(geom, feats[0], feats[1], feats[2], gps, pos, x)
+    # oracle on the same (possibly bf16-rounded) inputs, fp32 math
+    fr = [f.float().contiguous().requires_grad_(True) for f in feats]
+    gr, pr = gps.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    ref = R.build_tokens(*[R.anchor_pool(f, A, A) for f in fr], gr, pr, S, 1)
+    assert_close(x.view(B, T, C), ref, 2e-6, 1e-6, "tokens_fwd")
+    # backward
+    dx = torch.randn(B, T, C, generator=g).to(cuda_dev)
+    dres = [_feat(B * S, C, H, H, g, cuda_dev, dt, nhwc) for _ in range(3)]
+    ref.backward(dx)
+    douts = [torch.empty_like(f) for f in feats]
+    dgps = torch.empty(B, 2, C, device=cuda_dev)
+    dpos = torch.empty(1, T, C, device=cuda_dev)
+    K.tokens_bwd(geom, dx.contiguous(), dres, douts, dgps, dpos)
+    tol = 1e-2 if dt == torch.bfloat16 else 2e-6
+    for d, f, r in zip(douts, fr, dres):
+        assert_close(d.float(), f.grad + r.float(), tol, 1e-6, "tokens_bwd dfeat")
+    assert_close(dgps, gr.grad, 1e-6, 1e-7, "dgps")
+    assert_close(dpos, pr.grad, 2e-6, 1e-6, "dpos_emb")
+    # without the residual-branch gradient
+    K.tokens_bwd(geom, dx.contiguous(), None, douts, dgps, dpos)
+    assert_close(douts[1].float(), fr[1].grad, tol, 1e-6, "tokens_bwd no-res")
+
+
+@pytest.mark.parametrize("M,C", [(962, 64), (1924, 128), (300, 256), (11544, 512), (77, 1024), (10, 8)])
+@pytest.mark.parametrize("ydt", [torch.float32, torch.bfloat16])
+def test_layernorm(K, cuda_dev, M, C, ydt):
+    g = _gen(2)
+    x = (torch.randn(M, C, generator=g) * 2 + 0.5).to(cuda_dev)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(cuda_dev)
+    b = (0.1 * torch.randn(C, generator=g)).to(cuda_dev)
+    y = torch.empty(M, C, device=cuda_dev, dtype=ydt)
+    mean = torch.empty(M, device=cuda_dev)
+    rstd = torch.empty(M, device=cuda_dev)
+    K.layernorm_fwd(x, w, b, y, mean, rstd)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = R.layer_norm(xr, wr, br)
+    assert_close(y.float(), ref, 5e-3 if ydt == torch.bfloat16 else 1e-5, 1e-6, "ln fwd")
+    assert_close(mean, x.mean(-1), 1e-5, 1e-6, "mean")
+    dy = torch.randn(M, C, generator=g).to(cuda_dev).to(ydt)
+    add = torch.randn(M, C, generator=g).to(cuda_dev)
+    ref.backward(dy.float())
+    dx = torch.empty(M, C, device=cuda_dev)
+    dg = torch.zeros(C, device=cuda_dev)
+    db = torch.zeros(C, device=cuda_dev)
+    K.layernorm_bwd(dy, x, w, mean, rstd, add, dx, dg, db)
+    assert_close(dx, xr.grad + add, 2e-5, 1e-6, "ln dx")
+    assert_close(dg, wr.grad, 1e-4, 1e-5, "ln dgamma")
+    assert_close(db, br.grad, 1e-4, 1e-5, "ln dbeta")
+    K.layernorm_bwd(dy, x, w, mean, rstd, None, dx, dg, db)  # accumulates into dg/db
+    assert_close(dx, xr.grad, 2e-5, 1e-6, "ln dx no-add")
+    assert_close(dg, 2 * wr.grad, 1e-4, 1e-5, "ln dgamma accumulate")
+
+
+@pytest.mark.parametrize("shape", STAGE_SHAPES)
+@pytest.mark.parametrize("variant", ["nchw_f32", "nchw_bf16", "nhwc_f32"])
+def test_upsample_add_fwd_bwd(K, cuda_dev, shape, variant):
+    import torch.nn.functional as F
+    B, S, A, C, H = shape
+    nhwc = variant.startswith("nhwc")
+    dt = torch.bfloat16 if variant.endswith("bf16") else torch.float32
+    g = _gen(3)
+    T = 3 * S * A * A + 2
+    scale = H // A
+    feats = [_feat(B * S, C, H, H, g, cuda_dev, dt, nhwc) for _ in range(3)]
+    y = torch.randn(B, T, C, generator=g).to(cuda_dev)
+    geom = K.make_geom(B, S, 1, A, A, C, H, H, K.DSF_BF16 if dt == torch.bfloat16 else K.DSF_F32, K.DSF_NHWC if nhwc else K.DSF_NCHW)
+    outs = [torch.empty_like(f) for f in feats]
+    K.upsample_add_fwd(geom, y.view(B * T, C), feats, outs)
+    yr = y.clone().requires_grad_(True)
+    maps = yr[:, :T - 2].reshape(B, 3 * S, A, A, C).permute(0, 1, 4, 2, 3)
+    refs = []
+    for m in range(3):
+        tok = maps[:, m * S:(m + 1) * S].reshape(B * S, C, A, A)
+        up = R.bilinear_upsample(tok, scale)
+        if scale > 1:
+            assert_close(up, F.interpolate(tok, scale_factor=scale, mode="bilinear"), 1e-6, 1e-7, "oracle vs F.interpolate")
+        refs.append(feats[m].float() + up)
+    tol = 1e-2 if dt == torch.bfloat16 else 1e-6
+    for o, r in zip(outs, refs):
+        assert_close(o.float(), r, tol, 1e-6, "upsample_add_fwd")
+    douts = [_feat(B * S, C, H, H, g, cuda_dev, dt, nhwc) for _ in range(3)]
+    dgps = torch.randn(B, 2, C, generator=g).to(cuda_dev)
+    sum((r * d.float()).sum() for r, d in zip(refs, douts)).backward()
+    dy = torch.empty(B * T, C, device=cuda_dev)
+    K.upsample_add_bwd(geom, douts, dgps, dy)
+    dy = dy.view(B, T, C)
+    assert_close(dy[:, :T - 2], yr.grad[:, :T - 2], 1e-5, 1e-6, "upsample_add_bwd")
+    assert_close(dy[:, T - 2:], dgps, 0, 0, "gps rows")
+    K.upsample_add_bwd(geom, douts, None, dy)
+    assert float(dy.view(B, T, C)[:, T - 2:].abs().max()) == 0.0
+
+
+def test_gemm_f32_variants(K, cuda_dev):
+    from deepsense6g_tii_b200._capi import GemmF32Desc, EPI_BIAS, EPI_RELU, EPI_RESIDUAL, EPI_ACCUM
+    g = _gen(4)
+    M, N, Kd = 203, 130, 77
+    x = torch.randn(M, Kd, generator=g).to(cuda_dev)
+    w = torch.randn(N, Kd, generator=g).to(cuda_dev)
+    b = torch.randn(N, generator=g).to(cuda_dev)
+    res = torch.randn(M, N, generator=g).to(cuda_dev)
+    out = torch.empty(M, N, device=cuda_dev)
+    K.gemm_f32(GemmF32Desc(M, N, Kd, 1, 1, 0, 0, Kd, 1, 0, 0, Kd, 1, 0, 0, N, 1, 1.0, EPI_BIAS | EPI_RELU | EPI_RESIDUAL), x, w, out, b, res)
+    assert_close(out, torch.relu(x @ w.t() + b) + res, 1e-5, 1e-6, "NT")
+    dy = torch.randn(M, N, generator=g).to(cuda_dev)
+    dw = torch.ones(N, Kd, device=cuda_dev)
+    K.gemm_f32(GemmF32Desc(N, Kd, M, 1, 1, 0, 0, 1, N, 0, 0, 1, Kd, 0, 0, Kd, 1, 0.5, EPI_ACCUM), dy, x, dw)
+    assert_close(dw, 1 + 0.5 * dy.t() @ x, 1e-5, 1e-6, "TN accumulate")
+    dx = torch.empty(M, Kd, device=cuda_dev)
+    K.gemm_f32(GemmF32Desc(M, Kd, N, 1, 1, 0, 0, N, 1, 0, 0, 1, Kd, 0, 0, Kd, 1, 1.0, 0), dy, w, dx)
+    assert_close(dx, dy @ w, 1e-5, 1e-6, "NN")
+    # batched attention-shaped contraction with head strides
+    B, T, C, nh = 2, 70, 24, 3
+    hs = C // nh
+    qkv = torch.randn(B * T, 3 * C, generator=g).to(cuda_dev)
+    P = torch.empty(B, nh, T, T, device=cuda_dev)
+    ld = 3 * C
+    K.gemm_f32(GemmF32Desc(T, T, hs, B, nh, T * ld, hs, ld, 1, T * ld, hs, ld, 1, nh * T * T, T * T, T, 1, 0.25, 0), qkv, qkv[:, C:], P)
+    q = qkv[:, :C].view(B, T, nh, hs).transpose(1, 2)
+    k = qkv[:, C:2 * C].view(B, T, nh, hs).transpose(1, 2)
+    assert_close(P, 0.25 * q @ k.transpose(-1, -2), 1e-5, 1e-6, "batched QK^T")
+
+
+def test_softmax_colsum_relu_cast(K, cuda_dev):
+    g = _gen(5)
+    rows, T = 37, 962
+    s = (3 * torch.randn(rows, T, generator=g)).to(cuda_dev)
+    p = s.clone()
+    K.softmax_fwd(p, rows, T)
+    assert_close(p, torch.softmax(s, -1), 1e-5, 1e-8, "softmax")
+    dp = torch.randn(rows, T, generator=g).to(cuda_dev)
+    ref = p * (dp - (dp * p).sum(-1, keepdim=True))
+    K.softmax_bwd(dp, p, rows, T)
+    assert_close(dp, ref, 1e-5, 1e-8, "softmax bwd")
+    for dt in (torch.float32, torch.bfloat16):
+        X = torch.randn(1001, 194, generator=g).to(cuda_dev).to(dt)
+        out = torch.ones(194, device=cuda_dev)
+        K.colsum(X, out)
+        assert_close(out, 1 + X.float().sum(0), 1e-5, 1e-5, "colsum")
+        h = torch.randn(64, 96, generator=g).to(cuda_dev).to(dt)
+        d = torch.randn(64, 96, generator=g).to(cuda_dev).to(dt)
+        ref = torch.where(h > 0, d, torch.zeros_like(d))
+        K.relu_bwd(d, h)
+        assert torch.equal(d, ref)
+    src = torch.randn(1003, generator=g).to(cuda_dev)
+    dst = torch.empty(1003, device=cuda_dev, dtype=torch.bfloat16)
+    K.cast_f32_bf16(src, dst)
+    assert torch.equal(dst, src.to(torch.bfloat16))
+
+
+GEMM_SHAPES = [(128, 64, 64), (128, 128, 64), (300, 128, 128), (962, 192, 64), (1000, 256, 512), (11544, 512, 512),
+               (2048, 1536, 512), (1924, 512, 2048), (1924, 2048, 512), (130, 64, 256)]
+
+
+@pytest.mark.parametrize("M,N,Kd", GEMM_SHAPES)
+def test_gemm_bf16_nt(K, cuda_dev, M, N, Kd):
+    g = _gen(6)
+    a = torch.randn(M, Kd, generator=g).to(cuda_dev).to(torch.bfloat16)
+    w = (0.05 * torch.randn(N, Kd, generator=g)).to(cuda_dev).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    res = torch.randn(M, N, generator=g).to(cuda_dev)
+    ref = a.float() @ w.float().t()
+    out = torch.empty(M, N, device=cuda_dev, dtype=torch.bfloat16)
+    K.gemm_bf16_nt(a, w, out)
+    torch.cuda.synchronize()
+    assert_close(out.float(), ref, 6e-3, 1e-4, "plain bf16 out")
+    K.gemm_bf16_nt(a, w, out, bias=bias, relu=True)
+    assert_close(out.float(), torch.relu(ref + bias), 6e-3, 1e-4, "bias+relu")
+    out32 = torch.empty(M, N, device=cuda_dev, dtype=torch.float32)
+    K.gemm_bf16_nt(a, w, out32, bias=bias, residual=res)
+    assert_close(out32, ref + bias + res, 1e-5, 1e-5, "bias+residual fp32 out")
+    K.gemm_bf16_nt(a, w, out32, residual=out32.clone())
+    assert_close(out32, 2 * ref + bias + res, 1e-5, 1e-5, "residual aliasing a copy")
+
+
+@pytest.mark.parametrize("M,No,Ko", [(64, 64, 64), (128, 128, 128), (200, 64, 192), (962, 192, 64), (1924, 512, 512),
+                                     (11544, 512, 2048), (11544, 2048, 512), (5000, 1536, 512), (77, 128, 64)])
+def test_gemm_bf16_tn(K, cuda_dev, M, No, Ko):
+    g = _gen(7)
+    dy = (0.1 * torch.randn(M, No, generator=g)).to(cuda_dev).to(torch.bfloat16)
+    x = torch.randn(M, Ko, generator=g).to(cuda_dev).to(torch.bfloat16)
+    ref = dy.float().t() @ x.float()
+    out = torch.zeros(No, Ko, device=cuda_dev)
+    K.gemm_bf16_tn(dy, x, out)
+    torch.cuda.synchronize()
+    assert_close(out, ref, 2e-5, 1e-5, "wgrad")
+    K.gemm_bf16_tn(dy, x, out)
+    assert_close(out, 2 * ref, 2e-5, 1e-5, "wgrad accumulates")
+
+
+def _attn_ref(qkv, B, T, C, nh):
+    hs = C // nh
+    q, k, v = [t.reshape(B, T, nh, hs).transpose(1, 2) for t in qkv.view(B, T, 3 * C).split(C, dim=-1)]
+    att = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hs), dim=-1)
+    lse = torch.logsumexp((q @ k.transpose(-1, -2)) / math.sqrt(hs), dim=-1)
+    return (att @ v).transpose(1, 2).reshape(B * T, C), lse
+
+
+@pytest.mark.parametrize("B,T,C,nh", [(1, 128, 64, 4), (2, 64, 128, 4), (2, 130, 256, 4), (1, 962, 512, 4), (2, 962, 64, 4),
+                                      (1, 962, 128, 4), (1, 962, 256, 4), (1, 300, 128, 1), (1, 3842, 64, 4)])
+def test_attention_fwd_bwd(K, cuda_dev, B, T, C, nh):
+    g = _gen(8)
+    qkv = torch.randn(B * T, 3 * C, generator=g).to(cuda_dev).to(torch.bfloat16)
+    y = torch.empty(B * T, C, device=cuda_dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, nh, T, device=cuda_dev)
+    K.attn_fwd(qkv, y, lse, B, T, C, nh)
+    torch.cuda.synchronize()
+    qr = qkv.float().requires_grad_(True)
+    ref, lse_ref = _attn_ref(qr, B, T, C, nh)
+    assert_close(lse, lse_ref, 1e-4, 1e-4, "lse")
+    assert_close(y.float(), ref, 1e-2, 1e-4, "attn fwd")
+    dy = torch.randn(B * T, C, generator=g).to(cuda_dev).to(torch.bfloat16)
+    ref.backward(dy.float())
+    delta = torch.empty(B, nh, T, device=cuda_dev)
+    dqkv = torch.empty(B * T, 3 * C, device=cuda_dev, dtype=torch.bfloat16)
+    K.attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh)
+    torch.cuda.synchronize()
+    for nm, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        assert_close(dqkv[:, sl].float(), qr.grad[:, sl], 2e-2, 1e-4, nm)
+
+
+def test_error_paths(K, cuda_dev):
+    x = torch.zeros(4, 6, device=cuda_dev)
+    with pytest.raises(RuntimeError, match="multiple of 4"):
+        K.layernorm_fwd(x, x[0], x[0], torch.empty_like(x), x[:, 0].contiguous(), x[:, 0].contiguous())
+    a = torch.zeros(128, 48, device=cuda_dev, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        K.gemm_bf16_nt(a, a, torch.empty(128, 128, device=cuda_dev, dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError, match="head size"):
+        K.attn_fwd(torch.zeros(8, 3 * 24, device=cuda_dev, dtype=torch.bfloat16), torch.zeros(8, 24, device=cuda_dev, dtype=torch.bfloat16),
+                   torch.zeros(1, 1, 8, device=cuda_dev), 1, 8, 24, 1)
+    geom = K.make_geom(1, 1, 1, 4, 4, 8, 10, 10, K.DSF_F32)
+    with pytest.raises(RuntimeError, match="not a multiple of the anchor grid"):
+        K.tokens_fwd(geom, x, x, x, x, x, x)

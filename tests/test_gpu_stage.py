@@ -1,0 +1,137 @@
+"""Whole-stage GPU parity: the fused fusion stage (FusionStageFn / drop-in GPT) against
+  (1) the committed golden vectors produced by the reference classes (tests/golden, oracle/make_golden.py)
+  (2) the oracle restatement run in fp32 on the same device, at the real stage shapes.
+Tolerances are north_star's: <= 1e-3 relative in fp32 mode, <= 2e-2 in bf16 mode.
+"""
+import pytest
+import torch
+
+from conftest import GPT_CASES, STAGE_CASES, assert_close, load_golden
+from oracle import fusion_ref as R
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2}
+
+
+def _cfg(c, mode, residual=True):
+    return dict(seq_len=c["S"], n_views=1, vert_anchors=c["A"], horz_anchors=c["A"], n_head=c["n_head"], n_layer=c["L"],
+                compute_dtype=mode, residual=residual)
+
+
+def _run_stage(g, dev, mode):
+    from deepsense6g_tii_b200.functional import fusion_stage, param_names
+    c = g["cfg"]
+    names = param_names(c["L"])
+    p = {k: v.to(dev).requires_grad_(True) for k, v in g["param"].items()}
+    ins = {k: v.to(dev).requires_grad_(True) for k, v in g["in"].items()}
+    outs = fusion_stage(_cfg(c, mode, residual=c["scale"] != 0), ins["img"], ins["lidar"], ins["radar"], ins["gps"], [p[n] for n in names])
+    order = ("img", "lidar", "radar", "gps")
+    loss = sum((o.float() * g["probe"][n].to(dev)).sum() for o, n in zip(outs, order))
+    loss.backward()
+    torch.cuda.synchronize()
+    return dict(zip(order, outs)), p, ins
+
+
+@pytest.mark.parametrize("case", GPT_CASES + STAGE_CASES)
+def test_stage_fp32_matches_reference_golden(cuda_dev, case):
+    g = load_golden(case)
+    outs, p, ins = _run_stage(g, cuda_dev, torch.float32)
+    for n, o in outs.items():
+        assert_close(o, g["out"][n], 1e-3, 1e-6, "out/" + n)
+    for n, t in ins.items():
+        assert_close(t.grad, g["gin"][n], 1e-3, 1e-6, "gin/" + n)
+    for n, t in p.items():
+        assert_close(t.grad, g["gparam"][n], 1e-3, 1e-6, "gparam/" + n)
+
+
+def test_stage_bf16_matches_reference_golden(cuda_dev):
+    g = load_golden("gpt_c64_t962")
+    outs, p, ins = _run_stage(g, cuda_dev, torch.bfloat16)
+    for n, o in outs.items():
+        assert_close(o.float(), g["out"][n], 2e-2, 1e-4, "out/" + n)
+    for n, t in ins.items():
+        assert_close(t.grad, g["gin"][n], 2e-2, 1e-4, "gin/" + n)
+    for n, t in p.items():
+        assert_close(t.grad, g["gparam"][n], 2e-2, 2e-4, "gparam/" + n)
+
+
+def test_gpt_module_dropin_loads_reference_state_dict(cuda_dev):
+    """Drop-in GPT: same ctor args, strict state_dict load, same forward signature / outputs."""
+    import types
+    from deepsense6g_tii_b200 import GPT
+    g = load_golden("gpt_tiny")
+    c = g["cfg"]
+    cfg = types.SimpleNamespace(n_views=1, fusion_dtype=torch.float32)
+    m = GPT(c["C"], c["n_head"], 4, c["L"], c["A"], c["A"], c["S"], 0.0, 0.0, 0.0, cfg)
+    missing = m.load_state_dict(g["param"], strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    m = m.to(cuda_dev)
+    ins = [g["in"][n].to(cuda_dev) for n in ("img", "lidar", "radar", "gps")]
+    outs = m(*ins)
+    for o, n in zip(outs, ("img", "lidar", "radar", "gps")):
+        assert o.shape == g["out"][n].shape
+        assert_close(o, g["out"][n], 1e-3, 1e-6, n)
+    with pytest.raises(RuntimeError):
+        m(*[t.cpu() for t in ins])  # no CPU fallback
+    m2 = GPT(c["C"], c["n_head"], 4, c["L"], c["A"], c["A"], c["S"], 0.1, 0.1, 0.1, cfg).to(cuda_dev)
+    with pytest.raises(NotImplementedError):
+        m2.train()(*ins)
+
+
+REAL = [  # (B, C, H, L) at 8x8 anchors, seq_len 5: the four stages of the 256x256 model + one scaled-config stage
+    (2, 64, 64, 8), (2, 128, 32, 8), (2, 256, 16, 8), (2, 512, 8, 8),
+]
+
+
+@pytest.mark.parametrize("B,C,H,L", REAL)
+@pytest.mark.parametrize("mode", [torch.float32, torch.bfloat16])
+def test_stage_real_shapes_vs_oracle(cuda_dev, B, C, H, L, mode):
+    from deepsense6g_tii_b200.functional import fusion_stage, param_names
+    S, A, nh = 5, 8, 4
+    T = 3 * S * A * A + 2
+    gen = torch.Generator().manual_seed(100 + C)
+    p0 = R.init_gpt_params(C, nh, 4, L, T, generator=gen, pos_std=0.02)
+    p0 = {k: (v + 0.01 * torch.randn(v.shape, generator=gen)).to(cuda_dev) for k, v in p0.items()}
+    feats = [torch.randn(B * S, C, H, H, generator=gen).to(cuda_dev) for _ in range(3)]
+    gps = torch.randn(B, 2, C, generator=gen).to(cuda_dev)
+    probes = [torch.randn(f.shape, generator=gen).to(cuda_dev) for f in feats] + [torch.randn(B, 2, C, generator=gen).to(cuda_dev)]
+    names = param_names(L)
+
+    def leafs():
+        return ({k: v.clone().requires_grad_(True) for k, v in p0.items()},
+                [f.clone().requires_grad_(True) for f in feats] + [gps.clone().requires_grad_(True)])
+
+    po, io = leafs()
+    (a, b, c), gout = R.fusion_stage(po, io[:3], io[3], nh, S, A, A)
+    ref = (a, b, c, gout)
+    sum((o * pr).sum() for o, pr in zip(ref, probes)).backward()
+    pk, ik = leafs()
+    cfg = dict(seq_len=S, n_views=1, vert_anchors=A, horz_anchors=A, n_head=nh, n_layer=L, compute_dtype=mode)
+    got = fusion_stage(cfg, ik[0], ik[1], ik[2], ik[3], [pk[n] for n in names])
+    sum((o.float() * pr).sum() for o, pr in zip(got, probes)).backward()
+    torch.cuda.synchronize()
+    tol = TOL[mode]
+    for i, (x, y) in enumerate(zip(got, ref)):
+        assert_close(x.float(), y, tol, 1e-5, "out%d" % i)
+    for i, (x, y) in enumerate(zip(ik, io)):
+        assert_close(x.grad, y.grad, tol, 1e-5, "gin%d" % i)
+    for n in names:
+        assert_close(pk[n].grad, po[n].grad, tol, 2e-5 if mode == torch.float32 else 5e-4, "g/" + n)
+
+
+def test_stage_scaled_config_16x16_anchors(cuda_dev):
+    """configs[4]: 16x16 anchors -> T = 3842 tokens; bf16 mode, stage-1-like C=64, 2 layers, B=1."""
+    from deepsense6g_tii_b200.functional import fusion_stage, param_names
+    S, A, nh, C, L, B, H = 5, 16, 4, 64, 2, 1, 32
+    T = 3 * S * A * A + 2
+    gen = torch.Generator().manual_seed(5)
+    p0 = {k: v.to(cuda_dev) for k, v in R.init_gpt_params(C, nh, 4, L, T, generator=gen, pos_std=0.02).items()}
+    feats = [torch.randn(B * S, C, H, H, generator=gen).to(cuda_dev) for _ in range(3)]
+    gps = torch.randn(B, 2, C, generator=gen).to(cuda_dev)
+    names = param_names(L)
+    (a, b, c), gout = R.fusion_stage(p0, feats, gps, nh, S, A, A)
+    cfg = dict(seq_len=S, n_views=1, vert_anchors=A, horz_anchors=A, n_head=nh, n_layer=L, compute_dtype=torch.bfloat16)
+    got = fusion_stage(cfg, feats[0], feats[1], feats[2], gps, [p0[n] for n in names])
+    for x, y in zip(got, (a, b, c, gout)):
+        assert_close(x.float(), y, 2e-2, 1e-4, "scaled")
