@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native GPT fusion stage.
+
+Metric (BASELINE.json): train samples/sec (fwd+bwd).  Workload at every N: BASELINE.json configs[1],
+"single GPT fusion stage microbench (n_embd 512, 8 layers, 4 heads, 8x8 anchors, ~960 tokens) fwd+bwd,
+bf16" = the stage-4 fusion stage of model2_seq.py (Encoder.forward:571-579 + GPT:175-287) at per-GPU
+batch 12, seq_len 5 -> T = 962 tokens, synthetic (60, 512, 8, 8) feature maps per modality.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU): every rank runs its own batch-12 shard (weak scaling)
+and the GPT gradients are all-reduced over NCCL every step (DDP semantics of train2_seq.py:538 replaced
+by one-process-per-GPU).  Rank 0 prints ONE JSON line.
+
+--impl reference times the reference's own CPU implementation of the same path (the oracle port of
+model2_seq.py in oracle/fusion_ref.py — /root/reference does not exist on the GPU box) on the host
+cores, on a bounded sample (batch 2) of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C, L, NH, A, S, V, BATCH, SCALE = 512, 8, 4, 8, 5, 1, 12, 1
+T = (V + 2) * S * A * A + 2
+WORKLOAD = "gpt_fusion_stage n_embd=512 n_layer=8 n_head=4 anchors=8x8 seq_len=5 T=962 batch=12/GPU fwd+bwd"
+FWD_FLOPS_PER_SAMPLE = L * (24.0 * T * C * C + 4.0 * T * T * C)  # 63.58 GF
+CPU_SAMPLE_BATCH = 2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_inputs(gen, batch, device="cpu", pin=False):
+    """Synthetic stage-4 inputs: post-ReLU-like trunk features (non-negative, ~unit scale) and GPS embeddings."""
+    feats = [torch.randn(batch * S, C, A * SCALE, A * SCALE, generator=gen).abs_() for _ in range(3)]
+    gps = torch.randn(batch, 2, C, generator=gen)
+    probes = [torch.randn(f.shape, generator=gen) * 1e-3 for f in feats] + [torch.randn(batch, 2, C, generator=gen) * 1e-3]
+    ts = feats + [gps] + probes
+    if pin:
+        ts = [t.pin_memory() for t in ts]
+    if device != "cpu":
+        ts = [t.to(device) for t in ts]
+    return ts[:3], ts[3], ts[4:]
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def cpu_step_fn():
+    from oracle import fusion_ref as R
+    gen = torch.Generator().manual_seed(0)
+    p = R.init_gpt_params(C, NH, 4, L, T, generator=gen, pos_std=0.02)
+    p = {k: v.requires_grad_(True) for k, v in p.items()}
+    feats, gps, probes = synth_inputs(gen, CPU_SAMPLE_BATCH)
+    feats = [f.requires_grad_(True) for f in feats]
+    gps.requires_grad_(True)
+
+    def step():
+        for t in list(p.values()) + feats + [gps]:
+            t.grad = None
+        (a, b, c), g = R.fusion_stage(p, feats, gps, NH, S, A, A)
+        loss = sum((o * pr).sum() for o, pr in zip((a, b, c, g), probes))
+        loss.backward()
+        return float(loss)
+    return step
+
+
+def time_cpu(steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_fn()
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return CPU_SAMPLE_BATCH * steps / dt, dt / steps * 1e3
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    v, ms = time_cpu(steps, warmup)
+    cores = torch.get_num_threads()
+    sample = "oracle port (oracle/fusion_ref.py) of the same stage, fp32, batch %d per step, %d threads, %s" % (CPU_SAMPLE_BATCH, cores, cpu_model())
+    print(json.dumps({
+        "impl": "reference", "metric": "train samples/sec (fwd+bwd)", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample_batch": CPU_SAMPLE_BATCH},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def build_gpt(device):
+    import types
+    from deepsense6g_tii_b200 import GPT
+    cfg = types.SimpleNamespace(n_views=V, fusion_dtype=torch.bfloat16)
+    torch.manual_seed(100)  # the reference's seed (train2_seq.py:430-434)
+    m = GPT(C, NH, 4, L, A, A, S, 0.0, 0.0, 0.0, cfg)
+    with torch.no_grad():
+        m.pos_emb.normal_(0, 0.02)
+    return m.to(device)
+
+
+def profile_families(gpt, feats, gps, probes):
+    """One instrumented fwd+bwd: CUDA events around every C-ABI call, summed per kernel family."""
+    from deepsense6g_tii_b200 import _capi
+    names = ["tokens_fwd", "tokens_bwd", "layernorm_fwd", "layernorm_bwd", "gemm_bf16_nt", "gemm_bf16_tn", "colsum", "relu_bwd",
+             "attn_fwd", "attn_bwd", "upsample_add_fwd", "upsample_add_bwd", "cast_f32_bf16"]
+    rec, orig = [], {}
+    for n in names:
+        f = getattr(_capi, n)
+        orig[n] = f
+
+        def wrap(*a, _f=f, _n=n, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _f(*a, **k)
+            e1.record()
+            shape = None
+            if _n == "gemm_bf16_nt":
+                shape = (a[0].shape[0], a[1].shape[0], a[0].shape[1])
+            elif _n == "gemm_bf16_tn":
+                shape = (a[0].shape[0], a[0].shape[1], a[1].shape[1])
+            rec.append((_n, e0, e1, shape))
+        setattr(_capi, n, wrap)
+    try:
+        import deepsense6g_tii_b200.functional as Fn
+        Fn.K = _capi
+        one_step(gpt, feats, gps, probes)
+        torch.cuda.synchronize()
+    finally:
+        for n, f in orig.items():
+            setattr(_capi, n, f)
+    fam = {}
+    for n, e0, e1, shape in rec:
+        d = fam.setdefault(n, {"launch_calls": 0, "ms": 0.0, "flops": 0.0})
+        d["launch_calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        if shape is not None:
+            d["flops"] += 2.0 * shape[0] * shape[1] * shape[2]
+    b = feats[0].shape[0] // S
+    if "attn_fwd" in fam:
+        fam["attn_fwd"]["flops"] = L * 4.0 * T * T * C * b
+    if "attn_bwd" in fam:
+        fam["attn_bwd"]["flops"] = L * 2 * 4.0 * T * T * C * b  # 2x forward (recompute not counted)
+    return fam
+
+
+def one_step(gpt, feats, gps, probes):
+    for p in gpt.parameters():
+        p.grad = None
+    for t in feats:
+        t.grad = None
+    gps.grad = None
+    outs = gpt.fuse(feats[0], feats[1], feats[2], gps)
+    loss = sum((o.float() * pr).sum() for o, pr in zip(outs, probes))
+    loss.backward()
+    return loss
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from deepsense6g_tii_b200 import _capi
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _capi.check_device()
+    gpt = build_gpt(dev)
+    model = gpt
+    if world > 1:
+        # same initial weights on every rank; gradients all-reduced (mean) over NCCL every step
+        flat = torch.cat([p.data.view(-1) for p in gpt.parameters()])
+        dist.broadcast(flat, 0)
+        off = 0
+        for p in gpt.parameters():
+            p.data.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+    gen = torch.Generator().manual_seed(rank)  # data generator seed 0 + rank
+    feats_h, gps_h, probes_h = synth_inputs(gen, BATCH, pin=True)
+    feats = [f.to(dev).requires_grad_(True) for f in feats_h]
+    gps = gps_h.to(dev).requires_grad_(True)
+    probes = [p.to(dev) for p in probes_h]
+    grad_buf = torch.empty(sum(p.numel() for p in gpt.parameters()), device=dev) if world > 1 else None
+
+    def allreduce_grads():
+        if world == 1:
+            return
+        off = 0
+        for p in gpt.parameters():
+            grad_buf[off:off + p.numel()].copy_(p.grad.view(-1)); off += p.numel()
+        dist.all_reduce(grad_buf)
+        grad_buf.div_(world)
+
+    def step_resident():
+        loss = one_step(model, feats, gps, probes)
+        allreduce_grads()
+        return loss
+
+    dfeats = [torch.empty_like(f) for f in feats]
+    dgps = torch.empty_like(gps)
+    loss_h = torch.empty((), pin_memory=True)
+
+    def step_e2e():
+        # host -> device copy of this step's inputs from pinned memory, fwd+bwd, device -> host read of the loss
+        for d, h in zip(dfeats, feats_h):
+            d.copy_(h, non_blocking=True)
+        dgps.copy_(gps_h, non_blocking=True)
+        fi = [d.requires_grad_(True) for d in dfeats]
+        gi = dgps.requires_grad_(True)
+        loss = one_step(model, fi, gi, probes)
+        allreduce_grads()
+        loss_h.copy_(loss.detach(), non_blocking=True)
+        for d in dfeats:
+            d.requires_grad_(False)
+        dgps.requires_grad_(False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _capi.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        n1 = _capi.launch_count()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, n1 - n0, clocks
+
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    ms, launches, clocks = timed(step_resident, steps, warmup, ClockSampler(local_rank) if rank == 0 else None)
+    value = BATCH * world * steps / (ms * 1e-3)
+    ms_e2e, _, _ = timed(step_e2e, steps, 2)
+    e2e_value = BATCH * world * steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        return
+    pk = peaks()
+    fam = profile_families(gpt, feats, gps, probes)
+    total_ms = sum(d["ms"] for d in fam.values())
+    tc = {k: d for k, d in fam.items() if d["flops"] > 0}
+    dom = max(tc, key=lambda k: tc[k]["ms"])
+    achieved = tc[dom]["flops"] / (tc[dom]["ms"] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tc_sust"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tc_sust"], "traffic": None, "peak_source": pk["src"] + " bf16_tflops_sustained",
+                "launches_per_step": tc[dom]["launch_calls"], "avg_launch_ms": tc[dom]["ms"] / tc[dom]["launch_calls"],
+                "share_of_step": tc[dom]["ms"] / total_ms,
+                "families": {k: {"ms": round(d["ms"], 4), "calls": d["launch_calls"],
+                                 "tflops": (d["flops"] / (d["ms"] * 1e-3) / 1e12) if d["flops"] else None} for k, d in fam.items()}}
+    cpu_v, cpu_ms = time_cpu(2, 1)
+    cores = torch.get_num_threads()
+    h2d = sum(t.numel() * t.element_size() for t in feats_h) + gps_h.numel() * gps_h.element_size()
+    step_flops = 3.0 * FWD_FLOPS_PER_SAMPLE * BATCH
+    out = {
+        "metric": "train samples/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "seq_len": S, "parallelism": "dp%d" % world,
+                   "l2": "per-step working set ~1.5 GB of saved activations > 126 MB L2; no explicit flush",
+                   "grad_allreduce": "NCCL all-reduce of 25.7 M fp32 grads per step" if world > 1 else "none (1 GPU)"},
+        "stage_tflops": step_flops * world / (ms / steps * 1e-3) / 1e12,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "oracle port fp32, batch %d, 1 warm-up + 2 timed steps, %s" % (CPU_SAMPLE_BATCH, cpu_model())},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the fusion stage has no CPU path (use --impl reference for the CPU baseline)")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,7 +20,7 @@ EPI_BIAS, EPI_RELU, EPI_RESIDUAL, EPI_ACCUM = 1, 2, 4, 8
 
 # every symbol include/dsfuse.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "dsf_version", "dsf_last_error", "dsf_check_device", "dsf_tokens_fwd", "dsf_tokens_bwd",
+    "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_tokens_fwd", "dsf_tokens_bwd",
     "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_f32",
     "dsf_colsum", "dsf_relu_bwd", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd",
     "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16",
@@ -53,6 +53,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.dsf_last_error.restype = c_char_p
         L.dsf_version.restype = c_int32
+        L.dsf_launch_count.restype = c_int64
         P = c_void_p
         sig = {
             "dsf_check_device": [],
@@ -109,6 +110,11 @@ def _req(t, dtype=None, name="tensor"):
         raise RuntimeError("%s must be contiguous" % name)
     if dtype is not None and t.dtype != dtype:
         raise RuntimeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+def launch_count():
+    """Kernels launched through the C ABI so far (every launch site passes through check_launch)."""
+    return int(lib().dsf_launch_count())
 
 
 def check_device():

@@ -6,6 +6,7 @@
 namespace dsf {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;  // kernels launched through the C ABI (bench.py's gpu_launches)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -15,6 +16,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int check_launch(const char* what) {
+  __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: CUDA error: %s", what, cudaGetErrorString(e));
@@ -38,6 +40,7 @@ int num_sms() {
 }  // namespace dsf
 
 extern "C" int dsf_version(void) { return DSF_VERSION; }
+extern "C" int64_t dsf_launch_count(void) { return (int64_t)__atomic_load_n(&dsf::g_launches, __ATOMIC_RELAXED); }
 extern "C" const char* dsf_last_error(void) { return dsf::g_err; }
 
 extern "C" int dsf_check_device(void) {

@@ -50,6 +50,8 @@ enum {
 
 int dsf_version(void);
 const char* dsf_last_error(void);
+/* Number of kernels launched through this library since load (process-wide, monotonically increasing). */
+int64_t dsf_launch_count(void);
 /* 0 if the current device is sm_100 and the kernels can run on it, DSF_EARCH otherwise. */
 int dsf_check_device(void);
 

@@ -85,7 +85,7 @@ REAL = [  # (B, C, H, L) at 8x8 anchors, seq_len 5: the four stages of the 256x2
 
 
 @pytest.mark.parametrize("B,C,H,L", REAL)
-@pytest.mark.parametrize("mode", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", [torch.float32, torch.bfloat16], ids=["float32", "bfloat16"])
 def test_stage_real_shapes_vs_oracle(cuda_dev, B, C, H, L, mode):
     from deepsense6g_tii_b200.functional import fusion_stage, param_names
     S, A, nh = 5, 8, 4
