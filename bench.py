@@ -112,7 +112,7 @@ def cpu_step_fn():
         (a, b, c), g = R.fusion_stage(p, feats, gps, NH, S, A, A)
         loss = sum((o * pr).sum() for o, pr in zip((a, b, c, g), probes))
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 

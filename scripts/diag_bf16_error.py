@@ -40,9 +40,20 @@ def run_mine(mode):
 def rel(a, b):
     return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
 
-ref = run_oracle(False)
+def run_oracle64():
+    p = {k: v.double().clone().requires_grad_(True) for k, v in p0.items()}
+    i = [f.double().clone().requires_grad_(True) for f in feats] + [gps.double().clone().requires_grad_(True)]
+    (a, b, c), g = R.fusion_stage(p, i[:3], i[3], nh, S, A, A)
+    outs = (a, b, c, g)
+    sum((o * pr.double()).sum() for o, pr in zip(outs, probes)).backward()
+    return outs, p, i
+
+print("allow_tf32 matmul/cudnn:", torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32,
+      "float32_matmul_precision:", torch.get_float32_matmul_precision(), "env:",
+      {k: v for k, v in os.environ.items() if "TF32" in k})
+ref = run_oracle64()
 rows = {}
-for tag, res in (("mine_f32", run_mine(torch.float32)), ("mine_bf16", run_mine(torch.bfloat16)), ("torch_autocast", run_oracle(True))):
+for tag, res in (("mine_f32", run_mine(torch.float32)), ("mine_bf16", run_oracle(False)), ("torch_autocast", run_oracle(True))):
     d = {}
     for j, (x, y) in enumerate(zip(res[0], ref[0])):
         d["out%d" % j] = rel(x, y)
