@@ -22,7 +22,7 @@ EPI_BIAS, EPI_RELU, EPI_RESIDUAL, EPI_ACCUM = 1, 2, 4, 8
 SYMBOLS = [
     "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_tokens_fwd", "dsf_tokens_bwd",
     "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_f32",
-    "dsf_colsum", "dsf_relu_bwd", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd",
+    "dsf_colsum", "dsf_relu_bwd", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_set_impl",
     "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16",
 ]
 
@@ -70,6 +70,7 @@ def lib():
             "dsf_softmax_bwd": [P, P, c_int64, c_int32, P],
             "dsf_attn_fwd": [P, P, P, c_int32, c_int32, c_int32, c_int32, P],
             "dsf_attn_bwd": [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P],
+            "dsf_attn_set_impl": [c_int32],
             "dsf_upsample_add_fwd": [POINTER(Geom), P, P, P, P, P, P, P, P],
             "dsf_upsample_add_bwd": [POINTER(Geom), P, P, P, P, P, P],
             "dsf_cast_f32_bf16": [P, P, c_int64, P],
@@ -190,6 +191,11 @@ def attn_fwd(qkv, y, lse, B, T, C, nh):
 
 def attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh):
     _chk(lib().dsf_attn_bwd(_p(qkv), _p(y), _p(dy), _p(lse), _p(delta), _p(dqkv), B, T, C, nh, _stream()), "dsf_attn_bwd")
+
+
+def attn_set_impl(impl):
+    """0 = default, 1 = v1 (simple), 2 = v2 (pipelined); process-wide."""
+    _chk(lib().dsf_attn_set_impl(impl), "dsf_attn_set_impl")
 
 
 def upsample_add_fwd(g, y, feats, outs):

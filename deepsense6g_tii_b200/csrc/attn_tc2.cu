@@ -1,0 +1,679 @@
+// K4 (v2): warp-specialised, TMA-fed flash attention forward / backward on tcgen05 + TMEM.
+// Same math and I/O contract as attn_tc.cu (model2_seq.py:102-106 and its autograd); the difference is
+// the schedule:
+//   * a producer warp streams Q / K / V / dO tiles with 3-D TMA (tensor maps over (3C, T, B), out-of-range
+//     token rows zero-filled) into swizzled shared memory through an mbarrier ring,
+//   * one elected thread issues every tcgen05.mma, running ahead of the math warps (S(j+1) is issued before
+//     softmax(j) finishes; the P.V / dV / dK / dQ MMAs are issued as soon as the bf16 tile lands in smem),
+//   * forward: two softmax warpgroups (2 x 128 query rows) share each K/V tile (ping-pong on the tensor pipe),
+//   * backward: accumulators (dK, dV / dQ) stay in TMEM across the whole loop, S/dP are double-buffered.
+// Shared-memory operand images: TMA tiles are [half][row][ROWB bytes] with the hardware swizzle that matches
+// ROWB (128/64/32 B for head sizes >=64/32/16); the same image is read as a K-major operand (rows = M/N)
+// or an MN-major operand (rows = K).  P / dS tiles written by threads use the no-swizzle core-matrix layout.
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace dsf {
+
+using namespace tc;
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int HS>
+struct HeadCfg {
+  static constexpr int BOXC = HS < 64 ? HS : 64;  // TMA box columns (elements)
+  static constexpr int ROWB = BOXC * 2;           // bytes per shared-memory row of one box
+  static constexpr int NHALF = HS / BOXC;         // boxes per tile along the head dimension
+  static constexpr uint32_t SWZ = ROWB == 128 ? SWZ_128B : (ROWB == 64 ? SWZ_64B : SWZ_32B);
+  static constexpr int KPH = ROWB / 32;           // UMMA K-steps (16 elements) per box
+};
+
+// K-major operand over a TMA tile of R rows (rows = M or N index); k-step kk covers head dims 16kk..16kk+15
+template <int HS>
+__device__ __forceinline__ uint64_t kmaj_desc(uint32_t tile, int R, int kk) {
+  using H = HeadCfg<HS>;
+  const uint32_t off = (uint32_t)(kk / H::KPH) * R * H::ROWB + (uint32_t)(kk % H::KPH) * 32;
+  return make_smem_desc(tile + off, 16, 8 * H::ROWB, H::SWZ);
+}
+// MN-major operand over a TMA tile of R rows (rows = K index, N = HS); k-step kk covers rows 16kk..16kk+15
+template <int HS>
+__device__ __forceinline__ uint64_t mnmaj_desc(uint32_t tile, int R, int kk) {
+  using H = HeadCfg<HS>;
+  return make_smem_desc(tile + (uint32_t)kk * 16 * H::ROWB, (uint32_t)R * H::ROWB, 8 * H::ROWB, H::SWZ);
+}
+// K-major operand over a thread-written no-swizzle [128 x KC] bf16 tile (core matrices: 128 B along K, KC*16 B along M)
+template <int KC>
+__device__ __forceinline__ uint64_t pdesc(uint32_t tile, int kk) {
+  return make_smem_desc(tile + (uint32_t)kk * 256, 128, KC * 16, SWZ_NONE);
+}
+
+// D[128 x NB] (+)= A(tile, RA rows, K-major) . B(tile, RB rows, K-major)^T, contraction over the head dim
+template <int HS>
+__device__ __forceinline__ void mma_over_head(uint32_t tmem_d, uint32_t a_tile, int RA, uint32_t b_tile, int RB, uint32_t idesc) {
+#pragma unroll
+  for (int kk = 0; kk < HS / 16; ++kk) tc_mma_bf16(tmem_d, kmaj_desc<HS>(a_tile, RA, kk), kmaj_desc<HS>(b_tile, RB, kk), idesc, kk != 0);
+}
+// D[128 x HS] (+)= P(no-swizzle [128 x KC]) . B(tile with KC rows, MN-major)
+template <int HS, int KC>
+__device__ __forceinline__ void mma_over_rows(uint32_t tmem_d, uint32_t p_tile, uint32_t b_tile, uint32_t idesc, bool accumulate) {
+#pragma unroll
+  for (int kk = 0; kk < KC / 16; ++kk) tc_mma_bf16(tmem_d, pdesc<KC>(p_tile, kk), mnmaj_desc<HS>(b_tile, KC, kk), idesc, accumulate || kk != 0);
+}
+
+template <int HS>
+__device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap* m, uint32_t bar, int col0, int row0, int b, int R) {
+  using H = HeadCfg<HS>;
+#pragma unroll
+  for (int hf = 0; hf < H::NHALF; ++hf) tma_load_3d(dst + hf * R * H::ROWB, m, bar, col0 + hf * H::BOXC, row0, b);
+}
+
+// write 32 bf16 values (16 packed words) of row `row`, columns c..c+31 of a no-swizzle [128 x KC] tile
+template <int KC>
+__device__ __forceinline__ void store_p32(uint8_t* tile, int row, int c, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    uint8_t* dst = tile + ((size_t)(row >> 3) * (KC / 8) + (c >> 3) + cc) * 128 + (row & 7) * 16;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * cc], pk[4 * cc + 1], pk[4 * cc + 2], pk[4 * cc + 3]);
+  }
+}
+
+__device__ __forceinline__ void store_row16_bf16(__nv_bfloat16* dst, const uint32_t (&a)[16], float scale) {
+#pragma unroll
+  for (int e = 0; e < 16; e += 8)
+    *reinterpret_cast<uint4*>(dst + e) =
+        make_uint4(pack_bf16x2(__uint_as_float(a[e]) * scale, __uint_as_float(a[e + 1]) * scale),
+                   pack_bf16x2(__uint_as_float(a[e + 2]) * scale, __uint_as_float(a[e + 3]) * scale),
+                   pack_bf16x2(__uint_as_float(a[e + 4]) * scale, __uint_as_float(a[e + 5]) * scale),
+                   pack_bf16x2(__uint_as_float(a[e + 6]) * scale, __uint_as_float(a[e + 7]) * scale));
+}
+
+// =============================================================================================== forward
+template <int HS, int BKV, int ST>
+struct Fwd2 {
+  static constexpr int Q_BYTES = 128 * HS * 2, KV_BYTES = BKV * HS * 2, P_BYTES = 128 * BKV * 2;
+  static constexpr int Q_OFF = 0, K_OFF = 2 * Q_BYTES, V_OFF = K_OFF + ST * KV_BYTES, P_OFF = V_OFF + ST * KV_BYTES;
+  static constexpr int BAR_OFF = P_OFF + 2 * P_BYTES;
+  static constexpr int NBAR = 1 + 2 * ST + 6;
+  static constexpr int DYN = BAR_OFF + NBAR * 8 + 16 + 1024;
+  static constexpr int THREADS = 320;  // 8 softmax warps, 1 MMA warp, 1 TMA warp
+  static_assert(2 * BKV + 2 * HS <= 512, "TMEM budget");
+};
+
+template <int HS, int BKV, int ST>
+__global__ void __launch_bounds__(320, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, __nv_bfloat16* __restrict__ y,
+                 float* __restrict__ lse, int T, int C, int nh, float scale_log2) {
+  using L = Fwd2<HS, BKV, ST>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar0 = sbase + L::BAR_OFF;
+  const uint32_t q_full = bar0, kv_full = bar0 + 8, kv_empty = kv_full + 8 * ST, s_full = kv_empty + 8 * ST, p_full = s_full + 16,
+                 o_done = p_full + 16, tmem_slot = o_done + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (T + BKV - 1) / BKV;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ST; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(p_full + 8 * w, 128); mbar_init(o_done + 8 * w, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 9 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 9) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * L::Q_BYTES);
+      for (int w = 0; w < 2; ++w) tma_tile<HS>(sbase + L::Q_OFF + w * L::Q_BYTES, &tmQ, q_full, h * HS, q0 + 128 * w, b, 128);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % ST;
+        if (j >= ST) mbar_wait(kv_empty + 8 * st, ((j / ST) - 1) & 1);
+        mbar_expect_tx(kv_full + 8 * st, 2 * L::KV_BYTES);
+        tma_tile<HS>(sbase + L::K_OFF + st * L::KV_BYTES, &tmKV, kv_full + 8 * st, C + h * HS, j * BKV, b, BKV);
+        tma_tile<HS>(sbase + L::V_OFF + st * L::KV_BYTES, &tmKV, kv_full + 8 * st, 2 * C + h * HS, j * BKV, b, BKV);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, HS, 0, 1);
+      mbar_wait(q_full, 0);
+      mbar_wait(kv_full, 0);
+      tc_fence_after();
+      for (int w = 0; w < 2; ++w) {
+        mma_over_head<HS>(tmem_base + w * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF, BKV, idesc_s);
+        tc_commit(s_full + 8 * w);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % ST;
+        for (int w = 0; w < 2; ++w) {
+          mbar_wait(p_full + 8 * w, j & 1);
+          tc_fence_after();
+          mma_over_rows<HS, BKV>(tmem_base + 2 * BKV + w * HS, sbase + L::P_OFF + w * L::P_BYTES, sbase + L::V_OFF + st * L::KV_BYTES,
+                                 idesc_o, j > 0);
+          tc_commit(o_done + 8 * w);
+          if (w == 1) tc_commit(kv_empty + 8 * st);
+          if (j + 1 < n_kv) {
+            const int sn = (j + 1) % ST;
+            if (w == 0) { mbar_wait(kv_full + 8 * sn, ((j + 1) / ST) & 1); tc_fence_after(); }
+            mma_over_head<HS>(tmem_base + w * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + sn * L::KV_BYTES, BKV, idesc_s);
+            tc_commit(s_full + 8 * w);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int w = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tm_s = tmem_base + w * BKV + lane_off, tm_o = tmem_base + 2 * BKV + w * HS + lane_off;
+    uint8_t* p_tile = smem + L::P_OFF + w * L::P_BYTES;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int kv0 = j * BKV;
+      mbar_wait(s_full + 8 * w, j & 1);
+      tc_fence_after();
+      float p_max = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tm_s + c, r);
+        tmem_wait_ld();
+        if (kv0 + c + 32 <= T) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) p_max = fmaxf(p_max, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kv0 + c + i < T) p_max = fmaxf(p_max, __uint_as_float(r[i]));
+        }
+      }
+      p_max *= scale_log2;
+      if (j > 0) mbar_wait(o_done + 8 * w, (j - 1) & 1);  // P.V(j-1) retired: O is stable, the P buffer is free
+      const bool need = p_max > m_run + 8.f;               // lazy rescale (exact: m only has to bound the exponent)
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = need ? p_max : m_run;
+        const float alpha = exp2f(m_run - m_new);
+        if (j > 0) {
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < HS; c += 16) {
+            uint32_t o[16];
+            tmem_ld16(tm_o + c, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tm_o + c, o);
+          }
+          tmem_wait_st();
+        }
+        l_run *= alpha;
+        m_run = m_new;
+      }
+      float l_add = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tm_s + c, r);
+        tmem_wait_ld();
+        uint32_t pk[16];
+        const bool full = kv0 + c + 32 <= T;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = exp2f(__uint_as_float(r[i]) * scale_log2 - m_run);
+          float p1 = exp2f(__uint_as_float(r[i + 1]) * scale_log2 - m_run);
+          if (!full) {
+            if (kv0 + c + i >= T) p0 = 0.f;
+            if (kv0 + c + i + 1 >= T) p1 = 0.f;
+          }
+          __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);  // the row sum uses what the P.V MMA will see
+          l_add += __low2float(pb) + __high2float(pb);
+          pk[i / 2] = *reinterpret_cast<uint32_t*>(&pb);
+        }
+        store_p32<BKV>(p_tile, row, c, pk);
+      }
+      l_run += l_add;
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(p_full + 8 * w);
+    }
+    mbar_wait(o_done + 8 * w, (n_kv - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + 128 * w + row;
+    const float inv_l = 1.0f / l_run;
+    __nv_bfloat16* yrow = y + ((size_t)b * T + q) * C + h * HS;
+#pragma unroll 1
+    for (int c = 0; c < HS; c += 16) {
+      uint32_t o[16];
+      tmem_ld16(tm_o + c, o);
+      tmem_wait_ld();
+      if (q < T) store_row16_bf16(yrow + c, o, inv_l);
+    }
+    if (q < T) lse[((size_t)b * nh + h) * T + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// =============================================================================================== backward: dK, dV
+// CTA = 128 keys (K, V resident); loop over BQ-query tiles.  Threads own key rows:
+//   S^T = K Q^T, dP^T = V dO^T -> P^T = exp2(S^T*c - lse), dS^T = P^T (dP^T - delta) * scale -> dV += P^T dO, dK += dS^T Q
+template <int HS, int BQ, int ST>
+struct BwdKV2 {
+  static constexpr int KV_BYTES = 128 * HS * 2, Q_BYTES = BQ * HS * 2, P_BYTES = 128 * BQ * 2;
+  static constexpr int K_OFF = 0, V_OFF = KV_BYTES, Q_OFF = 2 * KV_BYTES, DO_OFF = Q_OFF + ST * Q_BYTES;
+  static constexpr int PT_OFF = DO_OFF + ST * Q_BYTES, DST_OFF = PT_OFF + 2 * P_BYTES;
+  static constexpr int STAT_OFF = DST_OFF + 2 * P_BYTES;  // [2 buffers][lse | delta][BQ] floats
+  static constexpr int BAR_OFF = STAT_OFF + 2 * 2 * BQ * 4;
+  static constexpr int NBAR = 2 + 2 * ST + 6;
+  static constexpr int DYN = BAR_OFF + NBAR * 8 + 16 + 1024;
+  static_assert(4 * BQ + 2 * HS <= 512, "TMEM budget");
+  static_assert(DYN <= 232448, "shared memory budget");
+};
+
+template <int HS, int BQ, int ST>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
+                    float scale) {
+  using L = BwdKV2<HS, BQ, ST>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar0 = sbase + L::BAR_OFF;
+  const uint32_t kv_full = bar0, acc_done = bar0 + 8, q_full = bar0 + 16, q_empty = q_full + 8 * ST, s_full = q_empty + 8 * ST,
+                 ds_full = s_full + 16, ds_empty = ds_full + 16, tmem_slot = ds_empty + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int n_q = (T + BQ - 1) / BQ;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    mbar_init(acc_done, 1);
+    for (int s = 0; s < ST; ++s) { mbar_init(q_full + 8 * s, 1); mbar_init(q_empty + 8 * s, 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 128); mbar_init(ds_empty + 8 * w, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 5 && lane == 0) { tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tm_dv = tmem_base + 4 * BQ, tm_dk = tm_dv + HS;
+
+  if (warp == 5) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * L::KV_BYTES);
+      tma_tile<HS>(sbase + L::K_OFF, &tmKV, kv_full, C + h * HS, kv0, b, 128);
+      tma_tile<HS>(sbase + L::V_OFF, &tmKV, kv_full, 2 * C + h * HS, kv0, b, 128);
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i % ST;
+        if (i >= ST) mbar_wait(q_empty + 8 * st, ((i / ST) - 1) & 1);
+        mbar_expect_tx(q_full + 8 * st, 2 * L::Q_BYTES);
+        tma_tile<HS>(sbase + L::Q_OFF + st * L::Q_BYTES, &tmQ, q_full + 8 * st, h * HS, i * BQ, b, BQ);
+        tma_tile<HS>(sbase + L::DO_OFF + st * L::Q_BYTES, &tmDO, q_full + 8 * st, h * HS, i * BQ, b, BQ);
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, BQ, 0, 0);
+      constexpr uint32_t idesc_g = make_idesc_bf16(128, HS, 0, 1);
+      mbar_wait(kv_full, 0);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      mma_over_head<HS>(tmem_base, sbase + L::K_OFF, 128, sbase + L::Q_OFF, BQ, idesc_s);
+      mma_over_head<HS>(tmem_base + BQ, sbase + L::V_OFF, 128, sbase + L::DO_OFF, BQ, idesc_s);
+      tc_commit(s_full);
+      for (int i = 0; i < n_q; ++i) {
+        const int bf = i & 1, st = i % ST;
+        if (i + 1 < n_q) {
+          const int sn = (i + 1) % ST, bn = (i + 1) & 1;
+          mbar_wait(q_full + 8 * sn, ((i + 1) / ST) & 1);
+          tc_fence_after();
+          mma_over_head<HS>(tmem_base + bn * 2 * BQ, sbase + L::K_OFF, 128, sbase + L::Q_OFF + sn * L::Q_BYTES, BQ, idesc_s);
+          mma_over_head<HS>(tmem_base + bn * 2 * BQ + BQ, sbase + L::V_OFF, 128, sbase + L::DO_OFF + sn * L::Q_BYTES, BQ, idesc_s);
+          tc_commit(s_full + 8 * bn);
+        }
+        mbar_wait(ds_full + 8 * bf, (i >> 1) & 1);
+        tc_fence_after();
+        mma_over_rows<HS, BQ>(tm_dv, sbase + L::PT_OFF + bf * L::P_BYTES, sbase + L::DO_OFF + st * L::Q_BYTES, idesc_g, i > 0);
+        mma_over_rows<HS, BQ>(tm_dk, sbase + L::DST_OFF + bf * L::P_BYTES, sbase + L::Q_OFF + st * L::Q_BYTES, idesc_g, i > 0);
+        tc_commit(q_empty + 8 * st);
+        tc_commit(ds_empty + 8 * bf);
+      }
+      tc_commit(acc_done);
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const bool key_ok = (kv0 + row) < T;
+    const float scale_log2 = scale * 1.4426950408889634f;
+    const float* lse_g = lse + ((size_t)b * nh + h) * T;
+    const float* delta_g = delta + ((size_t)b * nh + h) * T;
+    for (int i = 0; i < n_q; ++i) {
+      const int bf = i & 1, q0 = i * BQ;
+      float* st_lse = reinterpret_cast<float*>(smem + L::STAT_OFF) + bf * 2 * BQ;
+      float* st_delta = st_lse + BQ;
+      // the stats buffer bf was last read two iterations ago; every thread has passed the barrier below since then
+      for (int c = threadIdx.x; c < 2 * BQ; c += 128) {
+        const int qq = q0 + (c % BQ);
+        if (c < BQ) st_lse[c] = qq < T ? lse_g[qq] * 1.4426950408889634f : INFINITY;
+        else st_delta[c - BQ] = qq < T ? delta_g[qq] : 0.f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(s_full + 8 * bf, (i >> 1) & 1);
+      tc_fence_after();
+      if (i >= 2) mbar_wait(ds_empty + 8 * bf, ((i >> 1) - 1) & 1);
+      uint8_t* pt = smem + L::PT_OFF + bf * L::P_BYTES;
+      uint8_t* dst = smem + L::DST_OFF + bf * L::P_BYTES;
+      const uint32_t tm_s = tmem_base + bf * 2 * BQ + lane_off, tm_dp = tm_s + BQ;
+#pragma unroll 1
+      for (int c = 0; c < BQ; c += 32) {
+        uint32_t rs[32], rp[32];
+        tmem_ld32(tm_s + c, rs);
+        tmem_ld32(tm_dp + c, rp);
+        tmem_wait_ld();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = key_ok ? exp2f(__uint_as_float(rs[e]) * scale_log2 - st_lse[c + e]) : 0.f;
+          float p1 = key_ok ? exp2f(__uint_as_float(rs[e + 1]) * scale_log2 - st_lse[c + e + 1]) : 0.f;
+          const float d0 = p0 * (__uint_as_float(rp[e]) - st_delta[c + e]) * scale;
+          const float d1 = p1 * (__uint_as_float(rp[e + 1]) - st_delta[c + e + 1]) * scale;
+          pk[e / 2] = pack_bf16x2(p0, p1);
+          dk[e / 2] = pack_bf16x2(d0, d1);
+        }
+        store_p32<BQ>(pt, row, c, pk);
+        store_p32<BQ>(dst, row, c, dk);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(ds_full + 8 * bf);
+    }
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    const int ld = 3 * C;
+    __nv_bfloat16* dk_row = dqkv + ((size_t)b * T + kv0 + row) * ld + C + h * HS;
+    __nv_bfloat16* dv_row = dk_row + C;
+#pragma unroll 1
+    for (int c = 0; c < HS; c += 16) {
+      uint32_t a[16], v[16];
+      tmem_ld16(tm_dk + lane_off + c, a);
+      tmem_ld16(tm_dv + lane_off + c, v);
+      tmem_wait_ld();
+      if (key_ok) {
+        store_row16_bf16(dk_row + c, a, 1.0f);
+        store_row16_bf16(dv_row + c, v, 1.0f);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+// =============================================================================================== backward: dQ
+// CTA = 128 queries (Q, dO resident); loop over 64-key tiles.  Threads own query rows:
+//   S = Q K^T, dP = dO V^T -> dS = exp2(S*c - lse) (dP - delta) * scale -> dQ += dS K
+template <int HS, int ST>
+struct BwdQ2 {
+  static constexpr int BKV = 64;
+  static constexpr int Q_BYTES = 128 * HS * 2, KV_BYTES = BKV * HS * 2, DS_BYTES = 128 * BKV * 2;
+  static constexpr int Q_OFF = 0, DO_OFF = Q_BYTES, K_OFF = 2 * Q_BYTES, V_OFF = K_OFF + ST * KV_BYTES, DS_OFF = V_OFF + ST * KV_BYTES;
+  static constexpr int BAR_OFF = DS_OFF + 2 * DS_BYTES;
+  static constexpr int NBAR = 2 + 2 * ST + 6;
+  static constexpr int DYN = BAR_OFF + NBAR * 8 + 16 + 1024;
+  static_assert(4 * BKV + HS <= 512, "TMEM budget");
+};
+
+template <int HS, int ST>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmKV,
+                   const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
+                   float scale) {
+  using L = BwdQ2<HS, ST>;
+  constexpr int BKV = L::BKV;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar0 = sbase + L::BAR_OFF;
+  const uint32_t q_full = bar0, acc_done = bar0 + 8, kv_full = bar0 + 16, kv_empty = kv_full + 8 * ST, s_full = kv_empty + 8 * ST,
+                 ds_full = s_full + 16, ds_empty = ds_full + 16, tmem_slot = ds_empty + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (T + BKV - 1) / BKV;
+  constexpr uint32_t TMEM_COLS = (4 * BKV + HS) <= 256 ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(acc_done, 1);
+    for (int s = 0; s < ST; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 128); mbar_init(ds_empty + 8 * w, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  if (warp == 5 && lane == 0) { tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tm_dq = tmem_base + 4 * BKV;
+
+  if (warp == 5) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * L::Q_BYTES);
+      tma_tile<HS>(sbase + L::Q_OFF, &tmQ, q_full, h * HS, q0, b, 128);
+      tma_tile<HS>(sbase + L::DO_OFF, &tmDO, q_full, h * HS, q0, b, 128);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % ST;
+        if (j >= ST) mbar_wait(kv_empty + 8 * st, ((j / ST) - 1) & 1);
+        mbar_expect_tx(kv_full + 8 * st, 2 * L::KV_BYTES);
+        tma_tile<HS>(sbase + L::K_OFF + st * L::KV_BYTES, &tmKV, kv_full + 8 * st, C + h * HS, j * BKV, b, BKV);
+        tma_tile<HS>(sbase + L::V_OFF + st * L::KV_BYTES, &tmKV, kv_full + 8 * st, 2 * C + h * HS, j * BKV, b, BKV);
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
+      constexpr uint32_t idesc_q = make_idesc_bf16(128, HS, 0, 1);
+      mbar_wait(q_full, 0);
+      mbar_wait(kv_full, 0);
+      tc_fence_after();
+      mma_over_head<HS>(tmem_base, sbase + L::Q_OFF, 128, sbase + L::K_OFF, BKV, idesc_s);
+      mma_over_head<HS>(tmem_base + BKV, sbase + L::DO_OFF, 128, sbase + L::V_OFF, BKV, idesc_s);
+      tc_commit(s_full);
+      for (int j = 0; j < n_kv; ++j) {
+        const int bf = j & 1, st = j % ST;
+        if (j + 1 < n_kv) {
+          const int sn = (j + 1) % ST, bn = (j + 1) & 1;
+          mbar_wait(kv_full + 8 * sn, ((j + 1) / ST) & 1);
+          tc_fence_after();
+          mma_over_head<HS>(tmem_base + bn * 2 * BKV, sbase + L::Q_OFF, 128, sbase + L::K_OFF + sn * L::KV_BYTES, BKV, idesc_s);
+          mma_over_head<HS>(tmem_base + bn * 2 * BKV + BKV, sbase + L::DO_OFF, 128, sbase + L::V_OFF + sn * L::KV_BYTES, BKV, idesc_s);
+          tc_commit(s_full + 8 * bn);
+        }
+        mbar_wait(ds_full + 8 * bf, (j >> 1) & 1);
+        tc_fence_after();
+        mma_over_rows<HS, BKV>(tm_dq, sbase + L::DS_OFF + bf * L::DS_BYTES, sbase + L::K_OFF + st * L::KV_BYTES, idesc_q, j > 0);
+        tc_commit(kv_empty + 8 * st);
+        tc_commit(ds_empty + 8 * bf);
+      }
+      tc_commit(acc_done);
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int q = q0 + row;
+    const bool q_ok = q < T;
+    const float scale_log2 = scale * 1.4426950408889634f;
+    const float my_lse = q_ok ? lse[((size_t)b * nh + h) * T + q] * 1.4426950408889634f : INFINITY;
+    const float my_delta = q_ok ? delta[((size_t)b * nh + h) * T + q] : 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int bf = j & 1, kv0 = j * BKV;
+      mbar_wait(s_full + 8 * bf, (j >> 1) & 1);
+      tc_fence_after();
+      if (j >= 2) mbar_wait(ds_empty + 8 * bf, ((j >> 1) - 1) & 1);
+      uint8_t* ds = smem + L::DS_OFF + bf * L::DS_BYTES;
+      const uint32_t tm_s = tmem_base + bf * 2 * BKV + lane_off, tm_dp = tm_s + BKV;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t rs[32], rp[32];
+        tmem_ld32(tm_s + c, rs);
+        tmem_ld32(tm_dp + c, rp);
+        tmem_wait_ld();
+        uint32_t dk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = (kv0 + c + e < T) ? exp2f(__uint_as_float(rs[e]) * scale_log2 - my_lse) : 0.f;
+          float p1 = (kv0 + c + e + 1 < T) ? exp2f(__uint_as_float(rs[e + 1]) * scale_log2 - my_lse) : 0.f;
+          dk[e / 2] = pack_bf16x2(p0 * (__uint_as_float(rp[e]) - my_delta) * scale, p1 * (__uint_as_float(rp[e + 1]) - my_delta) * scale);
+        }
+        store_p32<BKV>(ds, row, c, dk);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(ds_full + 8 * bf);
+    }
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    __nv_bfloat16* dq_row = dqkv + ((size_t)b * T + q) * (3 * C) + h * HS;
+#pragma unroll 1
+    for (int c = 0; c < HS; c += 16) {
+      uint32_t a[16];
+      tmem_ld16(tm_dq + lane_off + c, a);
+      tmem_wait_ld();
+      if (q_ok) store_row16_bf16(dq_row + c, a, 1.0f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// =============================================================================================== host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode3() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// bf16 tensor (B, T, ncols) row-major; box = (box_cols, box_rows, 1); swizzle span = box_cols * 2 bytes
+static int make_tmap3(CUtensorMap* m, const void* base, int ncols, int T, int B, int box_cols, int box_rows) {
+  PFN_encodeTiled enc = get_encode3();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DSF_ELAUNCH; }
+  cuuint64_t gdim[3] = {(cuuint64_t)ncols, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)ncols * 2, (cuuint64_t)ncols * 2 * (cuuint64_t)T};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d) failed (%d) ncols=%d T=%d B=%d box=%dx%d", (int)r, ncols, T, B, box_cols, box_rows); return DSF_ELAUNCH; }
+  return DSF_OK;
+}
+
+template <int HS, int BKV, int ST>
+static int launch_fwd2(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st) {
+  using L = Fwd2<HS, BKV, ST>;
+  using H = HeadCfg<HS>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_fwd2_kernel<HS, BKV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
+      return check_launch("attn_fwd2/attr");
+    configured = true;
+  }
+  CUtensorMap tmQ, tmKV;
+  if (int e = make_tmap3(&tmQ, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
+  if (int e = make_tmap3(&tmKV, qkv, 3 * C, T, B, H::BOXC, BKV)) return e;
+  const float scale_log2 = (1.0f / sqrtf((float)HS)) * 1.4426950408889634f;
+  dim3 grid(cdiv(T, 256), nh, B);
+  attn_fwd2_kernel<HS, BKV, ST><<<grid, L::THREADS, L::DYN, st>>>(tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2);
+  return check_launch("attn_fwd2");
+}
+
+int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, int C, int nh, cudaStream_t st);  // attn_tc.cu
+
+template <int HS, int BQ, int STA, int STB>
+static int launch_bwd2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
+                       cudaStream_t st) {
+  using LA = BwdKV2<HS, BQ, STA>;
+  using LB = BwdQ2<HS, STB>;
+  using H = HeadCfg<HS>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
+      return check_launch("attn_bwd2/attr");
+    configured = true;
+  }
+  const float scale = 1.0f / sqrtf((float)HS);
+  if (int e = run_attn_delta(y, dy, delta, B, T, C, nh, st)) return e;
+  CUtensorMap tmKV128, tmQs, tmDOs, tmQ128, tmDO128, tmKV64;
+  if (int e = make_tmap3(&tmKV128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
+  if (int e = make_tmap3(&tmQs, qkv, 3 * C, T, B, H::BOXC, BQ)) return e;
+  if (int e = make_tmap3(&tmDOs, dy, C, T, B, H::BOXC, BQ)) return e;
+  if (int e = make_tmap3(&tmQ128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
+  if (int e = make_tmap3(&tmDO128, dy, C, T, B, H::BOXC, 128)) return e;
+  if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
+  dim3 grid(cdiv(T, 128), nh, B);
+  attn_bwd_kv2_kernel<HS, BQ, STA><<<grid, 192, LA::DYN, st>>>(tmKV128, tmQs, tmDOs, lse, delta, (__nv_bfloat16*)dqkv, T, C, nh, scale);
+  if (int e = check_launch("attn_bwd2/kv")) return e;
+  attn_bwd_q2_kernel<HS, STB><<<grid, 192, LB::DYN, st>>>(tmQ128, tmDO128, tmKV64, lse, delta, (__nv_bfloat16*)dqkv, T, C, nh, scale);
+  return check_launch("attn_bwd2/q");
+}
+
+int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st) {
+  switch (C / nh) {
+    case 16: return launch_fwd2<16, 128, 3>(qkv, y, lse, B, T, C, nh, st);
+    case 32: return launch_fwd2<32, 128, 3>(qkv, y, lse, B, T, C, nh, st);
+    case 64: return launch_fwd2<64, 128, 3>(qkv, y, lse, B, T, C, nh, st);
+    case 128: return launch_fwd2<128, 64, 3>(qkv, y, lse, B, T, C, nh, st);
+  }
+  set_error("attn_fwd: head size %d not supported (16, 32, 64, 128)", C / nh);
+  return DSF_EUNSUPPORTED;
+}
+
+int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
+                cudaStream_t st) {
+  switch (C / nh) {
+    case 16: return launch_bwd2<16, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
+    case 32: return launch_bwd2<32, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
+    case 64: return launch_bwd2<64, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
+    case 128: return launch_bwd2<128, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
+  }
+  set_error("attn_bwd: head size %d not supported (16, 32, 64, 128)", C / nh);
+  return DSF_EUNSUPPORTED;
+}
+
+}  // namespace dsf

@@ -140,6 +140,9 @@ int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int32_t T, int
 /*   dy (B,T,C) bf16 -> dqkv (B,T,3C) bf16.  delta (B,nh,T) fp32 is scratch (rowsum(dy*y)).         */
 int dsf_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* delta,
                  void* dqkv, int32_t B, int32_t T, int32_t C, int32_t nh, void* stream);
+/* Selects the attention implementation (process-wide; for tests and A/B timing): 0 = default,
+ * 1 = v1 (simple synchronous kernels), 2 = v2 (warp-specialised, TMA-fed, pipelined).              */
+int dsf_attn_set_impl(int32_t impl);
 
 /* K7 forward.  Replaces slice/view/permute/contiguous (model2_seq.py:275-286) + F.interpolate
  * (bilinear, align_corners=False; :521-523, 539-541, 558-560) + residual add (:524-526 ...).
