@@ -585,6 +585,7 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
 
 // v2 (warp-specialised, TMA-fed) implementations, attn_tc2.cu
 int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st);
+int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st);
 int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
                 cudaStream_t st);
 
@@ -593,14 +594,14 @@ int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, in
   return check_launch("attn_bwd/delta");
 }
 
-static int g_attn_impl = 0;  // 0 = default (v2), 1 = v1 (simple synchronous kernels), 2 = v2
+static int g_attn_impl = 0;  // 0 = default (newest), 1 = v1 (simple synchronous), 2 = v2 (pipelined), 3 = v3 (fwd: double-buffered S/P)
 
 }  // namespace dsf
 
 using namespace dsf;
 
 extern "C" int dsf_attn_set_impl(int32_t impl) {
-  DSF_REQUIRE(impl >= 0 && impl <= 2, "attn_set_impl: impl must be 0 (default), 1 or 2");
+  DSF_REQUIRE(impl >= 0 && impl <= 3, "attn_set_impl: impl must be 0 (default), 1, 2 or 3");
   g_attn_impl = impl;
   return DSF_OK;
 }
@@ -612,7 +613,8 @@ extern "C" int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int
   DSF_REQUIRE(B <= 65535 && nh <= 65535, "attn_fwd: grid too large");
   const int hs = C / nh;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_attn_impl != 1) return attn_fwd_v2(qkv, y, lse, B, T, C, nh, st);
+  if (g_attn_impl == 2) return attn_fwd_v2(qkv, y, lse, B, T, C, nh, st);
+  if (g_attn_impl != 1) return attn_fwd_v3(qkv, y, lse, B, T, C, nh, st);
   switch (hs) {
     case 16: return launch_attn_fwd<16, 128>(qkv, y, lse, B, T, C, nh, st);
     case 32: return launch_attn_fwd<32, 128>(qkv, y, lse, B, T, C, nh, st);

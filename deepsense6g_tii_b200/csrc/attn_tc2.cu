@@ -24,6 +24,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {  // 2^x, MUFU.EX2 without the denormal fix-up of exp2f()
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -292,7 +297,7 @@ struct BwdKV2 {
 };
 
 template <int HS, int BQ, int ST>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
                     float scale) {
@@ -311,11 +316,11 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     mbar_init(kv_full, 1);
     mbar_init(acc_done, 1);
     for (int s = 0; s < ST; ++s) { mbar_init(q_full + 8 * s, 1); mbar_init(q_empty + 8 * s, 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 128); mbar_init(ds_empty + 8 * w, 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256); mbar_init(ds_empty + 8 * w, 1); }
     fence_barrier_init();
   }
-  if (warp == 4) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  if (warp == 5 && lane == 0) { tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 9 && lane == 0) { tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -323,7 +328,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tm_dv = tmem_base + 4 * BQ, tm_dk = tm_dv + HS;
 
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * L::KV_BYTES);
       tma_tile<HS>(sbase + L::K_OFF, &tmKV, kv_full, C + h * HS, kv0, b, 128);
@@ -336,7 +341,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         tma_tile<HS>(sbase + L::DO_OFF + st * L::Q_BYTES, &tmDO, q_full + 8 * st, h * HS, i * BQ, b, BQ);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BQ, 0, 0);
       constexpr uint32_t idesc_g = make_idesc_bf16(128, HS, 0, 1);
@@ -366,8 +371,9 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       tc_commit(acc_done);
     }
   } else {
-    const int row = warp * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int wg = warp >> 2;  // two compute warpgroups split the tile's columns
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const bool key_ok = (kv0 + row) < T;
     const float scale_log2 = scale * 1.4426950408889634f;
     const float* lse_g = lse + ((size_t)b * nh + h) * T;
@@ -377,12 +383,12 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       float* st_lse = reinterpret_cast<float*>(smem + L::STAT_OFF) + bf * 2 * BQ;
       float* st_delta = st_lse + BQ;
       // the stats buffer bf was last read two iterations ago; every thread has passed the barrier below since then
-      for (int c = threadIdx.x; c < 2 * BQ; c += 128) {
+      for (int c = threadIdx.x; c < 2 * BQ; c += 256) {
         const int qq = q0 + (c % BQ);
         if (c < BQ) st_lse[c] = qq < T ? lse_g[qq] * 1.4426950408889634f : INFINITY;
         else st_delta[c - BQ] = qq < T ? delta_g[qq] : 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       mbar_wait(s_full + 8 * bf, (i >> 1) & 1);
       tc_fence_after();
       if (i >= 2) mbar_wait(ds_empty + 8 * bf, ((i >> 1) - 1) & 1);
@@ -390,20 +396,27 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       uint8_t* dst = smem + L::DST_OFF + bf * L::P_BYTES;
       const uint32_t tm_s = tmem_base + bf * 2 * BQ + lane_off, tm_dp = tm_s + BQ;
 #pragma unroll 1
-      for (int c = 0; c < BQ; c += 32) {
+      for (int c = wg * (BQ / 2); c < (wg + 1) * (BQ / 2); c += 32) {
         uint32_t rs[32], rp[32];
         tmem_ld32(tm_s + c, rs);
         tmem_ld32(tm_dp + c, rp);
         tmem_wait_ld();
         uint32_t pk[16], dk[16];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = key_ok ? exp2f(__uint_as_float(rs[e]) * scale_log2 - st_lse[c + e]) : 0.f;
-          float p1 = key_ok ? exp2f(__uint_as_float(rs[e + 1]) * scale_log2 - st_lse[c + e + 1]) : 0.f;
-          const float d0 = p0 * (__uint_as_float(rp[e]) - st_delta[c + e]) * scale;
-          const float d1 = p1 * (__uint_as_float(rp[e + 1]) - st_delta[c + e + 1]) * scale;
-          pk[e / 2] = pack_bf16x2(p0, p1);
-          dk[e / 2] = pack_bf16x2(d0, d1);
+        for (int e = 0; e < 32; e += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(st_lse + c + e);
+          const float4 d4 = *reinterpret_cast<const float4*>(st_delta + c + e);
+          const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+          float p[4], d[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            p[u] = key_ok ? ex2_approx(fmaf(__uint_as_float(rs[e + u]), scale_log2, -ls[u])) : 0.f;
+            d[u] = p[u] * (__uint_as_float(rp[e + u]) - dl[u]) * scale;
+          }
+          pk[e / 2] = pack_bf16x2(p[0], p[1]);
+          pk[e / 2 + 1] = pack_bf16x2(p[2], p[3]);
+          dk[e / 2] = pack_bf16x2(d[0], d[1]);
+          dk[e / 2 + 1] = pack_bf16x2(d[2], d[3]);
         }
         store_p32<BQ>(pt, row, c, pk);
         store_p32<BQ>(dst, row, c, dk);
@@ -418,20 +431,16 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     __nv_bfloat16* dk_row = dqkv + ((size_t)b * T + kv0 + row) * ld + C + h * HS;
     __nv_bfloat16* dv_row = dk_row + C;
 #pragma unroll 1
-    for (int c = 0; c < HS; c += 16) {
-      uint32_t a[16], v[16];
-      tmem_ld16(tm_dk + lane_off + c, a);
-      tmem_ld16(tm_dv + lane_off + c, v);
+    for (int c = 0; c < HS; c += 16) {  // warpgroup 0 drains dK, warpgroup 1 drains dV
+      uint32_t a[16];
+      tmem_ld16((wg == 0 ? tm_dk : tm_dv) + lane_off + c, a);
       tmem_wait_ld();
-      if (key_ok) {
-        store_row16_bf16(dk_row + c, a, 1.0f);
-        store_row16_bf16(dv_row + c, v, 1.0f);
-      }
+      if (key_ok) store_row16_bf16((wg == 0 ? dk_row : dv_row) + c, a, 1.0f);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 // =============================================================================================== backward: dQ
@@ -449,7 +458,7 @@ struct BwdQ2 {
 };
 
 template <int HS, int ST>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmKV,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
                    float scale) {
@@ -470,11 +479,11 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(q_full, 1);
     mbar_init(acc_done, 1);
     for (int s = 0; s < ST; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 128); mbar_init(ds_empty + 8 * w, 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256); mbar_init(ds_empty + 8 * w, 1); }
     fence_barrier_init();
   }
-  if (warp == 4) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  if (warp == 5 && lane == 0) { tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); }
+  if (warp == 8) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  if (warp == 9 && lane == 0) { tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -482,7 +491,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tm_dq = tmem_base + 4 * BKV;
 
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {
       mbar_expect_tx(q_full, 2 * L::Q_BYTES);
       tma_tile<HS>(sbase + L::Q_OFF, &tmQ, q_full, h * HS, q0, b, 128);
@@ -495,7 +504,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_tile<HS>(sbase + L::V_OFF + st * L::KV_BYTES, &tmKV, kv_full + 8 * st, 2 * C + h * HS, j * BKV, b, BKV);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
       constexpr uint32_t idesc_q = make_idesc_bf16(128, HS, 0, 1);
@@ -524,8 +533,9 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_commit(acc_done);
     }
   } else {
-    const int row = warp * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int wg = warp >> 2;  // two compute warpgroups split the tile's columns
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const int q = q0 + row;
     const bool q_ok = q < T;
     const float scale_log2 = scale * 1.4426950408889634f;
@@ -539,7 +549,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint8_t* ds = smem + L::DS_OFF + bf * L::DS_BYTES;
       const uint32_t tm_s = tmem_base + bf * 2 * BKV + lane_off, tm_dp = tm_s + BKV;
 #pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
+      for (int c = wg * (BKV / 2); c < (wg + 1) * (BKV / 2); c += 32) {
         uint32_t rs[32], rp[32];
         tmem_ld32(tm_s + c, rs);
         tmem_ld32(tm_dp + c, rp);
@@ -547,8 +557,8 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         uint32_t dk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          float p0 = (kv0 + c + e < T) ? exp2f(__uint_as_float(rs[e]) * scale_log2 - my_lse) : 0.f;
-          float p1 = (kv0 + c + e + 1 < T) ? exp2f(__uint_as_float(rs[e + 1]) * scale_log2 - my_lse) : 0.f;
+          float p0 = (kv0 + c + e < T) ? ex2_approx(fmaf(__uint_as_float(rs[e]), scale_log2, -my_lse)) : 0.f;
+          float p1 = (kv0 + c + e + 1 < T) ? ex2_approx(fmaf(__uint_as_float(rs[e + 1]), scale_log2, -my_lse)) : 0.f;
           dk[e / 2] = pack_bf16x2(p0 * (__uint_as_float(rp[e]) - my_delta) * scale, p1 * (__uint_as_float(rp[e + 1]) - my_delta) * scale);
         }
         store_p32<BKV>(ds, row, c, dk);
@@ -560,8 +570,11 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(acc_done, 0);
     tc_fence_after();
     __nv_bfloat16* dq_row = dqkv + ((size_t)b * T + q) * (3 * C) + h * HS;
+    constexpr int CH = HS >= 32 ? HS / 2 : HS;  // columns drained by each warpgroup (hs = 16: warpgroup 0 only)
+    const int c_lo = HS >= 32 ? wg * CH : 0;
+    const int c_hi = (HS >= 32 || wg == 0) ? c_lo + CH : c_lo;
 #pragma unroll 1
-    for (int c = 0; c < HS; c += 16) {
+    for (int c = c_lo; c < c_hi; c += 16) {
       uint32_t a[16];
       tmem_ld16(tm_dq + lane_off + c, a);
       tmem_wait_ld();
@@ -570,7 +583,200 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 8) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// =============================================================================================== forward (v3 schedule)
+// Same roles as attn_fwd2_kernel, but S and P are double-buffered PER warpgroup so the softmax warps never
+// wait for the tensor pipe: S_w(j+2) is issued as soon as softmax_w(j) has drained its S buffer, and
+// softmax_w(j+1) may write its P tile while P.V_w(j) is still reading the other one.  K and V ride in
+// separate TMA rings because K(j+2) is consumed two iterations ahead of V(j).  BKV = 64.
+template <int HS, int KST, int VST>
+struct Fwd3 {
+  static constexpr int BKV = 64;
+  static constexpr int Q_BYTES = 128 * HS * 2, KV_BYTES = BKV * HS * 2, P_BYTES = 128 * BKV * 2;
+  static constexpr int Q_OFF = 0, K_OFF = 2 * Q_BYTES, V_OFF = K_OFF + KST * KV_BYTES, P_OFF = V_OFF + VST * KV_BYTES;
+  static constexpr int BAR_OFF = P_OFF + 4 * P_BYTES;
+  static constexpr int NBAR = 1 + 2 * KST + 2 * VST + 12;
+  static constexpr int DYN = BAR_OFF + NBAR * 8 + 16 + 1024;
+  static constexpr int THREADS = 320;
+  static_assert(4 * BKV + 2 * HS <= 512, "TMEM budget");
+  static_assert(DYN <= 232448, "shared memory budget");
+};
+
+template <int HS, int KST, int VST>
+__global__ void __launch_bounds__(320, 1)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, __nv_bfloat16* __restrict__ y,
+                 float* __restrict__ lse, int T, int C, int nh, float scale_log2) {
+  using L = Fwd3<HS, KST, VST>;
+  constexpr int BKV = L::BKV;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar0 = sbase + L::BAR_OFF;
+  const uint32_t q_full = bar0, k_full = bar0 + 8, k_empty = k_full + 8 * KST, v_full = k_empty + 8 * KST, v_empty = v_full + 8 * VST,
+                 s_full = v_empty + 8 * VST, p_full = s_full + 32, p_empty = p_full + 32, tmem_slot = p_empty + 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (T + BKV - 1) / BKV;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KST; ++s) { mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1); }
+    for (int s = 0; s < VST; ++s) { mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(p_full + 8 * i, 128); mbar_init(p_empty + 8 * i, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 9 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 9) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * L::Q_BYTES);
+      for (int w = 0; w < 2; ++w) tma_tile<HS>(sbase + L::Q_OFF + w * L::Q_BYTES, &tmQ, q_full, h * HS, q0 + 128 * w, b, 128);
+      for (int j = 0; j < n_kv; ++j) {
+        const int ks = j % KST, vs = j % VST;
+        if (j >= KST) mbar_wait(k_empty + 8 * ks, ((j / KST) - 1) & 1);
+        mbar_expect_tx(k_full + 8 * ks, L::KV_BYTES);
+        tma_tile<HS>(sbase + L::K_OFF + ks * L::KV_BYTES, &tmKV, k_full + 8 * ks, C + h * HS, j * BKV, b, BKV);
+        if (j >= VST) mbar_wait(v_empty + 8 * vs, ((j / VST) - 1) & 1);
+        mbar_expect_tx(v_full + 8 * vs, L::KV_BYTES);
+        tma_tile<HS>(sbase + L::V_OFF + vs * L::KV_BYTES, &tmKV, v_full + 8 * vs, 2 * C + h * HS, j * BKV, b, BKV);
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, HS, 0, 1);
+      mbar_wait(q_full, 0);
+      for (int jj = 0; jj < 2 && jj < n_kv; ++jj) {
+        mbar_wait(k_full + 8 * (jj % KST), (jj / KST) & 1);
+        tc_fence_after();
+        for (int w = 0; w < 2; ++w) {
+          mma_over_head<HS>(tmem_base + (w * 2 + jj) * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + (jj % KST) * L::KV_BYTES,
+                            BKV, idesc_s);
+          tc_commit(s_full + 8 * (w * 2 + jj));
+        }
+        tc_commit(k_empty + 8 * (jj % KST));
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int buf = j & 1, vs = j % VST;
+        mbar_wait(v_full + 8 * vs, (j / VST) & 1);
+        for (int w = 0; w < 2; ++w) {
+          const int sb = w * 2 + buf;
+          mbar_wait(p_full + 8 * sb, (j >> 1) & 1);
+          tc_fence_after();
+          mma_over_rows<HS, BKV>(tmem_base + 4 * BKV + w * HS, sbase + L::P_OFF + sb * L::P_BYTES, sbase + L::V_OFF + vs * L::KV_BYTES, idesc_o,
+                                 j > 0);
+          tc_commit(p_empty + 8 * sb);
+          if (w == 1) tc_commit(v_empty + 8 * vs);
+          if (j + 2 < n_kv) {
+            const int ks = (j + 2) % KST;
+            if (w == 0) { mbar_wait(k_full + 8 * ks, ((j + 2) / KST) & 1); tc_fence_after(); }
+            mma_over_head<HS>(tmem_base + sb * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + ks * L::KV_BYTES, BKV, idesc_s);
+            tc_commit(s_full + 8 * sb);
+            if (w == 1) tc_commit(k_empty + 8 * ks);
+          }
+        }
+      }
+    }
+  } else {
+    const int w = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tm_o = tmem_base + 4 * BKV + w * HS + lane_off;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int kv0 = j * BKV, buf = j & 1, sb = w * 2 + buf;
+      const uint32_t tm_s = tmem_base + sb * BKV + lane_off;
+      uint8_t* p_tile = smem + L::P_OFF + sb * L::P_BYTES;
+      mbar_wait(s_full + 8 * sb, (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tm_s, r0);
+      tmem_ld32(tm_s + 32, r1);
+      tmem_wait_ld();
+      float p_max = -INFINITY;
+      if (kv0 + BKV <= T) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p_max = fmaxf(p_max, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (kv0 + i < T) p_max = fmaxf(p_max, __uint_as_float(r0[i]));
+          if (kv0 + 32 + i < T) p_max = fmaxf(p_max, __uint_as_float(r1[i]));
+        }
+      }
+      p_max *= scale_log2;
+      const bool need = p_max > m_run + 8.f;  // lazy rescale (exact: m only has to bound the exponent)
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = need ? p_max : m_run;
+        const float alpha = ex2_approx(m_run - m_new);
+        if (j > 0) {
+          mbar_wait(p_empty + 8 * (w * 2 + ((j - 1) & 1)), ((j - 1) >> 1) & 1);  // P.V(j-1) retired: O is stable
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < HS; c += 16) {
+            uint32_t o[16];
+            tmem_ld16(tm_o + c, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tm_o + c, o);
+          }
+          tmem_wait_st();
+        }
+        l_run *= alpha;
+        m_run = m_new;
+      }
+      if (j >= 2) mbar_wait(p_empty + 8 * sb, ((j >> 1) - 1) & 1);  // P.V(j-2) retired: this P buffer is free
+      float l_add = 0.f;
+      const bool full = kv0 + BKV <= T;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const uint32_t a0 = half ? r1[i] : r0[i], a1 = half ? r1[i + 1] : r0[i + 1];
+          float p0 = ex2_approx(fmaf(__uint_as_float(a0), scale_log2, -m_run));
+          float p1 = ex2_approx(fmaf(__uint_as_float(a1), scale_log2, -m_run));
+          if (!full) {
+            if (kv0 + half * 32 + i >= T) p0 = 0.f;
+            if (kv0 + half * 32 + i + 1 >= T) p1 = 0.f;
+          }
+          __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);  // the row sum uses what the P.V MMA will see
+          l_add += __low2float(pb) + __high2float(pb);
+          pk[i / 2] = *reinterpret_cast<uint32_t*>(&pb);
+        }
+        store_p32<BKV>(p_tile, row, half * 32, pk);
+      }
+      l_run += l_add;
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(p_full + 8 * sb);
+    }
+    mbar_wait(p_empty + 8 * (w * 2 + ((n_kv - 1) & 1)), ((n_kv - 1) >> 1) & 1);
+    tc_fence_after();
+    const int q = q0 + 128 * w + row;
+    const float inv_l = 1.0f / l_run;
+    __nv_bfloat16* yrow = y + ((size_t)b * T + q) * C + h * HS;
+#pragma unroll 1
+    for (int c = 0; c < HS; c += 16) {
+      uint32_t o[16];
+      tmem_ld16(tm_o + c, o);
+      tmem_wait_ld();
+      if (q < T) store_row16_bf16(yrow + c, o, inv_l);
+    }
+    if (q < T) lse[((size_t)b * nh + h) * T + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 // =============================================================================================== host
@@ -622,6 +828,25 @@ static int launch_fwd2(const void* qkv, void* y, float* lse, int B, int T, int C
   return check_launch("attn_fwd2");
 }
 
+template <int HS, int KST, int VST>
+static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st) {
+  using L = Fwd3<HS, KST, VST>;
+  using H = HeadCfg<HS>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
+      return check_launch("attn_fwd3/attr");
+    configured = true;
+  }
+  CUtensorMap tmQ, tmKV;
+  if (int e = make_tmap3(&tmQ, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
+  if (int e = make_tmap3(&tmKV, qkv, 3 * C, T, B, H::BOXC, L::BKV)) return e;
+  const float scale_log2 = (1.0f / sqrtf((float)HS)) * 1.4426950408889634f;
+  dim3 grid(cdiv(T, 256), nh, B);
+  attn_fwd3_kernel<HS, KST, VST><<<grid, L::THREADS, L::DYN, st>>>(tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2);
+  return check_launch("attn_fwd3");
+}
+
 int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, int C, int nh, cudaStream_t st);  // attn_tc.cu
 
 template <int HS, int BQ, int STA, int STB>
@@ -647,9 +872,9 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   if (int e = make_tmap3(&tmDO128, dy, C, T, B, H::BOXC, 128)) return e;
   if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
   dim3 grid(cdiv(T, 128), nh, B);
-  attn_bwd_kv2_kernel<HS, BQ, STA><<<grid, 192, LA::DYN, st>>>(tmKV128, tmQs, tmDOs, lse, delta, (__nv_bfloat16*)dqkv, T, C, nh, scale);
+  attn_bwd_kv2_kernel<HS, BQ, STA><<<grid, 320, LA::DYN, st>>>(tmKV128, tmQs, tmDOs, lse, delta, (__nv_bfloat16*)dqkv, T, C, nh, scale);
   if (int e = check_launch("attn_bwd2/kv")) return e;
-  attn_bwd_q2_kernel<HS, STB><<<grid, 192, LB::DYN, st>>>(tmQ128, tmDO128, tmKV64, lse, delta, (__nv_bfloat16*)dqkv, T, C, nh, scale);
+  attn_bwd_q2_kernel<HS, STB><<<grid, 320, LB::DYN, st>>>(tmQ128, tmDO128, tmKV64, lse, delta, (__nv_bfloat16*)dqkv, T, C, nh, scale);
   return check_launch("attn_bwd2/q");
 }
 
@@ -659,6 +884,17 @@ int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int n
     case 32: return launch_fwd2<32, 128, 3>(qkv, y, lse, B, T, C, nh, st);
     case 64: return launch_fwd2<64, 128, 3>(qkv, y, lse, B, T, C, nh, st);
     case 128: return launch_fwd2<128, 64, 3>(qkv, y, lse, B, T, C, nh, st);
+  }
+  set_error("attn_fwd: head size %d not supported (16, 32, 64, 128)", C / nh);
+  return DSF_EUNSUPPORTED;
+}
+
+int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st) {
+  switch (C / nh) {
+    case 16: return launch_fwd3<16, 3, 2>(qkv, y, lse, B, T, C, nh, st);
+    case 32: return launch_fwd3<32, 3, 2>(qkv, y, lse, B, T, C, nh, st);
+    case 64: return launch_fwd3<64, 3, 2>(qkv, y, lse, B, T, C, nh, st);
+    case 128: return launch_fwd3<128, 3, 2>(qkv, y, lse, B, T, C, nh, st);
   }
   set_error("attn_fwd: head size %d not supported (16, 32, 64, 128)", C / nh);
   return DSF_EUNSUPPORTED;

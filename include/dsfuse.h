@@ -141,7 +141,8 @@ int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int32_t T, int
 int dsf_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* delta,
                  void* dqkv, int32_t B, int32_t T, int32_t C, int32_t nh, void* stream);
 /* Selects the attention implementation (process-wide; for tests and A/B timing): 0 = default,
- * 1 = v1 (simple synchronous kernels), 2 = v2 (warp-specialised, TMA-fed, pipelined).              */
+ * 1 = v1 (simple synchronous kernels), 2 = v2 (warp-specialised, TMA-fed, pipelined),
+ * 3 = v3 (v2 + per-warpgroup double-buffered S/P in the forward).                                  */
 int dsf_attn_set_impl(int32_t impl);
 
 /* K7 forward.  Replaces slice/view/permute/contiguous (model2_seq.py:275-286) + F.interpolate
