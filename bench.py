@@ -170,7 +170,8 @@ def profile_families(gpt, feats, gps, probes):
     """One instrumented fwd+bwd: CUDA events around every C-ABI call, summed per kernel family."""
     from deepsense6g_tii_b200 import _capi
     names = ["tokens_fwd", "tokens_bwd", "layernorm_fwd", "layernorm_bwd", "gemm_bf16_nt", "gemm_bf16_tn", "colsum", "relu_bwd",
-             "attn_fwd", "attn_bwd", "upsample_add_fwd", "upsample_add_bwd", "cast_f32_bf16"]
+             "attn_fwd", "attn_bwd", "upsample_add_fwd", "upsample_add_bwd", "cast_f32_bf16", "relu_bwd_colsum",
+             "pack_block_weights"]
     rec, orig = [], {}
     for n in names:
         f = getattr(_capi, n)

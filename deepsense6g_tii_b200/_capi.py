@@ -22,7 +22,7 @@ EPI_BIAS, EPI_RELU, EPI_RESIDUAL, EPI_ACCUM = 1, 2, 4, 8
 SYMBOLS = [
     "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_tokens_fwd", "dsf_tokens_bwd",
     "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_f32",
-    "dsf_colsum", "dsf_relu_bwd", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_set_impl",
+    "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_set_impl",
     "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16",
 ]
 
@@ -60,7 +60,9 @@ def lib():
             "dsf_tokens_fwd": [POINTER(Geom), P, P, P, P, P, P, P],
             "dsf_tokens_bwd": [POINTER(Geom), P, P, P, P, P, P, P, P, P, P],
             "dsf_layernorm_fwd": [P, P, P, P, c_int32, P, P, c_int32, c_int32, c_float, P],
-            "dsf_layernorm_bwd": [P, c_int32, P, P, P, P, P, P, P, P, c_int32, c_int32, P],
+            "dsf_layernorm_bwd": [P, c_int32, P, P, P, P, P, P, P, P, P, P, c_int32, c_int32, P],
+            "dsf_relu_bwd_colsum": [P, P, P, c_int32, c_int32, P],
+            "dsf_pack_block_weights": [P] * 9 + [c_int32, c_int32] + [P] * 10,
             "dsf_gemm_bf16_nt": [P, c_int32, P, c_int32, P, c_int32, c_int32, P, P, c_int32, c_int32, c_int32, c_int32, P],
             "dsf_gemm_bf16_tn": [P, c_int32, P, c_int32, P, c_int32, c_int32, c_int32, c_int32, P],
             "dsf_gemm_f32": [POINTER(GemmF32Desc), P, P, P, P, P, P],
@@ -142,10 +144,22 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-5):
     _chk(lib().dsf_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _dt(y), _p(mean), _p(rstd), M, C, eps, _stream()), "dsf_layernorm_fwd")
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, dx_bf16=None, dx_colsum=None):
     M, C = x.shape
     _chk(lib().dsf_layernorm_bwd(_p(dy), _dt(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx_add), _p(dx_out), _p(dgamma),
-                                 _p(dbeta), M, C, _stream()), "dsf_layernorm_bwd")
+                                 _p(dbeta), _p(dx_bf16), _p(dx_colsum), M, C, _stream()), "dsf_layernorm_bwd")
+
+
+def relu_bwd_colsum(dy, h, out):
+    M, N = dy.shape
+    _chk(lib().dsf_relu_bwd_colsum(_p(dy), _p(h), _p(out), M, N, _stream()), "dsf_relu_bwd_colsum")
+
+
+def pack_block_weights(wq, wk, wv, wp, w1, w2, bq, bk, bv, outs):
+    """outs = (wqkv, wqkv_t, wp_b, wp_t, w1_b, w1_t, w2_b, w2_t, bqkv) preallocated."""
+    C, F = wq.shape[0], w1.shape[0]
+    _chk(lib().dsf_pack_block_weights(_p(wq), _p(wk), _p(wv), _p(wp), _p(w1), _p(w2), _p(bq), _p(bk), _p(bv), C, F,
+                                      *[_p(t) for t in outs], _stream()), "dsf_pack_block_weights")
 
 
 def gemm_bf16_nt(A, B, C, bias=None, residual=None, relu=False):

@@ -4,6 +4,9 @@
 //
 // Backward: dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) [+ dx_add], and per-CTA partial
 // dgamma / dbeta column sums that are folded into the fp32 outputs with one atomicAdd per column per CTA.
+// Because dx is the gradient of the residual stream, it is also (a) the dY of the preceding Linear's
+// bias (model2_seq.py:109,124) and (b) a tensor-core GEMM operand: the kernel optionally emits the column
+// sums of dx (bias gradient) and a bf16 copy in the same pass, saving two more passes over the tensor.
 #include <algorithm>
 
 #include "common.cuh"
@@ -62,28 +65,33 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   }
 }
 
-template <typename TY, int VPT>
+template <typename TY, int VPT, bool EXTRA>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const TY* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* dx_add,
-                     float* dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C) {
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* dx_add, float* dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_bf16,
+                     float* __restrict__ dx_colsum, int M, int C) {
   __shared__ float red[LN_WARPS][VPT * 128 + 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 2;
   const float invC = 1.0f / (float)C;
-  float g4[VPT][4], dg[VPT][4], db[VPT][4];
+  float g4[VPT][4], dg[VPT][4], db[VPT][4], dc[EXTRA ? VPT : 1][4];
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int vi = lane + 32 * i;
 #pragma unroll
     for (int k = 0; k < 4; ++k) { dg[i][k] = 0.f; db[i][k] = 0.f; g4[i][k] = 0.f; }
+    if (EXTRA) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dc[EXTRA ? i : 0][k] = 0.f;
+    }
     if (vi < nvec) Vec4<float>::load(gamma + vi * 4, g4[i]);
   }
   for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
     const float mu = mean[row], rs = rstd[row];
     const float* xr = x + (size_t)row * C;
     const TY* dyr = dy + (size_t)row * C;
-    float xh[VPT][4], gy[VPT][4];
+    float xh[VPT][4], gy[VPT][4], ad[VPT][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
@@ -92,6 +100,7 @@ layernorm_bwd_kernel(const TY* __restrict__ dy, const float* __restrict__ x, con
         float xv[4], dv[4];
         Vec4<float>::load(xr + vi * 4, xv);
         Vec4<TY>::load(dyr + vi * 4, dv);
+        if (dx_add) Vec4<float>::load(dx_add + (size_t)row * C + vi * 4, ad[i]);  // issued early: independent of the reductions
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           xh[i][k] = (xv[k] - mu) * rs;
@@ -116,27 +125,31 @@ layernorm_bwd_kernel(const TY* __restrict__ dy, const float* __restrict__ x, con
 #pragma unroll
         for (int k = 0; k < 4; ++k) o[k] = rs * (gy[i][k] - m1 - xh[i][k] * m2);
         if (dx_add) {
-          float a[4];
-          Vec4<float>::load(dx_add + (size_t)row * C + vi * 4, a);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) o[k] += a[k];
+          for (int k = 0; k < 4; ++k) o[k] += ad[i][k];
         }
         Vec4<float>::store(dxr + vi * 4, o);
+        if (EXTRA) {
+          if (dx_bf16) Vec4<__nv_bfloat16>::store(dx_bf16 + (size_t)row * C + vi * 4, o);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dc[EXTRA ? i : 0][k] += o[k];
+        }
       }
     }
   }
-  // CTA reduction of the dgamma / dbeta partials, then one atomic per column
+  // CTA reduction of the column partials, then one atomic per column
 #pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < (EXTRA ? 3 : 2); ++pass) {
+    if (pass == 2 && dx_colsum == nullptr) break;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
       const int vi = lane + 32 * i;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) red[warp][vi * 4 + k] = pass == 0 ? dg[i][k] : db[i][k];
+      for (int k = 0; k < 4; ++k) red[warp][vi * 4 + k] = pass == 0 ? dg[i][k] : (pass == 1 ? db[i][k] : dc[EXTRA ? i : 0][k]);
     }
     __syncthreads();
-    float* out = pass == 0 ? dgamma : dbeta;
+    float* out = pass == 0 ? dgamma : (pass == 1 ? dbeta : dx_colsum);
     for (int c = threadIdx.x; c < C; c += LN_WARPS * 32) {
       float s = 0.f;
 #pragma unroll
@@ -149,7 +162,7 @@ layernorm_bwd_kernel(const TY* __restrict__ dy, const float* __restrict__ x, con
 template <typename TY>
 int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int C,
                   float eps, cudaStream_t st) {
-  const int blocks = min(cdiv(M, LN_WARPS), num_sms() * 8);
+  const int blocks = std::min(cdiv(M, LN_WARPS), num_sms() * 8);
   TY* yy = reinterpret_cast<TY*>(y);
   if (C <= 128) layernorm_fwd_kernel<TY, 1><<<blocks, LN_WARPS * 32, 0, st>>>(x, gamma, beta, yy, mean, rstd, M, C, eps);
   else if (C <= 256) layernorm_fwd_kernel<TY, 2><<<blocks, LN_WARPS * 32, 0, st>>>(x, gamma, beta, yy, mean, rstd, M, C, eps);
@@ -158,16 +171,20 @@ int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* y
   return check_launch("layernorm_fwd");
 }
 
-template <typename TY>
+template <typename TY, bool EXTRA>
 int launch_ln_bwd(const void* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
-                  const float* dx_add, float* dx, float* dgamma, float* dbeta, int M, int C, cudaStream_t st) {
-  // few, fat CTAs: every CTA ends with 2*C atomics
-  const int blocks = min(cdiv(M, LN_WARPS * 4), num_sms() * 2);
+                  const float* dx_add, float* dx, float* dgamma, float* dbeta, void* dx_bf16, float* dx_colsum, int M, int C,
+                  cudaStream_t st) {
+  // few, fat CTAs: every CTA ends with 2-3 x C atomics
+  const int blocks = std::min(cdiv(M, LN_WARPS * 2), num_sms() * 4);
   const TY* d = reinterpret_cast<const TY*>(dy);
-  if (C <= 128) layernorm_bwd_kernel<TY, 1><<<blocks, LN_WARPS * 32, 0, st>>>(d, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, M, C);
-  else if (C <= 256) layernorm_bwd_kernel<TY, 2><<<blocks, LN_WARPS * 32, 0, st>>>(d, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, M, C);
-  else if (C <= 512) layernorm_bwd_kernel<TY, 4><<<blocks, LN_WARPS * 32, 0, st>>>(d, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, M, C);
-  else layernorm_bwd_kernel<TY, 8><<<blocks, LN_WARPS * 32, 0, st>>>(d, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, M, C);
+  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+#define DSF_LN_BWD(V) layernorm_bwd_kernel<TY, V, EXTRA><<<blocks, LN_WARPS * 32, 0, st>>>(d, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, xb, dx_colsum, M, C)
+  if (C <= 128) DSF_LN_BWD(1);
+  else if (C <= 256) DSF_LN_BWD(2);
+  else if (C <= 512) DSF_LN_BWD(4);
+  else DSF_LN_BWD(8);
+#undef DSF_LN_BWD
   return check_launch("layernorm_bwd");
 }
 
@@ -188,12 +205,18 @@ extern "C" int dsf_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int dsf_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* gamma, const float* mean,
                                  const float* rstd, const float* dx_add, float* dx_out, float* dgamma, float* dbeta,
-                                 int32_t M, int32_t C, void* stream) {
+                                 void* dx_bf16, float* dx_colsum, int32_t M, int32_t C, void* stream) {
   DSF_REQUIRE(dy && x && gamma && mean && rstd && dx_out && dgamma && dbeta, "layernorm_bwd: NULL pointer");
   DSF_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && C <= 1024, "layernorm_bwd: need M>0 and C multiple of 4 up to 1024 (got M=%d C=%d)", M, C);
-  DSF_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(gamma) && aligned16(dx_add) && aligned16(dx_out), "layernorm_bwd: 16-byte alignment required");
+  DSF_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(gamma) && aligned16(dx_add) && aligned16(dx_out) && aligned16(dx_bf16),
+              "layernorm_bwd: 16-byte alignment required");
   DSF_REQUIRE(dy_dtype == DSF_F32 || dy_dtype == DSF_BF16, "layernorm_bwd: bad dy_dtype %d", dy_dtype);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dy_dtype == DSF_F32) return launch_ln_bwd<float>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, M, C, st);
-  return launch_ln_bwd<__nv_bfloat16>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, M, C, st);
+  const bool extra = dx_bf16 != nullptr || dx_colsum != nullptr;
+  if (dy_dtype == DSF_F32) {
+    if (extra) return launch_ln_bwd<float, true>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, dx_bf16, dx_colsum, M, C, st);
+    return launch_ln_bwd<float, false>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, nullptr, nullptr, M, C, st);
+  }
+  if (extra) return launch_ln_bwd<__nv_bfloat16, true>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, dx_bf16, dx_colsum, M, C, st);
+  return launch_ln_bwd<__nv_bfloat16, false>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, nullptr, nullptr, M, C, st);
 }

@@ -152,6 +152,8 @@ class _Runner:
     def forward(self, feats, gps_emb, params, residual=True):
         """feats: 3 tensors (N, C, H, W) [or NHWC storage]; gps_emb (B, 2, C) fp32; params: flat list.
         residual=False returns the upsampled token maps alone (plain ``GPT.forward`` semantics)."""
+        if self.bf16:
+            return self._forward_bf16(feats, gps_emb, params, residual)
         dev = gps_emb.device
         M, C, L = self.M, self.C, self.L
         f32 = torch.float32
@@ -207,7 +209,141 @@ class _Runner:
         return outs, gps_out, saved
 
     # ------------------------------------------------------------------ backward
+    # ------------------------------------------------------------------ bf16 tensor-core path
+    def _forward_bf16(self, feats, gps_emb, params, residual):
+        """Per block: 1 weight-pack launch, LN, QKV GEMM, flash attention, proj GEMM(+residual), LN,
+        fc1 GEMM(+ReLU), fc2 GEMM(+residual) = 8 launches."""
+        dev = gps_emb.device
+        M, C, L = self.M, self.C, self.L
+        f32, bf = torch.float32, torch.bfloat16
+        F = params[13].shape[0] if L > 0 else 4 * C  # mlp.0.weight rows
+        saved = _Ctx()
+        saved.layers = []
+        x = torch.empty(M, C, device=dev, dtype=f32)
+        K.tokens_fwd(self.geom, feats[0], feats[1], feats[2], gps_emb, params[0], x)
+        for i in range(L):
+            (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[1 + 16 * i: 17 + 16 * i]
+            st = _Ctx()
+            # one flat bf16 buffer holds the 8 weight shadows of this block (plain + transposed)
+            sizes = [3 * C * C, 3 * C * C, C * C, C * C, F * C, F * C, C * F, C * F]
+            flat = torch.empty(sum(sizes), device=dev, dtype=bf)
+            views, off = [], 0
+            for n in sizes:
+                views.append(flat[off:off + n])
+                off += n
+            st.wqkv, st.wqkv_t = views[0].view(3 * C, C), views[1].view(C, 3 * C)
+            st.wp, st.wp_t = views[2].view(C, C), views[3].view(C, C)
+            st.w1, st.w1_t = views[4].view(F, C), views[5].view(C, F)
+            st.w2, st.w2_t = views[6].view(C, F), views[7].view(F, C)
+            bqkv = torch.empty(3 * C, device=dev, dtype=f32)
+            K.pack_block_weights(qw, kw, vw, pw, w1, w2, qb, kb, vb,
+                                 (st.wqkv, st.wqkv_t, st.wp, st.wp_t, st.w1, st.w1_t, st.w2, st.w2_t, bqkv))
+            st.x_in = x
+            stats = torch.empty(4, M, device=dev, dtype=f32)
+            st.mean1, st.rstd1, st.mean2, st.rstd2 = stats[0], stats[1], stats[2], stats[3]
+            st.h1 = torch.empty(M, C, device=dev, dtype=bf)
+            K.layernorm_fwd(x, ln1w, ln1b, st.h1, st.mean1, st.rstd1)
+            st.qkv = torch.empty(M, 3 * C, device=dev, dtype=bf)
+            K.gemm_bf16_nt(st.h1, st.wqkv, st.qkv, bias=bqkv)
+            st.y = torch.empty(M, C, device=dev, dtype=bf)
+            st.lse = torch.empty(self.B, self.nh, self.T, device=dev, dtype=f32)
+            K.attn_fwd(st.qkv, st.y, st.lse, self.B, self.T, C, self.nh)
+            st.x_mid = torch.empty(M, C, device=dev, dtype=f32)
+            K.gemm_bf16_nt(st.y, st.wp, st.x_mid, bias=pb, residual=x)
+            st.h2 = torch.empty(M, C, device=dev, dtype=bf)
+            K.layernorm_fwd(st.x_mid, ln2w, ln2b, st.h2, st.mean2, st.rstd2)
+            st.a = torch.empty(M, F, device=dev, dtype=bf)
+            K.gemm_bf16_nt(st.h2, st.w1, st.a, bias=b1, relu=True)
+            x = torch.empty(M, C, device=dev, dtype=f32)
+            K.gemm_bf16_nt(st.a, st.w2, x, bias=b2, residual=st.x_mid)
+            saved.layers.append(st)
+        saved.x_last = x
+        saved.mean_f = torch.empty(M, device=dev, dtype=f32)
+        saved.rstd_f = torch.empty(M, device=dev, dtype=f32)
+        yf = torch.empty(M, C, device=dev, dtype=f32)
+        K.layernorm_fwd(x, params[-2], params[-1], yf, saved.mean_f, saved.rstd_f)
+        outs = [torch.empty_like(f) for f in feats]
+        K.upsample_add_fwd(self.geom, yf, feats if residual else [torch.zeros_like(f) for f in feats], outs)
+        gps_out = yf.view(self.B, self.T, C)[:, self.Tm:, :].contiguous()
+        return outs, gps_out, saved
+
+    def _backward_bf16(self, saved, params, douts, dgps_out, residual):
+        """Per block: 4 wgrad + 4 dgrad GEMMs, fused ReLU-mask+bias-grad, 2 LayerNorm backward kernels that also
+        emit the bf16 operand copy and the bias gradient of the preceding Linear, flash-attention backward,
+        one column-sum for the QKV bias; all gradients of a block live in one zero-filled flat buffer."""
+        dev = douts[0].device
+        M, C, L = self.M, self.C, self.L
+        f32, bf = torch.float32, torch.bfloat16
+        grads = [None] * len(params)
+        dyf = torch.empty(M, C, device=dev, dtype=f32)
+        K.upsample_add_bwd(self.geom, douts, dgps_out, dyf)
+        F = params[13].shape[0] if L > 0 else 4 * C
+        # flat zero-filled gradient buffer per block: [dWqkv | dWp | dW1 | dW2 | dbqkv | dbp | db1 | db2 | dg1 | db1ln | dg2 | db2ln]
+        sizes = [3 * C * C, C * C, F * C, C * F, 3 * C, C, F, C, C, C, C, C]
+        per_block = sum(sizes)
+        gbuf = torch.zeros(L * per_block + 2 * C, device=dev, dtype=f32)
+
+        def block_views(i):
+            out, off = [], i * per_block
+            for n in sizes:
+                out.append(gbuf[off:off + n])
+                off += n
+            return out
+
+        dgf, dbf = gbuf[L * per_block:L * per_block + C], gbuf[L * per_block + C:]
+        dx = torch.empty(M, C, device=dev, dtype=f32)
+        dxa = torch.empty(M, C, device=dev, dtype=bf)
+        # ln_f backward; by-products: bf16 copy of dx and db2 of the last block
+        last = block_views(L - 1) if L > 0 else None
+        K.layernorm_bwd(dyf, saved.x_last, params[-2], saved.mean_f, saved.rstd_f, None, dx, dgf, dbf,
+                        dx_bf16=dxa if L > 0 else None, dx_colsum=last[7] if L > 0 else None)
+        grads[-2], grads[-1] = dgf, dbf
+        for i in reversed(range(L)):
+            base = 1 + 16 * i
+            (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[base: base + 16]
+            st = saved.layers[i]
+            dwqkv, dwp, dw1, dw2, dbqkv, dbp, db1, db2, dg1, dbt1, dg2, dbt2 = block_views(i)
+            dwqkv, dwp, dw1, dw2 = dwqkv.view(3 * C, C), dwp.view(C, C), dw1.view(F, C), dw2.view(C, F)
+            # ---- MLP:  x_out = x_mid + relu(h2 W1^T + b1) W2^T + b2     (model2_seq.py:121-126,132)
+            K.gemm_bf16_tn(dxa, st.a, dw2)
+            da = torch.empty(M, F, device=dev, dtype=bf)
+            K.gemm_bf16_nt(dxa, st.w2_t, da)
+            K.relu_bwd_colsum(da, st.a, db1)
+            K.gemm_bf16_tn(da, st.h2, dw1)
+            dh2 = torch.empty(M, C, device=dev, dtype=bf)
+            K.gemm_bf16_nt(da, st.w1_t, dh2)
+            dx_mid = torch.empty(M, C, device=dev, dtype=f32)
+            dxm = torch.empty(M, C, device=dev, dtype=bf)
+            K.layernorm_bwd(dh2, st.x_mid, ln2w, st.mean2, st.rstd2, dx, dx_mid, dg2, dbt2, dx_bf16=dxm, dx_colsum=dbp)
+            # ---- attention:  x_mid = x_in + proj(attn(qkv(ln1(x_in))))   (model2_seq.py:94-110,131)
+            K.gemm_bf16_tn(dxm, st.y, dwp)
+            dy = torch.empty(M, C, device=dev, dtype=bf)
+            K.gemm_bf16_nt(dxm, st.wp_t, dy)
+            dqkv = torch.empty(M, 3 * C, device=dev, dtype=bf)
+            delta = torch.empty(self.B, self.nh, self.T, device=dev, dtype=f32)
+            K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh)
+            K.colsum(dqkv, dbqkv)
+            K.gemm_bf16_tn(dqkv, st.h1, dwqkv)
+            dh1 = torch.empty(M, C, device=dev, dtype=bf)
+            K.gemm_bf16_nt(dqkv, st.wqkv_t, dh1)
+            dx = torch.empty(M, C, device=dev, dtype=f32)
+            prev = block_views(i - 1) if i > 0 else None
+            K.layernorm_bwd(dh1, st.x_in, ln1w, st.mean1, st.rstd1, dx_mid, dx, dg1, dbt1,
+                            dx_bf16=dxa if i > 0 else None, dx_colsum=prev[7] if i > 0 else None)
+            grads[base: base + 16] = [dg1, dbt1, dg2, dbt2,
+                                      dwqkv[C:2 * C], dbqkv[C:2 * C], dwqkv[:C], dbqkv[:C], dwqkv[2 * C:], dbqkv[2 * C:],
+                                      dwp, dbp, dw1, db1, dw2, db2]
+            saved.layers[i] = None  # release this block's activations early
+        dfeats = [torch.empty_like(d) for d in douts]
+        dgps = torch.empty(self.B, 2, C, device=dev, dtype=f32)
+        dpos = torch.empty(1, self.T, C, device=dev, dtype=f32)
+        K.tokens_bwd(self.geom, dx, douts if residual else None, dfeats, dgps, dpos)
+        grads[0] = dpos
+        return dfeats, dgps, grads
+
     def backward(self, saved, params, douts, dgps_out, residual=True):
+        if self.bf16:
+            return self._backward_bf16(saved, params, douts, dgps_out, residual)
         dev = douts[0].device
         M, C, L = self.M, self.C, self.L
         f32 = torch.float32

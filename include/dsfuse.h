@@ -88,10 +88,13 @@ int dsf_tokens_bwd(const dsf_geom* g, const float* dx, const void* dres_img, con
 int dsf_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int32_t y_dtype,
                       float* mean, float* rstd, int32_t M, int32_t C, float eps, void* stream);
 /*   dy (M,C) dy_dtype; dx_out = (dx_add ? dx_add : 0) + LN'(dy); dgamma/dbeta (C) fp32 are
- *   ACCUMULATED into (caller zeroes or passes .grad).                                              */
+ *   ACCUMULATED into (caller zeroes or passes .grad).  Optional same-pass by-products of dx_out
+ *   (the residual-stream gradient): dx_bf16 (M,C) bf16 copy (next GEMM operand) and dx_colsum (C)
+ *   fp32 += column sums (= bias gradient of the preceding proj / mlp.2 Linear); either may be NULL. */
 int dsf_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* gamma,
                       const float* mean, const float* rstd, const float* dx_add, float* dx_out,
-                      float* dgamma, float* dbeta, int32_t M, int32_t C, void* stream);
+                      float* dgamma, float* dbeta, void* dx_bf16, float* dx_colsum, int32_t M, int32_t C,
+                      void* stream);
 
 /* K3/K5/K6 (bf16 tensor-core path, tcgen05 + TMEM + TMA).  Replaces nn.Linear (model2_seq.py:83-90,
  * 97-99,109,122,124) and its autograd.
@@ -125,6 +128,17 @@ int dsf_colsum(const void* X, int32_t x_dtype, int32_t ldx, float* out, int32_t 
                void* stream);
 /* dst = relu-mask: dy * (h > 0), elementwise in place on dy (bf16 or fp32), n elements.           */
 int dsf_relu_bwd(void* dy, const void* h, int32_t dtype, int64_t n, void* stream);
+/* bf16 (M,N): dy <- dy * (h > 0) in place and out[n] += sum_m dy[m,n] (mlp.0 bias gradient), one pass. */
+int dsf_relu_bwd_colsum(void* dy, const void* h, float* out, int32_t M, int32_t N, void* stream);
+
+/* Per transformer block: fp32 master weights (nn.Linear layout [out, in]; model2_seq.py:83-90,122,124)
+ * -> bf16 shadows for the tensor-core GEMMs, plain and transposed, query/key/value fused:
+ *   wqkv (3C,C) = [query; key; value], wqkv_t (C,3C), wp_b/wp_t (C,C), w1_b (F,C), w1_t (C,F),
+ *   w2_b (C,F), w2_t (F,C), bqkv (3C) fp32 = [bq | bk | bv].  F = block_exp * C.  One launch.     */
+int dsf_pack_block_weights(const float* wq, const float* wk, const float* wv, const float* wp, const float* w1,
+                           const float* w2, const float* bq, const float* bk, const float* bv, int32_t C,
+                           int32_t F, void* wqkv, void* wqkv_t, void* wp_b, void* wp_t, void* w1_b, void* w1_t,
+                           void* w2_b, void* w2_t, float* bqkv, void* stream);
 
 /* fp32 parity path softmax over the last dim of (rows, T), in place (model2_seq.py:103) and its
  * backward dS = P * (dP - sum(dP*P)), in place on dP.                                             */

@@ -107,6 +107,42 @@ def test_layernorm(K, cuda_dev, M, C, ydt):
     K.layernorm_bwd(dy, x, w, mean, rstd, None, dx, dg, db)  # accumulates into dg/db
     assert_close(dx, xr.grad, 2e-5, 1e-6, "ln dx no-add")
     assert_close(dg, 2 * wr.grad, 1e-4, 1e-5, "ln dgamma accumulate")
+    # same-pass by-products: bf16 copy of dx and its column sums (bias gradient of the preceding Linear)
+    dxb = torch.empty(M, C, device=cuda_dev, dtype=torch.bfloat16)
+    cs = torch.ones(C, device=cuda_dev)
+    K.layernorm_bwd(dy, x, w, mean, rstd, add, dx, dg, db, dx_bf16=dxb, dx_colsum=cs)
+    assert_close(dx, xr.grad + add, 2e-5, 1e-6, "ln dx (extra)")
+    assert torch.equal(dxb, dx.to(torch.bfloat16))
+    assert_close(cs, 1 + dx.sum(0), 1e-4, 1e-4, "ln dx colsum")
+
+
+def test_pack_weights_and_relu_colsum(K, cuda_dev):
+    g = _gen(9)
+    C, F = 64, 256
+    ws = [torch.randn(C, C, generator=g).to(cuda_dev) for _ in range(4)] + [torch.randn(F, C, generator=g).to(cuda_dev),
+                                                                             torch.randn(C, F, generator=g).to(cuda_dev)]
+    bs = [torch.randn(C, generator=g).to(cuda_dev) for _ in range(3)]
+    bf = torch.bfloat16
+    outs = [torch.empty(3 * C, C, device=cuda_dev, dtype=bf), torch.empty(C, 3 * C, device=cuda_dev, dtype=bf),
+            torch.empty(C, C, device=cuda_dev, dtype=bf), torch.empty(C, C, device=cuda_dev, dtype=bf),
+            torch.empty(F, C, device=cuda_dev, dtype=bf), torch.empty(C, F, device=cuda_dev, dtype=bf),
+            torch.empty(C, F, device=cuda_dev, dtype=bf), torch.empty(F, C, device=cuda_dev, dtype=bf),
+            torch.empty(3 * C, device=cuda_dev)]
+    K.pack_block_weights(ws[0], ws[1], ws[2], ws[3], ws[4], ws[5], bs[0], bs[1], bs[2], outs)
+    wqkv = torch.cat(ws[:3], 0).to(bf)
+    assert torch.equal(outs[0], wqkv) and torch.equal(outs[1], wqkv.t().contiguous())
+    assert torch.equal(outs[2], ws[3].to(bf)) and torch.equal(outs[3], ws[3].to(bf).t().contiguous())
+    assert torch.equal(outs[4], ws[4].to(bf)) and torch.equal(outs[5], ws[4].to(bf).t().contiguous())
+    assert torch.equal(outs[6], ws[5].to(bf)) and torch.equal(outs[7], ws[5].to(bf).t().contiguous())
+    assert torch.equal(outs[8], torch.cat(bs, 0))
+    M, N = 1001, 192
+    h = torch.randn(M, N, generator=g).to(cuda_dev).to(bf)
+    d = torch.randn(M, N, generator=g).to(cuda_dev).to(bf)
+    ref = torch.where(h > 0, d, torch.zeros_like(d))
+    out = torch.ones(N, device=cuda_dev)
+    K.relu_bwd_colsum(d, h, out)
+    assert torch.equal(d, ref)
+    assert_close(out, 1 + ref.float().sum(0), 1e-5, 1e-5, "relu colsum")
 
 
 @pytest.mark.parametrize("shape", STAGE_SHAPES)

@@ -142,21 +142,27 @@ def test_stage_real_shapes_vs_oracle(cuda_dev, B, C, H, L, mode):
     got = fusion_stage(cfg, ik[0], ik[1], ik[2], ik[3], [pk[n] for n in names])
     sum((o.float() * pr).sum() for o, pr in zip(got, probes)).backward()
     torch.cuda.synchronize()
-    if mode == torch.float32:
-        for i, (x, y) in enumerate(zip(got, ref)):
-            assert_close(x, y, 1e-4, 1e-6, "out%d" % i)
-        for i, (x, y) in enumerate(zip(ik, io)):
-            assert_close(x.grad, y.grad, 1e-3, 1e-6, "gin%d" % i)
-        for n in names:
-            assert_close(pk[n].grad, po[n].grad, 1e-3 if po[n].dim() > 1 and n != "pos_emb" else 3e-3, 2e-5, "g/" + n)
-    else:
-        aref, apo, aio = oracle(torch.float32, autocast=True)
-        for i, (x, y) in enumerate(zip(got, ref)):
-            assert_close(x.float(), y, 1e-2, 1e-5, "out%d" % i)
-        for i, (x, y) in enumerate(zip(ik, io)):
-            assert_close(x.grad, y.grad, bf16_bound(rel_err(aio[i].grad, y.grad)), 1e-5, "gin%d" % i)
-        for n in names:
-            assert_close(pk[n].grad, po[n].grad, bf16_bound(rel_err(apo[n].grad, po[n].grad)), 5e-4, "g/" + n)
+    # calibration run: the same oracle code in the stock precision of the mode under test
+    cref, cpo, cio = oracle(torch.float32, autocast=(mode == torch.bfloat16))
+    base = 1e-3 if mode == torch.float32 else 2e-2
+
+    def bound(cal_err, floor):
+        return max(floor, 1.25 * cal_err)
+
+    for i, (x, y) in enumerate(zip(got, ref)):
+        assert_close(x.float(), y, 1e-4 if mode == torch.float32 else 1e-2, 1e-5, "out%d" % i)
+    for i, (x, y) in enumerate(zip(ik, io)):
+        assert_close(x.grad, y.grad, bound(rel_err(cio[i].grad, y.grad), base), 1e-5, "gin%d" % i)
+    for n in names:
+        g_ref = po[n].grad
+        if n.endswith("attn.key.bias"):
+            # mathematically zero (softmax is invariant to a key-bias shift): only rounding noise is left;
+            # it must stay small next to the query-bias gradient of the same layer
+            q_norm = float(po[n.replace("key", "query")].grad.norm())
+            assert float(pk[n].grad.norm()) <= max(base, 1.25 * float(cpo[n].grad.norm()) / q_norm) * q_norm, n
+            continue
+        floor = base if (g_ref.dim() > 1 or mode == torch.bfloat16) else 3 * base
+        assert_close(pk[n].grad, g_ref, bound(rel_err(cpo[n].grad, g_ref), floor), 2e-5, "g/" + n)
 
 
 def test_stage_scaled_config_16x16_anchors(cuda_dev):
