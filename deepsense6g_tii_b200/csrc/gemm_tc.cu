@@ -311,7 +311,21 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int ldc,
 
 }  // namespace dsf
 
+namespace dsf {
+// v2 (persistent, double-buffered TMEM accumulators, 128 x 256 tiles), gemm_tc2.cu
+int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, const float* bias, const float* residual, int M,
+               int N, int K, int flags, cudaStream_t st);
+int gemm_tn_v2(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st);
+static int g_gemm_impl = 0;  // 0 = default (v2), 1 = v1 (one CTA per 128 x 128 tile), 2 = v2
+}  // namespace dsf
+
 using namespace dsf;
+
+extern "C" int dsf_gemm_set_impl(int32_t impl) {
+  DSF_REQUIRE(impl >= 0 && impl <= 2, "gemm_set_impl: impl must be 0 (default), 1 or 2");
+  g_gemm_impl = impl;
+  return DSF_OK;
+}
 
 extern "C" int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32_t ldb, void* C, int32_t ldc, int32_t c_dtype,
                                 const float* bias, const float* residual, int32_t M, int32_t N, int32_t K, int32_t epi_flags,
@@ -326,6 +340,7 @@ extern "C" int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32
   DSF_REQUIRE(!(epi_flags & DSF_EPI_BIAS) || bias, "gemm_bf16_nt: bias flag without bias pointer");
   DSF_REQUIRE(!(epi_flags & DSF_EPI_RESIDUAL) || residual, "gemm_bf16_nt: residual flag without residual pointer");
   DSF_REQUIRE(!(epi_flags & DSF_EPI_ACCUM), "gemm_bf16_nt: ACCUM is not supported on the NT path");
+  if (g_gemm_impl != 1) return gemm_nt_v2(A, lda, B, ldb, C, ldc, c_dtype, bias, residual, M, N, K, epi_flags, (cudaStream_t)stream);
   const int BN = (N % 128 == 0) ? 128 : 64;
   CUtensorMap tmA, tmB;
   if (int e = make_tmap_bf16(&tmA, A, M, K, lda, GT_BM)) return e;
@@ -343,6 +358,7 @@ extern "C" int dsf_gemm_bf16_tn(const void* A, int32_t lda, const void* B, int32
   DSF_REQUIRE(Nout % 64 == 0 && Kout % 64 == 0, "gemm_bf16_tn: output extents (%d, %d) must be multiples of 64", Nout, Kout);
   DSF_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= Nout && ldb >= Kout && ldc >= Kout, "gemm_bf16_tn: bad leading dimensions");
   DSF_REQUIRE(aligned16(A) && aligned16(B) && aligned16(C), "gemm_bf16_tn: 16-byte alignment required");
+  if (g_gemm_impl != 1) return gemm_tn_v2(A, lda, B, ldb, C, ldc, M, Nout, Kout, (cudaStream_t)stream);
   const int BN = (Kout % 128 == 0) ? 128 : 64;
   CUtensorMap tmA, tmB;
   if (int e = make_tmap_bf16(&tmA, A, M, Nout, lda, GT_BK)) return e;

@@ -1,0 +1,342 @@
+// K3/K5/K6 (v2): persistent, warp-specialised bf16 GEMMs on tcgen05.
+//   NT: C[M,N] = A[M,K] . B[N,K]^T (+bias)(relu)(+residual) — 128 x BN tiles (BN = 256 / 128 / 64), one CTA per SM
+//       looping over tiles; the fp32 accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of
+//       tile i (8 warps, TMEM -> registers -> global) overlaps the TMA/MMA main loop of tile i+1.
+//   TN: C[N',K'] += A[M,N']^T . B[M,K'] (weight gradient) — 128 x BN tiles, contraction split across CTAs,
+//       vectorised fp32 reductions (red.global.add.v4.f32) into the gradient buffer.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue
+// (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace dsf {
+
+using namespace tc;
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rows, int cols, int ld, int box_rows);  // gemm_tc.cu
+
+constexpr int G2_BM = 128, G2_BK = 64, G2_THREADS = 320;
+
+struct EpiArgs2 {
+  void* C;
+  int ldc;
+  int c_dtype;
+  const float* bias;
+  const float* residual;
+  int flags;
+};
+
+__device__ __forceinline__ void epi_store32(const EpiArgs2& e, int row, int n, const uint32_t (&r)[32]) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (e.flags & DSF_EPI_BIAS) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (e.flags & DSF_EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  const size_t off = (size_t)row * e.ldc + n;
+  if (e.flags & DSF_EPI_RESIDUAL) {
+    const float4* rp = reinterpret_cast<const float4*>(e.residual + off);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = rp[j];
+      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+    }
+  }
+  if (e.c_dtype == DSF_F32) {
+    float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + off);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+    uint4* cp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.C) + off);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      cp[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                         pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+  }
+}
+
+template <int BN, int STAGES>
+struct G2Smem {
+  static constexpr int A_BYTES = G2_BM * G2_BK * 2;
+  static constexpr int B_BYTES = BN * G2_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int DYN = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static_assert(DYN <= 232448, "shared memory budget");
+};
+
+// ---------------------------------------------------------------------------------- NT, persistent
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiArgs2 epi, int M, int N, int K,
+                int m_tiles, int n_tiles) {
+  using L = G2Smem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = base + L::BAR_OFF, bar_empty = bar_full + STAGES * 8, acc_full = bar_empty + STAGES * 8,
+                 acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = K / G2_BK;
+  const int total = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a * 8, 1); mbar_init(acc_empty + a * 8, 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;  // k-block counter across all tiles of this CTA
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * G2_BM, n0 = (tile / m_tiles) * BN;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
+          const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+          tma_load_2d(sa, &tmA, bar_full + s * 8, kb * G2_BK, m0);
+          tma_load_2d(sb, &tmB, bar_full + s * 8, kb * G2_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(G2_BM, BN, 0, 0);
+      int it = 0, i = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+        const int ab = i & 1;
+        mbar_wait(acc_empty + ab * 8, ((i >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + ab * BN;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+          const uint64_t da = make_smem_desc(sa, 16, 1024, SWZ_128B);
+          const uint64_t db = make_smem_desc(sb, 16, 1024, SWZ_128B);
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k) tc_mma_bf16(acc, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kb | k) != 0);
+          tc_commit(bar_empty + s * 8);
+        }
+        tc_commit(acc_full + ab * 8);
+      }
+    }
+  } else {
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int ch = (warp - 2) >> 2;    // column half handled by this warp
+    constexpr int HALF = BN / 2;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
+      const int ab = i & 1;
+      const int m0 = (tile % m_tiles) * G2_BM, n0 = (tile / m_tiles) * BN;
+      mbar_wait(acc_full + ab * 8, (i >> 1) & 1);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t tacc = tmem_base + ab * BN + ((uint32_t)(q * 32) << 16) + ch * HALF;
+#pragma unroll 1
+      for (int c = 0; c < HALF; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tacc + c, r);
+        tmem_wait_ld();
+        if (row < M) epi_store32(epi, row, n0 + ch * HALF + c, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + ab * 8);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, L::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------- TN (wgrad), split contraction
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C, int ldc, int M, int Nout,
+                int Kout, int m_chunk) {
+  using L = G2Smem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = base + L::BAR_OFF, bar_empty = bar_full + STAGES * 8, bar_acc = bar_empty + STAGES * 8, tmem_slot = bar_acc + 8 * 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * G2_BM;  // rows of C (N' index)
+  const int k0 = blockIdx.x * BN;     // cols of C (K' index)
+  const int m_lo = blockIdx.z * m_chunk, m_hi = min(M, m_lo + m_chunk);
+  const int num_it = (m_hi - m_lo + G2_BK - 1) / G2_BK;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int BOX_BYTES = G2_BK * 128;  // 64 rows x 128 B
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < num_it; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
+        mbar_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
+        const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+        const int m = m_lo + it * G2_BK;
+#pragma unroll
+        for (int j = 0; j < G2_BM / 64; ++j) tma_load_2d(sa + j * BOX_BYTES, &tmA, bar_full + s * 8, n0 + j * 64, m);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * BOX_BYTES, &tmB, bar_full + s * 8, k0 + j * 64, m);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(G2_BM, BN, 1, 1);
+      for (int it = 0; it < num_it; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+        const uint64_t da = make_smem_desc(sa, BOX_BYTES, 1024, SWZ_128B);
+        const uint64_t db = make_smem_desc(sb, BOX_BYTES, 1024, SWZ_128B);
+#pragma unroll
+        for (int k = 0; k < G2_BK / 16; ++k) tc_mma_bf16(tmem_base, desc_advance(da, k * 2048), desc_advance(db, k * 2048), idesc, (it | k) != 0);
+        tc_commit(bar_empty + s * 8);
+      }
+      tc_commit(bar_acc);
+    }
+  } else {
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int q = warp & 3, ch = (warp - 2) >> 2;
+    constexpr int HALF = BN / 2;
+    const int row = n0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < HALF; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ch * HALF + c, r);
+      tmem_wait_ld();
+      if (row < Nout) {
+        float* cp = C + (size_t)row * ldc + k0 + ch * HALF + c;
+        if (k0 + ch * HALF + c + 32 <= Kout) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(cp + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (k0 + ch * HALF + c + j < Kout) atomicAdd(cp + j, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int STAGES>
+static int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiArgs2& epi, int M, int N, int K, cudaStream_t st) {
+  using L = G2Smem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_nt2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
+      return check_launch("gemm_nt2/attr");
+    configured = true;
+  }
+  const int m_tiles = cdiv(M, G2_BM), n_tiles = N / BN;
+  const int grid = std::min(m_tiles * n_tiles, num_sms());
+  gemm_nt2_kernel<BN, STAGES><<<grid, G2_THREADS, L::DYN, st>>>(tmA, tmB, epi, M, N, K, m_tiles, n_tiles);
+  return check_launch("gemm_nt2");
+}
+
+template <int BN, int STAGES>
+static int launch_tn2(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st) {
+  using L = G2Smem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_tn2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
+      return check_launch("gemm_tn2/attr");
+    configured = true;
+  }
+  const int tiles = cdiv(Nout, G2_BM) * cdiv(Kout, BN);
+  // one wave of CTAs: split the contraction so that tiles * splits ~ number of SMs (chunks are multiples of 64 rows)
+  int splits = std::max(1, std::min(cdiv(M, 2 * G2_BK), num_sms() / std::max(1, tiles)));
+  int m_chunk = cdiv(cdiv(M, splits), G2_BK) * G2_BK;
+  splits = cdiv(M, m_chunk);
+  dim3 grid(cdiv(Kout, BN), cdiv(Nout, G2_BM), splits);
+  gemm_tn2_kernel<BN, STAGES><<<grid, G2_THREADS, L::DYN, st>>>(tmA, tmB, C, ldc, M, Nout, Kout, m_chunk);
+  return check_launch("gemm_tn2");
+}
+
+// tile-shape choice: fewest "rounds" of 128 x BN tiles over the SMs, weighted by the per-tile efficiency of wider tiles
+static int pick_bn_nt(int M, int N) {
+  const int sms = num_sms();
+  const int m_tiles = cdiv(M, G2_BM);
+  int best = 64;
+  double best_cost = 1e30;
+  const int cands[3] = {256, 128, 64};
+  const double tile_eff[3] = {1.0, 0.85, 0.6};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (N % bn) continue;
+    const int tiles = m_tiles * (N / bn);
+    const double cost = (double)cdiv(tiles, sms) * bn / tile_eff[i];
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, const float* bias, const float* residual, int M,
+               int N, int K, int flags, cudaStream_t st) {
+  const int BN = pick_bn_nt(M, N);
+  CUtensorMap tmA, tmB;
+  if (int e = make_tmap_bf16(&tmA, A, M, K, lda, G2_BM)) return e;
+  if (int e = make_tmap_bf16(&tmB, B, N, K, ldb, BN)) return e;
+  EpiArgs2 epi{C, ldc, c_dtype, bias, residual, flags};
+  if (BN == 256) return launch_nt2<256, 4>(tmA, tmB, epi, M, N, K, st);
+  if (BN == 128) return launch_nt2<128, 6>(tmA, tmB, epi, M, N, K, st);
+  return launch_nt2<64, 8>(tmA, tmB, epi, M, N, K, st);
+}
+
+int gemm_tn_v2(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st) {
+  const int BN = (Kout % 256 == 0) ? 256 : ((Kout % 128 == 0) ? 128 : 64);
+  CUtensorMap tmA, tmB;
+  if (int e = make_tmap_bf16(&tmA, A, M, Nout, lda, G2_BK)) return e;
+  if (int e = make_tmap_bf16(&tmB, B, M, Kout, ldb, G2_BK)) return e;
+  if (BN == 256) return launch_tn2<256, 4>(tmA, tmB, C, ldc, M, Nout, Kout, st);
+  if (BN == 128) return launch_tn2<128, 6>(tmA, tmB, C, ldc, M, Nout, Kout, st);
+  return launch_tn2<64, 8>(tmA, tmB, C, ldc, M, Nout, Kout, st);
+}
+
+}  // namespace dsf

@@ -310,7 +310,7 @@ class _Runner:
             K.gemm_bf16_nt(dxa, st.w2_t, da)
             K.relu_bwd_colsum(da, st.a, db1)
             K.gemm_bf16_tn(da, st.h2, dw1)
-            dh2 = torch.empty(M, C, device=dev, dtype=bf)
+            dh2 = torch.empty(M, C, device=dev, dtype=f32)  # fp32: feeds LayerNorm backward, not a GEMM
             K.gemm_bf16_nt(da, st.w1_t, dh2)
             dx_mid = torch.empty(M, C, device=dev, dtype=f32)
             dxm = torch.empty(M, C, device=dev, dtype=bf)
@@ -324,7 +324,7 @@ class _Runner:
             K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh)
             K.colsum(dqkv, dbqkv)
             K.gemm_bf16_tn(dqkv, st.h1, dwqkv)
-            dh1 = torch.empty(M, C, device=dev, dtype=bf)
+            dh1 = torch.empty(M, C, device=dev, dtype=f32)
             K.gemm_bf16_nt(dqkv, st.wqkv_t, dh1)
             dx = torch.empty(M, C, device=dev, dtype=f32)
             prev = block_views(i - 1) if i > 0 else None

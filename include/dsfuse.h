@@ -108,6 +108,9 @@ int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32_t ldb, voi
                      int32_t K, int32_t epi_flags, void* stream);
 int dsf_gemm_bf16_tn(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc,
                      int32_t M, int32_t Nout, int32_t Kout, void* stream);
+/* Selects the tensor-core GEMM implementation (process-wide; tests and A/B timing): 0 = default,
+ * 1 = v1 (one CTA per 128x128 tile), 2 = v2 (persistent, 128x256 tiles, double-buffered TMEM).    */
+int dsf_gemm_set_impl(int32_t impl);
 
 /* fp32 parity path: generic strided, two-level batched SIMT GEMM (FFMA).
  *   C[b1,b2][m,n] = alpha * sum_k A[b1,b2][m,k] * B[b1,b2][n,k]  (+bias)(relu)(+residual)(+C)      */

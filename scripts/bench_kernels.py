@@ -50,14 +50,18 @@ if "gemm" in what:
         w = torch.randn(N, Kd, device=dev).to(torch.bfloat16)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         bias = torch.randn(N, device=dev)
-        t = timeit(lambda: K.gemm_bf16_nt(a, w, out, bias=bias))
         tt = timeit(lambda: torch.matmul(a, w.t()))
         dy = torch.randn(M, N, device=dev).to(torch.bfloat16)
         dw = torch.zeros(N, Kd, device=dev)
-        t2 = timeit(lambda: K.gemm_bf16_tn(dy, a, dw))
         fl = 2.0 * M * N * Kd
-        print("gemm M=%d N=%d K=%d: nt %.4f ms (%.0f TF/s) | cublas %.4f ms (%.0f TF/s) | tn(wgrad) %.4f ms (%.0f TF/s)"
-              % (M, N, Kd, t, fl / t / 1e9, tt, fl / tt / 1e9, t2, fl / t2 / 1e9))
+        line = "gemm M=%d N=%d K=%d: cublas %.4f ms (%.0f TF/s)" % (M, N, Kd, tt, fl / tt / 1e9)
+        for impl in (1, 2):
+            K.gemm_set_impl(impl)
+            t = timeit(lambda: K.gemm_bf16_nt(a, w, out, bias=bias))
+            t2 = timeit(lambda: K.gemm_bf16_tn(dy, a, dw))
+            line += " | v%d nt %.4f ms (%.0f TF/s) tn %.4f ms (%.0f TF/s)" % (impl, t, fl / t / 1e9, t2, fl / t2 / 1e9)
+        K.gemm_set_impl(0)
+        print(line)
 
 if "elem" in what:
     M, C = 11544, 512

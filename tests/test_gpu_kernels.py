@@ -245,8 +245,15 @@ GEMM_SHAPES = [(128, 64, 64), (128, 128, 64), (300, 128, 128), (962, 192, 64), (
                (2048, 1536, 512), (1924, 512, 2048), (1924, 2048, 512), (130, 64, 256)]
 
 
-@pytest.mark.parametrize("M,N,Kd", GEMM_SHAPES)
-def test_gemm_bf16_nt(K, cuda_dev, M, N, Kd):
+@pytest.fixture(params=[1, 2], ids=["gemm_v1", "gemm_v2"])
+def gemm_impl(request, K):
+    K.gemm_set_impl(request.param)
+    yield request.param
+    K.gemm_set_impl(0)
+
+
+@pytest.mark.parametrize("M,N,Kd", GEMM_SHAPES + [(11544, 2048, 512), (11544, 512, 2048), (300, 1536, 128), (5, 256, 64)])
+def test_gemm_bf16_nt(K, cuda_dev, gemm_impl, M, N, Kd):
     g = _gen(6)
     a = torch.randn(M, Kd, generator=g).to(cuda_dev).to(torch.bfloat16)
     w = (0.05 * torch.randn(N, Kd, generator=g)).to(cuda_dev).to(torch.bfloat16)
@@ -268,7 +275,7 @@ def test_gemm_bf16_nt(K, cuda_dev, M, N, Kd):
 
 @pytest.mark.parametrize("M,No,Ko", [(64, 64, 64), (128, 128, 128), (200, 64, 192), (962, 192, 64), (1924, 512, 512),
                                      (11544, 512, 2048), (11544, 2048, 512), (5000, 1536, 512), (77, 128, 64)])
-def test_gemm_bf16_tn(K, cuda_dev, M, No, Ko):
+def test_gemm_bf16_tn(K, cuda_dev, gemm_impl, M, No, Ko):
     g = _gen(7)
     dy = (0.1 * torch.randn(M, No, generator=g)).to(cuda_dev).to(torch.bfloat16)
     x = torch.randn(M, Ko, generator=g).to(cuda_dev).to(torch.bfloat16)
