@@ -48,6 +48,23 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rows, int cols, int ld,
   return DSF_OK;
 }
 
+// row-major matrix [rows, cols] of bf16 (dtype DSF_BF16) or fp32 (DSF_F32), leading dimension ld (elements);
+// box = box_cols x box_rows with box_cols * elem_size == 128 B, 128B swizzle (used for the TMA-store epilogue)
+int make_tmap_2d(CUtensorMap* m, const void* base, int dtype, int rows, int cols, int ld, int box_cols, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DSF_ELAUNCH; }
+  const int es = dtype == DSF_F32 ? 4 : 2;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, dtype == DSF_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                   gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d) failed (%d) rows=%d cols=%d ld=%d box=%dx%d", (int)r, rows, cols, ld, box_cols, box_rows); return DSF_ELAUNCH; }
+  return DSF_OK;
+}
+
 // ---------------------------------------------------------------------------------- epilogue helpers
 struct EpiArgs {
   void* C;

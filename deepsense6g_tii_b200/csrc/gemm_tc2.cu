@@ -15,6 +15,7 @@ namespace dsf {
 using namespace tc;
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rows, int cols, int ld, int box_rows);  // gemm_tc.cu
+int make_tmap_2d(CUtensorMap* m, const void* base, int dtype, int rows, int cols, int ld, int box_cols, int box_rows);
 
 constexpr int G2_BM = 128, G2_BK = 64, G2_THREADS = 320;
 
@@ -64,12 +65,39 @@ __device__ __forceinline__ void epi_store32(const EpiArgs2& e, int row, int n, c
   }
 }
 
-template <int BN, int STAGES>
+// epilogue math on 32 accumulator columns of one row: (+bias)(relu)(+residual); row_ok guards the residual read
+__device__ __forceinline__ void epi_math32(const EpiArgs2& e, int row, int n, const uint32_t (&r)[32], float (&v)[32], bool row_ok) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (e.flags & DSF_EPI_BIAS) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (e.flags & DSF_EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if ((e.flags & DSF_EPI_RESIDUAL) && row_ok) {
+    const float4* rp = reinterpret_cast<const float4*>(e.residual + (size_t)row * e.ldc + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = rp[j];
+      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+    }
+  }
+}
+
+template <int BN, int STAGES, bool STAGED = true>
 struct G2Smem {
   static constexpr int A_BYTES = G2_BM * G2_BK * 2;
   static constexpr int B_BYTES = BN * G2_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;  // 8 epilogue warps x 2 buffers x 4 KB (TMA-store staging)
+  static constexpr int STAGING_BYTES = STAGED ? 8 * 2 * 4096 : 0;
+  static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;
   static constexpr int DYN = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static_assert(DYN <= 232448, "shared memory budget");
@@ -78,8 +106,8 @@ struct G2Smem {
 // ---------------------------------------------------------------------------------- NT, persistent
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(G2_THREADS, 1)
-gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiArgs2 epi, int M, int N, int K,
-                int m_tiles, int n_tiles) {
+gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                EpiArgs2 epi, int M, int N, int K, int m_tiles, int n_tiles) {
   using L = G2Smem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -144,26 +172,70 @@ gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int ch = (warp - 2) >> 2;    // column half handled by this warp
-    constexpr int HALF = BN / 2;
-    int i = 0;
+    constexpr int NSPLIT = BN >= 128 ? 2 : 1;  // BN = 64: warps 2..5 drain the whole tile, warps 6..9 only hand the buffer back
+    constexpr int HALF = BN / NSPLIT;
+    int i = 0, nbox = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
       const int ab = i & 1;
       const int m0 = (tile % m_tiles) * G2_BM, n0 = (tile / m_tiles) * BN;
       mbar_wait(acc_full + ab * 8, (i >> 1) & 1);
       tc_fence_after();
+      if (ch >= NSPLIT || m0 + q * 32 >= M) {  // nothing to store for this warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + ab * 8);
+        continue;
+      }
       const int row = m0 + q * 32 + lane;
       const uint32_t tacc = tmem_base + ab * BN + ((uint32_t)(q * 32) << 16) + ch * HALF;
+      // coalesced epilogue: registers -> this warp's 128B-swizzled staging box [32 rows x 128 B] -> TMA store
+      const uint32_t stg = base + L::STAGING_OFF + (warp - 2) * 8192;
+      const int CW = epi.c_dtype == DSF_F32 ? 32 : 64;  // columns per 128-byte staged row
 #pragma unroll 1
-      for (int c = 0; c < HALF; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tacc + c, r);
-        tmem_wait_ld();
-        if (row < M) epi_store32(epi, row, n0 + ch * HALF + c, r);
+      for (int c = 0; c < HALF; c += CW, ++nbox) {
+        const uint32_t sbuf = stg + (nbox & 1) * 4096;
+        if (lane == 0) bulk_wait_read<1>();  // the store issued two boxes ago has finished reading this buffer
+        __syncwarp();
+        const int ncol = n0 + ch * HALF + c;
+        uint32_t w[32];  // 128 bytes of this thread's output row
+        if (epi.c_dtype == DSF_F32) {
+          uint32_t r[32];
+          tmem_ld32(tacc + c, r);
+          tmem_wait_ld();
+          float v[32];
+          epi_math32(epi, row, ncol, r, v, row < M);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
+        } else {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c + hh * 32, r);
+            tmem_wait_ld();
+            float v[32];
+            epi_math32(epi, row, ncol + hh * 32, r, v, row < M);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[hh * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = sbuf + lane * 128 + ((j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[4 * j]), "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                       : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC, sbuf, ncol, m0 + q * 32);
+          bulk_commit();
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + ab * 8);
     }
+    if (lane == 0) bulk_wait<0>();  // all stores complete before shared memory is released
   }
   tc_fence_before();
   __syncthreads();
@@ -179,7 +251,7 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C, int ldc, int M, int Nout,
                 int Kout, int m_chunk) {
-  using L = G2Smem<BN, STAGES>;
+  using L = G2Smem<BN, STAGES, false>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = base + L::BAR_OFF, bar_empty = bar_full + STAGES * 8, bar_acc = bar_empty + STAGES * 8, tmem_slot = bar_acc + 8 * 4;
@@ -266,7 +338,8 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 template <int BN, int STAGES>
-static int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiArgs2& epi, int M, int N, int K, cudaStream_t st) {
+static int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const EpiArgs2& epi, int M, int N, int K,
+                      cudaStream_t st) {
   using L = G2Smem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -276,13 +349,13 @@ static int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiA
   }
   const int m_tiles = cdiv(M, G2_BM), n_tiles = N / BN;
   const int grid = std::min(m_tiles * n_tiles, num_sms());
-  gemm_nt2_kernel<BN, STAGES><<<grid, G2_THREADS, L::DYN, st>>>(tmA, tmB, epi, M, N, K, m_tiles, n_tiles);
+  gemm_nt2_kernel<BN, STAGES><<<grid, G2_THREADS, L::DYN, st>>>(tmA, tmB, tmC, epi, M, N, K, m_tiles, n_tiles);
   return check_launch("gemm_nt2");
 }
 
 template <int BN, int STAGES>
 static int launch_tn2(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st) {
-  using L = G2Smem<BN, STAGES>;
+  using L = G2Smem<BN, STAGES, false>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_tn2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
@@ -323,10 +396,12 @@ int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc,
   CUtensorMap tmA, tmB;
   if (int e = make_tmap_bf16(&tmA, A, M, K, lda, G2_BM)) return e;
   if (int e = make_tmap_bf16(&tmB, B, N, K, ldb, BN)) return e;
+  CUtensorMap tmC;  // store boxes: 32 rows x 128 bytes
+  if (int e = make_tmap_2d(&tmC, C, c_dtype, M, N, ldc, c_dtype == DSF_F32 ? 32 : 64, 32)) return e;
   EpiArgs2 epi{C, ldc, c_dtype, bias, residual, flags};
-  if (BN == 256) return launch_nt2<256, 4>(tmA, tmB, epi, M, N, K, st);
-  if (BN == 128) return launch_nt2<128, 6>(tmA, tmB, epi, M, N, K, st);
-  return launch_nt2<64, 8>(tmA, tmB, epi, M, N, K, st);
+  if (BN == 256) return launch_nt2<256, 3>(tmA, tmB, tmC, epi, M, N, K, st);
+  if (BN == 128) return launch_nt2<128, 4>(tmA, tmB, tmC, epi, M, N, K, st);
+  return launch_nt2<64, 5>(tmA, tmB, tmC, epi, M, N, K, st);
 }
 
 int gemm_tn_v2(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st) {
