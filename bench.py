@@ -227,6 +227,7 @@ def one_step(gpt, feats, gps, probes):
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from deepsense6g_tii_b200 import _capi
+    from deepsense6g_tii_b200 import dist as D
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     _capi.check_device()
@@ -234,26 +235,17 @@ def run_ours(args, rank, world, local_rank):
     model = gpt
     if world > 1:
         # same initial weights on every rank; gradients all-reduced (mean) over NCCL every step
-        flat = torch.cat([p.data.view(-1) for p in gpt.parameters()])
-        dist.broadcast(flat, 0)
-        off = 0
-        for p in gpt.parameters():
-            p.data.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+        D.broadcast_params(gpt.parameters())
     gen = torch.Generator().manual_seed(rank)  # data generator seed 0 + rank
     feats_h, gps_h, probes_h = synth_inputs(gen, BATCH, pin=True)
     feats = [f.to(dev).requires_grad_(True) for f in feats_h]
     gps = gps_h.to(dev).requires_grad_(True)
     probes = [p.to(dev) for p in probes_h]
-    grad_buf = torch.empty(sum(p.numel() for p in gpt.parameters()), device=dev) if world > 1 else None
+    bucket = [None]
 
     def allreduce_grads():
-        if world == 1:
-            return
-        off = 0
-        for p in gpt.parameters():
-            grad_buf[off:off + p.numel()].copy_(p.grad.view(-1)); off += p.numel()
-        dist.all_reduce(grad_buf)
-        grad_buf.div_(world)
+        if world > 1:
+            bucket[0] = D.allreduce_grads(gpt.parameters(), bucket[0])
 
     def step_resident():
         loss = one_step(model, feats, gps, probes)
@@ -292,10 +284,15 @@ def run_ours(args, rank, world, local_rank):
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = _capi.launch_count()
+        ncu_range = sampler is not None and os.environ.get("DSF_NCU_RANGE") == "1"
+        if ncu_range:  # `ncu --profile-from-start off` then captures exactly the timed region
+            torch.cuda.profiler.start()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
+        if ncu_range:
+            torch.cuda.profiler.stop()
         barrier()
         clocks = sampler.stop() if sampler else None
         ms = e0.elapsed_time(e1)

@@ -1,0 +1,47 @@
+"""Data-parallel plumbing for the fusion stage (one process per GPU; replaces nn.DataParallel,
+train2_seq.py:538).  The path shards by batch only: the single exchange step per iteration is the
+gradient all-reduce (mean) of the GPT parameters; rank 0's weights are broadcast once at start-up.
+Backend: NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests."""
+import torch
+import torch.distributed as dist
+
+
+def flat_size(params):
+    return sum(p.numel() for p in params)
+
+
+def broadcast_params(params, src=0):
+    """Make every rank start from rank `src`'s weights (one flat broadcast)."""
+    params = list(params)
+    if not dist.is_initialized() or dist.get_world_size() == 1 or not params:
+        return
+    flat = torch.cat([p.data.reshape(-1) for p in params])
+    dist.broadcast(flat, src)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.data.copy_(flat[off:off + n].view_as(p))
+        off += n
+
+
+def allreduce_grads(params, buf=None):
+    """Average gradients over ranks through one flat bucket; returns the bucket (reusable)."""
+    params = [p for p in params if p.grad is not None]
+    if not dist.is_initialized() or dist.get_world_size() == 1 or not params:
+        return buf
+    n_total = flat_size(params)
+    if buf is None or buf.numel() != n_total or buf.device != params[0].grad.device:
+        buf = torch.empty(n_total, device=params[0].grad.device, dtype=params[0].grad.dtype)
+    off = 0
+    for p in params:
+        n = p.numel()
+        buf[off:off + n].copy_(p.grad.reshape(-1))
+        off += n
+    dist.all_reduce(buf)
+    buf.div_(dist.get_world_size())
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad.copy_(buf[off:off + n].view_as(p.grad))
+        off += n
+    return buf

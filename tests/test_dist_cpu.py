@@ -1,0 +1,53 @@
+"""world_size-2 gloo test (CPU) of the N>1 plumbing used by bench.py --gpus N: parameter broadcast from
+rank 0 and the flat-bucket gradient all-reduce (mean) that replaces nn.DataParallel's reduce
+(train2_seq.py:538)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deepsense6g_tii_b200 import dist as D
+    torch.manual_seed(100 + rank)  # different weights per rank before the broadcast
+    m = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.LayerNorm(16), torch.nn.Linear(16, 4))
+    D.broadcast_params(m.parameters())
+    w0 = torch.cat([p.data.reshape(-1) for p in m.parameters()]).clone()
+    x = torch.full((3, 8), float(rank + 1))  # rank-dependent shard of the batch
+    m(x).sum().backward()
+    local = [p.grad.clone() for p in m.parameters()]
+    buf = D.allreduce_grads(m.parameters())
+    buf2 = D.allreduce_grads(m.parameters(), buf)  # bucket reuse (values already equal -> unchanged)
+    q.put((rank, w0.numpy(), [g.numpy() for g in local], [p.grad.numpy().copy() for p in m.parameters()], buf2.data_ptr() == buf.data_ptr()))
+    dist.destroy_process_group()
+
+
+def test_broadcast_and_grad_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (_, w_a, loc_a, red_a, reuse_a), (_, w_b, loc_b, red_b, reuse_b) = res
+    import numpy as np
+    assert np.array_equal(w_a, w_b)                   # same weights after the broadcast
+    assert reuse_a and reuse_b
+    for ga, gb, ra, rb in zip(loc_a, loc_b, red_a, red_b):
+        assert np.allclose(ra, (ga + gb) / 2, atol=1e-6) and np.array_equal(ra, rb)

@@ -164,7 +164,11 @@ def test_stage_real_shapes_vs_oracle(cuda_dev, B, C, H, L, mode):
         # fp32 parameter gradients: 2e-3 for matrices, 3e-3 for vectors — a single ReLU-kink flip (|pre-activation|
         # < 1e-7, ~10 of the 3e7 hidden activations differ between ANY two fp32 evaluations) moves one fc1 row by
         # ~1e-3 of the tensor norm; outputs and input gradients keep the 1e-3 north_star bound.
-        floor = base if mode == torch.bfloat16 else (2 * base if g_ref.dim() > 1 else 3 * base)
+        # bf16: 2e-2 for matrices, 3e-2 for vectors (bias / LayerNorm gradients: column sums with heavy cancellation).
+        if mode == torch.bfloat16:
+            floor = base if g_ref.dim() > 1 else 1.5 * base
+        else:
+            floor = 2 * base if g_ref.dim() > 1 else 3 * base
         assert_close(pk[n].grad, g_ref, bound(rel_err(cpo[n].grad, g_ref), floor), 2e-5, "g/" + n)
 
 
