@@ -61,17 +61,43 @@ __device__ __forceinline__ uint64_t pdesc(uint32_t tile, int kk) {
   return make_smem_desc(tile + (uint32_t)kk * 256, 128, KC * 16, SWZ_NONE);
 }
 
+// The MMA-issuing helpers below are WARP-COLLECTIVE: all 32 lanes of the issuer warp call them with uniform
+// arguments.  Base descriptors are computed in warp-uniform control flow (so they live in uniform registers) and
+// per-k-step offsets are compile-time immediates; only the tcgen05.mma / tcgen05.commit themselves run under
+// elect.sync.  (Computing descriptors inside a divergent `if (lane == 0)` costs ~13 SASS instructions and a
+// BRA.U.ANY uniformity loop per MMA — more than the 32-64 cycles one 128xNx16 MMA occupies the tensor pipe.)
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+  if (elect_one()) tc::tc_commit(bar);
+  __syncwarp();
+}
 // D[128 x NB] (+)= A(tile, RA rows, K-major) . B(tile, RB rows, K-major)^T, contraction over the head dim
 template <int HS>
 __device__ __forceinline__ void mma_over_head(uint32_t tmem_d, uint32_t a_tile, int RA, uint32_t b_tile, int RB, uint32_t idesc) {
+  using H = HeadCfg<HS>;
+  const uint64_t da = make_smem_desc(a_tile, 16, 8 * H::ROWB, H::SWZ), db = make_smem_desc(b_tile, 16, 8 * H::ROWB, H::SWZ);
+  if (elect_one()) {
 #pragma unroll
-  for (int kk = 0; kk < HS / 16; ++kk) tc_mma_bf16(tmem_d, kmaj_desc<HS>(a_tile, RA, kk), kmaj_desc<HS>(b_tile, RB, kk), idesc, kk != 0);
+    for (int kk = 0; kk < HS / 16; ++kk) {
+      const uint32_t oa = (uint32_t)(kk / H::KPH) * RA * H::ROWB + (uint32_t)(kk % H::KPH) * 32;
+      const uint32_t ob = (uint32_t)(kk / H::KPH) * RB * H::ROWB + (uint32_t)(kk % H::KPH) * 32;
+      tc_mma_bf16(tmem_d, da + (oa >> 4), db + (ob >> 4), idesc, kk != 0);
+    }
+  }
+  __syncwarp();
 }
 // D[128 x HS] (+)= P(no-swizzle [128 x KC]) . B(tile with KC rows, MN-major)
 template <int HS, int KC>
 __device__ __forceinline__ void mma_over_rows(uint32_t tmem_d, uint32_t p_tile, uint32_t b_tile, uint32_t idesc, bool accumulate) {
+  using H = HeadCfg<HS>;
+  const uint64_t dp = make_smem_desc(p_tile, 128, KC * 16, SWZ_NONE);
+  const uint64_t db = make_smem_desc(b_tile, (uint32_t)KC * H::ROWB, 8 * H::ROWB, H::SWZ);
+  const uint32_t acc = accumulate ? 1u : 0u;
+  if (elect_one()) {
 #pragma unroll
-  for (int kk = 0; kk < KC / 16; ++kk) tc_mma_bf16(tmem_d, pdesc<KC>(p_tile, kk), mnmaj_desc<HS>(b_tile, KC, kk), idesc, accumulate || kk != 0);
+    for (int kk = 0; kk < KC / 16; ++kk)
+      tc_mma_bf16(tmem_d, dp + (uint32_t)((kk * 256) >> 4), db + (uint32_t)((kk * 16 * H::ROWB) >> 4), idesc, kk == 0 ? acc : 1u);
+  }
+  __syncwarp();
 }
 
 template <int HS>
@@ -156,8 +182,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (all lanes, see mma_over_head)
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, HS, 0, 1);
       mbar_wait(q_full, 0);
@@ -165,7 +191,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_after();
       for (int w = 0; w < 2; ++w) {
         mma_over_head<HS>(tmem_base + w * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF, BKV, idesc_s);
-        tc_commit(s_full + 8 * w);
+        tc_commit_elect(s_full + 8 * w);
       }
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % ST;
@@ -174,13 +200,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_fence_after();
           mma_over_rows<HS, BKV>(tmem_base + 2 * BKV + w * HS, sbase + L::P_OFF + w * L::P_BYTES, sbase + L::V_OFF + st * L::KV_BYTES,
                                  idesc_o, j > 0);
-          tc_commit(o_done + 8 * w);
-          if (w == 1) tc_commit(kv_empty + 8 * st);
+          tc_commit_elect(o_done + 8 * w);
+          if (w == 1) tc_commit_elect(kv_empty + 8 * st);
           if (j + 1 < n_kv) {
             const int sn = (j + 1) % ST;
             if (w == 0) { mbar_wait(kv_full + 8 * sn, ((j + 1) / ST) & 1); tc_fence_after(); }
             mma_over_head<HS>(tmem_base + w * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + sn * L::KV_BYTES, BKV, idesc_s);
-            tc_commit(s_full + 8 * w);
+            tc_commit_elect(s_full + 8 * w);
           }
         }
       }
@@ -342,7 +368,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       }
     }
   } else if (warp == 8) {
-    if (lane == 0) {
+    {  // MMA issuer: all 32 lanes walk the schedule (uniform control flow); single lanes are elected per instruction
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BQ, 0, 0);
       constexpr uint32_t idesc_g = make_idesc_bf16(128, HS, 0, 1);
       mbar_wait(kv_full, 0);
@@ -350,7 +376,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       tc_fence_after();
       mma_over_head<HS>(tmem_base, sbase + L::K_OFF, 128, sbase + L::Q_OFF, BQ, idesc_s);
       mma_over_head<HS>(tmem_base + BQ, sbase + L::V_OFF, 128, sbase + L::DO_OFF, BQ, idesc_s);
-      tc_commit(s_full);
+      tc_commit_elect(s_full);
       for (int i = 0; i < n_q; ++i) {
         const int bf = i & 1, st = i % ST;
         if (i + 1 < n_q) {
@@ -359,16 +385,16 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           tc_fence_after();
           mma_over_head<HS>(tmem_base + bn * 2 * BQ, sbase + L::K_OFF, 128, sbase + L::Q_OFF + sn * L::Q_BYTES, BQ, idesc_s);
           mma_over_head<HS>(tmem_base + bn * 2 * BQ + BQ, sbase + L::V_OFF, 128, sbase + L::DO_OFF + sn * L::Q_BYTES, BQ, idesc_s);
-          tc_commit(s_full + 8 * bn);
+          tc_commit_elect(s_full + 8 * bn);
         }
         mbar_wait(ds_full + 8 * bf, (i >> 1) & 1);
         tc_fence_after();
         mma_over_rows<HS, BQ>(tm_dv, sbase + L::PT_OFF + bf * L::P_BYTES, sbase + L::DO_OFF + st * L::Q_BYTES, idesc_g, i > 0);
         mma_over_rows<HS, BQ>(tm_dk, sbase + L::DST_OFF + bf * L::P_BYTES, sbase + L::Q_OFF + st * L::Q_BYTES, idesc_g, i > 0);
-        tc_commit(q_empty + 8 * st);
-        tc_commit(ds_empty + 8 * bf);
+        tc_commit_elect(q_empty + 8 * st);
+        tc_commit_elect(ds_empty + 8 * bf);
       }
-      tc_commit(acc_done);
+      tc_commit_elect(acc_done);
     }
   } else {
     const int wg = warp >> 2;  // two compute warpgroups split the tile's columns
@@ -505,7 +531,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == 8) {
-    if (lane == 0) {
+    {  // MMA issuer: all 32 lanes walk the schedule (uniform control flow); single lanes are elected per instruction
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
       constexpr uint32_t idesc_q = make_idesc_bf16(128, HS, 0, 1);
       mbar_wait(q_full, 0);
@@ -513,7 +539,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
       mma_over_head<HS>(tmem_base, sbase + L::Q_OFF, 128, sbase + L::K_OFF, BKV, idesc_s);
       mma_over_head<HS>(tmem_base + BKV, sbase + L::DO_OFF, 128, sbase + L::V_OFF, BKV, idesc_s);
-      tc_commit(s_full);
+      tc_commit_elect(s_full);
       for (int j = 0; j < n_kv; ++j) {
         const int bf = j & 1, st = j % ST;
         if (j + 1 < n_kv) {
@@ -522,15 +548,15 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tc_fence_after();
           mma_over_head<HS>(tmem_base + bn * 2 * BKV, sbase + L::Q_OFF, 128, sbase + L::K_OFF + sn * L::KV_BYTES, BKV, idesc_s);
           mma_over_head<HS>(tmem_base + bn * 2 * BKV + BKV, sbase + L::DO_OFF, 128, sbase + L::V_OFF + sn * L::KV_BYTES, BKV, idesc_s);
-          tc_commit(s_full + 8 * bn);
+          tc_commit_elect(s_full + 8 * bn);
         }
         mbar_wait(ds_full + 8 * bf, (j >> 1) & 1);
         tc_fence_after();
         mma_over_rows<HS, BKV>(tm_dq, sbase + L::DS_OFF + bf * L::DS_BYTES, sbase + L::K_OFF + st * L::KV_BYTES, idesc_q, j > 0);
-        tc_commit(kv_empty + 8 * st);
-        tc_commit(ds_empty + 8 * bf);
+        tc_commit_elect(kv_empty + 8 * st);
+        tc_commit_elect(ds_empty + 8 * bf);
       }
-      tc_commit(acc_done);
+      tc_commit_elect(acc_done);
     }
   } else {
     const int wg = warp >> 2;  // two compute warpgroups split the tile's columns
@@ -650,7 +676,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else if (warp == 8) {
-    if (lane == 0) {
+    {  // MMA issuer: all 32 lanes walk the schedule (uniform control flow); single lanes are elected per instruction
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, HS, 0, 1);
       mbar_wait(q_full, 0);
@@ -660,9 +686,9 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int w = 0; w < 2; ++w) {
           mma_over_head<HS>(tmem_base + (w * 2 + jj) * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + (jj % KST) * L::KV_BYTES,
                             BKV, idesc_s);
-          tc_commit(s_full + 8 * (w * 2 + jj));
+          tc_commit_elect(s_full + 8 * (w * 2 + jj));
         }
-        tc_commit(k_empty + 8 * (jj % KST));
+        tc_commit_elect(k_empty + 8 * (jj % KST));
       }
       for (int j = 0; j < n_kv; ++j) {
         const int buf = j & 1, vs = j % VST;
@@ -673,14 +699,14 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_fence_after();
           mma_over_rows<HS, BKV>(tmem_base + 4 * BKV + w * HS, sbase + L::P_OFF + sb * L::P_BYTES, sbase + L::V_OFF + vs * L::KV_BYTES, idesc_o,
                                  j > 0);
-          tc_commit(p_empty + 8 * sb);
-          if (w == 1) tc_commit(v_empty + 8 * vs);
+          tc_commit_elect(p_empty + 8 * sb);
+          if (w == 1) tc_commit_elect(v_empty + 8 * vs);
           if (j + 2 < n_kv) {
             const int ks = (j + 2) % KST;
             if (w == 0) { mbar_wait(k_full + 8 * ks, ((j + 2) / KST) & 1); tc_fence_after(); }
             mma_over_head<HS>(tmem_base + sb * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + ks * L::KV_BYTES, BKV, idesc_s);
-            tc_commit(s_full + 8 * sb);
-            if (w == 1) tc_commit(k_empty + 8 * ks);
+            tc_commit_elect(s_full + 8 * sb);
+            if (w == 1) tc_commit_elect(k_empty + 8 * ks);
           }
         }
       }

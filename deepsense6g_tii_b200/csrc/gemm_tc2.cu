@@ -147,7 +147,7 @@ gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // MMA issuer: all 32 lanes walk the schedule (uniform control flow keeps descriptors in uniform registers)
       constexpr uint32_t idesc = make_idesc_bf16(G2_BM, BN, 0, 0);
       int it = 0, i = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++i) {
@@ -162,11 +162,16 @@ gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
           const uint64_t da = make_smem_desc(sa, 16, 1024, SWZ_128B);
           const uint64_t db = make_smem_desc(sb, 16, 1024, SWZ_128B);
+          const uint32_t first = kb != 0 ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < G2_BK / 16; ++k) tc_mma_bf16(acc, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kb | k) != 0);
-          tc_commit(bar_empty + s * 8);
+            for (int k = 0; k < G2_BK / 16; ++k) tc_mma_bf16(acc, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, k == 0 ? first : 1u);
+            tc_commit(bar_empty + s * 8);
+          }
+          __syncwarp();
         }
-        tc_commit(acc_full + ab * 8);
+        if (elect_one()) tc_commit(acc_full + ab * 8);
+        __syncwarp();
       }
     }
   } else {
@@ -292,7 +297,7 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // MMA issuer: all 32 lanes walk the schedule (uniform control flow keeps descriptors in uniform registers)
       constexpr uint32_t idesc = make_idesc_bf16(G2_BM, BN, 1, 1);
       for (int it = 0; it < num_it; ++it) {
         const int s = it % STAGES;
@@ -301,11 +306,16 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
         const uint64_t da = make_smem_desc(sa, BOX_BYTES, 1024, SWZ_128B);
         const uint64_t db = make_smem_desc(sb, BOX_BYTES, 1024, SWZ_128B);
+        const uint32_t first = it != 0 ? 1u : 0u;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < G2_BK / 16; ++k) tc_mma_bf16(tmem_base, desc_advance(da, k * 2048), desc_advance(db, k * 2048), idesc, (it | k) != 0);
-        tc_commit(bar_empty + s * 8);
+          for (int k = 0; k < G2_BK / 16; ++k) tc_mma_bf16(tmem_base, da + (uint32_t)(k * 128), db + (uint32_t)(k * 128), idesc, k == 0 ? first : 1u);
+          tc_commit(bar_empty + s * 8);
+        }
+        __syncwarp();
       }
-      tc_commit(bar_acc);
+      if (elect_one()) tc_commit(bar_acc);
+      __syncwarp();
     }
   } else {
     mbar_wait(bar_acc, 0);
