@@ -1,0 +1,89 @@
+"""Whole-model GPU parity of the drop-in ``TransFuser`` / ``Encoder`` (reference API, model2_seq.py:406-597,
+850-894) against the oracle restatement of ``Encoder.forward`` (oracle/model_ref.py, pinned to the live
+reference in tests/test_oracle.py) evaluated on the SAME module object (shared weights) in fp32.
+north_star: <= 1e-3 (fp32 mode) / 2e-2 (bf16 mode) on the logits, top-1 beam agreement."""
+import types
+
+import pytest
+import torch
+
+from conftest import assert_close, rel_err
+from oracle import model_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(dtype, n_layer=8, **kw):
+    d = dict(seq_len=5, pred_len=4, n_views=1, vert_anchors=8, horz_anchors=8, n_embd=512, block_exp=4, n_layer=n_layer, n_head=4,
+             embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0, add_velocity=1, fusion_dtype=dtype)
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def _inputs(B, dev, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    imgs = [(torch.rand(B, 3, 256, 256, generator=g) * 255).to(dev) for _ in range(5)]
+    lids = [(torch.rand(B, 1, 256, 256, generator=g) < 0.05).float().to(dev) for _ in range(5)]
+    rads = [torch.rand(B, 2, 256, 256, generator=g).to(dev) for _ in range(5)]
+    ang = (torch.rand(B, 2, 1, generator=g) - 0.5) * 3.14159
+    return imgs, lids, rads, ang.expand(B, 2, 2).contiguous().to(dev)
+
+
+def _build(dev, dtype, n_layer=8, **kw):
+    from deepsense6g_tii_b200 import TransFuser
+    torch.manual_seed(100)
+    m = TransFuser(_cfg(dtype, n_layer, **kw), dev)
+    with torch.no_grad():
+        for k in (1, 2, 3, 4):
+            getattr(m.encoder, "transformer%d" % k).pos_emb.normal_(0, 0.02)
+    return m
+
+
+WATCH = ["join.0.weight", "encoder.transformer1.pos_emb", "encoder.transformer4.blocks.7.mlp.0.weight",
+         "encoder.transformer2.blocks.0.attn.query.weight", "encoder.vel_emb1.weight", "encoder.image_encoder.features.conv1.weight",
+         "encoder.radar_encoder._model.layer2.0.conv1.weight"]
+
+
+@pytest.mark.parametrize("mode", [torch.float32, torch.bfloat16], ids=["float32", "bfloat16"])
+def test_transfuser_forward_backward_vs_oracle(cuda_dev, mode):
+    B = 2
+    m = _build(cuda_dev, mode).train()
+    ins = _inputs(B, cuda_dev)
+    probe = torch.randn(B, 64, generator=torch.Generator().manual_seed(1)).to(cuda_dev)
+    out = m(*ins)
+    assert out.shape == (B, 64)
+    (out * probe).sum().backward()
+    got = {n: p.grad.clone() for n, p in m.named_parameters() if n in WATCH}
+    m.zero_grad(set_to_none=True)
+    ref = model_ref.transfuser_forward(m, *ins)
+    (ref * probe).sum().backward()
+    tol = 1e-3 if mode == torch.float32 else 2e-2
+    assert_close(out.float(), ref, tol, 1e-5, "logits")
+    assert torch.equal(out.argmax(-1), ref.argmax(-1)), "top-1 beam index"
+    gtol = 2e-3 if mode == torch.float32 else 6e-2
+    params = dict(m.named_parameters())
+    for n in WATCH:
+        assert_close(got[n], params[n].grad, gtol, 1e-6, "grad " + n)
+
+
+def test_channels_last_trunks_use_nhwc_kernels(cuda_dev):
+    """Trunks in channels_last hand NHWC storage to the fusion stage; results equal the NCHW run."""
+    m = _build(cuda_dev, torch.float32, n_layer=2).eval()
+    ins = _inputs(1, cuda_dev, seed=3)
+    with torch.no_grad():
+        a = m(*ins)
+        m = m.to(memory_format=torch.channels_last)
+        b = m(*[[t.contiguous(memory_format=torch.channels_last) for t in ins[0]], ins[1], ins[2], ins[3]])
+    assert_close(b, a, 1e-4, 1e-5, "channels_last")
+
+
+def test_missing_modality_zeroes_inputs_ahead_of_conv1(cuda_dev):
+    """config.modality_missing='lidar_radar' (mambafuser_seq.py:361-391, 418-420): the stacked lidar/radar inputs are replaced
+    by zeros before conv1 -> identical to feeding zero tensors."""
+    m = _build(cuda_dev, torch.float32, n_layer=1).eval()
+    imgs, lids, rads, gps = _inputs(1, cuda_dev, seed=4)
+    with torch.no_grad():
+        ref = m(imgs, [torch.zeros_like(t) for t in lids], [torch.zeros_like(t) for t in rads], gps)
+        m.config.modality_missing = "lidar_radar"
+        got = m(imgs, lids, rads, gps)
+    assert rel_err(got, ref) < 1e-6

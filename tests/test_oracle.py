@@ -100,3 +100,26 @@ def test_init_law_matches_reference():
     assert set(sd.keys()) == set(p.keys())
     for k in sd:
         assert sd[k].shape == p[k].shape, k
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree absent (GPU box)")
+def test_encoder_restatement_matches_reference_live():
+    """oracle/model_ref.encoder_forward against the reference's own Encoder.forward (CPU fp32, B=1)."""
+    from oracle import model_ref
+    M, _ = ref_import.load_reference()
+    cfg = ref_import.make_config(n_layer=2)
+    torch.manual_seed(4)
+    enc = M.Encoder(cfg).eval()
+    with torch.no_grad():
+        for k in (1, 2, 3, 4):
+            getattr(enc, "transformer%d" % k).pos_emb.normal_(0, 0.02)
+    gen = torch.Generator().manual_seed(5)
+    imgs = [torch.rand(1, 3, 256, 256, generator=gen) * 255 for _ in range(5)]
+    lids = [torch.rand(1, 1, 256, 256, generator=gen) for _ in range(5)]
+    rads = [torch.rand(1, 2, 256, 256, generator=gen) for _ in range(5)]
+    gps = torch.rand(1, 2, 2, generator=gen)
+    with torch.no_grad():
+        ref = enc(imgs, lids, rads, gps)
+        got = model_ref.encoder_forward(enc, imgs, lids, rads, gps)
+    assert got.shape == ref.shape == (1, 512)
+    assert rel_err(got, ref) < 1e-4
