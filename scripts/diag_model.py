@@ -8,6 +8,10 @@ from deepsense6g_tii_b200 import TransFuser
 mode = torch.float32 if (len(sys.argv) < 2 or sys.argv[1] == "f32") else torch.bfloat16
 n_layer = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 dev = torch.device("cuda")
+if os.environ.get("NO_TF32", "1") == "1":
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+print("cudnn.allow_tf32 =", torch.backends.cudnn.allow_tf32)
 cfg = types.SimpleNamespace(seq_len=5, pred_len=4, n_views=1, vert_anchors=8, horz_anchors=8, n_embd=512, block_exp=4, n_layer=n_layer, n_head=4,
                             embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0, add_velocity=1, fusion_dtype=mode)
 torch.manual_seed(100)
@@ -28,6 +32,12 @@ got = {n: p.grad.clone() for n, p in m.named_parameters()}
 m.zero_grad(set_to_none=True)
 ref = model_ref.transfuser_forward(m, imgs, lids, rads, gps)
 (ref * probe).sum().backward()
+ref_g = {n: p.grad.clone() for n, p in m.named_parameters()}
+m.zero_grad(set_to_none=True)
+ref2 = model_ref.transfuser_forward(m, imgs, lids, rads, gps)
+(ref2 * probe).sum().backward()
+print("oracle-vs-oracle logits %.3e  worst grad %.3e" % (float((ref2 - ref).norm() / ref.norm()),
+      max(float((ref_g[n] - p.grad).norm() / (p.grad.norm() + 1e-30)) for n, p in m.named_parameters() if "key.bias" not in n)))
 print("logits rel err %.3e" % float((out.float() - ref).norm() / ref.norm()))
 rows = []
 for n, p in m.named_parameters():
