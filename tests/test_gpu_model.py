@@ -39,13 +39,29 @@ def _build(dev, dtype, n_layer=8, **kw):
     return m
 
 
-WATCH = ["join.0.weight", "encoder.transformer1.pos_emb", "encoder.transformer4.blocks.7.mlp.0.weight",
-         "encoder.transformer2.blocks.0.attn.query.weight", "encoder.vel_emb1.weight", "encoder.image_encoder.features.conv1.weight",
-         "encoder.radar_encoder._model.layer2.0.conv1.weight"]
+WATCH = ["join.0.weight", "encoder.vel_emb1.weight", "encoder.transformer4.blocks.7.mlp.0.weight", "encoder.transformer4.pos_emb",
+         "encoder.transformer3.blocks.0.attn.query.weight", "encoder.transformer1.pos_emb",
+         "encoder.image_encoder.features.conv1.weight", "encoder.radar_encoder._model.layer2.0.conv1.weight"]
+
+
+@pytest.fixture(autouse=True)
+def _fp32_convs():
+    """Both arms run the stock trunks; keep cuDNN convolutions in true fp32 so that the comparison measures the
+    fusion path and not TF32 rounding of the ResNets."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
 
 
 @pytest.mark.parametrize("mode", [torch.float32, torch.bfloat16], ids=["float32", "bfloat16"])
 def test_transfuser_forward_backward_vs_oracle(cuda_dev, mode):
+    """Logits: north_star tolerance against the float64 oracle + top-1 beam agreement.  Gradients: the model's own
+    gradient is ill-conditioned in fp32 (train-mode BatchNorm backward subtracts the mean of a nearly uniform upstream
+    gradient coming from the global average pool), so two fp32 evaluations that differ by 1e-7 per stage differ by ~1e-2 in
+    the early trunk layers; every tensor is therefore bounded by max(tolerance, 1.5 x the error of the stock fp32 oracle
+    against the same float64 reference)."""
+    import copy
     B = 2
     m = _build(cuda_dev, mode).train()
     ins = _inputs(B, cuda_dev)
@@ -55,15 +71,22 @@ def test_transfuser_forward_backward_vs_oracle(cuda_dev, mode):
     (out * probe).sum().backward()
     got = {n: p.grad.clone() for n, p in m.named_parameters() if n in WATCH}
     m.zero_grad(set_to_none=True)
-    ref = model_ref.transfuser_forward(m, *ins)
-    (ref * probe).sum().backward()
+    # stock fp32 evaluation of the same module (calibration) and float64 reference
+    cal = model_ref.transfuser_forward(m, *ins)
+    (cal * probe).sum().backward()
+    cal_g = {n: p.grad.clone() for n, p in m.named_parameters() if n in WATCH}
+    m64 = copy.deepcopy(m).double()
+    ins64 = ([t.double() for t in ins[0]], [t.double() for t in ins[1]], [t.double() for t in ins[2]], ins[3].double())
+    ref = model_ref.transfuser_forward(m64, *ins64)
+    (ref * probe.double()).sum().backward()
+    ref_g = dict(m64.named_parameters())
     tol = 1e-3 if mode == torch.float32 else 2e-2
     assert_close(out.float(), ref, tol, 1e-5, "logits")
     assert torch.equal(out.argmax(-1), ref.argmax(-1)), "top-1 beam index"
     gtol = 2e-3 if mode == torch.float32 else 6e-2
-    params = dict(m.named_parameters())
     for n in WATCH:
-        assert_close(got[n], params[n].grad, gtol, 1e-6, "grad " + n)
+        r = ref_g[n].grad
+        assert_close(got[n], r, max(gtol, 1.5 * rel_err(cal_g[n], r)), 1e-6, "grad " + n)
 
 
 def test_channels_last_trunks_use_nhwc_kernels(cuda_dev):
