@@ -24,8 +24,10 @@ def _gpt_params(gpt):
     return {k: v for k, v in gpt.named_parameters()}
 
 
-def encoder_forward(enc, image_list, lidar_list, radar_list, gps):
-    """Restates model2_seq.py:473-597 (four fusion stages interleaved with the three ResNet trunks)."""
+def encoder_forward(enc, image_list, lidar_list, radar_list, gps, stage_autocast=False):
+    """Restates model2_seq.py:473-597 (four fusion stages interleaved with the three ResNet trunks).
+    stage_autocast=True evaluates ONLY the fusion stages under torch.autocast(bf16) (trunks stay fp32): the stock-PyTorch
+    calibration for the bf16 tensor-core mode."""
     cfg = enc.config
     S = cfg.seq_len
     image_list = [normalize_imagenet(t) for t in image_list]
@@ -47,14 +49,16 @@ def encoder_forward(enc, image_list, lidar_list, radar_list, gps):
             layer = "layer%d" % (k + 1)
             feats = [getattr(ie, layer)(feats[0]), getattr(le, layer)(feats[1]), getattr(re_, layer)(feats[2])]
         g = vel(g)
-        feats, g = R.fusion_stage(_gpt_params(gpt), feats, g, cfg.n_head, S, cfg.vert_anchors, cfg.horz_anchors, V)
-        feats = list(feats)
+        with torch.autocast(feats[0].device.type, dtype=torch.bfloat16, enabled=stage_autocast):
+            feats, g = R.fusion_stage(_gpt_params(gpt), feats, g, cfg.n_head, S, cfg.vert_anchors, cfg.horz_anchors, V)
+        feats = [f.float() if stage_autocast else f for f in feats]
+        g = g.float() if stage_autocast else g
     pooled = [torch.flatten(ie.avgpool(feats[0]), 1).view(bz, V * S, -1),
               torch.flatten(le.avgpool(feats[1]), 1).view(bz, S, -1),
               torch.flatten(re_.avgpool(feats[2]), 1).view(bz, S, -1)]
     return torch.cat(pooled + [g], dim=1).sum(dim=1)
 
 
-def transfuser_forward(model, image_list, lidar_list, radar_list, gps):
+def transfuser_forward(model, image_list, lidar_list, radar_list, gps, stage_autocast=False):
     """model2_seq.py:880-894."""
-    return model.join(encoder_forward(model.encoder, image_list, lidar_list, radar_list, gps))
+    return model.join(encoder_forward(model.encoder, image_list, lidar_list, radar_list, gps, stage_autocast))

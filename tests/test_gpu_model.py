@@ -71,8 +71,9 @@ def test_transfuser_forward_backward_vs_oracle(cuda_dev, mode):
     (out * probe).sum().backward()
     got = {n: p.grad.clone() for n, p in m.named_parameters() if n in WATCH}
     m.zero_grad(set_to_none=True)
-    # stock fp32 evaluation of the same module (calibration) and float64 reference
-    cal = model_ref.transfuser_forward(m, *ins)
+    # stock evaluation of the same module in the precision under test (fp32, or bf16 autocast inside the fusion stages
+    # only) = calibration; float64 = reference
+    cal = model_ref.transfuser_forward(m, *ins, stage_autocast=(mode == torch.bfloat16))
     (cal * probe).sum().backward()
     cal_g = {n: p.grad.clone() for n, p in m.named_parameters() if n in WATCH}
     m64 = copy.deepcopy(m).double()
@@ -87,6 +88,7 @@ def test_transfuser_forward_backward_vs_oracle(cuda_dev, mode):
     for n in WATCH:
         r = ref_g[n].grad
         assert_close(got[n], r, max(gtol, 1.5 * rel_err(cal_g[n], r)), 1e-6, "grad " + n)
+    assert rel_err(out.float(), ref) <= max(tol / 4, 1.5 * rel_err(cal.float(), ref)), "logits no worse than the stock path"
 
 
 def test_channels_last_trunks_use_nhwc_kernels(cuda_dev):
