@@ -45,3 +45,32 @@ def allreduce_grads(params, buf=None):
         p.grad.copy_(buf[off:off + n].view_as(p.grad))
         off += n
     return buf
+
+
+class OverlappedGradReducer:
+    """Bucketed gradient all-reduce overlapped with the fusion stage's own backward.
+
+    ``FusionStageFn`` keeps all gradients of one transformer block in ONE flat fp32 buffer and calls
+    ``block_ready(i, flat)`` as soon as the kernels producing block i's gradients are enqueued; the reducer
+    starts an asynchronous NCCL all-reduce (average) of that bucket, which runs while the backward of blocks
+    i-1 ... 0 is still computing.  ``finish(tensors)`` reduces the few remaining tensors (pos_emb, ln_f) and
+    makes the compute stream wait for every outstanding collective, so the gradients autograd receives are
+    already averaged.  With world_size 1 (or no process group) it is a no-op.
+    """
+
+    def __init__(self):
+        self.active = dist.is_initialized() and dist.get_world_size() > 1
+        self._works = []
+
+    def block_ready(self, index, flat):
+        if self.active:
+            self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.AVG, async_op=True))
+
+    def finish(self, tensors=()):
+        if not self.active:
+            return
+        for t in tensors:
+            self._works.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=True))
+        for w in self._works:
+            w.wait()
+        self._works = []

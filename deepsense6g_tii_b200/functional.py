@@ -60,6 +60,7 @@ class _Runner:
         self.M = B * self.T
         self.bf16 = compute_dtype == torch.bfloat16
         self.act = torch.bfloat16 if self.bf16 else torch.float32
+        self.grad_hook = None  # optional dist.OverlappedGradReducer (bf16 path)
         if self.bf16:
             if C % 64 != 0 or self.hs not in (16, 32, 64, 128):
                 raise RuntimeError("bf16 tensor-core mode needs n_embd %% 64 == 0 and head size in {16,32,64,128}; "
@@ -334,11 +335,15 @@ class _Runner:
                                       dwqkv[C:2 * C], dbqkv[C:2 * C], dwqkv[:C], dbqkv[:C], dwqkv[2 * C:], dbqkv[2 * C:],
                                       dwp, dbp, dw1, db1, dw2, db2]
             saved.layers[i] = None  # release this block's activations early
+            if self.grad_hook is not None:  # data parallel: start averaging this block's bucket while blocks i-1..0 compute
+                self.grad_hook.block_ready(i, gbuf[i * per_block:(i + 1) * per_block])
         dfeats = [torch.empty_like(d) for d in douts]
         dgps = torch.empty(self.B, 2, C, device=dev, dtype=f32)
         dpos = torch.empty(1, self.T, C, device=dev, dtype=f32)
         K.tokens_bwd(self.geom, dx, douts if residual else None, dfeats, dgps, dpos)
         grads[0] = dpos
+        if self.grad_hook is not None:
+            self.grad_hook.finish([dpos, gbuf[L * per_block:]])
         return dfeats, dgps, grads
 
     def backward(self, saved, params, douts, dgps_out, residual=True):
@@ -440,6 +445,7 @@ class FusionStageFn(torch.autograd.Function):
         gps_emb = gps_emb.contiguous().float()
         plist = [p.detach().contiguous().float() for p in params]
         residual = bool(cfg.get("residual", True))
+        r.grad_hook = cfg.get("grad_hook")
         outs, gps_out, saved = r.forward([img.detach(), lidar.detach(), radar.detach()], gps_emb.detach(), plist, residual)
         ctx.runner, ctx.saved_state, ctx.plist, ctx.residual = r, saved, plist, residual
         ctx.feat_mf = torch.channels_last if layout == K.DSF_NHWC else torch.contiguous_format

@@ -106,7 +106,14 @@ class GPT(nn.Module):
                 "embd_pdrop=attn_pdrop=resid_pdrop=0 (GlobalConfig(**kwargs), config_seq.py:43-45) or call .eval()")
         return dict(seq_len=self.seq_len, n_views=self.config.n_views, vert_anchors=self.vert_anchors,
                     horz_anchors=self.horz_anchors, n_head=self.n_head, n_layer=self.n_layer,
-                    compute_dtype=getattr(self.config, "fusion_dtype", torch.bfloat16), residual=residual)
+                    compute_dtype=getattr(self.config, "fusion_dtype", torch.bfloat16), residual=residual,
+                    grad_hook=getattr(self, "_grad_reducer", None))
+
+    def set_grad_reducer(self, reducer):
+        """Data-parallel training: a ``dist.OverlappedGradReducer`` that averages this GPT's gradients block by block
+        while the backward is still running (bf16 path).  With it set, ``.grad`` of the GPT parameters is already
+        averaged over ranks after ``backward()`` — do not all-reduce them again (exclude them from DDP)."""
+        self._grad_reducer = reducer
 
     def forward(self, image_tensor, lidar_tensor, radar_tensor, gps):
         """Reference semantics (model2_seq.py:248-287): inputs are already pooled to the anchor grid,
