@@ -313,6 +313,7 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     pk = peaks()
+    gpt.set_grad_reducer(None)  # the instrumented step runs on rank 0 only: no collectives in it
     fam = profile_families(gpt, feats, gps, probes)
     total_ms = sum(d["ms"] for d in fam.values())
     tc = {k: d for k, d in fam.items() if d["flops"] > 0}
