@@ -20,9 +20,9 @@ EPI_BIAS, EPI_RELU, EPI_RESIDUAL, EPI_ACCUM = 1, 2, 4, 8
 
 # every symbol include/dsfuse.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_tokens_fwd", "dsf_tokens_bwd",
+    "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_dropout_inplace", "dsf_tokens_fwd", "dsf_tokens_bwd",
     "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_set_impl", "dsf_gemm_f32",
-    "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_set_impl",
+    "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_set_impl", "dsf_attn_drop_words",
     "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16",
 ]
 
@@ -30,6 +30,15 @@ SYMBOLS = [
 class Geom(ctypes.Structure):
     """``dsf_geom`` (include/dsfuse.h)."""
     _fields_ = [(n, c_int32) for n in ("B", "S", "V", "A_h", "A_w", "C", "H", "W", "feat_dtype", "layout")]
+
+
+class Dropout(ctypes.Structure):
+    """``dsf_dropout`` (include/dsfuse.h): one nn.Dropout site; mask = f(seed, site, step, element index)."""
+    _fields_ = [("p", c_float), ("seed", ctypes.c_uint64), ("site", ctypes.c_uint32), ("step", ctypes.c_uint32)]
+
+
+def _dp(d):
+    return None if d is None else ctypes.byref(d)
 
 
 class GemmF32Desc(ctypes.Structure):
@@ -60,18 +69,19 @@ def lib():
             "dsf_tokens_fwd": [POINTER(Geom), P, P, P, P, P, P, P],
             "dsf_tokens_bwd": [POINTER(Geom), P, P, P, P, P, P, P, P, P, P],
             "dsf_layernorm_fwd": [P, P, P, P, c_int32, P, P, c_int32, c_int32, c_float, P],
-            "dsf_layernorm_bwd": [P, c_int32, P, P, P, P, P, P, P, P, P, P, c_int32, c_int32, P],
+            "dsf_layernorm_bwd": [P, c_int32, P, P, P, P, P, P, P, P, P, P, POINTER(Dropout), c_int32, c_int32, P],
+            "dsf_dropout_inplace": [P, c_int64, POINTER(Dropout), P],
             "dsf_relu_bwd_colsum": [P, P, P, c_int32, c_int32, P],
             "dsf_pack_block_weights": [P] * 9 + [c_int32, c_int32] + [P] * 10,
-            "dsf_gemm_bf16_nt": [P, c_int32, P, c_int32, P, c_int32, c_int32, P, P, c_int32, c_int32, c_int32, c_int32, P],
+            "dsf_gemm_bf16_nt": [P, c_int32, P, c_int32, P, c_int32, c_int32, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P],
             "dsf_gemm_bf16_tn": [P, c_int32, P, c_int32, P, c_int32, c_int32, c_int32, c_int32, P],
             "dsf_gemm_f32": [POINTER(GemmF32Desc), P, P, P, P, P, P],
             "dsf_colsum": [P, c_int32, c_int32, P, c_int32, c_int32, P],
             "dsf_relu_bwd": [P, P, c_int32, c_int64, P],
             "dsf_softmax_fwd": [P, c_int64, c_int32, P],
             "dsf_softmax_bwd": [P, P, c_int64, c_int32, P],
-            "dsf_attn_fwd": [P, P, P, c_int32, c_int32, c_int32, c_int32, P],
-            "dsf_attn_bwd": [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P],
+            "dsf_attn_fwd": [P, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P, P],
+            "dsf_attn_bwd": [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P, P],
             "dsf_attn_set_impl": [c_int32],
             "dsf_gemm_set_impl": [c_int32],
             "dsf_upsample_add_fwd": [POINTER(Geom), P, P, P, P, P, P, P, P],
@@ -82,6 +92,8 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = argtypes
             fn.restype = c_int32
+        L.dsf_attn_drop_words.argtypes = [c_int32, c_int32, c_int32]
+        L.dsf_attn_drop_words.restype = c_int64
         _lib = L
     return _lib
 
@@ -145,10 +157,14 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-5):
     _chk(lib().dsf_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _dt(y), _p(mean), _p(rstd), M, C, eps, _stream()), "dsf_layernorm_fwd")
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, dx_bf16=None, dx_colsum=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, dx_bf16=None, dx_colsum=None, byprod_drop=None):
     M, C = x.shape
     _chk(lib().dsf_layernorm_bwd(_p(dy), _dt(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx_add), _p(dx_out), _p(dgamma),
-                                 _p(dbeta), _p(dx_bf16), _p(dx_colsum), M, C, _stream()), "dsf_layernorm_bwd")
+                                 _p(dbeta), _p(dx_bf16), _p(dx_colsum), _dp(byprod_drop), M, C, _stream()), "dsf_layernorm_bwd")
+
+
+def dropout_inplace(x, drop):
+    _chk(lib().dsf_dropout_inplace(_p(x), x.numel(), _dp(drop), _stream()), "dsf_dropout_inplace")
 
 
 def relu_bwd_colsum(dy, h, out):
@@ -163,13 +179,13 @@ def pack_block_weights(wq, wk, wv, wp, w1, w2, bq, bk, bv, outs):
                                       *[_p(t) for t in outs], _stream()), "dsf_pack_block_weights")
 
 
-def gemm_bf16_nt(A, B, C, bias=None, residual=None, relu=False):
-    """C[M,N] = A[M,K] @ B[N,K]^T (+bias)(relu)(+residual fp32).  A, B bf16 2-D contiguous; C bf16 or fp32."""
+def gemm_bf16_nt(A, B, C, bias=None, residual=None, relu=False, drop=None):
+    """C[M,N] = A[M,K] @ B[N,K]^T (+bias)(relu)(dropout)(+residual fp32).  A, B bf16 2-D contiguous; C bf16 or fp32."""
     M, K = A.shape
     N = B.shape[0]
     flags = (EPI_BIAS if bias is not None else 0) | (EPI_RELU if relu else 0) | (EPI_RESIDUAL if residual is not None else 0)
     _chk(lib().dsf_gemm_bf16_nt(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), _dt(C), _p(bias), _p(residual),
-                                M, N, K, flags, _stream()), "dsf_gemm_bf16_nt")
+                                M, N, K, flags, _dp(drop), _stream()), "dsf_gemm_bf16_nt")
 
 
 def gemm_bf16_tn(A, B, C):
@@ -200,12 +216,18 @@ def softmax_bwd(dp, p, rows, T):
     _chk(lib().dsf_softmax_bwd(_p(dp), _p(p), rows, T, _stream()), "dsf_softmax_bwd")
 
 
-def attn_fwd(qkv, y, lse, B, T, C, nh):
-    _chk(lib().dsf_attn_fwd(_p(qkv), _p(y), _p(lse), B, T, C, nh, _stream()), "dsf_attn_fwd")
+def attn_drop_words(B, T, nh):
+    """int32 words of the attention-dropout keep bitmap for (B, nh, T) query rows."""
+    return int(lib().dsf_attn_drop_words(B, T, nh))
 
 
-def attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh):
-    _chk(lib().dsf_attn_bwd(_p(qkv), _p(y), _p(dy), _p(lse), _p(delta), _p(dqkv), B, T, C, nh, _stream()), "dsf_attn_bwd")
+def attn_fwd(qkv, y, lse, B, T, C, nh, drop=None, drop_bits=None):
+    _chk(lib().dsf_attn_fwd(_p(qkv), _p(y), _p(lse), B, T, C, nh, _dp(drop), _p(drop_bits), _stream()), "dsf_attn_fwd")
+
+
+def attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop=None, drop_bits=None):
+    _chk(lib().dsf_attn_bwd(_p(qkv), _p(y), _p(dy), _p(lse), _p(delta), _p(dqkv), B, T, C, nh, _dp(drop), _p(drop_bits), _stream()),
+         "dsf_attn_bwd")
 
 
 def gemm_set_impl(impl):

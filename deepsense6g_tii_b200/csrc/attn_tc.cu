@@ -585,9 +585,9 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
 
 // v2 (warp-specialised, TMA-fed) implementations, attn_tc2.cu
 int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st);
-int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st);
+int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, cudaStream_t st);
 int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
-                cudaStream_t st);
+                const dsf_dropout* drop, uint32_t* bits, cudaStream_t st);
 
 int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, int C, int nh, cudaStream_t st) {
   attn_delta_kernel<<<std::min(cdiv(B * T, 8), num_sms() * 8), 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, delta, B, T, C, nh);
@@ -606,15 +606,33 @@ extern "C" int dsf_attn_set_impl(int32_t impl) {
   return DSF_OK;
 }
 
-extern "C" int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int32_t T, int32_t C, int32_t nh, void* stream) {
+// attn_drop is implemented by the default (v3 forward / v2 backward) kernels only
+static int check_attn_drop(const char* who, const dsf_dropout* drop, const uint32_t* bits, bool& on) {
+  on = drop && drop->p > 0.f;
+  if (!on) return DSF_OK;
+  if (!(drop->p < 1.f)) { set_error("%s: dropout p must be in [0, 1)", who); return DSF_EINVAL; }
+  if (!bits) { set_error("%s: attention dropout needs the drop_bits buffer", who); return DSF_EINVAL; }
+  if (g_attn_impl == 1 || g_attn_impl == 2) { set_error("%s: attention dropout is only implemented in the default kernels", who); return DSF_EUNSUPPORTED; }
+  return DSF_OK;
+}
+
+extern "C" int64_t dsf_attn_drop_words(int32_t B, int32_t T, int32_t nh) {
+  if (B <= 0 || T <= 0 || nh <= 0) return 0;
+  return (int64_t)B * nh * T * (2 * cdiv(T, 64));
+}
+
+extern "C" int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int32_t T, int32_t C, int32_t nh, const dsf_dropout* drop,
+                            uint32_t* drop_bits, void* stream) {
   DSF_REQUIRE(qkv && y && lse, "attn_fwd: NULL pointer");
+  bool drop_on;
+  if (int e = check_attn_drop("attn_fwd", drop, drop_bits, drop_on)) return e;
   DSF_REQUIRE(B > 0 && T > 0 && C > 0 && nh > 0 && C % nh == 0, "attn_fwd: bad shape B=%d T=%d C=%d nh=%d", B, T, C, nh);
   DSF_REQUIRE(aligned16(qkv) && aligned16(y), "attn_fwd: 16-byte alignment required");
   DSF_REQUIRE(B <= 65535 && nh <= 65535, "attn_fwd: grid too large");
   const int hs = C / nh;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_attn_impl == 2) return attn_fwd_v2(qkv, y, lse, B, T, C, nh, st);
-  if (g_attn_impl != 1) return attn_fwd_v3(qkv, y, lse, B, T, C, nh, st);
+  if (g_attn_impl != 1) return attn_fwd_v3(qkv, y, lse, B, T, C, nh, drop_on ? drop : nullptr, drop_bits, st);
   switch (hs) {
     case 16: return launch_attn_fwd<16, 128>(qkv, y, lse, B, T, C, nh, st);
     case 32: return launch_attn_fwd<32, 128>(qkv, y, lse, B, T, C, nh, st);
@@ -627,14 +645,16 @@ extern "C" int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int
 }
 
 extern "C" int dsf_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int32_t B,
-                            int32_t T, int32_t C, int32_t nh, void* stream) {
+                            int32_t T, int32_t C, int32_t nh, const dsf_dropout* drop, const uint32_t* drop_bits, void* stream) {
   DSF_REQUIRE(qkv && y && dy && lse && delta && dqkv, "attn_bwd: NULL pointer");
+  bool drop_on;
+  if (int e = check_attn_drop("attn_bwd", drop, drop_bits, drop_on)) return e;
   DSF_REQUIRE(B > 0 && T > 0 && C > 0 && nh > 0 && C % nh == 0, "attn_bwd: bad shape B=%d T=%d C=%d nh=%d", B, T, C, nh);
   DSF_REQUIRE(aligned16(qkv) && aligned16(y) && aligned16(dy) && aligned16(dqkv), "attn_bwd: 16-byte alignment required");
   DSF_REQUIRE(B <= 65535 && nh <= 65535, "attn_bwd: grid too large");
   const int hs = C / nh;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_attn_impl != 1) return attn_bwd_v2(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
+  if (g_attn_impl != 1) return attn_bwd_v2(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop_on ? drop : nullptr, const_cast<uint32_t*>(drop_bits), st);
   switch (hs) {
     case 16: return launch_attn_bwd<16, 128>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
     case 32: return launch_attn_bwd<32, 128>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);

@@ -29,6 +29,32 @@ __device__ __forceinline__ float ex2_approx(float x) {  // 2^x, MUFU.EX2 without
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Attention-probability dropout (attn_drop, model2_seq.py:104).  Decisions use 8-bit thresholds (p is quantised to
+// k/256, scale = 256/(256-k)) so that one Philox4x32-10 call yields 16 of them; the forward kernel writes the keep
+// bits of every (b, h, q) row to a bitmap (Tw 32-bit words per row) and the backward kernels read them back.
+struct AttnDrop {
+  uint32_t thresh8;  // drop iff random byte < thresh8; 0 = disabled
+  float scale;
+  uint32_t k0, k1, site;
+  uint32_t* bits;    // (B, nh, T, Tw)
+  int Tw;
+};
+// keep bits of keys 32*word .. 32*word+31 of row `rowid`
+__device__ __forceinline__ uint32_t attn_keep_word(const AttnDrop& a, uint64_t rowid, uint32_t word) {
+  uint32_t out = 0;
+  const uint32_t t4 = a.thresh8 * 0x01010101u;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const uint4 r = philox4x32_10(a.k0, a.k1, (uint32_t)rowid, (uint32_t)(rowid >> 32), word * 2 + c, a.site);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t ge = __vcmpgeu4(w[k], t4) & 0x01010101u;           // one flag bit per byte
+      out |= (((ge * 0x01020408u) >> 24) & 0xFu) << (c * 16 + k * 4);   // gather the 4 flags into a nibble
+    }
+  }
+  return out;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -326,7 +352,7 @@ template <int HS, int BQ, int ST>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
-                    float scale) {
+                    float scale, AttnDrop ad) {
   using L = BwdKV2<HS, BQ, ST>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -404,16 +430,31 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     const float scale_log2 = scale * 1.4426950408889634f;
     const float* lse_g = lse + ((size_t)b * nh + h) * T;
     const float* delta_g = delta + ((size_t)b * nh + h) * T;
+    static_assert(BQ == 64, "the math warps split a 64-query tile in two 32-column halves");
+    const size_t bh = (size_t)b * nh + h;
+    const int kw = kv0 / 32 + (warp & 3);  // bitmap word holding this warp's 32 keys
+    // per-query statistics (thread c < 64: lse, 64 <= c < 128: delta) and, for attn-dropout, the keep word of query
+    // (wg*32 + lane); both are fetched one tile ahead so their global-memory latency hides behind the current tile
+    auto fetch = [&](int it, float& sv, uint32_t& wv) {
+      const int c = threadIdx.x, qq = it * BQ + (c & (BQ - 1));
+      sv = c < BQ ? (qq < T ? lse_g[qq] * 1.4426950408889634f : INFINITY) : (c < 2 * BQ && qq < T ? delta_g[qq] : 0.f);
+      wv = 0xFFFFFFFFu;
+      if (ad.thresh8) {
+        const int qd = it * BQ + wg * 32 + lane;
+        wv = qd < T ? ad.bits[(bh * T + qd) * ad.Tw + kw] : 0u;
+      }
+    };
+    float sv;
+    uint32_t wv;
+    fetch(0, sv, wv);
     for (int i = 0; i < n_q; ++i) {
-      const int bf = i & 1, q0 = i * BQ;
+      const int bf = i & 1;
       float* st_lse = reinterpret_cast<float*>(smem + L::STAT_OFF) + bf * 2 * BQ;
       float* st_delta = st_lse + BQ;
       // the stats buffer bf was last read two iterations ago; every thread has passed the barrier below since then
-      for (int c = threadIdx.x; c < 2 * BQ; c += 256) {
-        const int qq = q0 + (c % BQ);
-        if (c < BQ) st_lse[c] = qq < T ? lse_g[qq] * 1.4426950408889634f : INFINITY;
-        else st_delta[c - BQ] = qq < T ? delta_g[qq] : 0.f;
-      }
+      if (threadIdx.x < 2 * BQ) st_lse[threadIdx.x] = sv;  // st_delta directly follows st_lse
+      const uint32_t myw = wv;
+      if (i + 1 < n_q) fetch(i + 1, sv, wv);
       named_bar_sync(1, 256);
       mbar_wait(s_full + 8 * bf, (i >> 1) & 1);
       tc_fence_after();
@@ -437,7 +478,15 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             p[u] = key_ok ? ex2_approx(fmaf(__uint_as_float(rs[e + u]), scale_log2, -ls[u])) : 0.f;
-            d[u] = p[u] * (__uint_as_float(rp[e + u]) - dl[u]) * scale;
+            float dp = __uint_as_float(rp[e + u]);
+            if (ad.thresh8) {  // attn_drop: dV sees P*mask/(1-p); dP = dP_drop*mask/(1-p)
+              const float m = (__shfl_sync(0xffffffffu, myw, e + u) >> lane) & 1u ? ad.scale : 0.f;
+              dp *= m;
+              d[u] = p[u] * (dp - dl[u]) * scale;
+              p[u] *= m;
+            } else {
+              d[u] = p[u] * (dp - dl[u]) * scale;
+            }
           }
           pk[e / 2] = pack_bf16x2(p[0], p[1]);
           pk[e / 2 + 1] = pack_bf16x2(p[2], p[3]);
@@ -487,7 +536,7 @@ template <int HS, int ST>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmKV,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
-                   float scale) {
+                   float scale, AttnDrop ad) {
   using L = BwdQ2<HS, ST>;
   constexpr int BKV = L::BKV;
   extern __shared__ uint8_t smem_raw[];
@@ -567,8 +616,14 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float scale_log2 = scale * 1.4426950408889634f;
     const float my_lse = q_ok ? lse[((size_t)b * nh + h) * T + q] * 1.4426950408889634f : INFINITY;
     const float my_delta = q_ok ? delta[((size_t)b * nh + h) * T + q] : 0.f;
+    static_assert(BKV == 64, "the math warps split a 64-key tile in two 32-column halves");
+    // attn-dropout keep word of (my query row, keys 32*(2j + wg) ..), fetched one tile ahead
+    const uint32_t* my_bits = (ad.thresh8 && q_ok) ? ad.bits + (((size_t)b * nh + h) * T + q) * ad.Tw + wg : nullptr;
+    uint32_t wnext = my_bits ? my_bits[0] : 0xFFFFFFFFu;
     for (int j = 0; j < n_kv; ++j) {
       const int bf = j & 1, kv0 = j * BKV;
+      const uint32_t keepw = wnext;
+      if (my_bits && j + 1 < n_kv) wnext = my_bits[2 * (j + 1)];
       mbar_wait(s_full + 8 * bf, (j >> 1) & 1);
       tc_fence_after();
       if (j >= 2) mbar_wait(ds_empty + 8 * bf, ((j >> 1) - 1) & 1);
@@ -585,7 +640,12 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int e = 0; e < 32; e += 2) {
           float p0 = (kv0 + c + e < T) ? ex2_approx(fmaf(__uint_as_float(rs[e]), scale_log2, -my_lse)) : 0.f;
           float p1 = (kv0 + c + e + 1 < T) ? ex2_approx(fmaf(__uint_as_float(rs[e + 1]), scale_log2, -my_lse)) : 0.f;
-          dk[e / 2] = pack_bf16x2(p0 * (__uint_as_float(rp[e]) - my_delta) * scale, p1 * (__uint_as_float(rp[e + 1]) - my_delta) * scale);
+          float dp0 = __uint_as_float(rp[e]), dp1 = __uint_as_float(rp[e + 1]);
+          if (ad.thresh8) {  // dP = dP_drop * mask/(1-p)
+            dp0 *= (keepw >> e) & 1u ? ad.scale : 0.f;
+            dp1 *= (keepw >> (e + 1)) & 1u ? ad.scale : 0.f;
+          }
+          dk[e / 2] = pack_bf16x2(p0 * (dp0 - my_delta) * scale, p1 * (dp1 - my_delta) * scale);
         }
         store_p32<BKV>(ds, row, c, dk);
       }
@@ -633,7 +693,7 @@ struct Fwd3 {
 template <int HS, int KST, int VST>
 __global__ void __launch_bounds__(320, 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, __nv_bfloat16* __restrict__ y,
-                 float* __restrict__ lse, int T, int C, int nh, float scale_log2) {
+                 float* __restrict__ lse, int T, int C, int nh, float scale_log2, AttnDrop ad) {
   using L = Fwd3<HS, KST, VST>;
   constexpr int BKV = L::BKV;
   extern __shared__ uint8_t smem_raw[];
@@ -763,8 +823,15 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (j >= 2) mbar_wait(p_empty + 8 * sb, ((j >> 1) - 1) & 1);  // P.V(j-2) retired: this P buffer is free
       float l_add = 0.f;
       const bool full = kv0 + BKV <= T;
+      const int qrow = q0 + 128 * w + row;
+      const uint64_t rowid = ((uint64_t)b * nh + h) * T + qrow;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
+        uint32_t keepw = 0xFFFFFFFFu;
+        if (ad.thresh8) {  // attn_drop: decide 32 keys, remember the bits for the backward kernels
+          keepw = attn_keep_word(ad, rowid, (uint32_t)(kv0 / 32 + half));
+          if (qrow < T) ad.bits[rowid * ad.Tw + kv0 / 32 + half] = keepw;
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -775,9 +842,12 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             if (kv0 + half * 32 + i >= T) p0 = 0.f;
             if (kv0 + half * 32 + i + 1 >= T) p1 = 0.f;
           }
-          __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);  // the row sum uses what the P.V MMA will see
-          l_add += __low2float(pb) + __high2float(pb);
-          pk[i / 2] = *reinterpret_cast<uint32_t*>(&pb);
+          l_add += p0 + p1;  // softmax denominator: un-dropped probabilities (dropout acts on the normalised P)
+          if (ad.thresh8) {
+            p0 *= (keepw >> i) & 1u ? ad.scale : 0.f;
+            p1 *= (keepw >> (i + 1)) & 1u ? ad.scale : 0.f;
+          }
+          pk[i / 2] = pack_bf16x2(p0, p1);
         }
         store_p32<BKV>(p_tile, row, half * 32, pk);
       }
@@ -855,7 +925,7 @@ static int launch_fwd2(const void* qkv, void* y, float* lse, int B, int T, int C
 }
 
 template <int HS, int KST, int VST>
-static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st) {
+static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const AttnDrop& ad, cudaStream_t st) {
   using L = Fwd3<HS, KST, VST>;
   using H = HeadCfg<HS>;
   static bool configured = false;
@@ -869,7 +939,7 @@ static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C
   if (int e = make_tmap3(&tmKV, qkv, 3 * C, T, B, H::BOXC, L::BKV)) return e;
   const float scale_log2 = (1.0f / sqrtf((float)HS)) * 1.4426950408889634f;
   dim3 grid(cdiv(T, 256), nh, B);
-  attn_fwd3_kernel<HS, KST, VST><<<grid, L::THREADS, L::DYN, st>>>(tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2);
+  attn_fwd3_kernel<HS, KST, VST><<<grid, L::THREADS, L::DYN, st>>>(tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
   return check_launch("attn_fwd3");
 }
 
@@ -877,7 +947,7 @@ int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, in
 
 template <int HS, int BQ, int STA, int STB>
 static int launch_bwd2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
-                       cudaStream_t st) {
+                       const AttnDrop& ad, cudaStream_t st) {
   using LA = BwdKV2<HS, BQ, STA>;
   using LB = BwdQ2<HS, STB>;
   using H = HeadCfg<HS>;
@@ -898,9 +968,9 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   if (int e = make_tmap3(&tmDO128, dy, C, T, B, H::BOXC, 128)) return e;
   if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
   dim3 grid(cdiv(T, 128), nh, B);
-  attn_bwd_kv2_kernel<HS, BQ, STA><<<grid, 320, LA::DYN, st>>>(tmKV128, tmQs, tmDOs, lse, delta, (__nv_bfloat16*)dqkv, T, C, nh, scale);
+  attn_bwd_kv2_kernel<HS, BQ, STA><<<grid, 320, LA::DYN, st>>>(tmKV128, tmQs, tmDOs, lse, delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
   if (int e = check_launch("attn_bwd2/kv")) return e;
-  attn_bwd_q2_kernel<HS, STB><<<grid, 320, LB::DYN, st>>>(tmQ128, tmDO128, tmKV64, lse, delta, (__nv_bfloat16*)dqkv, T, C, nh, scale);
+  attn_bwd_q2_kernel<HS, STB><<<grid, 320, LB::DYN, st>>>(tmQ128, tmDO128, tmKV64, lse, delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
   return check_launch("attn_bwd2/q");
 }
 
@@ -915,24 +985,41 @@ int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int n
   return DSF_EUNSUPPORTED;
 }
 
-int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st) {
+// attn_drop arguments: 8-bit threshold (p quantised to k/256), bitmap of T_words = 2*ceil(T/64) words per (b, h, q) row
+static AttnDrop make_attn_drop(const dsf_dropout* d, uint32_t* bits, int T) {
+  AttnDrop a{0u, 1.0f, 0u, 0u, 0u, bits, 2 * cdiv(T, 64)};
+  if (d && d->p > 0.f && bits) {
+    int k = (int)lrintf(d->p * 256.0f);
+    k = std::max(1, std::min(255, k));
+    a.thresh8 = (uint32_t)k;
+    a.scale = 256.0f / (256.0f - (float)k);
+    a.k0 = (uint32_t)(d->seed & 0xFFFFFFFFull) ^ d->step;
+    a.k1 = (uint32_t)(d->seed >> 32);
+    a.site = d->site;
+  }
+  return a;
+}
+
+int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, cudaStream_t st) {
+  const AttnDrop ad = make_attn_drop(drop, bits, T);
   switch (C / nh) {
-    case 16: return launch_fwd3<16, 3, 2>(qkv, y, lse, B, T, C, nh, st);
-    case 32: return launch_fwd3<32, 3, 2>(qkv, y, lse, B, T, C, nh, st);
-    case 64: return launch_fwd3<64, 3, 2>(qkv, y, lse, B, T, C, nh, st);
-    case 128: return launch_fwd3<128, 3, 2>(qkv, y, lse, B, T, C, nh, st);
+    case 16: return launch_fwd3<16, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 32: return launch_fwd3<32, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 64: return launch_fwd3<64, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 128: return launch_fwd3<128, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
   }
   set_error("attn_fwd: head size %d not supported (16, 32, 64, 128)", C / nh);
   return DSF_EUNSUPPORTED;
 }
 
 int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
-                cudaStream_t st) {
+                const dsf_dropout* drop, uint32_t* bits, cudaStream_t st) {
+  const AttnDrop ad = make_attn_drop(drop, bits, T);
   switch (C / nh) {
-    case 16: return launch_bwd2<16, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
-    case 32: return launch_bwd2<32, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
-    case 64: return launch_bwd2<64, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
-    case 128: return launch_bwd2<128, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
+    case 16: return launch_bwd2<16, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+    case 32: return launch_bwd2<32, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+    case 64: return launch_bwd2<64, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+    case 128: return launch_bwd2<128, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
   }
   set_error("attn_bwd: head size %d not supported (16, 32, 64, 128)", C / nh);
   return DSF_EUNSUPPORTED;

@@ -74,6 +74,47 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---------------------------------------------------------------- counter-based dropout (Philox4x32-10)
+// nn.Dropout sites of the path (model2_seq.py:104,109,125,272).  The mask of element e of a site is a pure function of
+// (seed, site, step, e): component e%4 of philox(key = seed, counter = (e/4, site, step)); keep iff value >= p * 2^32,
+// kept values are scaled by 1/(1-p).  Forward and backward kernels recompute it, nothing is stored (attention excepted).
+struct DropArgs {
+  uint32_t thresh;  // drop iff random < thresh  (0 = dropout disabled)
+  float scale;      // 1 / (1 - p)
+  uint32_t seed_lo, seed_hi, site, step;
+};
+__host__ __device__ inline DropArgs make_drop(const dsf_dropout* d) {
+  DropArgs a{0u, 1.0f, 0u, 0u, 0u, 0u};
+  if (d && d->p > 0.f) {
+    const double t = (double)d->p * 4294967296.0;
+    a.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    a.scale = 1.0f / (1.0f - d->p);
+    a.seed_lo = (uint32_t)(d->seed & 0xFFFFFFFFull);
+    a.seed_hi = (uint32_t)(d->seed >> 32);
+    a.site = d->site;
+    a.step = d->step;
+  }
+  return a;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// scale factors (0 or 1/(1-p)) of the 4 consecutive elements e4*4 .. e4*4+3
+__device__ __forceinline__ void drop_scale4(const DropArgs& a, uint64_t e4, float (&m)[4]) {
+  const uint4 r = philox4x32_10(a.seed_lo, a.seed_hi, (uint32_t)e4, (uint32_t)(e4 >> 32), a.site, a.step);
+  m[0] = r.x >= a.thresh ? a.scale : 0.f;
+  m[1] = r.y >= a.thresh ? a.scale : 0.f;
+  m[2] = r.z >= a.thresh ? a.scale : 0.f;
+  m[3] = r.w >= a.thresh ? a.scale : 0.f;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -26,6 +26,8 @@ struct EpiArgs2 {
   const float* bias;
   const float* residual;
   int flags;
+  int N;          // row length for the dropout element index m*N + n
+  DropArgs drop;  // resid_drop (model2_seq.py:109,125): after bias/ReLU, before the residual add
 };
 
 __device__ __forceinline__ void epi_store32(const EpiArgs2& e, int row, int n, const uint32_t (&r)[32]) {
@@ -79,6 +81,15 @@ __device__ __forceinline__ void epi_math32(const EpiArgs2& e, int row, int n, co
   if (e.flags & DSF_EPI_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (e.drop.thresh) {
+    const uint64_t e4 = ((uint64_t)row * e.N + n) >> 2;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float m[4];
+      drop_scale4(e.drop, e4 + (j >> 2), m);
+      v[j] *= m[0]; v[j + 1] *= m[1]; v[j + 2] *= m[2]; v[j + 3] *= m[3];
+    }
   }
   if ((e.flags & DSF_EPI_RESIDUAL) && row_ok) {
     const float4* rp = reinterpret_cast<const float4*>(e.residual + (size_t)row * e.ldc + n);
@@ -401,14 +412,14 @@ static int pick_bn_nt(int M, int N) {
 }
 
 int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, const float* bias, const float* residual, int M,
-               int N, int K, int flags, cudaStream_t st) {
+               int N, int K, int flags, const dsf_dropout* drop, cudaStream_t st) {
   const int BN = pick_bn_nt(M, N);
   CUtensorMap tmA, tmB;
   if (int e = make_tmap_bf16(&tmA, A, M, K, lda, G2_BM)) return e;
   if (int e = make_tmap_bf16(&tmB, B, N, K, ldb, BN)) return e;
   CUtensorMap tmC;  // store boxes: 32 rows x 128 bytes
   if (int e = make_tmap_2d(&tmC, C, c_dtype, M, N, ldc, c_dtype == DSF_F32 ? 32 : 64, 32)) return e;
-  EpiArgs2 epi{C, ldc, c_dtype, bias, residual, flags};
+  EpiArgs2 epi{C, ldc, c_dtype, bias, residual, flags, N, make_drop(drop)};
   if (BN == 256) return launch_nt2<256, 3>(tmA, tmB, tmC, epi, M, N, K, st);
   if (BN == 128) return launch_nt2<128, 4>(tmA, tmB, tmC, epi, M, N, K, st);
   return launch_nt2<64, 5>(tmA, tmB, tmC, epi, M, N, K, st);

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const TY* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* dx_add, float* dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_bf16,
-                     float* __restrict__ dx_colsum, int M, int C) {
+                     float* __restrict__ dx_colsum, DropArgs drop, int M, int C) {
   __shared__ float red[LN_WARPS][VPT * 128 + 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 2;
@@ -130,6 +130,12 @@ layernorm_bwd_kernel(const TY* __restrict__ dy, const float* __restrict__ x, con
         }
         Vec4<float>::store(dxr + vi * 4, o);
         if (EXTRA) {
+          if (drop.thresh) {  // by-products are the gradient of the preceding Linear's PRE-dropout output
+            float m[4];
+            drop_scale4(drop, (uint64_t)row * nvec + vi, m);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] *= m[k];
+          }
           if (dx_bf16) Vec4<__nv_bfloat16>::store(dx_bf16 + (size_t)row * C + vi * 4, o);
 #pragma unroll
           for (int k = 0; k < 4; ++k) dc[EXTRA ? i : 0][k] += o[k];
@@ -173,13 +179,13 @@ int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* y
 
 template <typename TY, bool EXTRA>
 int launch_ln_bwd(const void* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
-                  const float* dx_add, float* dx, float* dgamma, float* dbeta, void* dx_bf16, float* dx_colsum, int M, int C,
+                  const float* dx_add, float* dx, float* dgamma, float* dbeta, void* dx_bf16, float* dx_colsum, DropArgs drop, int M, int C,
                   cudaStream_t st) {
   // few, fat CTAs: every CTA ends with 2-3 x C atomics
   const int blocks = std::min(cdiv(M, LN_WARPS * 2), num_sms() * 4);
   const TY* d = reinterpret_cast<const TY*>(dy);
   __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
-#define DSF_LN_BWD(V) layernorm_bwd_kernel<TY, V, EXTRA><<<blocks, LN_WARPS * 32, 0, st>>>(d, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, xb, dx_colsum, M, C)
+#define DSF_LN_BWD(V) layernorm_bwd_kernel<TY, V, EXTRA><<<blocks, LN_WARPS * 32, 0, st>>>(d, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, xb, dx_colsum, drop, M, C)
   if (C <= 128) DSF_LN_BWD(1);
   else if (C <= 256) DSF_LN_BWD(2);
   else if (C <= 512) DSF_LN_BWD(4);
@@ -205,7 +211,7 @@ extern "C" int dsf_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int dsf_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* gamma, const float* mean,
                                  const float* rstd, const float* dx_add, float* dx_out, float* dgamma, float* dbeta,
-                                 void* dx_bf16, float* dx_colsum, int32_t M, int32_t C, void* stream) {
+                                 void* dx_bf16, float* dx_colsum, const dsf_dropout* byprod_drop, int32_t M, int32_t C, void* stream) {
   DSF_REQUIRE(dy && x && gamma && mean && rstd && dx_out && dgamma && dbeta, "layernorm_bwd: NULL pointer");
   DSF_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && C <= 1024, "layernorm_bwd: need M>0 and C multiple of 4 up to 1024 (got M=%d C=%d)", M, C);
   DSF_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(gamma) && aligned16(dx_add) && aligned16(dx_out) && aligned16(dx_bf16),
@@ -213,10 +219,12 @@ extern "C" int dsf_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* 
   DSF_REQUIRE(dy_dtype == DSF_F32 || dy_dtype == DSF_BF16, "layernorm_bwd: bad dy_dtype %d", dy_dtype);
   cudaStream_t st = (cudaStream_t)stream;
   const bool extra = dx_bf16 != nullptr || dx_colsum != nullptr;
+  DSF_REQUIRE(!byprod_drop || (byprod_drop->p >= 0.f && byprod_drop->p < 1.f), "layernorm_bwd: dropout p must be in [0, 1)");
+  const DropArgs dr = make_drop(byprod_drop);
   if (dy_dtype == DSF_F32) {
-    if (extra) return launch_ln_bwd<float, true>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, dx_bf16, dx_colsum, M, C, st);
-    return launch_ln_bwd<float, false>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, nullptr, nullptr, M, C, st);
+    if (extra) return launch_ln_bwd<float, true>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, dx_bf16, dx_colsum, dr, M, C, st);
+    return launch_ln_bwd<float, false>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, nullptr, nullptr, dr, M, C, st);
   }
-  if (extra) return launch_ln_bwd<__nv_bfloat16, true>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, dx_bf16, dx_colsum, M, C, st);
-  return launch_ln_bwd<__nv_bfloat16, false>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, nullptr, nullptr, M, C, st);
+  if (extra) return launch_ln_bwd<__nv_bfloat16, true>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, dx_bf16, dx_colsum, dr, M, C, st);
+  return launch_ln_bwd<__nv_bfloat16, false>(dy, x, gamma, mean, rstd, dx_add, dx_out, dgamma, dbeta, nullptr, nullptr, dr, M, C, st);
 }

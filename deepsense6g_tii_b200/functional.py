@@ -16,7 +16,12 @@ kernels (no ATen math on the path).  Two compute modes:
   * ``torch.float32`` (parity mode, <= 1e-3 of the reference): FFMA GEMMs and materialised
     softmax attention, everything fp32.
 
-Dropout (model2_seq.py:104,109,125,272) is NOT implemented yet; non-zero probabilities raise.
+Dropout (model2_seq.py:104,109,125,272; bf16 mode only): ``cfg["dropout"] = dict(embd=p, attn=p, resid=p,
+seed=int, step=int[, capture=dict])``.  Masks are counter-based (Philox4x32-10 of (seed, site, step, element)),
+recomputed by the backward kernels; sites are numbered ``drop_site(...)``.  torch's own RNG stream cannot be
+reproduced bit for bit, so parity with dropout is tested by feeding the oracle the masks the kernels drew
+(``capture`` receives the attention keep-bitmaps; the elementwise masks are regenerated with
+``dsf_dropout_inplace`` on a tensor of ones).
 """
 import math
 
@@ -48,6 +53,11 @@ class _Ctx:
     pass
 
 
+def drop_site(kind, block=0):
+    """Site id of an nn.Dropout layer inside one GPT: 'embd' (:272), per block 'attn' (:104), 'proj' (:109), 'mlp' (:125)."""
+    return 0 if kind == "embd" else 1 + 3 * block + ("attn", "proj", "mlp").index(kind)
+
+
 class _Runner:
     """Holds shapes + mode and implements forward / backward over raw tensors."""
 
@@ -61,6 +71,7 @@ class _Runner:
         self.bf16 = compute_dtype == torch.bfloat16
         self.act = torch.bfloat16 if self.bf16 else torch.float32
         self.grad_hook = None  # optional dist.OverlappedGradReducer (bf16 path)
+        self.dropout = None    # cfg["dropout"] dict (bf16 path)
         if self.bf16:
             if C % 64 != 0 or self.hs not in (16, 32, 64, 128):
                 raise RuntimeError("bf16 tensor-core mode needs n_embd %% 64 == 0 and head size in {16,32,64,128}; "
@@ -222,6 +233,8 @@ class _Runner:
         saved.layers = []
         x = torch.empty(M, C, device=dev, dtype=f32)
         K.tokens_fwd(self.geom, feats[0], feats[1], feats[2], gps_emb, params[0], x)
+        if self._drop("embd") is not None:
+            K.dropout_inplace(x, self._drop("embd"))
         for i in range(L):
             (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[1 + 16 * i: 17 + 16 * i]
             st = _Ctx()
@@ -248,15 +261,20 @@ class _Runner:
             K.gemm_bf16_nt(st.h1, st.wqkv, st.qkv, bias=bqkv)
             st.y = torch.empty(M, C, device=dev, dtype=bf)
             st.lse = torch.empty(self.B, self.nh, self.T, device=dev, dtype=f32)
-            K.attn_fwd(st.qkv, st.y, st.lse, self.B, self.T, C, self.nh)
+            st.drop_bits = None
+            if self._drop("attn", i) is not None:
+                st.drop_bits = torch.empty(K.attn_drop_words(self.B, self.T, self.nh), device=dev, dtype=torch.int32)
+                if "capture" in self.dropout:
+                    self.dropout["capture"]["attn_bits.%d" % i] = st.drop_bits
+            K.attn_fwd(st.qkv, st.y, st.lse, self.B, self.T, C, self.nh, self._drop("attn", i), st.drop_bits)
             st.x_mid = torch.empty(M, C, device=dev, dtype=f32)
-            K.gemm_bf16_nt(st.y, st.wp, st.x_mid, bias=pb, residual=x)
+            K.gemm_bf16_nt(st.y, st.wp, st.x_mid, bias=pb, residual=x, drop=self._drop("proj", i))
             st.h2 = torch.empty(M, C, device=dev, dtype=bf)
             K.layernorm_fwd(st.x_mid, ln2w, ln2b, st.h2, st.mean2, st.rstd2)
             st.a = torch.empty(M, F, device=dev, dtype=bf)
             K.gemm_bf16_nt(st.h2, st.w1, st.a, bias=b1, relu=True)
             x = torch.empty(M, C, device=dev, dtype=f32)
-            K.gemm_bf16_nt(st.a, st.w2, x, bias=b2, residual=st.x_mid)
+            K.gemm_bf16_nt(st.a, st.w2, x, bias=b2, residual=st.x_mid, drop=self._drop("mlp", i))
             saved.layers.append(st)
         saved.x_last = x
         saved.mean_f = torch.empty(M, device=dev, dtype=f32)
@@ -267,6 +285,16 @@ class _Runner:
         K.upsample_add_fwd(self.geom, yf, feats if residual else [torch.zeros_like(f) for f in feats], outs)
         gps_out = yf.view(self.B, self.T, C)[:, self.Tm:, :].contiguous()
         return outs, gps_out, saved
+
+    def _drop(self, kind, block=0):
+        """``_capi.Dropout`` of one site, or None when that probability is 0 / dropout is off."""
+        d = self.dropout
+        if d is None:
+            return None
+        p = float(d.get("resid" if kind in ("proj", "mlp") else kind, 0.0))
+        if p <= 0.0:
+            return None
+        return K.Dropout(p, int(d["seed"]), drop_site(kind, block), int(d.get("step", 0)))
 
     def _backward_bf16(self, saved, params, douts, dgps_out, residual):
         """Per block: 4 wgrad + 4 dgrad GEMMs, fused ReLU-mask+bias-grad, 2 LayerNorm backward kernels that also
@@ -297,7 +325,8 @@ class _Runner:
         # ln_f backward; by-products: bf16 copy of dx and db2 of the last block
         last = block_views(L - 1) if L > 0 else None
         K.layernorm_bwd(dyf, saved.x_last, params[-2], saved.mean_f, saved.rstd_f, None, dx, dgf, dbf,
-                        dx_bf16=dxa if L > 0 else None, dx_colsum=last[7] if L > 0 else None)
+                        dx_bf16=dxa if L > 0 else None, dx_colsum=last[7] if L > 0 else None,
+                        byprod_drop=self._drop("mlp", L - 1) if L > 0 else None)
         grads[-2], grads[-1] = dgf, dbf
         for i in reversed(range(L)):
             base = 1 + 16 * i
@@ -315,14 +344,15 @@ class _Runner:
             K.gemm_bf16_nt(da, st.w1_t, dh2)
             dx_mid = torch.empty(M, C, device=dev, dtype=f32)
             dxm = torch.empty(M, C, device=dev, dtype=bf)
-            K.layernorm_bwd(dh2, st.x_mid, ln2w, st.mean2, st.rstd2, dx, dx_mid, dg2, dbt2, dx_bf16=dxm, dx_colsum=dbp)
+            K.layernorm_bwd(dh2, st.x_mid, ln2w, st.mean2, st.rstd2, dx, dx_mid, dg2, dbt2, dx_bf16=dxm, dx_colsum=dbp,
+                            byprod_drop=self._drop("proj", i))
             # ---- attention:  x_mid = x_in + proj(attn(qkv(ln1(x_in))))   (model2_seq.py:94-110,131)
             K.gemm_bf16_tn(dxm, st.y, dwp)
             dy = torch.empty(M, C, device=dev, dtype=bf)
             K.gemm_bf16_nt(dxm, st.wp_t, dy)
             dqkv = torch.empty(M, 3 * C, device=dev, dtype=bf)
             delta = torch.empty(self.B, self.nh, self.T, device=dev, dtype=f32)
-            K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh)
+            K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, self._drop("attn", i), st.drop_bits)
             K.colsum(dqkv, dbqkv)
             K.gemm_bf16_tn(dqkv, st.h1, dwqkv)
             dh1 = torch.empty(M, C, device=dev, dtype=f32)
@@ -330,7 +360,8 @@ class _Runner:
             dx = torch.empty(M, C, device=dev, dtype=f32)
             prev = block_views(i - 1) if i > 0 else None
             K.layernorm_bwd(dh1, st.x_in, ln1w, st.mean1, st.rstd1, dx_mid, dx, dg1, dbt1,
-                            dx_bf16=dxa if i > 0 else None, dx_colsum=prev[7] if i > 0 else None)
+                            dx_bf16=dxa if i > 0 else None, dx_colsum=prev[7] if i > 0 else None,
+                            byprod_drop=self._drop("mlp", i - 1) if i > 0 else None)
             grads[base: base + 16] = [dg1, dbt1, dg2, dbt2,
                                       dwqkv[C:2 * C], dbqkv[C:2 * C], dwqkv[:C], dbqkv[:C], dwqkv[2 * C:], dbqkv[2 * C:],
                                       dwp, dbp, dw1, db1, dw2, db2]
@@ -340,6 +371,8 @@ class _Runner:
         dfeats = [torch.empty_like(d) for d in douts]
         dgps = torch.empty(self.B, 2, C, device=dev, dtype=f32)
         dpos = torch.empty(1, self.T, C, device=dev, dtype=f32)
+        if self._drop("embd") is not None:
+            K.dropout_inplace(dx, self._drop("embd"))
         K.tokens_bwd(self.geom, dx, douts if residual else None, dfeats, dgps, dpos)
         grads[0] = dpos
         if self.grad_hook is not None:
@@ -408,6 +441,43 @@ class _Runner:
         return dfeats, dgps, grads
 
 
+def attn_drop_scale(p):
+    """Keep scale of attention dropout: p is quantised to k/256 in the kernels (include/dsfuse.h)."""
+    k = max(1, min(255, int(round(float(p) * 256.0))))
+    return 256.0 / (256.0 - k)
+
+
+def materialise_dropout_masks(dropout, B, T, C, n_head, n_layer, device):
+    """The multiplicative masks (0 or 1/(1-p)) a ``fusion_stage`` call with ``cfg["dropout"] = dropout`` drew, as
+    dense tensors keyed like ``oracle.fusion_ref`` expects: ``embd``, ``proj.{i}``, ``mlp.{i}`` (B,T,C) and
+    ``attn.{i}`` (B,nh,T,T).  Elementwise masks are regenerated by running ``dsf_dropout_inplace`` on ones; the
+    attention masks are unpacked from the keep-bitmaps in ``dropout["capture"]``.  Diagnostic / test helper."""
+    out = {}
+
+    def elem(kind, blk=0):
+        p = float(dropout.get("resid" if kind in ("proj", "mlp") else kind, 0.0))
+        if p <= 0.0:
+            return None
+        m = torch.ones(B, T, C, device=device, dtype=torch.float32)
+        K.dropout_inplace(m, K.Dropout(p, int(dropout["seed"]), drop_site(kind, blk), int(dropout.get("step", 0))))
+        return m
+
+    m = elem("embd")
+    if m is not None:
+        out["embd"] = m
+    for i in range(n_layer):
+        for kind in ("proj", "mlp"):
+            m = elem(kind, i)
+            if m is not None:
+                out["%s.%d" % (kind, i)] = m
+        if float(dropout.get("attn", 0.0)) > 0.0:
+            bits = dropout["capture"]["attn_bits.%d" % i].view(B, n_head, T, -1, 1)
+            sh = torch.arange(32, device=device, dtype=torch.int32)
+            keep = ((bits >> sh) & 1).reshape(B, n_head, T, -1)[..., :T]
+            out["attn.%d" % i] = keep.to(torch.float32) * attn_drop_scale(dropout["attn"])
+    return out
+
+
 def _layout_of(t):
     """NCHW-contiguous -> DSF_NCHW; channels_last storage -> DSF_NHWC."""
     if t.is_contiguous():
@@ -446,6 +516,13 @@ class FusionStageFn(torch.autograd.Function):
         plist = [p.detach().contiguous().float() for p in params]
         residual = bool(cfg.get("residual", True))
         r.grad_hook = cfg.get("grad_hook")
+        r.dropout = cfg.get("dropout")
+        if r.dropout is not None and any(float(r.dropout.get(k, 0.0)) > 0.0 for k in ("embd", "attn", "resid")):
+            if not r.bf16:
+                raise NotImplementedError("dropout is implemented in the bf16 tensor-core mode only (the fp32 mode is the "
+                                          "p = 0 parity path)")
+        else:
+            r.dropout = None
         outs, gps_out, saved = r.forward([img.detach(), lidar.detach(), radar.detach()], gps_emb.detach(), plist, residual)
         ctx.runner, ctx.saved_state, ctx.plist, ctx.residual = r, saved, plist, residual
         ctx.feat_mf = torch.channels_last if layout == K.DSF_NHWC else torch.contiguous_format

@@ -79,6 +79,8 @@ class GPT(nn.Module):
         self.ln_f = nn.LayerNorm(n_embd)
         self.block_size = seq_len
         self._pdrop = (float(embd_pdrop), float(attn_pdrop), float(resid_pdrop))
+        self._drop_step = 0
+        self._drop_capture = None  # tests: a dict that receives seed/step and the attention keep-bitmaps of the last call
         self.apply(self._init_weights)
         self._names = param_names(n_layer)
 
@@ -100,11 +102,19 @@ class GPT(nn.Module):
         return [table[n] for n in self._names]
 
     def _stage_cfg(self, residual):
+        dropout = None
         if self.training and any(p > 0.0 for p in self._pdrop):
-            raise NotImplementedError(
-                "dropout > 0 in training mode is not implemented in the B200 fusion path yet; build the config with "
-                "embd_pdrop=attn_pdrop=resid_pdrop=0 (GlobalConfig(**kwargs), config_seq.py:43-45) or call .eval()")
-        return dict(seq_len=self.seq_len, n_views=self.config.n_views, vert_anchors=self.vert_anchors,
+            # nn.Dropout semantics (model2_seq.py:104,109,125,272): active in train() only.  A fresh seed per call is
+            # drawn from torch's CPU generator (so torch.manual_seed governs it); the masks themselves are Philox
+            # functions of (seed, site, element) computed inside the kernels.
+            self._drop_step += 1
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+            dropout = dict(embd=self._pdrop[0], attn=self._pdrop[1], resid=self._pdrop[2], seed=seed, step=self._drop_step)
+            if self._drop_capture is not None:
+                self._drop_capture.clear()
+                self._drop_capture.update(seed=seed, step=self._drop_step)
+                dropout["capture"] = self._drop_capture
+        return dict(dropout=dropout, seq_len=self.seq_len, n_views=self.config.n_views, vert_anchors=self.vert_anchors,
                     horz_anchors=self.horz_anchors, n_head=self.n_head, n_layer=self.n_layer,
                     compute_dtype=getattr(self.config, "fusion_dtype", torch.bfloat16), residual=residual,
                     grad_hook=getattr(self, "_grad_reducer", None))

@@ -55,6 +55,19 @@ int64_t dsf_launch_count(void);
 /* 0 if the current device is sm_100 and the kernels can run on it, DSF_EARCH otherwise. */
 int dsf_check_device(void);
 
+/* One nn.Dropout site (model2_seq.py:104 attn_drop, :109/:125 resid_drop, :272 embd drop).  The keep/drop decision
+ * of element e is a pure function of (seed, site, step, e) (Philox4x32-10), so forward and backward kernels agree
+ * without storing masks; kept elements are scaled by 1/(1-p).  NULL or p == 0 disables dropout.               */
+typedef struct {
+  float p;        /* drop probability in [0, 1) */
+  uint64_t seed;  /* per-run seed */
+  uint32_t site;  /* which dropout layer (unique per site within a step) */
+  uint32_t step;  /* training-step / call counter */
+} dsf_dropout;
+
+/* x[e] *= mask(e)/(1-p), e in [0, n): embedding dropout on the token tensor (:272) and its backward. */
+int dsf_dropout_inplace(float* x, int64_t n, const dsf_dropout* d, void* stream);
+
 /* Geometry shared by the token kernels. */
 typedef struct {
   int32_t B;        /* samples */
@@ -91,10 +104,12 @@ int dsf_layernorm_fwd(const float* x, const float* gamma, const float* beta, voi
  *   ACCUMULATED into (caller zeroes or passes .grad).  Optional same-pass by-products of dx_out
  *   (the residual-stream gradient): dx_bf16 (M,C) bf16 copy (next GEMM operand) and dx_colsum (C)
  *   fp32 += column sums (= bias gradient of the preceding proj / mlp.2 Linear); either may be NULL. */
+/*   `byprod_drop` (nullable): the dropout site of that preceding Linear; its mask (element m*C + c) is applied
+ *   to the two by-products only (they are the gradient of the Linear's pre-dropout output), never to dx_out. */
 int dsf_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* gamma,
                       const float* mean, const float* rstd, const float* dx_add, float* dx_out,
-                      float* dgamma, float* dbeta, void* dx_bf16, float* dx_colsum, int32_t M, int32_t C,
-                      void* stream);
+                      float* dgamma, float* dbeta, void* dx_bf16, float* dx_colsum,
+                      const dsf_dropout* byprod_drop, int32_t M, int32_t C, void* stream);
 
 /* K3/K5/K6 (bf16 tensor-core path, tcgen05 + TMEM + TMA).  Replaces nn.Linear (model2_seq.py:83-90,
  * 97-99,109,122,124) and its autograd.
@@ -103,9 +118,11 @@ int dsf_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const fl
  *   TN:  C[N',K'] (+)= A[M,N']^T . B[M,K']   (weight gradient; contraction over the M rows)
  *        A, B bf16 row-major; C fp32.  With DSF_EPI_ACCUM the result is atomically added to C
  *        (split over M across CTAs); without it C must be zero-filled by the caller.              */
+/*        `drop` (nullable): dropout applied after bias/ReLU and BEFORE the residual add, element index m*N + n
+ *        (resid_drop of the proj / mlp.2 outputs, model2_seq.py:109,125).                              */
 int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32_t ldb, void* C, int32_t ldc,
                      int32_t c_dtype, const float* bias, const float* residual, int32_t M, int32_t N,
-                     int32_t K, int32_t epi_flags, void* stream);
+                     int32_t K, int32_t epi_flags, const dsf_dropout* drop, void* stream);
 int dsf_gemm_bf16_tn(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc,
                      int32_t M, int32_t Nout, int32_t Kout, void* stream);
 /* Selects the tensor-core GEMM implementation (process-wide; tests and A/B timing): 0 = default,
@@ -152,11 +169,17 @@ int dsf_softmax_bwd(float* dp, const float* p, int64_t rows, int32_t T, void* st
  *   qkv (B, T, 3C) bf16 = [q | k | v] per token, head h at columns h*hs within each third
  *   -> y (B, T, C) bf16 (heads re-assembled side by side), lse (B, nh, T) fp32 (natural log units
  *   of the scaled scores).  hs = C/nh in {16, 32, 64, 128}.                                        */
+/*   attn_drop (model2_seq.py:104; `drop` nullable): dropout on the normalised probabilities.  p is
+ *   quantised to k/256 (one Philox call decides 16 keys); the forward writes the keep bits of every
+ *   (b, h, query) row into drop_bits (dsf_attn_drop_words(B,T,nh) uint32 words, bit j%32 of word
+ *   j/32 = key j kept) and the backward reads them back.                                           */
+int64_t dsf_attn_drop_words(int32_t B, int32_t T, int32_t nh);
 int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int32_t T, int32_t C, int32_t nh,
-                 void* stream);
+                 const dsf_dropout* drop, uint32_t* drop_bits, void* stream);
 /*   dy (B,T,C) bf16 -> dqkv (B,T,3C) bf16.  delta (B,nh,T) fp32 is scratch (rowsum(dy*y)).         */
 int dsf_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* delta,
-                 void* dqkv, int32_t B, int32_t T, int32_t C, int32_t nh, void* stream);
+                 void* dqkv, int32_t B, int32_t T, int32_t C, int32_t nh, const dsf_dropout* drop,
+                 const uint32_t* drop_bits, void* stream);
 /* Selects the attention implementation (process-wide; for tests and A/B timing): 0 = default,
  * 1 = v1 (simple synchronous kernels), 2 = v2 (warp-specialised, TMA-fed, pipelined),
  * 3 = v3 (v2 + per-warpgroup double-buffered S/P in the forward).                                  */

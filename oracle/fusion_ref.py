@@ -73,9 +73,13 @@ def linear(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
     return x @ w.t() + b
 
 
-def self_attention(x: Tensor, p: Dict[str, Tensor], prefix: str, n_head: int) -> Tensor:
-    """``SelfAttention.forward`` (model2_seq.py:94-110), dropout off.  No mask: every token attends
-    to all T tokens (the "masked" in the reference docstring is vestigial)."""
+def self_attention(x: Tensor, p: Dict[str, Tensor], prefix: str, n_head: int, attn_mask: Tensor = None,
+                   resid_mask: Tensor = None) -> Tensor:
+    """``SelfAttention.forward`` (model2_seq.py:94-110).  No causal mask: every token attends to all T
+    tokens (the "masked" in the reference docstring is vestigial).  The two ``nn.Dropout`` sites
+    (attn_drop :104 on the probabilities, resid_drop :109 on the projection) are restated as a
+    multiplication by a caller-supplied tensor holding 0 or 1/(1-p) (``None`` = dropout off), which is
+    what ``nn.Dropout`` computes for a given Bernoulli draw."""
     b, t, c = x.shape
     hs = c // n_head
 
@@ -86,17 +90,26 @@ def self_attention(x: Tensor, p: Dict[str, Tensor], prefix: str, n_head: int) ->
     k, q, v = heads("key"), heads("query"), heads("value")
     att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(hs))
     att = torch.softmax(att, dim=-1)
+    if attn_mask is not None:
+        att = att * attn_mask
     y = (att @ v).transpose(1, 2).reshape(b, t, c)
-    return linear(y, p[prefix + "proj.weight"], p[prefix + "proj.bias"])
+    y = linear(y, p[prefix + "proj.weight"], p[prefix + "proj.bias"])
+    return y if resid_mask is None else y * resid_mask
 
 
-def block(x: Tensor, p: Dict[str, Tensor], i: int, n_head: int) -> Tensor:
-    """``Block.forward`` (model2_seq.py:128-134): pre-LN attention and ReLU MLP, both residual."""
+def block(x: Tensor, p: Dict[str, Tensor], i: int, n_head: int, masks: Dict[str, Tensor] = None) -> Tensor:
+    """``Block.forward`` (model2_seq.py:128-134): pre-LN attention and ReLU MLP, both residual.
+    ``masks``: optional dropout masks ``attn.{i}`` (B,nh,T,T), ``proj.{i}``, ``mlp.{i}`` (B,T,C)."""
     pre = "blocks.%d." % i
-    x = x + self_attention(layer_norm(x, p[pre + "ln1.weight"], p[pre + "ln1.bias"]), p, pre + "attn.", n_head)
+    m = masks or {}
+    x = x + self_attention(layer_norm(x, p[pre + "ln1.weight"], p[pre + "ln1.bias"]), p, pre + "attn.", n_head,
+                           m.get("attn.%d" % i), m.get("proj.%d" % i))
     h = layer_norm(x, p[pre + "ln2.weight"], p[pre + "ln2.bias"])
     h = torch.relu(linear(h, p[pre + "mlp.0.weight"], p[pre + "mlp.0.bias"]))
-    return x + linear(h, p[pre + "mlp.2.weight"], p[pre + "mlp.2.bias"])
+    h = linear(h, p[pre + "mlp.2.weight"], p[pre + "mlp.2.bias"])
+    if ("mlp.%d" % i) in m:  # nn.Dropout(resid_pdrop), model2_seq.py:125
+        h = h * m["mlp.%d" % i]
+    return x + h
 
 
 def n_layers_of(p: Dict[str, Tensor]) -> int:
@@ -107,8 +120,10 @@ def n_layers_of(p: Dict[str, Tensor]) -> int:
 
 
 def gpt_forward(p: Dict[str, Tensor], img: Tensor, lidar: Tensor, radar: Tensor, gps: Tensor,
-                n_head: int, seq_len: int, n_views: int = 1) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """``GPT.forward`` (model2_seq.py:248-287) with all dropout probabilities 0.
+                n_head: int, seq_len: int, n_views: int = 1, masks: Dict[str, Tensor] = None
+                ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """``GPT.forward`` (model2_seq.py:248-287).  Dropout is off unless ``masks`` supplies the Bernoulli
+    draws as 0 / 1/(1-p) tensors: ``embd`` (B,T,C) for :272 and the per-block entries of ``block``.
 
     Returns (image_out, lidar_out, radar_out, pos_out) in the reference's shapes:
     3 x (B*slots*S, C, A, A) and (B, 2, C).
@@ -116,8 +131,10 @@ def gpt_forward(p: Dict[str, Tensor], img: Tensor, lidar: Tensor, radar: Tensor,
     bz = lidar.shape[0] // seq_len
     c, va, ha = lidar.shape[1:4]
     x = build_tokens(img, lidar, radar, gps, p["pos_emb"], seq_len, n_views)
+    if masks is not None and "embd" in masks:
+        x = x * masks["embd"]
     for i in range(n_layers_of(p)):
-        x = block(x, p, i, n_head)
+        x = block(x, p, i, n_head, masks)
     x = layer_norm(x, p["ln_f.weight"], p["ln_f.bias"])
     n_map = (n_views + 2) * seq_len * va * ha
     pos_out = x[:, n_map:, :]
@@ -154,7 +171,7 @@ def bilinear_upsample(x: Tensor, scale: int) -> Tensor:
 
 
 def fusion_stage(p: Dict[str, Tensor], feats: Sequence[Tensor], gps_emb: Tensor, n_head: int,
-                 seq_len: int, va: int, ha: int, n_views: int = 1):
+                 seq_len: int, va: int, ha: int, n_views: int = 1, masks: Dict[str, Tensor] = None):
     """One fusion stage of ``Encoder.forward`` (model2_seq.py:515-526; same at :533-544, :552-563,
     :571-579): anchor pool x3 -> GPT -> bilinear upsample x3 -> residual add x3.
 
@@ -163,7 +180,7 @@ def fusion_stage(p: Dict[str, Tensor], feats: Sequence[Tensor], gps_emb: Tensor,
     """
     scale = feats[0].shape[2] // va
     pooled = [anchor_pool(f, va, ha) for f in feats]
-    io, lo, ro, gps_out = gpt_forward(p, pooled[0], pooled[1], pooled[2], gps_emb, n_head, seq_len, n_views)
+    io, lo, ro, gps_out = gpt_forward(p, pooled[0], pooled[1], pooled[2], gps_emb, n_head, seq_len, n_views, masks)
     outs = tuple(f + bilinear_upsample(o, scale) for f, o in zip(feats, (io, lo, ro)))
     return outs, gps_out
 

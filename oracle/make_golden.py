@@ -74,6 +74,57 @@ def gpt_case(name, C, n_head, L, A, S, B, seed, scale=None):
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def dropout_case(name, C, n_head, L, A, S, B, seed, p_drop=0.1):
+    """GPT-level fixture with the reference in train() mode and all four nn.Dropout sites at ``p_drop``
+    (config_seq.py:39-41; model2_seq.py:104,109,125,272).  The Bernoulli draws of every nn.Dropout module are
+    recovered with forward hooks (mask = (out != 0) / (1 - p); where the input is exactly 0 the mask is
+    irrelevant) and stored next to the outputs / gradients, so the restatement can be checked on the same draws."""
+    M, _ = ref_import.load_reference()
+    cfg = ref_import.make_config(seq_len=S, vert_anchors=A, horz_anchors=A, n_head=n_head, n_layer=L, n_views=1)
+    gen = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    gpt = M.GPT(C, n_head, cfg.block_exp, L, A, A, S, p_drop, p_drop, p_drop, cfg)
+    _perturb(gpt, gen)
+    gpt.train()
+    masks = {}
+
+    def hook(key):
+        def fn(mod, inp, out):
+            masks[key] = (out != 0).to(torch.float32) / (1.0 - mod.p)
+        return fn
+
+    gpt.drop.register_forward_hook(hook("embd"))
+    for i, blk in enumerate(gpt.blocks):
+        blk.attn.attn_drop.register_forward_hook(hook("attn.%d" % i))
+        blk.attn.resid_drop.register_forward_hook(hook("proj.%d" % i))
+        blk.mlp[3].register_forward_hook(hook("mlp.%d" % i))
+    feats = [torch.randn(B * S, C, A, A, generator=gen).requires_grad_(True) for _ in range(3)]
+    gps = torch.randn(B, 2, C, generator=gen).requires_grad_(True)
+    outs = gpt(feats[0], feats[1], feats[2], gps)
+    probes = [torch.randn(o.shape, generator=gen) for o in outs]
+    loss = sum((o * pr).sum() for o, pr in zip(outs, probes))
+    loss.backward()
+    d = {"meta": np.array([C, n_head, L, A, S, B, 0], dtype=np.int64)}
+    for k, v in gpt.state_dict().items():
+        d["param/" + k] = v.detach().numpy()
+    for k, prm in gpt.named_parameters():
+        d["gparam/" + k] = prm.grad.numpy()
+    for nm, t in zip(("img", "lidar", "radar"), feats):
+        d["in/" + nm] = t.detach().numpy()
+        d["gin/" + nm] = t.grad.numpy()
+    d["in/gps"] = gps.detach().numpy()
+    d["gin/gps"] = gps.grad.numpy()
+    for nm, o, pr in zip(("img", "lidar", "radar", "gps"), outs, probes):
+        d["out/" + nm] = o.detach().numpy()
+        d["probe/" + nm] = pr.numpy()
+    for k, m in masks.items():
+        d["mask/" + k] = m.numpy()
+    d["loss"] = np.array(loss.item(), dtype=np.float64)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), "masks:", sorted(masks))
+
+
 def op_case():
     """Operator-level fixtures: AdaptiveAvgPool2d((A,A)) and bilinear interpolate at scales 2/4/8."""
     gen = torch.Generator().manual_seed(7)
@@ -97,6 +148,9 @@ def op_case():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--dropout-only" in sys.argv:  # added later; leaves the earlier fixtures byte-identical
+        dropout_case("gpt_tiny_dropout", C=32, n_head=4, L=2, A=2, S=2, B=2, seed=21)
+        return
     op_case()
     gpt_case("gpt_tiny", C=32, n_head=4, L=2, A=2, S=2, B=2, seed=11)
     gpt_case("gpt_c64_t962", C=64, n_head=4, L=2, A=8, S=5, B=1, seed=12)
@@ -104,6 +158,7 @@ def main():
     gpt_case("stage_tiny_s8", C=16, n_head=4, L=1, A=2, S=2, B=1, seed=14, scale=8)
     gpt_case("stage_tiny_s2", C=32, n_head=2, L=1, A=4, S=1, B=2, seed=15, scale=2)
     gpt_case("stage_tiny_s1", C=32, n_head=4, L=1, A=2, S=2, B=2, seed=16, scale=1)
+    dropout_case("gpt_tiny_dropout", C=32, n_head=4, L=2, A=2, S=2, B=2, seed=21)
 
 
 if __name__ == "__main__":

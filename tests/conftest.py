@@ -19,7 +19,7 @@ def pytest_configure(config):
 def load_golden(name):
     """Returns dict with meta + torch tensors grouped by prefix."""
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
-    out = {"param": {}, "gparam": {}, "in": {}, "gin": {}, "out": {}, "probe": {}}
+    out = {"param": {}, "gparam": {}, "in": {}, "gin": {}, "out": {}, "probe": {}, "mask": {}}
     for k in z.files:
         if "/" in k:
             grp, nm = k.split("/", 1)

@@ -342,3 +342,121 @@ def test_error_paths(K, cuda_dev):
     geom = K.make_geom(1, 1, 1, 4, 4, 8, 10, 10, K.DSF_F32)
     with pytest.raises(RuntimeError, match="not a multiple of the anchor grid"):
         K.tokens_fwd(geom, x, x, x, x, x, x)
+
+
+# ------------------------------------------------------------------------------------------ dropout (model2_seq.py:104,109,125,272)
+def _mask_of(K, cuda_dev, shape, drop):
+    m = torch.ones(shape, device=cuda_dev)
+    K.dropout_inplace(m, drop)
+    return m
+
+
+def test_dropout_elementwise_mask_properties(K, cuda_dev):
+    """Counter-based masks: values are exactly 0 or 1/(1-p); the keep rate is 1-p within 5 sigma; the mask is a pure
+    function of (seed, site, step) and changes with each of them."""
+    n = 962 * 512 * 4
+    for p in (0.1, 0.5):
+        d = K.Dropout(p, 1234, 3, 7)
+        m = _mask_of(K, cuda_dev, (n,), d)
+        kept = m != 0
+        assert torch.all(m[kept] == torch.tensor(1.0 / (1.0 - p), dtype=torch.float32).to(cuda_dev))
+        rate = float(kept.float().mean())
+        assert abs(rate - (1 - p)) < 5 * math.sqrt(p * (1 - p) / n), rate
+        assert torch.equal(m, _mask_of(K, cuda_dev, (n,), K.Dropout(p, 1234, 3, 7)))
+        for other in (K.Dropout(p, 1235, 3, 7), K.Dropout(p, 1234, 4, 7), K.Dropout(p, 1234, 3, 8)):
+            agree = float((_mask_of(K, cuda_dev, (n,), other) == m).float().mean())
+            assert abs(agree - (p * p + (1 - p) * (1 - p))) < 0.01, agree  # independent draws
+    x = torch.randn(1024, device=cuda_dev)
+    y = x.clone()
+    K.dropout_inplace(y, K.Dropout(0.0, 1, 1, 1))
+    assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("M,N,Kd", [(300, 128, 64), (962, 512, 2048), (11544, 512, 512), (130, 64, 256)])
+def test_gemm_bf16_nt_dropout_epilogue(K, cuda_dev, M, N, Kd):
+    """resid_drop fused in the GEMM epilogue (:109,125): (A W^T + b) * mask + residual, mask element index m*N + n."""
+    g = _gen(16)
+    a = torch.randn(M, Kd, generator=g).to(cuda_dev).to(torch.bfloat16)
+    w = (0.05 * torch.randn(N, Kd, generator=g)).to(cuda_dev).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    res = torch.randn(M, N, generator=g).to(cuda_dev)
+    d = K.Dropout(0.1, 99, 5, 2)
+    mask = _mask_of(K, cuda_dev, (M, N), d)
+    out = torch.empty(M, N, device=cuda_dev)
+    K.gemm_bf16_nt(a, w, out, bias=bias, residual=res, drop=d)
+    assert_close(out, (a.float() @ w.float().t() + bias) * mask + res, 1e-5, 1e-5, "bias+dropout+residual")
+    outb = torch.empty(M, N, device=cuda_dev, dtype=torch.bfloat16)
+    K.gemm_bf16_nt(a, w, outb, bias=bias, drop=d)
+    assert_close(outb.float(), (a.float() @ w.float().t() + bias) * mask, 6e-3, 1e-4, "bias+dropout bf16")
+
+
+@pytest.mark.parametrize("M,C", [(962, 64), (300, 256), (1924, 512)])
+def test_layernorm_bwd_dropout_byproducts(K, cuda_dev, M, C):
+    """The by-products of LayerNorm backward (bf16 copy of dx and its column sums) carry the mask of the preceding
+    Linear's dropout; dx itself does not."""
+    g = _gen(17)
+    x = torch.randn(M, C, generator=g).to(cuda_dev)
+    gamma = torch.randn(C, generator=g).to(cuda_dev)
+    dy = torch.randn(M, C, generator=g).to(cuda_dev)
+    add = torch.randn(M, C, generator=g).to(cuda_dev)
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(M, device=cuda_dev), torch.empty(M, device=cuda_dev)
+    K.layernorm_fwd(x, gamma, torch.zeros_like(gamma), y, mean, rstd)
+    outs = []
+    for d in (None, K.Dropout(0.1, 5, 11, 3)):
+        dx = torch.empty_like(x)
+        dgm, dbt = torch.zeros(C, device=cuda_dev), torch.zeros(C, device=cuda_dev)
+        dxb = torch.empty(M, C, device=cuda_dev, dtype=torch.bfloat16)
+        cs = torch.zeros(C, device=cuda_dev)
+        K.layernorm_bwd(dy, x, gamma, mean, rstd, add, dx, dgm, dbt, dx_bf16=dxb, dx_colsum=cs, byprod_drop=d)
+        outs.append((dx, dxb, cs))
+    mask = _mask_of(K, cuda_dev, (M, C), K.Dropout(0.1, 5, 11, 3))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert_close(outs[1][1].float(), outs[0][0] * mask, 4e-3, 1e-5, "masked bf16 copy")
+    assert_close(outs[1][2], (outs[0][0] * mask).sum(0), 1e-4, 1e-4, "masked column sums")
+
+
+def _unpack_bits(bits, B, nh, T, dev):
+    sh = torch.arange(32, device=dev, dtype=torch.int32)
+    return ((bits.view(B, nh, T, -1, 1) >> sh) & 1).reshape(B, nh, T, -1)[..., :T].float()
+
+
+@pytest.mark.parametrize("B,T,C,nh", [(1, 128, 64, 4), (2, 130, 256, 4), (1, 962, 512, 4), (2, 962, 64, 4), (1, 962, 128, 4), (1, 513, 64, 1)])
+def test_attention_dropout_fwd_bwd(K, cuda_dev, B, T, C, nh):
+    """attn_drop (:104): softmax -> dropout -> @v.  The kernel's keep-bitmap is fed to a plain torch evaluation."""
+    from deepsense6g_tii_b200.functional import attn_drop_scale
+    g = _gen(18)
+    hs = C // nh
+    p = 0.1
+    d = K.Dropout(p, 4242, 1, 1)
+    qkv = torch.randn(B * T, 3 * C, generator=g).to(cuda_dev).to(torch.bfloat16)
+    y = torch.empty(B * T, C, device=cuda_dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, nh, T, device=cuda_dev)
+    bits = torch.zeros(K.attn_drop_words(B, T, nh), device=cuda_dev, dtype=torch.int32)
+    K.attn_fwd(qkv, y, lse, B, T, C, nh, d, bits)
+    torch.cuda.synchronize()
+    keep = _unpack_bits(bits, B, nh, T, cuda_dev)
+    k256 = round(p * 256)
+    rate = float(keep.mean())
+    assert abs(rate - (1 - k256 / 256)) < 5 * math.sqrt(p * (1 - p) / keep.numel()) + 1e-4, rate
+    mask = keep * attn_drop_scale(p)
+    qr = qkv.float().requires_grad_(True)
+    q, k, v = [t.reshape(B, T, nh, hs).transpose(1, 2) for t in qr.view(B, T, 3 * C).split(C, dim=-1)]
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(hs)
+    ref = ((torch.softmax(s, dim=-1) * mask) @ v).transpose(1, 2).reshape(B * T, C)
+    assert_close(lse, torch.logsumexp(s, dim=-1), 1e-4, 1e-4, "lse (un-dropped)")
+    assert_close(y.float(), ref, 1e-2, 1e-4, "attn fwd with dropout")
+    dy = torch.randn(B * T, C, generator=g).to(cuda_dev).to(torch.bfloat16)
+    ref.backward(dy.float())
+    delta = torch.empty(B, nh, T, device=cuda_dev)
+    dqkv = torch.empty(B * T, 3 * C, device=cuda_dev, dtype=torch.bfloat16)
+    K.attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, d, bits)
+    torch.cuda.synchronize()
+    for nm, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        assert_close(dqkv[:, sl].float(), qr.grad[:, sl], 2e-2, 1e-4, nm + " with dropout")
+    # a different seed draws a different bitmap; the same seed the same one
+    bits2 = torch.zeros_like(bits)
+    K.attn_fwd(qkv, y, lse, B, T, C, nh, K.Dropout(p, 4243, 1, 1), bits2)
+    assert not torch.equal(bits, bits2)
+    K.attn_fwd(qkv, y, lse, B, T, C, nh, d, bits2)
+    assert torch.equal(bits, bits2)

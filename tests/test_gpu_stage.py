@@ -187,3 +187,85 @@ def test_stage_scaled_config_16x16_anchors(cuda_dev):
     got = fusion_stage(cfg, feats[0], feats[1], feats[2], gps, [p0[n] for n in names])
     for x, y in zip(got, (a, b, c, gout)):
         assert_close(x.float(), y, 2e-2, 1e-4, "scaled")
+
+
+@pytest.mark.parametrize("B,C,H,L", [(2, 64, 32, 2), (1, 512, 8, 2), (2, 128, 32, 8)])
+def test_stage_dropout_matches_oracle_given_the_same_masks(cuda_dev, B, C, H, L):
+    """Training-mode dropout (p = 0.1 at all four sites, config_seq.py:39-41).  torch's RNG stream cannot be matched
+    bit for bit, so the masks the kernels drew are materialised and handed to the oracle restatement, which then
+    evaluates the reference math ``drop(x) = x * mask / (1-p)`` (nn.Dropout, model2_seq.py:104,109,125,272) in fp32.
+    Outputs, input gradients and parameter gradients must agree at the bf16 bounds of the p = 0 test."""
+    from conftest import rel_err
+    from deepsense6g_tii_b200.functional import fusion_stage, materialise_dropout_masks, param_names
+    S, A, nh = 5, 8, 4
+    T = 3 * S * A * A + 2
+    gen = torch.Generator().manual_seed(300 + C)
+    p0 = R.init_gpt_params(C, nh, 4, L, T, generator=gen, pos_std=0.02)
+    p0 = {k: (v + 0.01 * torch.randn(v.shape, generator=gen)).to(cuda_dev) for k, v in p0.items()}
+    feats = [torch.randn(B * S, C, H, H, generator=gen).to(cuda_dev) for _ in range(3)]
+    gps = torch.randn(B, 2, C, generator=gen).to(cuda_dev)
+    probes = [torch.randn(f.shape, generator=gen).to(cuda_dev) for f in feats] + [torch.randn(B, 2, C, generator=gen).to(cuda_dev)]
+    names = param_names(L)
+
+    def leafs():
+        return ({k: v.clone().requires_grad_(True) for k, v in p0.items()},
+                [f.clone().requires_grad_(True) for f in feats] + [gps.clone().requires_grad_(True)])
+
+    drop = dict(embd=0.1, attn=0.1, resid=0.1, seed=20260101, step=3, capture={})
+    cfg = dict(seq_len=S, n_views=1, vert_anchors=A, horz_anchors=A, n_head=nh, n_layer=L, compute_dtype=torch.bfloat16,
+               dropout=drop)
+    pk, ik = leafs()
+    got = fusion_stage(cfg, ik[0], ik[1], ik[2], ik[3], [pk[n] for n in names])
+    sum((o.float() * pr).sum() for o, pr in zip(got, probes)).backward()
+    torch.cuda.synchronize()
+    masks = materialise_dropout_masks(drop, B, T, C, nh, L, cuda_dev)
+    assert len(masks) == 1 + 3 * L
+
+    def oracle(autocast):
+        po, io = leafs()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            (a, b, c), gout = R.fusion_stage(po, io[:3], io[3], nh, S, A, A, masks=masks)
+        sum((o.float() * pr).sum() for o, pr in zip((a, b, c, gout), probes)).backward()
+        return (a, b, c, gout), po, io
+
+    ref, po, io = oracle(False)
+    cref, cpo, cio = oracle(True)  # calibration: the same masked math under stock bf16 autocast
+    for i, (x, y) in enumerate(zip(got, ref)):
+        assert_close(x.float(), y, 1e-2, 1e-5, "out%d" % i)
+    for i, (x, y) in enumerate(zip(ik, io)):
+        assert_close(x.grad, y.grad, max(2e-2, 1.25 * rel_err(cio[i].grad, y.grad)), 1e-5, "gin%d" % i)
+    for n in names:
+        g_ref = po[n].grad
+        if n.endswith("attn.key.bias"):
+            continue
+        floor = 2e-2 if g_ref.dim() > 1 else 3e-2
+        assert_close(pk[n].grad, g_ref, max(floor, 1.25 * rel_err(cpo[n].grad, g_ref)), 2e-5, "g/" + n)
+    # dropout really changed the result, and p = 0 sites stay untouched
+    cfg0 = dict(cfg, dropout=None)
+    base = fusion_stage(cfg0, feats[0], feats[1], feats[2], gps, [p0[n] for n in names])
+    assert rel_err(got[0].float(), base[0].float()) > 1e-3
+
+
+def test_gpt_module_train_mode_dropout_and_eval_mode(cuda_dev):
+    """Drop-in GPT: train() with the reference's default 0.1 probabilities runs (fresh masks per call, reproducible
+    under torch.manual_seed); eval() is deterministic and equals the p = 0 module."""
+    from types import SimpleNamespace
+    from deepsense6g_tii_b200.modules import GPT
+    cfg = SimpleNamespace(n_views=1, fusion_dtype=torch.bfloat16)
+    torch.manual_seed(0)
+    m = GPT(64, 4, 4, 2, 8, 8, 5, 0.1, 0.1, 0.1, cfg).to(cuda_dev)
+    ins = [torch.randn(10, 64, 8, 8, device=cuda_dev) for _ in range(3)] + [torch.randn(2, 2, 64, device=cuda_dev)]
+    m.train()
+    torch.manual_seed(5)
+    a1 = m(*ins)[0]
+    a2 = m(*ins)[0]
+    torch.manual_seed(5)
+    a3 = m(*ins)[0]
+    assert not torch.equal(a1, a2)
+    assert torch.equal(a1, a3)
+    a1.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    m.eval()
+    e1, e2 = m(*ins)[0], m(*ins)[0]
+    assert torch.equal(e1, e2)
+    assert not torch.equal(e1, a1)

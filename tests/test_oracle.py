@@ -45,6 +45,31 @@ def test_oracle_matches_golden(case):
     assert abs(loss.item() - float(g["loss"])) < 1e-3 * max(1.0, abs(float(g["loss"])))
 
 
+def test_oracle_dropout_matches_golden_on_the_reference_draws():
+    """Reference GPT in train() mode, p = 0.1 at all four nn.Dropout sites: given the Bernoulli draws recorded from
+    the reference run, the restatement reproduces outputs and every gradient."""
+    g = load_golden("gpt_tiny_dropout")
+    cfg = g["cfg"]
+    assert set(g["mask"]) == {"embd"} | {"%s.%d" % (k, i) for k in ("attn", "proj", "mlp") for i in range(cfg["L"])}
+    for m in g["mask"].values():  # 0 or 1/(1-p), roughly 10 % dropped
+        assert set(torch.unique(m).tolist()) <= {0.0, float(torch.tensor(1.0) / torch.tensor(0.9))}
+    p = {k: v.clone().requires_grad_(True) for k, v in g["param"].items()}
+    ins = {k: v.clone().requires_grad_(True) for k, v in g["in"].items()}
+    outs = R.gpt_forward(p, ins["img"], ins["lidar"], ins["radar"], ins["gps"], cfg["n_head"], cfg["S"], masks=g["mask"])
+    names = ("img", "lidar", "radar", "gps")
+    sum((o * g["probe"][n]).sum() for o, n in zip(outs, names)).backward()
+    for o, n in zip(outs, names):
+        assert rel_err(o, g["out"][n]) < TOL, n
+    for n, t in ins.items():
+        assert rel_err(t.grad, g["gin"][n]) < TOL, n
+    for n, t in p.items():
+        assert_close(t.grad, g["gparam"][n], 5e-5, 1e-7, n)
+    # and the masks matter: without them the result is far away
+    with torch.no_grad():
+        plain = R.gpt_forward(g["param"], *[g["in"][n] for n in names], cfg["n_head"], cfg["S"])
+    assert rel_err(plain[0], g["out"]["img"]) > 1e-2
+
+
 def test_ops_golden():
     z = np.load(GOLDEN + "/ops.npz")
     for s in (1, 2, 4, 8):
