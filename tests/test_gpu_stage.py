@@ -234,12 +234,18 @@ def test_stage_dropout_matches_oracle_given_the_same_masks(cuda_dev, B, C, H, L)
         assert_close(x.float(), y, 1e-2, 1e-5, "out%d" % i)
     for i, (x, y) in enumerate(zip(ik, io)):
         assert_close(x.grad, y.grad, max(2e-2, 1.25 * rel_err(cio[i].grad, y.grad)), 1e-5, "gin%d" % i)
+    bad = []
     for n in names:
         g_ref = po[n].grad
         if n.endswith("attn.key.bias"):
             continue
-        floor = 2e-2 if g_ref.dim() > 1 else 3e-2
-        assert_close(pk[n].grad, g_ref, max(floor, 1.25 * rel_err(cpo[n].grad, g_ref)), 2e-5, "g/" + n)
+        # floors: 2e-2 matrices; 4e-2 for 1-D parameters (column sums with heavy cancellation; each of the three
+        # dropout sites of a block multiplies the bf16 rounding noise that flows through it by 1/(1-p))
+        floor = 2e-2 if g_ref.dim() > 1 else 4e-2
+        err, bnd = rel_err(pk[n].grad, g_ref), max(floor, 1.25 * rel_err(cpo[n].grad, g_ref))
+        if err > bnd:
+            bad.append("%s: %.3e > %.3e" % (n, err, bnd))
+    assert not bad, bad
     # dropout really changed the result, and p = 0 sites stay untouched
     cfg0 = dict(cfg, dropout=None)
     base = fusion_stage(cfg0, feats[0], feats[1], feats[2], gps, [p0[n] for n in names])
