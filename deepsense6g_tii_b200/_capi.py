@@ -73,7 +73,7 @@ def lib():
             "dsf_dropout_inplace": [P, c_int64, POINTER(Dropout), P],
             "dsf_relu_bwd_colsum": [P, P, P, c_int32, c_int32, P],
             "dsf_pack_block_weights": [P] * 9 + [c_int32, c_int32] + [P] * 10,
-            "dsf_gemm_bf16_nt": [P, c_int32, P, c_int32, P, c_int32, c_int32, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P],
+            "dsf_gemm_bf16_nt": [P, c_int32, P, c_int32, P, c_int32, c_int32, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P, P],
             "dsf_gemm_bf16_tn": [P, c_int32, P, c_int32, P, c_int32, c_int32, c_int32, c_int32, P],
             "dsf_gemm_f32": [POINTER(GemmF32Desc), P, P, P, P, P, P],
             "dsf_colsum": [P, c_int32, c_int32, P, c_int32, c_int32, P],
@@ -179,13 +179,14 @@ def pack_block_weights(wq, wk, wv, wp, w1, w2, bq, bk, bv, outs):
                                       *[_p(t) for t in outs], _stream()), "dsf_pack_block_weights")
 
 
-def gemm_bf16_nt(A, B, C, bias=None, residual=None, relu=False, drop=None):
-    """C[M,N] = A[M,K] @ B[N,K]^T (+bias)(relu)(dropout)(+residual fp32).  A, B bf16 2-D contiguous; C bf16 or fp32."""
+def gemm_bf16_nt(A, B, C, bias=None, residual=None, relu=False, drop=None, relu_src=None):
+    """C[M,N] = A[M,K] @ B[N,K]^T (+bias)(relu)(* [relu_src > 0])(dropout)(+residual fp32).  A, B bf16 2-D contiguous;
+    C bf16 or fp32; relu_src bf16 with C's shape and leading dimension."""
     M, K = A.shape
     N = B.shape[0]
     flags = (EPI_BIAS if bias is not None else 0) | (EPI_RELU if relu else 0) | (EPI_RESIDUAL if residual is not None else 0)
     _chk(lib().dsf_gemm_bf16_nt(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), _dt(C), _p(bias), _p(residual),
-                                M, N, K, flags, _dp(drop), _stream()), "dsf_gemm_bf16_nt")
+                                M, N, K, flags, _dp(drop), _p(relu_src), _stream()), "dsf_gemm_bf16_nt")
 
 
 def gemm_bf16_tn(A, B, C):

@@ -331,7 +331,7 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int ldc,
 namespace dsf {
 // v2 (persistent, double-buffered TMEM accumulators, 128 x 256 tiles), gemm_tc2.cu
 int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, const float* bias, const float* residual, int M,
-               int N, int K, int flags, const dsf_dropout* drop, cudaStream_t st);
+               int N, int K, int flags, const dsf_dropout* drop, const void* relu_src, cudaStream_t st);
 int gemm_tn_v2(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st);
 static int g_gemm_impl = 0;  // 0 = default (v2), 1 = v1 (one CTA per 128 x 128 tile), 2 = v2
 }  // namespace dsf
@@ -346,7 +346,7 @@ extern "C" int dsf_gemm_set_impl(int32_t impl) {
 
 extern "C" int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32_t ldb, void* C, int32_t ldc, int32_t c_dtype,
                                 const float* bias, const float* residual, int32_t M, int32_t N, int32_t K, int32_t epi_flags,
-                                const dsf_dropout* drop, void* stream) {
+                                const dsf_dropout* drop, const void* relu_src, void* stream) {
   DSF_REQUIRE(A && B && C, "gemm_bf16_nt: NULL pointer");
   DSF_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16_nt: non-positive extent");
   DSF_REQUIRE(K % GT_BK == 0, "gemm_bf16_nt: K=%d must be a multiple of 64", K);
@@ -358,8 +358,9 @@ extern "C" int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32
   DSF_REQUIRE(!(epi_flags & DSF_EPI_RESIDUAL) || residual, "gemm_bf16_nt: residual flag without residual pointer");
   DSF_REQUIRE(!(epi_flags & DSF_EPI_ACCUM), "gemm_bf16_nt: ACCUM is not supported on the NT path");
   DSF_REQUIRE(!drop || (drop->p >= 0.f && drop->p < 1.f), "gemm_bf16_nt: dropout p must be in [0, 1)");
-  if (g_gemm_impl != 1) return gemm_nt_v2(A, lda, B, ldb, C, ldc, c_dtype, bias, residual, M, N, K, epi_flags, drop, (cudaStream_t)stream);
-  if (drop && drop->p > 0.f) { set_error("gemm_bf16_nt: dropout epilogue is only implemented in the v2 kernels"); return DSF_EUNSUPPORTED; }
+  DSF_REQUIRE(!relu_src || aligned16(relu_src), "gemm_bf16_nt: relu_src must be 16-byte aligned");
+  if (g_gemm_impl != 1) return gemm_nt_v2(A, lda, B, ldb, C, ldc, c_dtype, bias, residual, M, N, K, epi_flags, drop, relu_src, (cudaStream_t)stream);
+  if ((drop && drop->p > 0.f) || relu_src) { set_error("gemm_bf16_nt: dropout / relu-mask epilogues are only implemented in the v2 kernels"); return DSF_EUNSUPPORTED; }
   const int BN = (N % 128 == 0) ? 128 : 64;
   CUtensorMap tmA, tmB;
   if (int e = make_tmap_bf16(&tmA, A, M, K, lda, GT_BM)) return e;

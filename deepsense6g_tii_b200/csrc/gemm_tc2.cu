@@ -27,6 +27,7 @@ struct EpiArgs2 {
   const float* residual;
   int flags;
   int N;          // row length for the dropout element index m*N + n
+  const __nv_bfloat16* relu_src;  // nullable: v = relu_src[m,n] > 0 ? v : 0 (ReLU backward fused into the dgrad GEMM)
   DropArgs drop;  // resid_drop (model2_seq.py:109,125): after bias/ReLU, before the residual add
 };
 
@@ -81,6 +82,19 @@ __device__ __forceinline__ void epi_math32(const EpiArgs2& e, int row, int n, co
   if (e.flags & DSF_EPI_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (e.relu_src != nullptr && row_ok) {
+    const uint4* hp = reinterpret_cast<const uint4*>(e.relu_src + (size_t)row * e.ldc + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 h = __ldg(hp + j);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+        if (!((hw[k] & 0x8000u) == 0u && (hw[k] & 0x7FFFu) != 0u)) v[8 * j + 2 * k] = 0.f;
+        if (!((hw[k] & 0x80000000u) == 0u && (hw[k] & 0x7FFF0000u) != 0u)) v[8 * j + 2 * k + 1] = 0.f;
+      }
+    }
   }
   if (e.drop.thresh) {
     const uint64_t e4 = ((uint64_t)row * e.N + n) >> 2;
@@ -412,14 +426,14 @@ static int pick_bn_nt(int M, int N) {
 }
 
 int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, const float* bias, const float* residual, int M,
-               int N, int K, int flags, const dsf_dropout* drop, cudaStream_t st) {
+               int N, int K, int flags, const dsf_dropout* drop, const void* relu_src, cudaStream_t st) {
   const int BN = pick_bn_nt(M, N);
   CUtensorMap tmA, tmB;
   if (int e = make_tmap_bf16(&tmA, A, M, K, lda, G2_BM)) return e;
   if (int e = make_tmap_bf16(&tmB, B, N, K, ldb, BN)) return e;
   CUtensorMap tmC;  // store boxes: 32 rows x 128 bytes
   if (int e = make_tmap_2d(&tmC, C, c_dtype, M, N, ldc, c_dtype == DSF_F32 ? 32 : 64, 32)) return e;
-  EpiArgs2 epi{C, ldc, c_dtype, bias, residual, flags, N, make_drop(drop)};
+  EpiArgs2 epi{C, ldc, c_dtype, bias, residual, flags, N, reinterpret_cast<const __nv_bfloat16*>(relu_src), make_drop(drop)};
   if (BN == 256) return launch_nt2<256, 3>(tmA, tmB, tmC, epi, M, N, K, st);
   if (BN == 128) return launch_nt2<128, 4>(tmA, tmB, tmC, epi, M, N, K, st);
   return launch_nt2<64, 5>(tmA, tmB, tmC, epi, M, N, K, st);

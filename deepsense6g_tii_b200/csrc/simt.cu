@@ -131,6 +131,66 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, in
   }
 }
 
+// Vectorised variant (N and ldx multiples of 16 B / sizeof(T), 16-byte aligned base): each lane owns one 16-byte column
+// group, a warp covers 32 of them per row, the 8 warps of a CTA interleave rows with 4 independent loads in flight.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ X, int ldx, float* __restrict__ out, int M, int N, int rows_per_block) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  __shared__ float red[8][32 * VEC + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = (blockIdx.x * 32 + lane) * VEC;
+  const int m_lo = blockIdx.y * rows_per_block, m_hi = min(M, m_lo + rows_per_block);
+  float acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  if (n < N) {
+    const T* base = X + n;
+    int m = m_lo + w;
+    for (; m + 24 < m_hi; m += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(m + 8 * u) * ldx));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const T* e = reinterpret_cast<const T*>(&v[u]);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] += to_f<T>(e[k]);
+      }
+    }
+    for (; m < m_hi; m += 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)m * ldx));
+      const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] += to_f<T>(e[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) red[w][lane * VEC + k] = acc[k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VEC; c += 256) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += red[k][c];
+    const int nn = blockIdx.x * 32 * VEC + c;
+    if (nn < N) atomicAdd(out + nn, sum);
+  }
+}
+
+template <typename T>
+static void launch_colsum(const T* X, int ldx, float* out, int M, int N, cudaStream_t st) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  if (N % VEC == 0 && ldx % VEC == 0 && aligned16(X)) {
+    const int col_blocks = cdiv(N, 32 * VEC);
+    const int row_blocks = max(1, min(cdiv(M, 64), (num_sms() * 6) / col_blocks));
+    const int rpb = cdiv(M, row_blocks);
+    colsum_vec_kernel<T><<<dim3(col_blocks, cdiv(M, rpb)), 256, 0, st>>>(X, ldx, out, M, N, rpb);
+    return;
+  }
+  const int row_blocks = max(1, min(cdiv(M, 64), (num_sms() * 4) / max(1, cdiv(N, 64))));
+  const int rpb = cdiv(M, row_blocks);
+  colsum_kernel<T><<<dim3(cdiv(N, 64), cdiv(M, rpb)), 256, 0, st>>>(X, ldx, out, M, N, rpb);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) relu_bwd_kernel(T* __restrict__ dy, const T* __restrict__ h, int64_t n4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -186,11 +246,8 @@ extern "C" int dsf_softmax_bwd(float* dp, const float* p, int64_t rows, int32_t 
 extern "C" int dsf_colsum(const void* X, int32_t x_dtype, int32_t ldx, float* out, int32_t M, int32_t N, void* stream) {
   DSF_REQUIRE(X && out && M > 0 && N > 0 && ldx >= N, "colsum: bad arguments");
   DSF_REQUIRE(x_dtype == DSF_F32 || x_dtype == DSF_BF16, "colsum: bad dtype %d", x_dtype);
-  const int row_blocks = max(1, min(cdiv(M, 64), (num_sms() * 4) / max(1, cdiv(N, 64))));
-  const int rpb = cdiv(M, row_blocks);
-  dim3 grid(cdiv(N, 64), cdiv(M, rpb));
-  if (x_dtype == DSF_F32) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)X, ldx, out, M, N, rpb);
-  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)X, ldx, out, M, N, rpb);
+  if (x_dtype == DSF_F32) launch_colsum<float>((const float*)X, ldx, out, M, N, (cudaStream_t)stream);
+  else launch_colsum<__nv_bfloat16>((const __nv_bfloat16*)X, ldx, out, M, N, (cudaStream_t)stream);
   return check_launch("colsum");
 }
 

@@ -337,8 +337,8 @@ class _Runner:
             # ---- MLP:  x_out = x_mid + relu(h2 W1^T + b1) W2^T + b2     (model2_seq.py:121-126,132)
             K.gemm_bf16_tn(dxa, st.a, dw2)
             da = torch.empty(M, F, device=dev, dtype=bf)
-            K.gemm_bf16_nt(dxa, st.w2_t, da)
-            K.relu_bwd_colsum(da, st.a, db1)
+            K.gemm_bf16_nt(dxa, st.w2_t, da, relu_src=st.a)  # ReLU backward fused in the epilogue
+            K.colsum(da, db1)
             K.gemm_bf16_tn(da, st.h2, dw1)
             dh2 = torch.empty(M, C, device=dev, dtype=f32)  # fp32: feeds LayerNorm backward, not a GEMM
             K.gemm_bf16_nt(da, st.w1_t, dh2)

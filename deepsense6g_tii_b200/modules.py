@@ -79,7 +79,6 @@ class GPT(nn.Module):
         self.ln_f = nn.LayerNorm(n_embd)
         self.block_size = seq_len
         self._pdrop = (float(embd_pdrop), float(attn_pdrop), float(resid_pdrop))
-        self._drop_step = 0
         self._drop_capture = None  # tests: a dict that receives seed/step and the attention keep-bitmaps of the last call
         self.apply(self._init_weights)
         self._names = param_names(n_layer)
@@ -107,12 +106,11 @@ class GPT(nn.Module):
             # nn.Dropout semantics (model2_seq.py:104,109,125,272): active in train() only.  A fresh seed per call is
             # drawn from torch's CPU generator (so torch.manual_seed governs it); the masks themselves are Philox
             # functions of (seed, site, element) computed inside the kernels.
-            self._drop_step += 1
             seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
-            dropout = dict(embd=self._pdrop[0], attn=self._pdrop[1], resid=self._pdrop[2], seed=seed, step=self._drop_step)
+            dropout = dict(embd=self._pdrop[0], attn=self._pdrop[1], resid=self._pdrop[2], seed=seed, step=0)
             if self._drop_capture is not None:
                 self._drop_capture.clear()
-                self._drop_capture.update(seed=seed, step=self._drop_step)
+                self._drop_capture.update(seed=seed, step=0)
                 dropout["capture"] = self._drop_capture
         return dict(dropout=dropout, seq_len=self.seq_len, n_views=self.config.n_views, vert_anchors=self.vert_anchors,
                     horz_anchors=self.horz_anchors, n_head=self.n_head, n_layer=self.n_layer,

@@ -120,9 +120,12 @@ int dsf_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const fl
  *        (split over M across CTAs); without it C must be zero-filled by the caller.              */
 /*        `drop` (nullable): dropout applied after bias/ReLU and BEFORE the residual add, element index m*N + n
  *        (resid_drop of the proj / mlp.2 outputs, model2_seq.py:109,125).                              */
+/*        `relu_src` (nullable): bf16 (M,N) with leading dimension ldc; the result is zeroed where relu_src <= 0
+ *        (backward of nn.ReLU(True), model2_seq.py:123, fused into the mlp.2 data-gradient GEMM).            */
 int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32_t ldb, void* C, int32_t ldc,
                      int32_t c_dtype, const float* bias, const float* residual, int32_t M, int32_t N,
-                     int32_t K, int32_t epi_flags, const dsf_dropout* drop, void* stream);
+                     int32_t K, int32_t epi_flags, const dsf_dropout* drop, const void* relu_src,
+                     void* stream);
 int dsf_gemm_bf16_tn(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc,
                      int32_t M, int32_t Nout, int32_t Kout, void* stream);
 /* Selects the tensor-core GEMM implementation (process-wide; tests and A/B timing): 0 = default,

@@ -235,6 +235,13 @@ def test_softmax_colsum_relu_cast(K, cuda_dev):
         ref = torch.where(h > 0, d, torch.zeros_like(d))
         K.relu_bwd(d, h)
         assert torch.equal(d, ref)
+    # vectorised column-sum path (16-byte column groups), incl. a strided view, ragged row counts and the bench shape
+    for dt in (torch.float32, torch.bfloat16):
+        for (M, N, ld) in [(11544, 1536, 1536), (1001, 200, 200), (77, 2048, 2048), (5, 8, 8), (962, 512, 1536)]:
+            X = torch.randn(M, ld, generator=g).to(cuda_dev).to(dt)[:, :N]
+            out = torch.ones(N, device=cuda_dev)
+            K.colsum(X, out)
+            assert_close(out, 1 + X.float().sum(0), 2e-5, 1e-4, "colsum vec %s %s" % (dt, (M, N, ld)))
     src = torch.randn(1003, generator=g).to(cuda_dev)
     dst = torch.empty(1003, device=cuda_dev, dtype=torch.bfloat16)
     K.cast_f32_bf16(src, dst)
@@ -342,6 +349,21 @@ def test_error_paths(K, cuda_dev):
     geom = K.make_geom(1, 1, 1, 4, 4, 8, 10, 10, K.DSF_F32)
     with pytest.raises(RuntimeError, match="not a multiple of the anchor grid"):
         K.tokens_fwd(geom, x, x, x, x, x, x)
+
+
+@pytest.mark.parametrize("M,N,Kd", [(300, 128, 64), (11544, 2048, 512), (962, 256, 128), (130, 64, 256)])
+def test_gemm_bf16_nt_relu_mask_epilogue(K, cuda_dev, M, N, Kd):
+    """Backward of nn.ReLU(True) (:123) fused into the mlp.2 data-gradient GEMM: out = (A W^T) * [h > 0]."""
+    g = _gen(19)
+    a = torch.randn(M, Kd, generator=g).to(cuda_dev).to(torch.bfloat16)
+    w = (0.05 * torch.randn(N, Kd, generator=g)).to(cuda_dev).to(torch.bfloat16)
+    h = torch.relu(torch.randn(M, N, generator=g)).to(cuda_dev).to(torch.bfloat16)  # post-ReLU activations: exact zeros
+    h[0, :5] = -0.0
+    out = torch.empty(M, N, device=cuda_dev, dtype=torch.bfloat16)
+    K.gemm_bf16_nt(a, w, out, relu_src=h)
+    ref = (a.float() @ w.float().t()) * (h.float() > 0)
+    assert_close(out.float(), ref, 6e-3, 1e-4, "relu-mask epilogue")
+    assert torch.all(out[h.float() <= 0] == 0)
 
 
 # ------------------------------------------------------------------------------------------ dropout (model2_seq.py:104,109,125,272)
