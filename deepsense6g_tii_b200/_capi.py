@@ -20,7 +20,7 @@ EPI_BIAS, EPI_RELU, EPI_RESIDUAL, EPI_ACCUM = 1, 2, 4, 8
 
 # every symbol include/dsfuse.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_dropout_inplace", "dsf_tokens_fwd", "dsf_tokens_bwd",
+    "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_set_pdl", "dsf_dropout_inplace", "dsf_tokens_fwd", "dsf_tokens_bwd",
     "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_set_impl", "dsf_gemm_f32",
     "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_set_impl", "dsf_attn_drop_words",
     "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16",
@@ -83,6 +83,7 @@ def lib():
             "dsf_attn_fwd": [P, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P, P],
             "dsf_attn_bwd": [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P, P],
             "dsf_attn_set_impl": [c_int32],
+            "dsf_set_pdl": [c_int32],
             "dsf_gemm_set_impl": [c_int32],
             "dsf_upsample_add_fwd": [POINTER(Geom), P, P, P, P, P, P, P, P],
             "dsf_upsample_add_bwd": [POINTER(Geom), P, P, P, P, P, P],
@@ -232,8 +233,13 @@ def attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop=None, drop_bits=Non
 
 
 def gemm_set_impl(impl):
-    """0 = default, 1 = v1 (CTA per tile), 2 = v2 (persistent); process-wide."""
+    """0 = default (= 3), 1 = v1 (CTA per tile), 2 = v2 (persistent), 3 = v3 (NT on CTA pairs, cta_group::2); process-wide."""
     _chk(lib().dsf_gemm_set_impl(impl), "dsf_gemm_set_impl")
+
+
+def set_pdl(on):
+    """Programmatic dependent launch of the hot kernels on/off (default on); results are identical."""
+    _chk(lib().dsf_set_pdl(1 if on else 0), "dsf_set_pdl")
 
 
 def attn_set_impl(impl):

@@ -25,6 +25,9 @@ int check_launch(const char* what) {
   return DSF_OK;
 }
 
+static int g_pdl = 1;
+bool pdl_enabled() { return g_pdl != 0; }
+
 int num_sms() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
@@ -40,6 +43,10 @@ int num_sms() {
 }  // namespace dsf
 
 extern "C" int dsf_version(void) { return DSF_VERSION; }
+extern "C" int dsf_set_pdl(int32_t on) {
+  dsf::g_pdl = on ? 1 : 0;
+  return DSF_OK;
+}
 extern "C" int64_t dsf_launch_count(void) { return (int64_t)__atomic_load_n(&dsf::g_launches, __ATOMIC_RELAXED); }
 extern "C" const char* dsf_last_error(void) { return dsf::g_err; }
 

@@ -241,6 +241,8 @@ int launch_attn_fwd(const void* qkv, void* y, float* lse, int B, int T, int C, i
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dy, float* __restrict__ delta, int B, int T,
                   int C, int nh) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int hs = C / nh, gl = hs / 8;  // lanes per head (power of two, 2..16)
   const int nchunk = C / 8;
@@ -590,7 +592,8 @@ int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse
                 const dsf_dropout* drop, uint32_t* bits, cudaStream_t st);
 
 int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, int C, int nh, cudaStream_t st) {
-  attn_delta_kernel<<<std::min(cdiv(B * T, 8), num_sms() * 8), 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, delta, B, T, C, nh);
+  launch_pdl(attn_delta_kernel, dim3(std::min(cdiv(B * T, 8), num_sms() * 8)), dim3(256), 0, st, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy,
+             delta, B, T, C, nh);
   return check_launch("attn_bwd/delta");
 }
 

@@ -364,6 +364,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
   const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int n_q = (T + BQ - 1) / BQ;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
     mbar_init(acc_done, 1);
@@ -378,6 +379,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // set-up above overlaps the previous kernel's tail
   const uint32_t tm_dv = tmem_base + 4 * BQ, tm_dk = tm_dv + HS;
 
   if (warp == 9) {
@@ -550,6 +552,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int n_kv = (T + BKV - 1) / BKV;
   constexpr uint32_t TMEM_COLS = (4 * BKV + HS) <= 256 ? 256 : 512;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     mbar_init(acc_done, 1);
@@ -564,6 +567,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // set-up above overlaps the previous kernel's tail
   const uint32_t tm_dq = tmem_base + 4 * BKV;
 
   if (warp == 9) {
@@ -706,6 +710,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (T + BKV - 1) / BKV;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < KST; ++s) { mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1); }
@@ -720,6 +725,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // set-up above overlaps the previous kernel's tail
 
   if (warp == 9) {
     if (lane == 0) {
@@ -939,7 +945,7 @@ static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C
   if (int e = make_tmap3(&tmKV, qkv, 3 * C, T, B, H::BOXC, L::BKV)) return e;
   const float scale_log2 = (1.0f / sqrtf((float)HS)) * 1.4426950408889634f;
   dim3 grid(cdiv(T, 256), nh, B);
-  attn_fwd3_kernel<HS, KST, VST><<<grid, L::THREADS, L::DYN, st>>>(tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
+  launch_pdl(attn_fwd3_kernel<HS, KST, VST>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
   return check_launch("attn_fwd3");
 }
 
@@ -968,9 +974,9 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   if (int e = make_tmap3(&tmDO128, dy, C, T, B, H::BOXC, 128)) return e;
   if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
   dim3 grid(cdiv(T, 128), nh, B);
-  attn_bwd_kv2_kernel<HS, BQ, STA><<<grid, 320, LA::DYN, st>>>(tmKV128, tmQs, tmDOs, lse, delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
+  launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
   if (int e = check_launch("attn_bwd2/kv")) return e;
-  attn_bwd_q2_kernel<HS, STB><<<grid, 320, LB::DYN, st>>>(tmQ128, tmDO128, tmKV64, lse, delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
+  launch_pdl(attn_bwd_q2_kernel<HS, STB>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
   return check_launch("attn_bwd2/q");
 }
 

@@ -27,6 +27,30 @@ inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int num_sms();
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The hot kernels of the bf16 path are launched with cudaLaunchAttributeProgrammaticStreamSerialization: every kernel
+// executes pdl_trigger() first (its successor may start occupying SMs as soon as ALL of this grid's CTAs are
+// resident or done) and pdl_wait() before its first access to global memory (returns once the predecessor grid has
+// completed and flushed).  The successor's launch latency, barrier/TMEM set-up and tensor-map prefetch thereby overlap
+// the predecessor's tail.  Without the launch attribute both instructions are no-ops.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface in check_launch()
+}
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- scalar load/store by dtype
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }

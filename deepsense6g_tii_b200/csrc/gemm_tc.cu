@@ -333,14 +333,16 @@ namespace dsf {
 int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, const float* bias, const float* residual, int M,
                int N, int K, int flags, const dsf_dropout* drop, const void* relu_src, cudaStream_t st);
 int gemm_tn_v2(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st);
-static int g_gemm_impl = 0;  // 0 = default (v2), 1 = v1 (one CTA per 128 x 128 tile), 2 = v2
+extern bool g_nt_pairs;      // gemm_tc2.cu: NT GEMMs on CTA pairs (cta_group::2) where the shape allows
+static int g_gemm_impl = 0;  // 0 = default (v3), 1 = v1 (one CTA per 128 x 128 tile), 2 = v2 (persistent single CTA), 3 = v3 (CTA pairs)
 }  // namespace dsf
 
 using namespace dsf;
 
 extern "C" int dsf_gemm_set_impl(int32_t impl) {
-  DSF_REQUIRE(impl >= 0 && impl <= 2, "gemm_set_impl: impl must be 0 (default), 1 or 2");
+  DSF_REQUIRE(impl >= 0 && impl <= 3, "gemm_set_impl: impl must be 0 (default), 1, 2 or 3");
   g_gemm_impl = impl;
+  g_nt_pairs = (impl == 0 || impl == 3);
   return DSF_OK;
 }
 

@@ -7,6 +7,7 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue
 // (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
 #include <algorithm>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -28,6 +29,7 @@ struct EpiArgs2 {
   int flags;
   int N;          // row length for the dropout element index m*N + n
   const __nv_bfloat16* relu_src;  // nullable: v = relu_src[m,n] > 0 ? v : 0 (ReLU backward fused into the dgrad GEMM)
+  int ablate;     // diagnostics (DSF_GEMM_ABLATE): 1 = skip the epilogue body, 2 = skip the TMA loads (results are garbage)
   DropArgs drop;  // resid_drop (model2_seq.py:109,125): after bias/ReLU, before the residual add
 };
 
@@ -141,6 +143,7 @@ gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = K / G2_BK;
   const int total = m_tiles * n_tiles;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -155,6 +158,7 @@ gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -164,6 +168,7 @@ gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
+          if (epi.ablate & 2) { mbar_arrive(bar_full + s * 8); continue; }
           mbar_expect_tx(bar_full + s * 8, L::STAGE_BYTES);
           const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
           tma_load_2d(sa, &tmA, bar_full + s * 8, kb * G2_BK, m0);
@@ -210,7 +215,7 @@ gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m0 = (tile % m_tiles) * G2_BM, n0 = (tile / m_tiles) * BN;
       mbar_wait(acc_full + ab * 8, (i >> 1) & 1);
       tc_fence_after();
-      if (ch >= NSPLIT || m0 + q * 32 >= M) {  // nothing to store for this warp
+      if (ch >= NSPLIT || m0 + q * 32 >= M || (epi.ablate & 1)) {  // nothing to store for this warp
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + ab * 8);
@@ -248,6 +253,7 @@ gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int j = 0; j < 16; ++j) w[hh * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           }
         }
+        if (!(epi.ablate & 8)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t dst = sbuf + lane * 128 + ((j ^ (lane & 7)) << 4);
@@ -255,8 +261,14 @@ gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                        : "memory");
         }
         fence_proxy_async();
+        } else {
+          uint32_t acc = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc ^= w[j];
+          if (acc == 0x12345678u) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbuf), "r"(acc) : "memory");
+        }
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(epi.ablate & 4)) {
           tma_store_2d(&tmC, sbuf, ncol, m0 + q * 32);
           bulk_commit();
         }
@@ -270,6 +282,221 @@ gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, L::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------- NT, persistent, CTA pairs (cta_group::2)
+// v3: two CTAs of one cluster (one TPC) compute a 256 x BN tile with tcgen05.mma.cta_group::2.  CTA r of the pair loads its
+// own 128 rows of A and only HALF of the B tile (rows n0 + r*BN/2 ..); the tensor cores of both SMs read both halves.
+// Per k-block a CTA therefore pulls 16 KB (A) + BN/2 x 128 B (B) through the L2 -> SM fabric instead of 16 KB + BN x 128 B:
+// the NT GEMMs of this path are bound by exactly that traffic (11.4 TB/s measured = the chip's L2 request cap), not by
+// the tensor pipe.  Protocol (barrier offsets are identical in both CTAs):
+//   full[s]      leader only, count 1 + tx bytes of BOTH CTAs (the peer's TMA completes on the leader's barrier)
+//   empty[s]     both CTAs, count 1, arrived by the leader's multicast tcgen05.commit
+//   acc_full[a]  both CTAs, count 1, multicast commit after the last k-block of a tile
+//   acc_empty[a] leader only, count 16: the 8 epilogue warps of both CTAs
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // relaxed: the arrive only hands a drained TMEM buffer back (ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync);
+  // a release at cluster scope would cost a MEMBAR.GPU per epilogue warp and tile
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int BN, int STAGES>
+struct G3Smem {
+  static constexpr int A_BYTES = G2_BM * G2_BK * 2;        // this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BN / 2) * G2_BK * 2;     // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_BYTES = 8 * 2 * 4096;
+  static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;
+  static constexpr int DYN = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+  static_assert(DYN <= 232448, "shared memory budget");
+  static_assert(TMEM_COLS == 512 || TMEM_COLS == 256, "TMEM columns must be a power of two");
+};
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                EpiArgs2 epi, int M, int N, int K, int m_tiles, int n_tiles) {
+  using L = G3Smem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = base + L::BAR_OFF, bar_empty = bar_full + STAGES * 8, acc_full = bar_empty + STAGES * 8,
+                 acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int num_k = K / G2_BK;
+  const int total = m_tiles * n_tiles;  // 256 x BN tiles
+  pdl_trigger();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a * 8, 1); mbar_init(acc_empty + a * 8, 16); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc_pair(tmem_slot, L::TMEM_COLS); tmem_relinquish_pair(); }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / TMA completion
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t full0 = mapa_u32(bar_full, 0);  // the leader's full barriers
+      int it = 0;
+      for (int tile = pair; tile < total; tile += n_pairs) {
+        const int m0 = (tile % m_tiles) * 256 + (int)rank * G2_BM, n0 = (tile / m_tiles) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
+          if (epi.ablate & 2) { if (rank == 0) mbar_arrive(bar_full + s * 8); continue; }
+          if (rank == 0) mbar_expect_tx(bar_full + s * 8, 2 * L::STAGE_BYTES);
+          const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+          tma_load_2d_pair(sa, &tmA, full0 + s * 8, kb * G2_BK, m0);
+          tma_load_2d_pair(sb, &tmB, full0 + s * 8, kb * G2_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {  // MMA issuer of the pair: all 32 lanes walk the schedule, one elected lane issues
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+      int it = 0, i = 0;
+      for (int tile = pair; tile < total; tile += n_pairs, ++i) {
+        const int ab = i & 1;
+        mbar_wait(acc_empty + ab * 8, ((i >> 1) & 1) ^ 1);  // the epilogues of both CTAs have drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + ab * BN;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+          const uint64_t da = make_smem_desc(sa, 16, 1024, SWZ_128B);
+          const uint64_t db = make_smem_desc(sb, 16, 1024, SWZ_128B);
+          const uint32_t first = kb != 0 ? 1u : 0u;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < G2_BK / 16; ++k) tc_mma_bf16_pair(acc, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, k == 0 ? first : 1u);
+            tc_commit_pair(bar_empty + s * 8);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) tc_commit_pair(acc_full + ab * 8);
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int ch = (warp - 2) >> 2;    // column half handled by this warp
+    constexpr int HALF = BN / 2;
+    const uint32_t acc_empty0 = mapa_u32(acc_empty, 0);
+    int i = 0, nbox = 0;
+    for (int tile = pair; tile < total; tile += n_pairs, ++i) {
+      const int ab = i & 1;
+      const int m0 = (tile % m_tiles) * 256 + (int)rank * G2_BM, n0 = (tile / m_tiles) * BN;
+      mbar_wait(acc_full + ab * 8, (i >> 1) & 1);
+      tc_fence_after();
+      if (m0 + q * 32 < M && !(epi.ablate & 1)) {
+        const int row = m0 + q * 32 + lane;
+        const uint32_t tacc = tmem_base + ab * BN + ((uint32_t)(q * 32) << 16) + ch * HALF;
+        const uint32_t stg = base + L::STAGING_OFF + (warp - 2) * 8192;
+        const int CW = epi.c_dtype == DSF_F32 ? 32 : 64;  // columns per 128-byte staged row
+#pragma unroll 1
+        for (int c = 0; c < HALF; c += CW, ++nbox) {
+          const uint32_t sbuf = stg + (nbox & 1) * 4096;
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          const int ncol = n0 + ch * HALF + c;
+          uint32_t w[32];
+          if (epi.c_dtype == DSF_F32) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c, r);
+            tmem_wait_ld();
+            float v[32];
+            epi_math32(epi, row, ncol, r, v, row < M);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
+          } else {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t r[32];
+              tmem_ld32(tacc + c + hh * 32, r);
+              tmem_wait_ld();
+              float v[32];
+              epi_math32(epi, row, ncol + hh * 32, r, v, row < M);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) w[hh * 16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t dst = sbuf + lane * 128 + ((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[4 * j]), "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                         : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, sbuf, ncol, m0 + q * 32);
+            bulk_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc_empty0 + ab * 8);
+    }
+    if (lane == 0) bulk_wait<0>();  // all stores complete before shared memory is released
+  }
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch its barriers / TMEM
+  if (warp == 1) tmem_dealloc_pair(tmem_base, L::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------- TN (wgrad), split contraction
@@ -292,6 +519,7 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_it = (m_hi - m_lo + G2_BK - 1) / G2_BK;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   constexpr int BOX_BYTES = G2_BK * 128;  // 64 rows x 128 B
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -306,6 +534,7 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -384,7 +613,7 @@ static int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   }
   const int m_tiles = cdiv(M, G2_BM), n_tiles = N / BN;
   const int grid = std::min(m_tiles * n_tiles, num_sms());
-  gemm_nt2_kernel<BN, STAGES><<<grid, G2_THREADS, L::DYN, st>>>(tmA, tmB, tmC, epi, M, N, K, m_tiles, n_tiles);
+  launch_pdl(gemm_nt2_kernel<BN, STAGES>, dim3(grid), dim3(G2_THREADS), L::DYN, st, tmA, tmB, tmC, epi, M, N, K, m_tiles, n_tiles);
   return check_launch("gemm_nt2");
 }
 
@@ -403,8 +632,24 @@ static int launch_tn2(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, 
   int m_chunk = cdiv(cdiv(M, splits), G2_BK) * G2_BK;
   splits = cdiv(M, m_chunk);
   dim3 grid(cdiv(Kout, BN), cdiv(Nout, G2_BM), splits);
-  gemm_tn2_kernel<BN, STAGES><<<grid, G2_THREADS, L::DYN, st>>>(tmA, tmB, C, ldc, M, Nout, Kout, m_chunk);
+  launch_pdl(gemm_tn2_kernel<BN, STAGES>, grid, dim3(G2_THREADS), L::DYN, st, tmA, tmB, C, ldc, M, Nout, Kout, m_chunk);
   return check_launch("gemm_tn2");
+}
+
+template <int BN, int STAGES>
+static int launch_nt3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const EpiArgs2& epi, int M, int N, int K,
+                      cudaStream_t st) {
+  using L = G3Smem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_nt3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
+      return check_launch("gemm_nt3/attr");
+    configured = true;
+  }
+  const int m_tiles = cdiv(M, 256), n_tiles = N / BN;
+  const int pairs = std::min(m_tiles * n_tiles, num_sms() / 2);
+  launch_pdl(gemm_nt3_kernel<BN, STAGES>, dim3(2 * pairs), dim3(G2_THREADS), L::DYN, st, tmA, tmB, tmC, epi, M, N, K, m_tiles, n_tiles);
+  return check_launch("gemm_nt3");
 }
 
 // tile-shape choice: fewest "rounds" of 128 x BN tiles over the SMs, weighted by the per-tile efficiency of wider tiles
@@ -425,15 +670,32 @@ static int pick_bn_nt(int M, int N) {
   return best;
 }
 
+bool g_nt_pairs = true;  // dsf_gemm_set_impl(3) = on (default), (2) = single-CTA v2 only
+
 int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, const float* bias, const float* residual, int M,
                int N, int K, int flags, const dsf_dropout* drop, const void* relu_src, cudaStream_t st) {
-  const int BN = pick_bn_nt(M, N);
+  static const int ablate = getenv("DSF_GEMM_ABLATE") ? atoi(getenv("DSF_GEMM_ABLATE")) : 0;
   CUtensorMap tmA, tmB;
+  if (g_nt_pairs && N % 128 == 0 && M > 128) {
+    // CTA-pair kernel: 256 x BN tiles, each CTA loads BN/2 rows of B.  BN = 256 whenever N allows: one tcgen05.mma costs
+    // about the same ~85 ns for N = 128 as for N = 256 (operand reads from shared memory bound it), so narrow tiles
+    // waste the tensor pipe even when they would balance the 74 pairs better (measured: N = 512, K = 2048 runs 27.0 us
+    // with 256-wide and 30.2 us with 128-wide tiles).
+    const int BN3 = N % 256 == 0 ? 256 : 128;
+    if (int e = make_tmap_bf16(&tmA, A, M, K, lda, G2_BM)) return e;
+    if (int e = make_tmap_bf16(&tmB, B, N, K, ldb, BN3 / 2)) return e;
+    CUtensorMap tmC3;
+    if (int e = make_tmap_2d(&tmC3, C, c_dtype, M, N, ldc, c_dtype == DSF_F32 ? 32 : 64, 32)) return e;
+    EpiArgs2 epi3{C, ldc, c_dtype, bias, residual, flags, N, reinterpret_cast<const __nv_bfloat16*>(relu_src), ablate, make_drop(drop)};
+    if (BN3 == 256) return launch_nt3<256, 5>(tmA, tmB, tmC3, epi3, M, N, K, st);
+    return launch_nt3<128, 6>(tmA, tmB, tmC3, epi3, M, N, K, st);
+  }
+  const int BN = pick_bn_nt(M, N);
   if (int e = make_tmap_bf16(&tmA, A, M, K, lda, G2_BM)) return e;
   if (int e = make_tmap_bf16(&tmB, B, N, K, ldb, BN)) return e;
   CUtensorMap tmC;  // store boxes: 32 rows x 128 bytes
   if (int e = make_tmap_2d(&tmC, C, c_dtype, M, N, ldc, c_dtype == DSF_F32 ? 32 : 64, 32)) return e;
-  EpiArgs2 epi{C, ldc, c_dtype, bias, residual, flags, N, reinterpret_cast<const __nv_bfloat16*>(relu_src), make_drop(drop)};
+  EpiArgs2 epi{C, ldc, c_dtype, bias, residual, flags, N, reinterpret_cast<const __nv_bfloat16*>(relu_src), ablate, make_drop(drop)};
   if (BN == 256) return launch_nt2<256, 3>(tmA, tmB, tmC, epi, M, N, K, st);
   if (BN == 128) return launch_nt2<128, 4>(tmA, tmB, tmC, epi, M, N, K, st);
   return launch_nt2<64, 5>(tmA, tmB, tmC, epi, M, N, K, st);

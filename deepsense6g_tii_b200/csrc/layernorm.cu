@@ -8,6 +8,7 @@
 // bias (model2_seq.py:109,124) and (b) a tensor-core GEMM operand: the kernel optionally emits the column
 // sums of dx (bias gradient) and a bf16 copy in the same pass, saving two more passes over the tensor.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -20,6 +21,8 @@ template <typename TY, int VPT>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      TY* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int M, int C, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 2;
   const float invC = 1.0f / (float)C;
@@ -65,13 +68,21 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   }
 }
 
-template <typename TY, int VPT, bool EXTRA>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+// DROP is a template parameter: the Philox code costs ~13 registers, which would take the common p = 0 instantiation
+// from 2 to 1 resident CTAs per SM.
+template <typename TY, int VPT, bool EXTRA, bool DROP>
+__global__ void __launch_bounds__(LN_WARPS * 32, (VPT <= 4 && !DROP) ? 2 : 1)
 layernorm_bwd_kernel(const TY* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* dx_add, float* dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_bf16,
                      float* __restrict__ dx_colsum, DropArgs drop, int M, int C) {
-  __shared__ float red[LN_WARPS][VPT * 128 + 4];
+  // column partials of the CTA's warps: [quantity (dgamma, dbeta, by-product sums)][warp][column]; quantities are
+  // reduced one after another for C > 512 (static shared memory is capped at 48 KB), all at once otherwise
+  constexpr int NQ = EXTRA ? 3 : 2;
+  constexpr int QPP = VPT <= 4 ? NQ : 1;  // quantities per pass
+  __shared__ float red[QPP][LN_WARPS][VPT * 128];
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 2;
   const float invC = 1.0f / (float)C;
@@ -130,7 +141,7 @@ layernorm_bwd_kernel(const TY* __restrict__ dy, const float* __restrict__ x, con
         }
         Vec4<float>::store(dxr + vi * 4, o);
         if (EXTRA) {
-          if (drop.thresh) {  // by-products are the gradient of the preceding Linear's PRE-dropout output
+          if (DROP) {  // by-products are the gradient of the preceding Linear's PRE-dropout output
             float m[4];
             drop_scale4(drop, (uint64_t)row * nvec + vi, m);
 #pragma unroll
@@ -143,24 +154,32 @@ layernorm_bwd_kernel(const TY* __restrict__ dy, const float* __restrict__ x, con
       }
     }
   }
-  // CTA reduction of the column partials, then one atomic per column
+  // CTA reduction of the column partials, then one atomic per column and quantity
 #pragma unroll 1
-  for (int pass = 0; pass < (EXTRA ? 3 : 2); ++pass) {
-    if (pass == 2 && dx_colsum == nullptr) break;
-    __syncthreads();
+  for (int pass = 0; pass < NQ / QPP; ++pass) {
+    if (pass > 0) __syncthreads();
 #pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      const int vi = lane + 32 * i;
+    for (int qq = 0; qq < QPP; ++qq) {
+      const int qn = pass * QPP + qq;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) red[warp][vi * 4 + k] = pass == 0 ? dg[i][k] : (pass == 1 ? db[i][k] : dc[EXTRA ? i : 0][k]);
+      for (int i = 0; i < VPT; ++i) {
+        const int vi = lane + 32 * i;
+        const float* src = qn == 0 ? dg[i] : (qn == 1 ? db[i] : dc[EXTRA ? i : 0]);
+        *reinterpret_cast<float4*>(&red[qq][warp][vi * 4]) = make_float4(src[0], src[1], src[2], src[3]);
+      }
     }
     __syncthreads();
-    float* out = pass == 0 ? dgamma : (pass == 1 ? dbeta : dx_colsum);
-    for (int c = threadIdx.x; c < C; c += LN_WARPS * 32) {
-      float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
-      atomicAdd(out + c, s);
+    for (int qq = 0; qq < QPP; ++qq) {
+      const int qn = pass * QPP + qq;
+      float* out = qn == 0 ? dgamma : (qn == 1 ? dbeta : dx_colsum);
+      if (out == nullptr) continue;
+      for (int c = threadIdx.x; c < C; c += LN_WARPS * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) s += red[qq][w][c];
+        atomicAdd(out + c, s);
+      }
     }
   }
 }
@@ -170,10 +189,12 @@ int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* y
                   float eps, cudaStream_t st) {
   const int blocks = std::min(cdiv(M, LN_WARPS), num_sms() * 8);
   TY* yy = reinterpret_cast<TY*>(y);
-  if (C <= 128) layernorm_fwd_kernel<TY, 1><<<blocks, LN_WARPS * 32, 0, st>>>(x, gamma, beta, yy, mean, rstd, M, C, eps);
-  else if (C <= 256) layernorm_fwd_kernel<TY, 2><<<blocks, LN_WARPS * 32, 0, st>>>(x, gamma, beta, yy, mean, rstd, M, C, eps);
-  else if (C <= 512) layernorm_fwd_kernel<TY, 4><<<blocks, LN_WARPS * 32, 0, st>>>(x, gamma, beta, yy, mean, rstd, M, C, eps);
-  else layernorm_fwd_kernel<TY, 8><<<blocks, LN_WARPS * 32, 0, st>>>(x, gamma, beta, yy, mean, rstd, M, C, eps);
+#define DSF_LN_FWD(V) launch_pdl(layernorm_fwd_kernel<TY, V>, dim3(blocks), dim3(LN_WARPS * 32), 0, st, x, gamma, beta, yy, mean, rstd, M, C, eps)
+  if (C <= 128) DSF_LN_FWD(1);
+  else if (C <= 256) DSF_LN_FWD(2);
+  else if (C <= 512) DSF_LN_FWD(4);
+  else DSF_LN_FWD(8);
+#undef DSF_LN_FWD
   return check_launch("layernorm_fwd");
 }
 
@@ -182,15 +203,22 @@ int launch_ln_bwd(const void* dy, const float* x, const float* gamma, const floa
                   const float* dx_add, float* dx, float* dgamma, float* dbeta, void* dx_bf16, float* dx_colsum, DropArgs drop, int M, int C,
                   cudaStream_t st) {
   // few, fat CTAs: every CTA ends with 2-3 x C atomics
-  const int blocks = std::min(cdiv(M, LN_WARPS * 2), num_sms() * 4);
+  static const int mult = getenv("DSF_LN_BWD_MULT") ? std::max(1, atoi(getenv("DSF_LN_BWD_MULT"))) : 4;
+  const int blocks = std::min(cdiv(M, LN_WARPS * 2), num_sms() * mult);
   const TY* d = reinterpret_cast<const TY*>(dy);
   __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
-#define DSF_LN_BWD(V) layernorm_bwd_kernel<TY, V, EXTRA><<<blocks, LN_WARPS * 32, 0, st>>>(d, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, xb, dx_colsum, drop, M, C)
+#define DSF_LN_BWD1(V, D) launch_pdl(layernorm_bwd_kernel<TY, V, EXTRA, D>, dim3(blocks), dim3(LN_WARPS * 32), 0, st, d, x, gamma, mean, rstd, dx_add, dx, dgamma, dbeta, xb, dx_colsum, drop, M, C)
+#define DSF_LN_BWD(V)                                   \
+  do {                                                  \
+    if (EXTRA && drop.thresh != 0) DSF_LN_BWD1(V, EXTRA); \
+    else DSF_LN_BWD1(V, false);                         \
+  } while (0)
   if (C <= 128) DSF_LN_BWD(1);
   else if (C <= 256) DSF_LN_BWD(2);
   else if (C <= 512) DSF_LN_BWD(4);
   else DSF_LN_BWD(8);
 #undef DSF_LN_BWD
+#undef DSF_LN_BWD1
   return check_launch("layernorm_bwd");
 }
 

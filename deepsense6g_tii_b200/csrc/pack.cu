@@ -27,6 +27,8 @@ struct PackJobs {
 
 __global__ void __launch_bounds__(256) pack_block_weights_kernel(PackJobs p) {
   __shared__ float tile[32][33];
+  pdl_trigger();
+  pdl_wait();
   const int t = blockIdx.x;
   if (t >= p.n_tiles) {  // last CTA: bias concat [query | key | value]
     for (int i = threadIdx.x; i < 3 * p.C; i += 256) {
@@ -121,7 +123,7 @@ extern "C" int dsf_pack_block_weights(const float* wq, const float* wk, const fl
   }
   p.n_tiles = tiles;
   p.bq = bq; p.bk = bk; p.bv = bv; p.bqkv = bqkv; p.C = C;
-  pack_block_weights_kernel<<<tiles + 1, 256, 0, (cudaStream_t)stream>>>(p);
+  dsf::launch_pdl(pack_block_weights_kernel, dim3(tiles + 1), dim3(256), 0, (cudaStream_t)stream, p);
   return check_launch("pack_block_weights");
 }
 
@@ -138,6 +140,8 @@ extern "C" int dsf_relu_bwd_colsum(void* dy, const void* h, float* out, int32_t 
 // ---------------------------------------------------------------- embedding dropout (model2_seq.py:272) and its backward
 namespace dsf {
 __global__ void __launch_bounds__(256) dropout_inplace_kernel(float* __restrict__ x, int64_t n4, DropArgs a) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float v[4], m[4];
     Vec4<float>::load(x + i * 4, v);
@@ -157,6 +161,6 @@ extern "C" int dsf_dropout_inplace(float* x, int64_t n, const dsf_dropout* d, vo
   if (a.thresh == 0) return DSF_OK;
   const int64_t n4 = n / 4;
   const int blocks = (int)std::min<int64_t>(dsf::cdiv64(n4, 256), (int64_t)dsf::num_sms() * 16);
-  dsf::dropout_inplace_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n4, a);
+  dsf::launch_pdl(dsf::dropout_inplace_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, n4, a);
   return dsf::check_launch("dropout_inplace");
 }

@@ -137,6 +137,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ X, int ldx, float* __restrict__ out, int M, int N, int rows_per_block) {
   constexpr int VEC = 16 / (int)sizeof(T);
   __shared__ float red[8][32 * VEC + 1];
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n = (blockIdx.x * 32 + lane) * VEC;
   const int m_lo = blockIdx.y * rows_per_block, m_hi = min(M, m_lo + rows_per_block);
@@ -183,7 +185,7 @@ static void launch_colsum(const T* X, int ldx, float* out, int M, int N, cudaStr
     const int col_blocks = cdiv(N, 32 * VEC);
     const int row_blocks = max(1, min(cdiv(M, 64), (num_sms() * 6) / col_blocks));
     const int rpb = cdiv(M, row_blocks);
-    colsum_vec_kernel<T><<<dim3(col_blocks, cdiv(M, rpb)), 256, 0, st>>>(X, ldx, out, M, N, rpb);
+    launch_pdl(colsum_vec_kernel<T>, dim3(col_blocks, cdiv(M, rpb)), dim3(256), 0, st, X, ldx, out, M, N, rpb);
     return;
   }
   const int row_blocks = max(1, min(cdiv(M, 64), (num_sms() * 4) / max(1, cdiv(N, 64))));

@@ -54,6 +54,9 @@ const char* dsf_last_error(void);
 int64_t dsf_launch_count(void);
 /* 0 if the current device is sm_100 and the kernels can run on it, DSF_EARCH otherwise. */
 int dsf_check_device(void);
+/* Programmatic dependent launch of the hot kernels (default on): each kernel's launch latency and set-up overlap
+ * the tail of its predecessor in the stream; results are identical either way (process-wide; A/B timing). */
+int dsf_set_pdl(int32_t on);
 
 /* One nn.Dropout site (model2_seq.py:104 attn_drop, :109/:125 resid_drop, :272 embd drop).  The keep/drop decision
  * of element e is a pure function of (seed, site, step, e) (Philox4x32-10), so forward and backward kernels agree
@@ -128,8 +131,9 @@ int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32_t ldb, voi
                      void* stream);
 int dsf_gemm_bf16_tn(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc,
                      int32_t M, int32_t Nout, int32_t Kout, void* stream);
-/* Selects the tensor-core GEMM implementation (process-wide; tests and A/B timing): 0 = default,
- * 1 = v1 (one CTA per 128x128 tile), 2 = v2 (persistent, 128x256 tiles, double-buffered TMEM).    */
+/* Selects the tensor-core GEMM implementation (process-wide; tests and A/B timing): 0 = default (= 3),
+ * 1 = v1 (one CTA per 128x128 tile), 2 = v2 (persistent, 128x256 tiles, double-buffered TMEM),
+ * 3 = v3 (NT: CTA pairs, tcgen05.mma.cta_group::2 on 256x256 tiles where N % 256 == 0; otherwise v2). */
 int dsf_gemm_set_impl(int32_t impl);
 
 /* fp32 parity path: generic strided, two-level batched SIMT GEMM (FFMA).

@@ -56,11 +56,13 @@ if "gemm" in what:
         dw = torch.zeros(N, Kd, device=dev)
         fl = 2.0 * M * N * Kd
         line = "gemm M=%d N=%d K=%d: cublas %.4f ms (%.0f TF/s)" % (M, N, Kd, tt, fl / tt / 1e9)
-        for impl in (1, 2):
+        for impl in (2, 3):
             K.gemm_set_impl(impl)
             t = timeit(lambda: K.gemm_bf16_nt(a, w, out, bias=bias))
-            t2 = timeit(lambda: K.gemm_bf16_tn(dy, a, dw))
-            line += " | v%d nt %.4f ms (%.0f TF/s) tn %.4f ms (%.0f TF/s)" % (impl, t, fl / t / 1e9, t2, fl / t2 / 1e9)
+            line += " | v%d nt %.4f ms (%.0f TF/s)" % (impl, t, fl / t / 1e9)
+            if impl == 2:
+                t2 = timeit(lambda: K.gemm_bf16_tn(dy, a, dw))
+                line += " tn %.4f ms (%.0f TF/s)" % (t2, fl / t2 / 1e9)
         K.gemm_set_impl(0)
         print(line)
 
@@ -91,3 +93,40 @@ if "elem" in what:
     h = torch.randn(M, 4 * C, device=dev).to(torch.bfloat16)
     t = timeit(lambda: K.relu_bwd(big, h))
     print("relu_bwd M x 2048: %.4f ms (%.0f GB/s)" % (t, M * 4 * C * 6 / t / 1e6))
+
+if "ln" in what:
+    # LayerNorm backward as the step runs it: fp32 dy, residual-stream add, bf16 copy + column sums; 8 rotating buffer sets
+    # (8 x 106 MB) so that the inputs come from HBM like in the step
+    M, C = 11544, 512
+    sets = []
+    for _ in range(8):
+        sets.append(dict(dy=torch.randn(M, C, device=dev), x=torch.randn(M, C, device=dev), add=torch.randn(M, C, device=dev),
+                         dx=torch.empty(M, C, device=dev), dxb=torch.empty(M, C, device=dev, dtype=torch.bfloat16)))
+    g = torch.randn(C, device=dev)
+    mean, rstd = torch.zeros(M, device=dev), torch.ones(M, device=dev)
+    dg, db, cs = torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    it = [0]
+
+    def run():
+        s = sets[it[0] % 8]
+        it[0] += 1
+        K.layernorm_bwd(s["dy"], s["x"], g, mean, rstd, s["add"], s["dx"], dg, db, dx_bf16=s["dxb"], dx_colsum=cs)
+    t = timeit(run, iters=40, warm=8)
+    print("layernorm_bwd (step form, HBM-resident) mult=%s: %.4f ms (%.0f GB/s of 18 B/elem)"
+          % (os.environ.get("DSF_LN_BWD_MULT", "default"), t, M * C * 18 / t / 1e6))
+    yb = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+
+    def runf():
+        s = sets[it[0] % 8]
+        it[0] += 1
+        K.layernorm_fwd(s["x"], g, g, yb, mean, rstd)
+    t = timeit(runf, iters=40, warm=8)
+    print("layernorm_fwd (HBM-resident): %.4f ms (%.0f GB/s of 6 B/elem)" % (t, M * C * 6 / t / 1e6))
+    big = [torch.randn(M, 3 * C, device=dev).to(torch.bfloat16) for _ in range(8)]
+    o = torch.zeros(3 * C, device=dev)
+
+    def runc():
+        it[0] += 1
+        K.colsum(big[it[0] % 8], o)
+    t = timeit(runc, iters=40, warm=8)
+    print("colsum bf16 M x 1536 (HBM-resident): %.4f ms (%.0f GB/s)" % (t, M * 3 * C * 2 / t / 1e6))

@@ -252,7 +252,7 @@ GEMM_SHAPES = [(128, 64, 64), (128, 128, 64), (300, 128, 128), (962, 192, 64), (
                (2048, 1536, 512), (1924, 512, 2048), (1924, 2048, 512), (130, 64, 256)]
 
 
-@pytest.fixture(params=[1, 2], ids=["gemm_v1", "gemm_v2"])
+@pytest.fixture(params=[1, 2, 3], ids=["gemm_v1", "gemm_v2", "gemm_v3_pairs"])
 def gemm_impl(request, K):
     K.gemm_set_impl(request.param)
     yield request.param
