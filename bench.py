@@ -270,7 +270,8 @@ def run_ours(args, rank, world, local_rank):
     # replay removes the per-launch host cost and the launch gaps between dependent kernels.
     graph, graph_launches, graph_note = None, 0, "eager launches"
     pdl_note = ", programmatic dependent launch on" if args.pdl else ", programmatic dependent launch off"
-    use_graph = args.graph and (world == 1 or os.environ.get("DSF_GRAPH_DDP") == "1")
+    # (N > 1: the bucketed NCCL all-reduces issued from inside the backward are captured too; DSF_GRAPH_DDP=0 opts out)
+    use_graph = args.graph and (world == 1 or os.environ.get("DSF_GRAPH_DDP", "1") == "1")
     if use_graph:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -343,9 +344,19 @@ def run_ours(args, rank, world, local_rank):
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     ms, launches, clocks = timed(step_resident, steps, warmup, ClockSampler(local_rank) if rank == 0 else None)
     value = BATCH * world * steps / (ms * 1e-3)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms / steps, "value": value, "gpu_launches": launches}))
+        return
     ms_e2e, _, _ = timed(step_e2e, steps, 2)
     e2e_value = BATCH * world * steps / (ms_e2e * 1e-3)
 
+    synced = None
+    if world > 1:  # the replayed / eager steps really exchanged gradients: every rank holds the same averaged pos_emb gradient
+        g = gpt.pos_emb.grad.detach().reshape(-1)[:4096].contiguous()
+        gs = [torch.empty_like(g) for _ in range(world)]
+        dist.all_gather(gs, g)
+        synced = all(torch.equal(gs[0], t) for t in gs[1:]) and bool(torch.isfinite(g).all()) and float(g.abs().sum()) > 0
     if rank != 0:
         return
     pk = peaks()
@@ -371,7 +382,8 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "seq_len": S, "parallelism": "dp%d" % world,
                    "launch": graph_note + pdl_note,
                    "l2": "per-step working set ~1.5 GB of saved activations > 126 MB L2; no explicit flush",
-                   "grad_allreduce": "NCCL all-reduce (avg) of 25.7 M fp32 grads per step, one bucket per block, overlapped with backward" if world > 1 else "none (1 GPU)"},
+                   "grad_allreduce": "NCCL all-reduce (avg) of 25.7 M fp32 grads per step, one bucket per block, overlapped with backward" if world > 1 else "none (1 GPU)",
+                   "grads_identical_across_ranks": synced},
         "stage_tflops": step_flops * world / (ms / steps * 1e-3) / 1e12,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
@@ -388,6 +400,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: skip the e2e leg, the instrumented step and the CPU baseline")
     ap.add_argument("--no-pdl", dest="pdl", action="store_false", help="disable programmatic dependent launch of the hot kernels")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
