@@ -435,11 +435,13 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     static_assert(BQ == 64, "the math warps split a 64-query tile in two 32-column halves");
     const size_t bh = (size_t)b * nh + h;
     const int kw = kv0 / 32 + (warp & 3);  // bitmap word holding this warp's 32 keys
-    // per-query statistics (thread c < 64: lse, 64 <= c < 128: delta) and, for attn-dropout, the keep word of query
-    // (wg*32 + lane); both are fetched one tile ahead so their global-memory latency hides behind the current tile
+    // per-query statistics of this warpgroup's 32 query columns (thread t of the warpgroup: t < 32 lse, 32 <= t < 64
+    // delta) and, for attn-dropout, the keep word of query (wg*32 + lane); both are fetched one tile ahead so their
+    // global-memory latency hides behind the current tile.  Each warpgroup stages and synchronises on its own half.
+    const int tw = threadIdx.x & 127;
     auto fetch = [&](int it, float& sv, uint32_t& wv) {
-      const int c = threadIdx.x, qq = it * BQ + (c & (BQ - 1));
-      sv = c < BQ ? (qq < T ? lse_g[qq] * 1.4426950408889634f : INFINITY) : (c < 2 * BQ && qq < T ? delta_g[qq] : 0.f);
+      const int qq = it * BQ + wg * 32 + (tw & 31);
+      sv = tw < 32 ? (qq < T ? lse_g[qq] * 1.4426950408889634f : INFINITY) : (tw < 64 && qq < T ? delta_g[qq] : 0.f);
       wv = 0xFFFFFFFFu;
       if (ad.thresh8) {
         const int qd = it * BQ + wg * 32 + lane;
@@ -453,11 +455,12 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       const int bf = i & 1;
       float* st_lse = reinterpret_cast<float*>(smem + L::STAT_OFF) + bf * 2 * BQ;
       float* st_delta = st_lse + BQ;
-      // the stats buffer bf was last read two iterations ago; every thread has passed the barrier below since then
-      if (threadIdx.x < 2 * BQ) st_lse[threadIdx.x] = sv;  // st_delta directly follows st_lse
+      // the stats buffer bf was last read two iterations ago; every thread of the warpgroup has passed the barrier below since
+      if (tw < 32) st_lse[wg * 32 + tw] = sv;
+      else if (tw < 64) st_delta[wg * 32 + tw - 32] = sv;
       const uint32_t myw = wv;
       if (i + 1 < n_q) fetch(i + 1, sv, wv);
-      named_bar_sync(1, 256);
+      named_bar_sync(1 + wg, 128);
       mbar_wait(s_full + 8 * bf, (i >> 1) & 1);
       tc_fence_after();
       if (i >= 2) mbar_wait(ds_empty + 8 * bf, ((i >> 1) - 1) & 1);
@@ -479,15 +482,17 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           float p[4], d[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            p[u] = key_ok ? ex2_approx(fmaf(__uint_as_float(rs[e + u]), scale_log2, -ls[u])) : 0.f;
+            // rows of keys >= T hold finite garbage (K, V rows are zero-filled): they only reach the dK / dV rows of those
+            // keys, which are never stored.  The 1/sqrt(hs) factor of dS is applied once when dK is drained.
+            p[u] = ex2_approx(fmaf(__uint_as_float(rs[e + u]), scale_log2, -ls[u]));
             float dp = __uint_as_float(rp[e + u]);
             if (ad.thresh8) {  // attn_drop: dV sees P*mask/(1-p); dP = dP_drop*mask/(1-p)
               const float m = (__shfl_sync(0xffffffffu, myw, e + u) >> lane) & 1u ? ad.scale : 0.f;
               dp *= m;
-              d[u] = p[u] * (dp - dl[u]) * scale;
+              d[u] = p[u] * (dp - dl[u]);
               p[u] *= m;
             } else {
-              d[u] = p[u] * (dp - dl[u]) * scale;
+              d[u] = p[u] * (dp - dl[u]);
             }
           }
           pk[e / 2] = pack_bf16x2(p[0], p[1]);
@@ -512,7 +517,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       uint32_t a[16];
       tmem_ld16((wg == 0 ? tm_dk : tm_dv) + lane_off + c, a);
       tmem_wait_ld();
-      if (key_ok) store_row16_bf16((wg == 0 ? dk_row : dv_row) + c, a, 1.0f);
+      if (key_ok) store_row16_bf16((wg == 0 ? dk_row : dv_row) + c, a, wg == 0 ? scale : 1.0f);
     }
   }
   tc_fence_before();
@@ -640,16 +645,26 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld32(tm_dp + c, rp);
         tmem_wait_ld();
         uint32_t dk[16];
+        // the 1/sqrt(hs) factor of dS is applied once when dQ is drained; only the last key tile needs the column mask
+        if (kv0 + BKV <= T && !ad.thresh8) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = (kv0 + c + e < T) ? ex2_approx(fmaf(__uint_as_float(rs[e]), scale_log2, -my_lse)) : 0.f;
-          float p1 = (kv0 + c + e + 1 < T) ? ex2_approx(fmaf(__uint_as_float(rs[e + 1]), scale_log2, -my_lse)) : 0.f;
-          float dp0 = __uint_as_float(rp[e]), dp1 = __uint_as_float(rp[e + 1]);
-          if (ad.thresh8) {  // dP = dP_drop * mask/(1-p)
-            dp0 *= (keepw >> e) & 1u ? ad.scale : 0.f;
-            dp1 *= (keepw >> (e + 1)) & 1u ? ad.scale : 0.f;
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), scale_log2, -my_lse));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), scale_log2, -my_lse));
+            dk[e / 2] = pack_bf16x2(p0 * (__uint_as_float(rp[e]) - my_delta), p1 * (__uint_as_float(rp[e + 1]) - my_delta));
           }
-          dk[e / 2] = pack_bf16x2(p0 * (dp0 - my_delta) * scale, p1 * (dp1 - my_delta) * scale);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = (kv0 + c + e < T) ? ex2_approx(fmaf(__uint_as_float(rs[e]), scale_log2, -my_lse)) : 0.f;
+            float p1 = (kv0 + c + e + 1 < T) ? ex2_approx(fmaf(__uint_as_float(rs[e + 1]), scale_log2, -my_lse)) : 0.f;
+            float dp0 = __uint_as_float(rp[e]), dp1 = __uint_as_float(rp[e + 1]);
+            if (ad.thresh8) {  // dP = dP_drop * mask/(1-p)
+              dp0 *= (keepw >> e) & 1u ? ad.scale : 0.f;
+              dp1 *= (keepw >> (e + 1)) & 1u ? ad.scale : 0.f;
+            }
+            dk[e / 2] = pack_bf16x2(p0 * (dp0 - my_delta), p1 * (dp1 - my_delta));
+          }
         }
         store_p32<BKV>(ds, row, c, dk);
       }
@@ -668,7 +683,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint32_t a[16];
       tmem_ld16(tm_dq + lane_off + c, a);
       tmem_wait_ld();
-      if (q_ok) store_row16_bf16(dq_row + c, a, 1.0f);
+      if (q_ok) store_row16_bf16(dq_row + c, a, scale);
     }
   }
   tc_fence_before();
