@@ -296,12 +296,37 @@ def run_ours(args, rank, world, local_rank):
         else:
             step_eager()
 
-    def step_e2e():
-        # host -> device copy of this step's inputs from pinned memory, fwd+bwd, device -> host read of the loss
-        with torch.no_grad():
-            for d, h in zip(feats, feats_h):
+    # e2e pipeline: every step copies ONE batch of inputs pinned-host -> device (23.6 MB) and reads the loss back.  The
+    # copy of step k+1's batch runs on a copy stream into a double-buffered staging area while step k computes (what a
+    # training data loader with pinned-memory prefetch does); the compute stream then moves the staged batch into the
+    # step's input tensors (device-to-device, ~10 us) and runs the step.
+    copy_stream = torch.cuda.Stream()
+    host_in = feats_h + [gps_h]
+    stage = [[torch.empty_like(t, device=dev) for t in host_in] for _ in range(2)]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]  # batch landed in stage[i]
+    ev_free = [torch.cuda.Event() for _ in range(2)]   # the compute stream has consumed stage[i]
+    e2e_k = [0, False]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[i])
+            for d, h in zip(stage[i], host_in):
                 d.copy_(h, non_blocking=True)
-            gps.copy_(gps_h, non_blocking=True)
+            ev_ready[i].record(copy_stream)
+
+    def step_e2e():
+        i = e2e_k[0] & 1
+        if not e2e_k[1]:  # prime the pipeline (first warm-up step only)
+            prefetch(i)
+            e2e_k[1] = True
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev_ready[i])
+        with torch.no_grad():
+            for d, st_ in zip(feats + [gps], stage[i]):
+                d.copy_(st_, non_blocking=True)
+        ev_free[i].record(cur)
+        prefetch(i ^ 1)  # next step's batch: overlaps this step's compute
+        e2e_k[0] += 1
         if graph is not None:
             graph.replay()
             loss_h.copy_(graph_loss.detach(), non_blocking=True)
@@ -314,7 +339,7 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(fn, steps, warmup, sampler=None, finalize=None):
         for _ in range(warmup):
             fn()
         barrier()
@@ -328,6 +353,8 @@ def run_ours(args, rank, world, local_rank):
         e0.record()
         for _ in range(steps):
             fn()
+        if finalize is not None:
+            finalize()
         e1.record()
         if ncu_range:
             torch.cuda.profiler.stop()
@@ -348,7 +375,8 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms / steps, "value": value, "gpu_launches": launches}))
         return
-    ms_e2e, _, _ = timed(step_e2e, steps, 2)
+    # the K-th prefetch issued inside the region must also complete inside it: K steps <-> K host-to-device batch copies
+    ms_e2e, _, _ = timed(step_e2e, steps, 2, finalize=lambda: torch.cuda.current_stream().wait_event(ev_ready[e2e_k[0] & 1]))
     e2e_value = BATCH * world * steps / (ms_e2e * 1e-3)
 
     synced = None
@@ -366,8 +394,14 @@ def run_ours(args, rank, world, local_rank):
     tc = {k: d for k, d in fam.items() if d["flops"] > 0}
     dom = max(tc, key=lambda k: tc[k]["ms"])
     achieved = tc[dom]["flops"] / (tc[dom]["ms"] * 1e-3) / 1e12
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01g_traffic.json")
+    if dom == "gemm_bf16_nt" and os.path.isfile(tp):  # dram bytes per launch of the dominant kernel, from the committed ncu capture
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj["avg_dram_bytes_per_launch"], tj["source"]
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tc_sust"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tc_sust"], "traffic": None, "peak_source": pk["src"] + " bf16_tflops_sustained",
+                "frac": achieved / pk["tc_sust"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": pk["src"] + " bf16_tflops_sustained",
                 "launches_per_step": tc[dom]["launch_calls"], "avg_launch_ms": tc[dom]["ms"] / tc[dom]["launch_calls"],
                 "share_of_step": tc[dom]["ms"] / total_ms,
                 "families": {k: {"ms": round(d["ms"], 4), "calls": d["launch_calls"],
@@ -385,7 +419,8 @@ def run_ours(args, rank, world, local_rank):
                    "grad_allreduce": "NCCL all-reduce (avg) of 25.7 M fp32 grads per step, one bucket per block, overlapped with backward" if world > 1 else "none (1 GPU)",
                    "grads_identical_across_ranks": synced},
         "stage_tflops": step_flops * world / (ms / steps * 1e-3) / 1e12,
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps,
+                "pipeline": "one pinned-host -> device batch copy per step on a copy stream (double-buffered), overlapped with the previous step's compute; loss read back every step"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": "oracle port fp32, batch %d, 1 warm-up + 2 timed steps, %s" % (CPU_SAMPLE_BATCH, cpu_model())},
