@@ -241,6 +241,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     _capi.check_device()
     _capi.set_pdl(args.pdl)
+    sm_margin = int(os.environ.get("DSF_SM_MARGIN", "0")) if world > 1 else 0
+    _capi.set_sm_margin(sm_margin)
     gpt = build_gpt(dev)
     model = gpt
     if world > 1:
@@ -428,6 +430,119 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(out))
 
 
+# ----------------------------------------------------------------------------------------- full-model workload (configs[2])
+def run_model(args, rank, world, local_rank):
+    """BASELINE.json configs[2]: full model2_seq training step — drop-in TransFuser (ResNet trunks + 4 fusion stages on
+    the dsfuse kernels + join MLP), bf16, batch 12 per GPU, seq_len 5, 256x256 inputs, dropout 0.1 (config_seq.py:39-41),
+    focal loss + fused AdamW + EMA, synthetic data; N > 1: DistributedDataParallel over NCCL (batch-sharded)."""
+    import types
+    import torch.distributed as dist
+    from deepsense6g_tii_b200 import TransFuser, _capi
+    from deepsense6g_tii_b200.train import EMA, FocalLoss, synthetic_batch, train_step
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _capi.check_device()
+    _capi.set_pdl(args.pdl)
+    torch.backends.cudnn.benchmark = True  # as the reference (train2_seq.py:16)
+    cfg = types.SimpleNamespace(seq_len=S, pred_len=4, n_views=1, vert_anchors=A, horz_anchors=A, n_embd=512, block_exp=4, n_layer=L,
+                                n_head=NH, embd_pdrop=0.1, attn_pdrop=0.1, resid_pdrop=0.1, add_velocity=1, fusion_dtype=torch.bfloat16)
+    torch.manual_seed(100)
+    model = TransFuser(cfg, dev).to(memory_format=torch.channels_last).train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+    crit = FocalLoss()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    ema = EMA(model, 0.999)
+    ema.register()
+    gen = torch.Generator().manual_seed(rank)
+    host = synthetic_batch(BATCH, S, 256, generator=gen, pin=True)
+
+    def to_dev(b, stream=None):
+        imgs, lids, rads, gps, soft, beam = b
+        mv = lambda t: t.to(dev, non_blocking=True)
+        return ([mv(t).contiguous(memory_format=torch.channels_last) for t in imgs], [mv(t) for t in lids], [mv(t) for t in rads],
+                mv(gps), mv(soft), mv(beam))
+
+    resident = to_dev(host)
+    loss_h = torch.empty((), pin_memory=True)
+
+    def step_resident():
+        return train_step(net, resident, crit, opt, ema, autocast_dtype=torch.bfloat16)
+
+    copy_stream = torch.cuda.Stream()
+    nxt = {"b": None, "ev": None}
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            nxt["b"] = to_dev(host)
+            nxt["ev"] = torch.cuda.Event()
+            nxt["ev"].record(copy_stream)
+
+    def step_e2e():
+        if nxt["b"] is None:
+            prefetch()
+        torch.cuda.current_stream().wait_event(nxt["ev"])
+        b = nxt["b"]
+        for t in b[0] + b[1] + b[2] + list(b[3:]):
+            t.record_stream(torch.cuda.current_stream())
+        prefetch()  # next step's batch (94 MB pinned-host -> device) overlaps this step's compute
+        loss_h.copy_(train_step(net, b, crit, opt, ema, autocast_dtype=torch.bfloat16).detach(), non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, finalize=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _capi.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        if finalize is not None:
+            finalize()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, _capi.launch_count() - n0
+
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches = timed(step_resident, steps, warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _ = timed(step_e2e, steps, 2, finalize=lambda: torch.cuda.current_stream().wait_event(nxt["ev"]))
+    loss_val = float(loss_h)
+    if rank != 0:
+        return
+    h2d = sum(t.numel() * t.element_size() for t in host[0] + host[1] + host[2]) + sum(t.numel() * t.element_size() for t in host[3:])
+    n_params = sum(p.numel() for p in model.parameters())
+    print(json.dumps({
+        "metric": "train samples/sec (fwd+bwd)", "value": BATCH * world * steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "full model2_seq TransFuser training step: fwd + focal loss + bwd + fused AdamW + EMA, batch 12/GPU, seq_len 5, "
+                               "256x256 inputs, dropout 0.1, %d parameters, ResNet trunks in stock PyTorch (channels_last, bf16 autocast), "
+                               "4 fusion stages on dsfuse kernels" % n_params,
+                   "global_batch": BATCH * world, "seq_len": S, "parallelism": "dp%d" % world, "launch": "eager launches, PDL " + ("on" if args.pdl else "off"),
+                   "l2": "per-step working set (activations of 3 ResNets + 4 fusion stages) >> 126 MB L2; no explicit flush",
+                   "grad_allreduce": "torch DistributedDataParallel (NCCL, bucketed, overlapped)" if world > 1 else "none (1 GPU)"},
+        "e2e": {"value": BATCH * world * steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / steps, "pipeline": "next batch copied pinned-host -> device on a copy stream during the current step"},
+        "gpu_launches": launches, "clocks": clocks, "final_loss": loss_val,
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -435,6 +550,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--workload", default="stage", choices=["stage", "model"],
+                    help="stage = BASELINE.json configs[1] (default, the driver's line); model = configs[2], the full training step")
     ap.add_argument("--quick", action="store_true", help="profiling runs: skip the e2e leg, the instrumented step and the CPU baseline")
     ap.add_argument("--no-pdl", dest="pdl", action="store_false", help="disable programmatic dependent launch of the hot kernels")
     args = ap.parse_args()
@@ -451,7 +568,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.workload == "model":
+            run_model(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -20,7 +20,7 @@ EPI_BIAS, EPI_RELU, EPI_RESIDUAL, EPI_ACCUM = 1, 2, 4, 8
 
 # every symbol include/dsfuse.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_set_pdl", "dsf_dropout_inplace", "dsf_tokens_fwd", "dsf_tokens_bwd",
+    "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_set_pdl", "dsf_set_sm_margin", "dsf_dropout_inplace", "dsf_tokens_fwd", "dsf_tokens_bwd",
     "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_set_impl", "dsf_gemm_f32",
     "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_set_impl", "dsf_attn_drop_words",
     "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16",
@@ -84,6 +84,7 @@ def lib():
             "dsf_attn_bwd": [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P, P],
             "dsf_attn_set_impl": [c_int32],
             "dsf_set_pdl": [c_int32],
+            "dsf_set_sm_margin": [c_int32],
             "dsf_gemm_set_impl": [c_int32],
             "dsf_upsample_add_fwd": [POINTER(Geom), P, P, P, P, P, P, P, P],
             "dsf_upsample_add_bwd": [POINTER(Geom), P, P, P, P, P, P],
@@ -240,6 +241,11 @@ def gemm_set_impl(impl):
 def set_pdl(on):
     """Programmatic dependent launch of the hot kernels on/off (default on); results are identical."""
     _chk(lib().dsf_set_pdl(1 if on else 0), "dsf_set_pdl")
+
+
+def set_sm_margin(sms):
+    """Size persistent grids for (SM count - sms): leaves room for concurrently running NCCL kernels (even, 0..64)."""
+    _chk(lib().dsf_set_sm_margin(int(sms)), "dsf_set_sm_margin")
 
 
 def attn_set_impl(impl):

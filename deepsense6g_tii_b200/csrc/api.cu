@@ -1,6 +1,8 @@
 // Library-level entry points: version, error string, device check.
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dsf {
@@ -26,6 +28,7 @@ int check_launch(const char* what) {
 }
 
 static int g_pdl = 1;
+static int g_sm_margin = 0;  // SMs left to concurrent kernels of other streams (NCCL), see dsf_set_sm_margin
 bool pdl_enabled() { return g_pdl != 0; }
 
 int num_sms() {
@@ -37,12 +40,20 @@ int num_sms() {
     cached_dev = dev;
     if (cached <= 0) cached = 148;
   }
-  return cached;
+  return std::max(2, cached - g_sm_margin);
 }
 
 }  // namespace dsf
 
 extern "C" int dsf_version(void) { return DSF_VERSION; }
+extern "C" int dsf_set_sm_margin(int32_t sms) {
+  if (sms < 0 || sms > 64 || (sms & 1)) {
+    dsf::set_error("set_sm_margin: margin must be an even number in [0, 64]");
+    return DSF_EINVAL;
+  }
+  dsf::g_sm_margin = sms;
+  return DSF_OK;
+}
 extern "C" int dsf_set_pdl(int32_t on) {
   dsf::g_pdl = on ? 1 : 0;
   return DSF_OK;

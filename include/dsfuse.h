@@ -57,6 +57,10 @@ int dsf_check_device(void);
 /* Programmatic dependent launch of the hot kernels (default on): each kernel's launch latency and set-up overlap
  * the tail of its predecessor in the stream; results are identical either way (process-wide; A/B timing). */
 int dsf_set_pdl(int32_t on);
+/* Grids of the persistent kernels (one CTA per SM, static tile schedule) are sized for (SM count - margin): a kernel
+ * of another stream that occupies SMs at the same time (the NCCL all-reduce of the data-parallel step) would otherwise
+ * push some CTAs into a second wave and nearly double those launches.  Even number in [0, 64]; default 0. */
+int dsf_set_sm_margin(int32_t sms);
 
 /* One nn.Dropout site (model2_seq.py:104 attn_drop, :109/:125 resid_drop, :272 embd drop).  The keep/drop decision
  * of element e is a pure function of (seed, site, step, e) (Philox4x32-10), so forward and backward kernels agree
