@@ -587,9 +587,10 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
 
 // v2 (warp-specialised, TMA-fed) implementations, attn_tc2.cu
 int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st);
-int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, cudaStream_t st);
+int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem,
+                cudaStream_t st);
 int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
-                const dsf_dropout* drop, uint32_t* bits, cudaStream_t st);
+                const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem, cudaStream_t st);
 
 int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, int C, int nh, cudaStream_t st) {
   launch_pdl(attn_delta_kernel, dim3(std::min(cdiv(B * T, 8), num_sms() * 8)), dim3(256), 0, st, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy,
@@ -597,14 +598,16 @@ int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, in
   return check_launch("attn_bwd/delta");
 }
 
-static int g_attn_impl = 0;  // 0 = default (newest), 1 = v1 (simple synchronous), 2 = v2 (pipelined), 3 = v3 (fwd: double-buffered S/P)
+// 0 = default (= 4), 1 = v1 (simple synchronous), 2 = v2 (pipelined), 3 = v3 (fwd: double-buffered S/P, P through shared memory),
+// 4 = v4 (v3 schedule with P / dS kept in tensor memory: TS-mode tcgen05.mma, no shared-memory round trip)
+static int g_attn_impl = 0;
 
 }  // namespace dsf
 
 using namespace dsf;
 
 extern "C" int dsf_attn_set_impl(int32_t impl) {
-  DSF_REQUIRE(impl >= 0 && impl <= 3, "attn_set_impl: impl must be 0 (default), 1, 2 or 3");
+  DSF_REQUIRE(impl >= 0 && impl <= 4, "attn_set_impl: impl must be 0 (default), 1, 2, 3 or 4");
   g_attn_impl = impl;
   return DSF_OK;
 }
@@ -615,7 +618,7 @@ static int check_attn_drop(const char* who, const dsf_dropout* drop, const uint3
   if (!on) return DSF_OK;
   if (!(drop->p < 1.f)) { set_error("%s: dropout p must be in [0, 1)", who); return DSF_EINVAL; }
   if (!bits) { set_error("%s: attention dropout needs the drop_bits buffer", who); return DSF_EINVAL; }
-  if (g_attn_impl == 1 || g_attn_impl == 2) { set_error("%s: attention dropout is only implemented in the default kernels", who); return DSF_EUNSUPPORTED; }
+  if (g_attn_impl == 1 || g_attn_impl == 2) { set_error("%s: attention dropout is only implemented in the v3 / v4 kernels", who); return DSF_EUNSUPPORTED; }
   return DSF_OK;
 }
 
@@ -635,7 +638,7 @@ extern "C" int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int
   const int hs = C / nh;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_attn_impl == 2) return attn_fwd_v2(qkv, y, lse, B, T, C, nh, st);
-  if (g_attn_impl != 1) return attn_fwd_v3(qkv, y, lse, B, T, C, nh, drop_on ? drop : nullptr, drop_bits, st);
+  if (g_attn_impl != 1) return attn_fwd_v3(qkv, y, lse, B, T, C, nh, drop_on ? drop : nullptr, drop_bits, g_attn_impl == 4 || g_attn_impl == 0, st);
   switch (hs) {
     case 16: return launch_attn_fwd<16, 128>(qkv, y, lse, B, T, C, nh, st);
     case 32: return launch_attn_fwd<32, 128>(qkv, y, lse, B, T, C, nh, st);
@@ -657,7 +660,8 @@ extern "C" int dsf_attn_bwd(const void* qkv, const void* y, const void* dy, cons
   DSF_REQUIRE(B <= 65535 && nh <= 65535, "attn_bwd: grid too large");
   const int hs = C / nh;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_attn_impl != 1) return attn_bwd_v2(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop_on ? drop : nullptr, const_cast<uint32_t*>(drop_bits), st);
+  if (g_attn_impl != 1)
+    return attn_bwd_v2(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop_on ? drop : nullptr, const_cast<uint32_t*>(drop_bits), g_attn_impl == 4 || g_attn_impl == 0, st);
   switch (hs) {
     case 16: return launch_attn_bwd<16, 128>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
     case 32: return launch_attn_bwd<32, 128>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);

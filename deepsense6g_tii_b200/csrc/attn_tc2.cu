@@ -126,6 +126,25 @@ __device__ __forceinline__ void mma_over_rows(uint32_t tmem_d, uint32_t p_tile, 
   __syncwarp();
 }
 
+// D[128 x HS] (+)= P(tensor memory, [128 x KC] bf16 packed two per column at p_tmem) . B(tile with KC rows, MN-major)
+// SPLIT = false: the packed columns are contiguous (8 per K = 16 step).  SPLIT = true (backward kernels): the two math
+// warpgroups each overwrite the first 16 columns of their own 32-column region of the fp32 tile, so K-steps 0,1 sit at
+// columns 0 / 8 and K-steps 2,3 at columns 32 / 40.
+template <int HS, int KC, bool SPLIT = false>
+__device__ __forceinline__ void mma_over_rows_ts(uint32_t tmem_d, uint32_t p_tmem, uint32_t b_tile, uint32_t idesc, bool accumulate) {
+  using H = HeadCfg<HS>;
+  const uint64_t db = make_smem_desc(b_tile, (uint32_t)KC * H::ROWB, 8 * H::ROWB, H::SWZ);
+  const uint32_t acc = accumulate ? 1u : 0u;
+  if (elect_one()) {
+#pragma unroll
+    for (int kk = 0; kk < KC / 16; ++kk) {
+      const uint32_t col = SPLIT ? (uint32_t)((kk / 2) * 32 + (kk % 2) * 8) : (uint32_t)(kk * 8);
+      tc_mma_bf16_ts(tmem_d, p_tmem + col, db + (uint32_t)((kk * 16 * H::ROWB) >> 4), idesc, kk == 0 ? acc : 1u);
+    }
+  }
+  __syncwarp();
+}
+
 template <int HS>
 __device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap* m, uint32_t bar, int col0, int row0, int b, int R) {
   using H = HeadCfg<HS>;
@@ -348,7 +367,7 @@ struct BwdKV2 {
   static_assert(DYN <= 232448, "shared memory budget");
 };
 
-template <int HS, int BQ, int ST>
+template <int HS, int BQ, int ST, bool PT>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
@@ -417,8 +436,13 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         }
         mbar_wait(ds_full + 8 * bf, (i >> 1) & 1);
         tc_fence_after();
-        mma_over_rows<HS, BQ>(tm_dv, sbase + L::PT_OFF + bf * L::P_BYTES, sbase + L::DO_OFF + st * L::Q_BYTES, idesc_g, i > 0);
-        mma_over_rows<HS, BQ>(tm_dk, sbase + L::DST_OFF + bf * L::P_BYTES, sbase + L::Q_OFF + st * L::Q_BYTES, idesc_g, i > 0);
+        if (PT) {  // P^T / dS^T were written back over the S^T / dP^T tiles in tensor memory
+          mma_over_rows_ts<HS, BQ, true>(tm_dv, tmem_base + bf * 2 * BQ, sbase + L::DO_OFF + st * L::Q_BYTES, idesc_g, i > 0);
+          mma_over_rows_ts<HS, BQ, true>(tm_dk, tmem_base + bf * 2 * BQ + BQ, sbase + L::Q_OFF + st * L::Q_BYTES, idesc_g, i > 0);
+        } else {
+          mma_over_rows<HS, BQ>(tm_dv, sbase + L::PT_OFF + bf * L::P_BYTES, sbase + L::DO_OFF + st * L::Q_BYTES, idesc_g, i > 0);
+          mma_over_rows<HS, BQ>(tm_dk, sbase + L::DST_OFF + bf * L::P_BYTES, sbase + L::Q_OFF + st * L::Q_BYTES, idesc_g, i > 0);
+        }
         tc_commit_elect(q_empty + 8 * st);
         tc_commit_elect(ds_empty + 8 * bf);
       }
@@ -500,10 +524,16 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           dk[e / 2] = pack_bf16x2(d[0], d[1]);
           dk[e / 2 + 1] = pack_bf16x2(d[2], d[3]);
         }
-        store_p32<BQ>(pt, row, c, pk);
-        store_p32<BQ>(dst, row, c, dk);
+        if (PT) {
+          tmem_st16(tm_s + c, pk);
+          tmem_st16(tm_dp + c, dk);
+        } else {
+          store_p32<BQ>(pt, row, c, pk);
+          store_p32<BQ>(dst, row, c, dk);
+        }
       }
-      fence_proxy_async();
+      if (PT) tmem_wait_st();
+      else fence_proxy_async();
       tc_fence_before();
       mbar_arrive(ds_full + 8 * bf);
     }
@@ -539,7 +569,7 @@ struct BwdQ2 {
   static_assert(4 * BKV + HS <= 512, "TMEM budget");
 };
 
-template <int HS, int ST>
+template <int HS, int ST, bool PT>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmKV,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
@@ -610,7 +640,8 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         mbar_wait(ds_full + 8 * bf, (j >> 1) & 1);
         tc_fence_after();
-        mma_over_rows<HS, BKV>(tm_dq, sbase + L::DS_OFF + bf * L::DS_BYTES, sbase + L::K_OFF + st * L::KV_BYTES, idesc_q, j > 0);
+        if (PT) mma_over_rows_ts<HS, BKV, true>(tm_dq, tmem_base + bf * 2 * BKV + BKV, sbase + L::K_OFF + st * L::KV_BYTES, idesc_q, j > 0);
+        else mma_over_rows<HS, BKV>(tm_dq, sbase + L::DS_OFF + bf * L::DS_BYTES, sbase + L::K_OFF + st * L::KV_BYTES, idesc_q, j > 0);
         tc_commit_elect(kv_empty + 8 * st);
         tc_commit_elect(ds_empty + 8 * bf);
       }
@@ -666,9 +697,11 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             dk[e / 2] = pack_bf16x2(p0 * (dp0 - my_delta), p1 * (dp1 - my_delta));
           }
         }
-        store_p32<BKV>(ds, row, c, dk);
+        if (PT) tmem_st16(tm_dp + c, dk);  // dS over the dP tile it came from
+        else store_p32<BKV>(ds, row, c, dk);
       }
-      fence_proxy_async();
+      if (PT) tmem_wait_st();
+      else fence_proxy_async();
       tc_fence_before();
       mbar_arrive(ds_full + 8 * bf);
     }
@@ -709,7 +742,9 @@ struct Fwd3 {
   static_assert(DYN <= 232448, "shared memory budget");
 };
 
-template <int HS, int KST, int VST>
+// PT = true: the bf16 probabilities never touch shared memory — the softmax warps write them back (packed two per column)
+// over the S tile they came from and P.V runs with its A operand in tensor memory (tcgen05.mma [d], [a], b-desc).
+template <int HS, int KST, int VST, bool PT>
 __global__ void __launch_bounds__(320, 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, __nv_bfloat16* __restrict__ y,
                  float* __restrict__ lse, int T, int C, int nh, float scale_log2, AttnDrop ad) {
@@ -778,8 +813,11 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const int sb = w * 2 + buf;
           mbar_wait(p_full + 8 * sb, (j >> 1) & 1);
           tc_fence_after();
-          mma_over_rows<HS, BKV>(tmem_base + 4 * BKV + w * HS, sbase + L::P_OFF + sb * L::P_BYTES, sbase + L::V_OFF + vs * L::KV_BYTES, idesc_o,
-                                 j > 0);
+          if (PT)
+            mma_over_rows_ts<HS, BKV>(tmem_base + 4 * BKV + w * HS, tmem_base + sb * BKV, sbase + L::V_OFF + vs * L::KV_BYTES, idesc_o, j > 0);
+          else
+            mma_over_rows<HS, BKV>(tmem_base + 4 * BKV + w * HS, sbase + L::P_OFF + sb * L::P_BYTES, sbase + L::V_OFF + vs * L::KV_BYTES, idesc_o,
+                                   j > 0);
           tc_commit_elect(p_empty + 8 * sb);
           if (w == 1) tc_commit_elect(v_empty + 8 * vs);
           if (j + 2 < n_kv) {
@@ -870,10 +908,12 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
           pk[i / 2] = pack_bf16x2(p0, p1);
         }
-        store_p32<BKV>(p_tile, row, half * 32, pk);
+        if (PT) tmem_st16(tm_s + half * 16, pk);  // keys 32*half .. +31 -> packed columns 16*half .. +15 of the S tile
+        else store_p32<BKV>(p_tile, row, half * 32, pk);
       }
       l_run += l_add;
-      fence_proxy_async();
+      if (PT) tmem_wait_st();
+      else fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full + 8 * sb);
     }
@@ -945,13 +985,13 @@ static int launch_fwd2(const void* qkv, void* y, float* lse, int B, int T, int C
   return check_launch("attn_fwd2");
 }
 
-template <int HS, int KST, int VST>
+template <int HS, int KST, int VST, bool PT>
 static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const AttnDrop& ad, cudaStream_t st) {
   using L = Fwd3<HS, KST, VST>;
   using H = HeadCfg<HS>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("attn_fwd3/attr");
     configured = true;
   }
@@ -960,13 +1000,13 @@ static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C
   if (int e = make_tmap3(&tmKV, qkv, 3 * C, T, B, H::BOXC, L::BKV)) return e;
   const float scale_log2 = (1.0f / sqrtf((float)HS)) * 1.4426950408889634f;
   dim3 grid(cdiv(T, 256), nh, B);
-  launch_pdl(attn_fwd3_kernel<HS, KST, VST>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
+  launch_pdl(attn_fwd3_kernel<HS, KST, VST, PT>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
   return check_launch("attn_fwd3");
 }
 
 int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, int C, int nh, cudaStream_t st);  // attn_tc.cu
 
-template <int HS, int BQ, int STA, int STB>
+template <int HS, int BQ, int STA, int STB, bool PT>
 static int launch_bwd2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
                        const AttnDrop& ad, cudaStream_t st) {
   using LA = BwdKV2<HS, BQ, STA>;
@@ -974,8 +1014,8 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   using H = HeadCfg<HS>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
       return check_launch("attn_bwd2/attr");
     configured = true;
   }
@@ -989,9 +1029,9 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   if (int e = make_tmap3(&tmDO128, dy, C, T, B, H::BOXC, 128)) return e;
   if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
   dim3 grid(cdiv(T, 128), nh, B);
-  launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
+  launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
   if (int e = check_launch("attn_bwd2/kv")) return e;
-  launch_pdl(attn_bwd_q2_kernel<HS, STB>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
+  launch_pdl(attn_bwd_q2_kernel<HS, STB, PT>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
   return check_launch("attn_bwd2/q");
 }
 
@@ -1021,26 +1061,43 @@ static AttnDrop make_attn_drop(const dsf_dropout* d, uint32_t* bits, int T) {
   return a;
 }
 
-int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, cudaStream_t st) {
+int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem,
+                cudaStream_t st) {
   const AttnDrop ad = make_attn_drop(drop, bits, T);
+  if (p_in_tmem) {
+    switch (C / nh) {
+      case 16: return launch_fwd3<16, 3, 2, true>(qkv, y, lse, B, T, C, nh, ad, st);
+      case 32: return launch_fwd3<32, 3, 2, true>(qkv, y, lse, B, T, C, nh, ad, st);
+      case 64: return launch_fwd3<64, 3, 2, true>(qkv, y, lse, B, T, C, nh, ad, st);
+      case 128: return launch_fwd3<128, 3, 2, true>(qkv, y, lse, B, T, C, nh, ad, st);
+    }
+  }
   switch (C / nh) {
-    case 16: return launch_fwd3<16, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
-    case 32: return launch_fwd3<32, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
-    case 64: return launch_fwd3<64, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
-    case 128: return launch_fwd3<128, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 16: return launch_fwd3<16, 3, 2, false>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 32: return launch_fwd3<32, 3, 2, false>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 64: return launch_fwd3<64, 3, 2, false>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 128: return launch_fwd3<128, 3, 2, false>(qkv, y, lse, B, T, C, nh, ad, st);
   }
   set_error("attn_fwd: head size %d not supported (16, 32, 64, 128)", C / nh);
   return DSF_EUNSUPPORTED;
 }
 
 int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
-                const dsf_dropout* drop, uint32_t* bits, cudaStream_t st) {
+                const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem, cudaStream_t st) {
   const AttnDrop ad = make_attn_drop(drop, bits, T);
+  if (p_in_tmem) {
+    switch (C / nh) {
+      case 16: return launch_bwd2<16, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+      case 32: return launch_bwd2<32, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+      case 64: return launch_bwd2<64, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+      case 128: return launch_bwd2<128, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+    }
+  }
   switch (C / nh) {
-    case 16: return launch_bwd2<16, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
-    case 32: return launch_bwd2<32, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
-    case 64: return launch_bwd2<64, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
-    case 128: return launch_bwd2<128, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+    case 16: return launch_bwd2<16, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+    case 32: return launch_bwd2<32, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+    case 64: return launch_bwd2<64, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+    case 128: return launch_bwd2<128, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
   }
   set_error("attn_bwd: head size %d not supported (16, 32, 64, 128)", C / nh);
   return DSF_EUNSUPPORTED;

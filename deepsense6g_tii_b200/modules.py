@@ -234,9 +234,10 @@ class Encoder(nn.Module):
         bz, _, h, w = lidar_list[0].shape
         cfg.n_views = len(image_list) // cfg.seq_len  # the reference mutates the shared config too (:489)
         S, V = cfg.seq_len, cfg.n_views
-        img = torch.stack(image_list, dim=1).view(bz * V * S, image_list[0].shape[1], h, w)
-        lid = torch.stack(lidar_list, dim=1).view(bz * S, lidar_list[0].shape[1], h, w)
-        rad = torch.stack(radar_list, dim=1).view(bz * S, radar_list[0].shape[1], h, w)
+        # (the reference uses .view here, :491-493; reshape also accepts channels_last frames)
+        img = torch.stack(image_list, dim=1).reshape(bz * V * S, image_list[0].shape[1], h, w)
+        lid = torch.stack(lidar_list, dim=1).reshape(bz * S, lidar_list[0].shape[1], h, w)
+        rad = torch.stack(radar_list, dim=1).reshape(bz * S, radar_list[0].shape[1], h, w)
         img, lid, rad = self._apply_missing("image", img), self._apply_missing("lidar", lid), self._apply_missing("radar", rad)
 
         ie, le, re_ = self.image_encoder.features, self.lidar_encoder._model, self.radar_encoder._model

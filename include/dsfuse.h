@@ -191,9 +191,10 @@ int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int32_t T, int
 int dsf_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* delta,
                  void* dqkv, int32_t B, int32_t T, int32_t C, int32_t nh, const dsf_dropout* drop,
                  const uint32_t* drop_bits, void* stream);
-/* Selects the attention implementation (process-wide; for tests and A/B timing): 0 = default,
+/* Selects the attention implementation (process-wide; for tests and A/B timing): 0 = default (= 4),
  * 1 = v1 (simple synchronous kernels), 2 = v2 (warp-specialised, TMA-fed, pipelined),
- * 3 = v3 (v2 + per-warpgroup double-buffered S/P in the forward).                                  */
+ * 3 = v3 (v2 + per-warpgroup double-buffered S/P in the forward), 4 = v4 (v3 schedule, the bf16 P / dS tiles
+ * stay in tensor memory and feed tcgen05.mma as its A operand instead of going through shared memory). */
 int dsf_attn_set_impl(int32_t impl);
 
 /* K7 forward.  Replaces slice/view/permute/contiguous (model2_seq.py:275-286) + F.interpolate
