@@ -24,6 +24,7 @@ reproduced bit for bit, so parity with dropout is tested by feeding the oracle t
 ``dsf_dropout_inplace`` on a tensor of ones).
 """
 import math
+import os
 
 import torch
 
@@ -51,6 +52,17 @@ def _f32_linear_desc(M, N, Kd, flags, trans=None):
 
 class _Ctx:
     pass
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One extra stream per device for the weight-gradient GEMMs of the backward (see ``_backward_bf16``)."""
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
 
 
 def drop_site(kind, block=0):
@@ -319,6 +331,35 @@ class _Runner:
                 off += n
             return out
 
+        # The four weight-gradient GEMMs of a block only feed the optimizer, so they run on a second stream next to the
+        # data-gradient chain: their CTAs fill the SMs that chain leaves idle (second, partly filled rounds of the
+        # N = n_embd GEMMs and of the attention kernels, tails of the short HBM-bound kernels).  fork() orders a wgrad
+        # after everything enqueued so far on the main stream; join() makes the main stream wait for the side stream
+        # (before buffers the wgrads read are overwritten or released, and before the block's gradients are handed on).
+        # Default: on while the step is being captured into a CUDA graph (the fork/join events become graph edges, free
+        # at replay: -0.2 ms per step), off for eager launches (creating and recording ~40 events per step costs more host
+        # time than the overlap returns).  DSF_WGRAD_STREAM=1 / 0 forces it.
+        env = os.environ.get("DSF_WGRAD_STREAM")
+        use_side = (env == "1") if env in ("0", "1") else torch.cuda.is_current_stream_capturing()
+        main = torch.cuda.current_stream()
+        side = _side_stream(dev) if use_side else None
+
+        def fork(fn):
+            if side is None:
+                fn()
+                return
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                fn()
+
+        def join():
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                main.wait_event(ev)
+
         dgf, dbf = gbuf[L * per_block:L * per_block + C], gbuf[L * per_block + C:]
         dx = torch.empty(M, C, device=dev, dtype=f32)
         dxa = torch.empty(M, C, device=dev, dtype=bf)
@@ -335,11 +376,11 @@ class _Runner:
             dwqkv, dwp, dw1, dw2, dbqkv, dbp, db1, db2, dg1, dbt1, dg2, dbt2 = block_views(i)
             dwqkv, dwp, dw1, dw2 = dwqkv.view(3 * C, C), dwp.view(C, C), dw1.view(F, C), dw2.view(C, F)
             # ---- MLP:  x_out = x_mid + relu(h2 W1^T + b1) W2^T + b2     (model2_seq.py:121-126,132)
-            K.gemm_bf16_tn(dxa, st.a, dw2)
+            fork(lambda: K.gemm_bf16_tn(dxa, st.a, dw2))
             da = torch.empty(M, F, device=dev, dtype=bf)
             K.gemm_bf16_nt(dxa, st.w2_t, da, relu_src=st.a)  # ReLU backward fused in the epilogue
             K.colsum(da, db1)
-            K.gemm_bf16_tn(da, st.h2, dw1)
+            fork(lambda: K.gemm_bf16_tn(da, st.h2, dw1))
             dh2 = torch.empty(M, C, device=dev, dtype=f32)  # fp32: feeds LayerNorm backward, not a GEMM
             K.gemm_bf16_nt(da, st.w1_t, dh2)
             dx_mid = torch.empty(M, C, device=dev, dtype=f32)
@@ -347,16 +388,17 @@ class _Runner:
             K.layernorm_bwd(dh2, st.x_mid, ln2w, st.mean2, st.rstd2, dx, dx_mid, dg2, dbt2, dx_bf16=dxm, dx_colsum=dbp,
                             byprod_drop=self._drop("proj", i))
             # ---- attention:  x_mid = x_in + proj(attn(qkv(ln1(x_in))))   (model2_seq.py:94-110,131)
-            K.gemm_bf16_tn(dxm, st.y, dwp)
+            fork(lambda: K.gemm_bf16_tn(dxm, st.y, dwp))
             dy = torch.empty(M, C, device=dev, dtype=bf)
             K.gemm_bf16_nt(dxm, st.wp_t, dy)
             dqkv = torch.empty(M, 3 * C, device=dev, dtype=bf)
             delta = torch.empty(self.B, self.nh, self.T, device=dev, dtype=f32)
             K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, self._drop("attn", i), st.drop_bits)
             K.colsum(dqkv, dbqkv)
-            K.gemm_bf16_tn(dqkv, st.h1, dwqkv)
+            fork(lambda: K.gemm_bf16_tn(dqkv, st.h1, dwqkv))
             dh1 = torch.empty(M, C, device=dev, dtype=f32)
             K.gemm_bf16_nt(dqkv, st.wqkv_t, dh1)
+            join()  # the next kernel overwrites dxa (read by this block's first wgrad); the block's buffers are released below
             dx = torch.empty(M, C, device=dev, dtype=f32)
             prev = block_views(i - 1) if i > 0 else None
             K.layernorm_bwd(dh1, st.x_in, ln1w, st.mean1, st.rstd1, dx_mid, dx, dg1, dbt1,
