@@ -243,15 +243,19 @@ class _Runner:
         F = params[13].shape[0] if L > 0 else 4 * C  # mlp.0.weight rows
         saved = _Ctx()
         saved.layers = []
-        x = torch.empty(M, C, device=dev, dtype=f32)
-        K.tokens_fwd(self.geom, feats[0], feats[1], feats[2], gps_emb, params[0], x)
-        if self._drop("embd") is not None:
-            K.dropout_inplace(x, self._drop("embd"))
-        for i in range(L):
+        # Weight shadows (fp32 -> bf16, plain + transposed, one launch per block) do not depend on the activations: under
+        # graph capture they are packed on the side stream while the token kernel and the first blocks run.
+        env = os.environ.get("DSF_WGRAD_STREAM")
+        use_side = (env == "1") if env in ("0", "1") else torch.cuda.is_current_stream_capturing()
+        main = torch.cuda.current_stream()
+        side = _side_stream(dev) if use_side else None
+        sizes = [3 * C * C, 3 * C * C, C * C, C * C, F * C, F * C, C * F, C * F]
+        packed = []
+
+        def pack(i):
             (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[1 + 16 * i: 17 + 16 * i]
             st = _Ctx()
             # one flat bf16 buffer holds the 8 weight shadows of this block (plain + transposed)
-            sizes = [3 * C * C, 3 * C * C, C * C, C * C, F * C, F * C, C * F, C * F]
             flat = torch.empty(sum(sizes), device=dev, dtype=bf)
             views, off = [], 0
             for n in sizes:
@@ -261,9 +265,34 @@ class _Runner:
             st.wp, st.wp_t = views[2].view(C, C), views[3].view(C, C)
             st.w1, st.w1_t = views[4].view(F, C), views[5].view(C, F)
             st.w2, st.w2_t = views[6].view(C, F), views[7].view(F, C)
-            bqkv = torch.empty(3 * C, device=dev, dtype=f32)
+            st.bqkv = torch.empty(3 * C, device=dev, dtype=f32)
             K.pack_block_weights(qw, kw, vw, pw, w1, w2, qb, kb, vb,
-                                 (st.wqkv, st.wqkv_t, st.wp, st.wp_t, st.w1, st.w1_t, st.w2, st.w2_t, bqkv))
+                                 (st.wqkv, st.wqkv_t, st.wp, st.wp_t, st.w1, st.w1_t, st.w2, st.w2_t, st.bqkv))
+            return st
+
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                for i in range(L):
+                    st = pack(i)
+                    st.packed_ev = torch.cuda.Event()
+                    st.packed_ev.record(side)
+                    packed.append(st)
+        x = torch.empty(M, C, device=dev, dtype=f32)
+        K.tokens_fwd(self.geom, feats[0], feats[1], feats[2], gps_emb, params[0], x)
+        if self._drop("embd") is not None:
+            K.dropout_inplace(x, self._drop("embd"))
+        for i in range(L):
+            (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[1 + 16 * i: 17 + 16 * i]
+            if side is not None:
+                st = packed[i]
+                main.wait_event(st.packed_ev)
+                st.packed_ev = None
+            else:
+                st = pack(i)
+            bqkv = st.bqkv
             st.x_in = x
             stats = torch.empty(4, M, device=dev, dtype=f32)
             st.mean1, st.rstd1, st.mean2, st.rstd2 = stats[0], stats[1], stats[2], stats[3]
@@ -379,8 +408,11 @@ class _Runner:
             fork(lambda: K.gemm_bf16_tn(dxa, st.a, dw2))
             da = torch.empty(M, F, device=dev, dtype=bf)
             K.gemm_bf16_nt(dxa, st.w2_t, da, relu_src=st.a)  # ReLU backward fused in the epilogue
-            K.colsum(da, db1)
-            fork(lambda: K.gemm_bf16_tn(da, st.h2, dw1))
+
+            def mlp0_grads():
+                K.colsum(da, db1)
+                K.gemm_bf16_tn(da, st.h2, dw1)
+            fork(mlp0_grads)
             dh2 = torch.empty(M, C, device=dev, dtype=f32)  # fp32: feeds LayerNorm backward, not a GEMM
             K.gemm_bf16_nt(da, st.w1_t, dh2)
             dx_mid = torch.empty(M, C, device=dev, dtype=f32)
@@ -394,8 +426,11 @@ class _Runner:
             dqkv = torch.empty(M, 3 * C, device=dev, dtype=bf)
             delta = torch.empty(self.B, self.nh, self.T, device=dev, dtype=f32)
             K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, self._drop("attn", i), st.drop_bits)
-            K.colsum(dqkv, dbqkv)
-            fork(lambda: K.gemm_bf16_tn(dqkv, st.h1, dwqkv))
+
+            def qkv_grads():
+                K.colsum(dqkv, dbqkv)
+                K.gemm_bf16_tn(dqkv, st.h1, dwqkv)
+            fork(qkv_grads)
             dh1 = torch.empty(M, C, device=dev, dtype=f32)
             K.gemm_bf16_nt(dqkv, st.wqkv_t, dh1)
             join()  # the next kernel overwrites dxa (read by this block's first wgrad); the block's buffers are released below
