@@ -22,7 +22,7 @@ EPI_BIAS, EPI_RELU, EPI_RESIDUAL, EPI_ACCUM = 1, 2, 4, 8
 SYMBOLS = [
     "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_set_pdl", "dsf_set_sm_margin", "dsf_dropout_inplace", "dsf_tokens_fwd", "dsf_tokens_bwd",
     "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_set_impl", "dsf_gemm_f32",
-    "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_set_impl", "dsf_attn_drop_words",
+    "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_bwd_parts", "dsf_attn_set_impl", "dsf_attn_drop_words",
     "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16",
 ]
 
@@ -82,6 +82,7 @@ def lib():
             "dsf_softmax_bwd": [P, P, c_int64, c_int32, P],
             "dsf_attn_fwd": [P, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P, P],
             "dsf_attn_bwd": [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P, P],
+            "dsf_attn_bwd_parts": [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P, c_int32, P],
             "dsf_attn_set_impl": [c_int32],
             "dsf_set_pdl": [c_int32],
             "dsf_set_sm_margin": [c_int32],
@@ -228,9 +229,10 @@ def attn_fwd(qkv, y, lse, B, T, C, nh, drop=None, drop_bits=None):
     _chk(lib().dsf_attn_fwd(_p(qkv), _p(y), _p(lse), B, T, C, nh, _dp(drop), _p(drop_bits), _stream()), "dsf_attn_fwd")
 
 
-def attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop=None, drop_bits=None):
-    _chk(lib().dsf_attn_bwd(_p(qkv), _p(y), _p(dy), _p(lse), _p(delta), _p(dqkv), B, T, C, nh, _dp(drop), _p(drop_bits), _stream()),
-         "dsf_attn_bwd")
+def attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop=None, drop_bits=None, parts=7):
+    """parts: bit mask 1 = delta, 2 = dK/dV kernel, 4 = dQ kernel (2 and 4 are independent once 1 has run)."""
+    _chk(lib().dsf_attn_bwd_parts(_p(qkv), _p(y), _p(dy), _p(lse), _p(delta), _p(dqkv), B, T, C, nh, _dp(drop), _p(drop_bits), parts,
+                                  _stream()), "dsf_attn_bwd")
 
 
 def gemm_set_impl(impl):

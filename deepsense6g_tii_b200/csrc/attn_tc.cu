@@ -590,7 +590,7 @@ int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int n
 int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem,
                 cudaStream_t st);
 int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
-                const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem, cudaStream_t st);
+                const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem, int parts, cudaStream_t st);
 
 int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, int C, int nh, cudaStream_t st) {
   launch_pdl(attn_delta_kernel, dim3(std::min(cdiv(B * T, 8), num_sms() * 8)), dim3(256), 0, st, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy,
@@ -650,8 +650,24 @@ extern "C" int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int
   }
 }
 
+static int attn_bwd_impl(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int32_t B, int32_t T,
+                         int32_t C, int32_t nh, const dsf_dropout* drop, const uint32_t* drop_bits, int parts, void* stream);
+
 extern "C" int dsf_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int32_t B,
                             int32_t T, int32_t C, int32_t nh, const dsf_dropout* drop, const uint32_t* drop_bits, void* stream) {
+  return attn_bwd_impl(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop, drop_bits, 7, stream);
+}
+
+extern "C" int dsf_attn_bwd_parts(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int32_t B,
+                                  int32_t T, int32_t C, int32_t nh, const dsf_dropout* drop, const uint32_t* drop_bits, int32_t parts,
+                                  void* stream) {
+  DSF_REQUIRE(parts > 0 && parts <= 7, "attn_bwd_parts: parts must be a non-empty subset of {1 = delta, 2 = dK/dV, 4 = dQ}");
+  DSF_REQUIRE(parts == 7 || g_attn_impl != 1, "attn_bwd_parts: the v1 kernels only run all three parts together");
+  return attn_bwd_impl(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop, drop_bits, parts, stream);
+}
+
+static int attn_bwd_impl(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int32_t B, int32_t T,
+                         int32_t C, int32_t nh, const dsf_dropout* drop, const uint32_t* drop_bits, int parts, void* stream) {
   DSF_REQUIRE(qkv && y && dy && lse && delta && dqkv, "attn_bwd: NULL pointer");
   bool drop_on;
   if (int e = check_attn_drop("attn_bwd", drop, drop_bits, drop_on)) return e;
@@ -661,7 +677,7 @@ extern "C" int dsf_attn_bwd(const void* qkv, const void* y, const void* dy, cons
   const int hs = C / nh;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_attn_impl != 1)
-    return attn_bwd_v2(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop_on ? drop : nullptr, const_cast<uint32_t*>(drop_bits), g_attn_impl == 4 || g_attn_impl == 0, st);
+    return attn_bwd_v2(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop_on ? drop : nullptr, const_cast<uint32_t*>(drop_bits), g_attn_impl == 4 || g_attn_impl == 0, parts, st);
   switch (hs) {
     case 16: return launch_attn_bwd<16, 128>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
     case 32: return launch_attn_bwd<32, 128>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);

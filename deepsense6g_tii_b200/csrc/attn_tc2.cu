@@ -1008,7 +1008,7 @@ int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, in
 
 template <int HS, int BQ, int STA, int STB, bool PT>
 static int launch_bwd2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
-                       const AttnDrop& ad, cudaStream_t st) {
+                       const AttnDrop& ad, int parts, cudaStream_t st) {
   using LA = BwdKV2<HS, BQ, STA>;
   using LB = BwdQ2<HS, STB>;
   using H = HeadCfg<HS>;
@@ -1020,7 +1020,9 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
     configured = true;
   }
   const float scale = 1.0f / sqrtf((float)HS);
-  if (int e = run_attn_delta(y, dy, delta, B, T, C, nh, st)) return e;
+  if (parts & 1) {
+    if (int e = run_attn_delta(y, dy, delta, B, T, C, nh, st)) return e;
+  }
   CUtensorMap tmKV128, tmQs, tmDOs, tmQ128, tmDO128, tmKV64;
   if (int e = make_tmap3(&tmKV128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
   if (int e = make_tmap3(&tmQs, qkv, 3 * C, T, B, H::BOXC, BQ)) return e;
@@ -1029,10 +1031,15 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   if (int e = make_tmap3(&tmDO128, dy, C, T, B, H::BOXC, 128)) return e;
   if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
   dim3 grid(cdiv(T, 128), nh, B);
-  launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
-  if (int e = check_launch("attn_bwd2/kv")) return e;
-  launch_pdl(attn_bwd_q2_kernel<HS, STB, PT>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
-  return check_launch("attn_bwd2/q");
+  if (parts & 2) {
+    launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
+    if (int e = check_launch("attn_bwd2/kv")) return e;
+  }
+  if (parts & 4) {
+    launch_pdl(attn_bwd_q2_kernel<HS, STB, PT>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
+    if (int e = check_launch("attn_bwd2/q")) return e;
+  }
+  return DSF_OK;
 }
 
 int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st) {
@@ -1083,21 +1090,21 @@ int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int n
 }
 
 int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
-                const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem, cudaStream_t st) {
+                const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem, int parts, cudaStream_t st) {
   const AttnDrop ad = make_attn_drop(drop, bits, T);
   if (p_in_tmem) {
     switch (C / nh) {
-      case 16: return launch_bwd2<16, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
-      case 32: return launch_bwd2<32, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
-      case 64: return launch_bwd2<64, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
-      case 128: return launch_bwd2<128, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+      case 16: return launch_bwd2<16, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
+      case 32: return launch_bwd2<32, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
+      case 64: return launch_bwd2<64, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
+      case 128: return launch_bwd2<128, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
     }
   }
   switch (C / nh) {
-    case 16: return launch_bwd2<16, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
-    case 32: return launch_bwd2<32, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
-    case 64: return launch_bwd2<64, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
-    case 128: return launch_bwd2<128, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, st);
+    case 16: return launch_bwd2<16, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
+    case 32: return launch_bwd2<32, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
+    case 64: return launch_bwd2<64, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
+    case 128: return launch_bwd2<128, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
   }
   set_error("attn_bwd: head size %d not supported (16, 32, 64, 128)", C / nh);
   return DSF_EUNSUPPORTED;

@@ -425,7 +425,14 @@ class _Runner:
             K.gemm_bf16_nt(dxm, st.wp_t, dy)
             dqkv = torch.empty(M, 3 * C, device=dev, dtype=bf)
             delta = torch.empty(self.B, self.nh, self.T, device=dev, dtype=f32)
-            K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, self._drop("attn", i), st.drop_bits)
+            if side is None:
+                K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, self._drop("attn", i), st.drop_bits)
+            else:  # the dQ kernel runs next to the dK/dV kernel: together they leave one partly filled round instead of two
+                adrop = self._drop("attn", i)
+                K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, adrop, st.drop_bits, parts=1)
+                fork(lambda: K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, adrop, st.drop_bits, parts=4))
+                K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, adrop, st.drop_bits, parts=2)
+                join()
 
             def qkv_grads():
                 K.colsum(dqkv, dbqkv)

@@ -191,6 +191,11 @@ int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int32_t T, int
 int dsf_attn_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* delta,
                  void* dqkv, int32_t B, int32_t T, int32_t C, int32_t nh, const dsf_dropout* drop,
                  const uint32_t* drop_bits, void* stream);
+/*   The backward is three launches: 1 = delta (rowsum(dy*y)), 2 = dK/dV kernel, 4 = dQ kernel; 2 and 4 only need 1 and
+ *   are independent of each other, so a caller may issue them on two streams (`parts` = bit mask of what to launch). */
+int dsf_attn_bwd_parts(const void* qkv, const void* y, const void* dy, const float* lse, float* delta,
+                       void* dqkv, int32_t B, int32_t T, int32_t C, int32_t nh, const dsf_dropout* drop,
+                       const uint32_t* drop_bits, int32_t parts, void* stream);
 /* Selects the attention implementation (process-wide; for tests and A/B timing): 0 = default (= 4),
  * 1 = v1 (simple synchronous kernels), 2 = v2 (warp-specialised, TMA-fed, pipelined),
  * 3 = v3 (v2 + per-warpgroup double-buffered S/P in the forward), 4 = v4 (v3 schedule, the bf16 P / dS tiles
