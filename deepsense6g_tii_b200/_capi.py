@@ -34,7 +34,8 @@ class Geom(ctypes.Structure):
 
 class Dropout(ctypes.Structure):
     """``dsf_dropout`` (include/dsfuse.h): one nn.Dropout site; mask = f(seed, site, step, element index)."""
-    _fields_ = [("p", c_float), ("seed", ctypes.c_uint64), ("site", ctypes.c_uint32), ("step", ctypes.c_uint32)]
+    _fields_ = [("p", c_float), ("seed", ctypes.c_uint64), ("site", ctypes.c_uint32), ("step", ctypes.c_uint32),
+                ("seed_dev", c_void_p)]  # nullable device pointer to a uint64 XOR-ed into the seed (graph-safe reseeding)
 
 
 def _dp(d):

@@ -38,6 +38,7 @@ struct AttnDrop {
   uint32_t k0, k1, site;
   uint32_t* bits;    // (B, nh, T, Tw)
   int Tw;
+  const unsigned long long* seed_dev;  // nullable device word XOR-ed into the Philox key (graph-safe reseeding)
 };
 // keep bits of keys 32*word .. 32*word+31 of row `rowid`
 __device__ __forceinline__ uint32_t attn_keep_word(const AttnDrop& a, uint64_t rowid, uint32_t word) {
@@ -776,6 +777,11 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_wait();  // set-up above overlaps the previous kernel's tail
+  if (ad.thresh8 && ad.seed_dev != nullptr) {  // graph-safe reseeding: fold the device word into the Philox key
+    const unsigned long long sd = __ldg(ad.seed_dev);
+    ad.k0 ^= (uint32_t)(sd & 0xFFFFFFFFull);
+    ad.k1 ^= (uint32_t)(sd >> 32);
+  }
 
   if (warp == 9) {
     if (lane == 0) {
@@ -1055,7 +1061,7 @@ int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int n
 
 // attn_drop arguments: 8-bit threshold (p quantised to k/256), bitmap of T_words = 2*ceil(T/64) words per (b, h, q) row
 static AttnDrop make_attn_drop(const dsf_dropout* d, uint32_t* bits, int T) {
-  AttnDrop a{0u, 1.0f, 0u, 0u, 0u, bits, 2 * cdiv(T, 64)};
+  AttnDrop a{0u, 1.0f, 0u, 0u, 0u, bits, 2 * cdiv(T, 64), nullptr};
   if (d && d->p > 0.f && bits) {
     int k = (int)lrintf(d->p * 256.0f);
     k = std::max(1, std::min(255, k));
@@ -1064,6 +1070,7 @@ static AttnDrop make_attn_drop(const dsf_dropout* d, uint32_t* bits, int T) {
     a.k0 = (uint32_t)(d->seed & 0xFFFFFFFFull) ^ d->step;
     a.k1 = (uint32_t)(d->seed >> 32);
     a.site = d->site;
+    a.seed_dev = reinterpret_cast<const unsigned long long*>(d->seed_dev);
   }
   return a;
 }

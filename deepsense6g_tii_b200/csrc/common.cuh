@@ -106,9 +106,10 @@ struct DropArgs {
   uint32_t thresh;  // drop iff random < thresh  (0 = dropout disabled)
   float scale;      // 1 / (1 - p)
   uint32_t seed_lo, seed_hi, site, step;
+  const unsigned long long* seed_dev;  // nullable device word XOR-ed into the seed (graph-safe reseeding)
 };
 __host__ __device__ inline DropArgs make_drop(const dsf_dropout* d) {
-  DropArgs a{0u, 1.0f, 0u, 0u, 0u, 0u};
+  DropArgs a{0u, 1.0f, 0u, 0u, 0u, 0u, nullptr};
   if (d && d->p > 0.f) {
     const double t = (double)d->p * 4294967296.0;
     a.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
@@ -117,6 +118,16 @@ __host__ __device__ inline DropArgs make_drop(const dsf_dropout* d) {
     a.seed_hi = (uint32_t)(d->seed >> 32);
     a.site = d->site;
     a.step = d->step;
+    a.seed_dev = reinterpret_cast<const unsigned long long*>(d->seed_dev);
+  }
+  return a;
+}
+// fold the device-resident seed word in (once per thread, after griddepcontrol.wait: an earlier kernel of the stream bumps it)
+__device__ __forceinline__ DropArgs resolve_drop(DropArgs a) {
+  if (a.thresh != 0u && a.seed_dev != nullptr) {
+    const unsigned long long s = __ldg(a.seed_dev);
+    a.seed_lo ^= (uint32_t)(s & 0xFFFFFFFFull);
+    a.seed_hi ^= (uint32_t)(s >> 32);
   }
   return a;
 }

@@ -207,6 +207,7 @@ gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int ch = (warp - 2) >> 2;    // column half handled by this warp
+    epi.drop = resolve_drop(epi.drop);
     constexpr int NSPLIT = BN >= 128 ? 2 : 1;  // BN = 64: warps 2..5 drain the whole tile, warps 6..9 only hand the buffer back
     constexpr int HALF = BN / NSPLIT;
     int i = 0, nbox = 0;
@@ -434,6 +435,7 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int ch = (warp - 2) >> 2;    // column half handled by this warp
+    epi.drop = resolve_drop(epi.drop);
     constexpr int HALF = BN / 2;
     const uint32_t acc_empty0 = mapa_u32(acc_empty, 0);
     int i = 0, nbox = 0;

@@ -83,6 +83,7 @@ layernorm_bwd_kernel(const TY* __restrict__ dy, const float* __restrict__ x, con
   __shared__ float red[QPP][LN_WARPS][VPT * 128];
   pdl_trigger();
   pdl_wait();
+  if (DROP) drop = resolve_drop(drop);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 2;
   const float invC = 1.0f / (float)C;

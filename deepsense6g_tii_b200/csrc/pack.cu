@@ -142,6 +142,7 @@ namespace dsf {
 __global__ void __launch_bounds__(256) dropout_inplace_kernel(float* __restrict__ x, int64_t n4, DropArgs a) {
   pdl_trigger();
   pdl_wait();
+  a = resolve_drop(a);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float v[4], m[4];
     Vec4<float>::load(x + i * 4, v);

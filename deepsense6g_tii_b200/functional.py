@@ -17,7 +17,8 @@ kernels (no ATen math on the path).  Two compute modes:
     softmax attention, everything fp32.
 
 Dropout (model2_seq.py:104,109,125,272; bf16 mode only): ``cfg["dropout"] = dict(embd=p, attn=p, resid=p,
-seed=int, step=int[, capture=dict])``.  Masks are counter-based (Philox4x32-10 of (seed, site, step, element)),
+seed=int, step=int[, seed_dev=int64 device tensor][, capture=dict])``; with ``seed_dev`` the kernels use
+``seed ^ seed_dev[0]`` read on the device, so a CUDA-graph replay draws new masks whenever that word was bumped.  Masks are counter-based (Philox4x32-10 of (seed, site, step, element)),
 recomputed by the backward kernels; sites are numbered ``drop_site(...)``.  torch's own RNG stream cannot be
 reproduced bit for bit, so parity with dropout is tested by feeding the oracle the masks the kernels drew
 (``capture`` receives the attention keep-bitmaps; the elementwise masks are regenerated with
@@ -335,7 +336,8 @@ class _Runner:
         p = float(d.get("resid" if kind in ("proj", "mlp") else kind, 0.0))
         if p <= 0.0:
             return None
-        return K.Dropout(p, int(d["seed"]), drop_site(kind, block), int(d.get("step", 0)))
+        sd = d.get("seed_dev")  # int64 device tensor (1 element) or None
+        return K.Dropout(p, int(d["seed"]), drop_site(kind, block), int(d.get("step", 0)), None if sd is None else sd.data_ptr())
 
     def _backward_bf16(self, saved, params, douts, dgps_out, residual):
         """Per block: 4 wgrad + 4 dgrad GEMMs, fused ReLU-mask+bias-grad, 2 LayerNorm backward kernels that also
@@ -543,7 +545,9 @@ def materialise_dropout_masks(dropout, B, T, C, n_head, n_layer, device):
         if p <= 0.0:
             return None
         m = torch.ones(B, T, C, device=device, dtype=torch.float32)
-        K.dropout_inplace(m, K.Dropout(p, int(dropout["seed"]), drop_site(kind, blk), int(dropout.get("step", 0))))
+        sd = dropout.get("seed_dev")
+        K.dropout_inplace(m, K.Dropout(p, int(dropout["seed"]), drop_site(kind, blk), int(dropout.get("step", 0)),
+                                       None if sd is None else sd.data_ptr()))
         return m
 
     m = elem("embd")

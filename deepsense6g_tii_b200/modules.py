@@ -79,6 +79,10 @@ class GPT(nn.Module):
         self.ln_f = nn.LayerNorm(n_embd)
         self.block_size = seq_len
         self._pdrop = (float(embd_pdrop), float(attn_pdrop), float(resid_pdrop))
+        # graph-safe dropout: a device-resident call counter (not part of the state dict) that a captured step bumps at
+        # every replay; its value is XOR-ed into the seed inside the kernels
+        self.register_buffer("_drop_counter", torch.zeros(1, dtype=torch.int64), persistent=False)
+        self._drop_base_seed = None
         self._drop_capture = None  # tests: a dict that receives seed/step and the attention keep-bitmaps of the last call
         self.apply(self._init_weights)
         self._names = param_names(n_layer)
@@ -106,8 +110,19 @@ class GPT(nn.Module):
             # nn.Dropout semantics (model2_seq.py:104,109,125,272): active in train() only.  A fresh seed per call is
             # drawn from torch's CPU generator (so torch.manual_seed governs it); the masks themselves are Philox
             # functions of (seed, site, element) computed inside the kernels.
-            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
-            dropout = dict(embd=self._pdrop[0], attn=self._pdrop[1], resid=self._pdrop[2], seed=seed, step=0)
+            if self._drop_counter.is_cuda and torch.cuda.is_current_stream_capturing():
+                # The host-side seed is frozen into the captured kernels' arguments, so freshness must come from the device:
+                # bump the counter (captured -> once per replay) and hand this call its own snapshot of it, which stays
+                # valid for the backward even if the module is called again before that backward runs.
+                if self._drop_base_seed is None:
+                    self._drop_base_seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+                seed = self._drop_base_seed
+                self._drop_counter.add_(1)
+                seed_dev = self._drop_counter.clone()
+            else:
+                seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+                seed_dev = None
+            dropout = dict(embd=self._pdrop[0], attn=self._pdrop[1], resid=self._pdrop[2], seed=seed, step=0, seed_dev=seed_dev)
             if self._drop_capture is not None:
                 self._drop_capture.clear()
                 self._drop_capture.update(seed=seed, step=0)

@@ -70,6 +70,8 @@ typedef struct {
   uint64_t seed;  /* per-run seed */
   uint32_t site;  /* which dropout layer (unique per site within a step) */
   uint32_t step;  /* training-step / call counter */
+  const uint64_t* seed_dev; /* nullable DEVICE pointer: when set, the kernels use seed ^ *seed_dev.  Lets a CUDA-graph-
+                             * captured step draw fresh masks at every replay (the caller bumps the word on the device) */
 } dsf_dropout;
 
 /* x[e] *= mask(e)/(1-p), e in [0, n): embedding dropout on the token tensor (:272) and its backward. */

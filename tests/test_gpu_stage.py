@@ -306,3 +306,51 @@ def test_programmatic_dependent_launch_does_not_change_results(cuda_dev):
             assert torch.equal(a, b)
         for a, b, n in zip(grads, res[0][1], names):
             assert_close(a, b, 1e-4, 1e-6, n)
+
+
+def test_dropout_is_graph_safe_fresh_masks_per_replay(cuda_dev):
+    """A train-mode GPT forward+backward captured into a CUDA graph: the host seed is frozen into the kernel arguments,
+    the device-resident call counter is not — every replay draws new masks, forward and backward of one replay use the
+    same ones, and a replay equals an eager call seeded with (base seed ^ counter value)."""
+    from types import SimpleNamespace
+    from deepsense6g_tii_b200.functional import fusion_stage, param_names
+    from deepsense6g_tii_b200.modules import GPT
+    cfg = SimpleNamespace(n_views=1, fusion_dtype=torch.bfloat16)
+    torch.manual_seed(0)
+    m = GPT(64, 4, 4, 2, 8, 8, 5, 0.1, 0.1, 0.1, cfg).to(cuda_dev).train()
+    ins = [torch.randn(10, 64, 8, 8, device=cuda_dev) for _ in range(3)] + [torch.randn(2, 2, 64, device=cuda_dev)]
+
+    def step():
+        for p in m.parameters():
+            p.grad = None
+        out = m(*ins)
+        sum(o.float().square().sum() for o in out).backward()
+        return out
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        outs = step()
+    res = []
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        res.append((outs[0].detach().clone(), m.pos_emb.grad.clone(), int(m._drop_counter.item())))
+    assert res[0][2] + 1 == res[1][2] == res[2][2] - 1            # the captured add_ runs once per replay
+    assert not torch.equal(res[0][0], res[1][0]) and not torch.equal(res[1][0], res[2][0])   # fresh masks
+    # eager evaluation with the effective seed of the last replay: identical forward, same gradient up to atomics order
+    eff = m._drop_base_seed ^ res[2][2]
+    names = param_names(2)
+    table = dict(m.named_parameters())
+    pk = [table[n].detach().clone().requires_grad_(True) for n in names]
+    scfg = dict(seq_len=5, n_views=1, vert_anchors=8, horz_anchors=8, n_head=4, n_layer=2, compute_dtype=torch.bfloat16, residual=False,
+                dropout=dict(embd=0.1, attn=0.1, resid=0.1, seed=eff, step=0))
+    eo = fusion_stage(scfg, ins[0], ins[1], ins[2], ins[3], pk)
+    sum(o.float().square().sum() for o in eo).backward()
+    assert torch.equal(eo[0], res[2][0])
+    assert_close(pk[0].grad, res[2][1], 1e-4, 1e-6, "pos_emb grad of the replay = eager with the effective seed")
