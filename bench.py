@@ -542,7 +542,8 @@ def run_model(args, rank, world, local_rank):
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
     crit = FocalLoss()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    use_graph = args.graph and world == 1
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
     ema = EMA(model, 0.999)
     ema.register()
     gen = torch.Generator().manual_seed(rank)
@@ -557,27 +558,79 @@ def run_model(args, rank, world, local_rank):
     resident = to_dev(host)
     loss_h = torch.empty((), pin_memory=True)
 
+    def step_eager(b=None):
+        return train_step(net, resident if b is None else b, crit, opt, ema, autocast_dtype=torch.bfloat16)
+
+    # N = 1: the whole training step (trunks, 4 fusion stages with graph-safe dropout, loss, backward, capturable fused
+    # AdamW, multi-tensor EMA) is captured in one CUDA graph on static input tensors and replayed.
+    graph, graph_loss, launch_note, graph_launches = None, None, "eager launches", 0
+    if use_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step_eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = _capi.launch_count()
+        try:
+            with torch.cuda.graph(graph):
+                graph_loss = step_eager()
+            launch_note = "whole training step captured in one CUDA graph (%d dsfuse kernels per replay)" % (_capi.launch_count() - n0)
+            graph_launches = _capi.launch_count() - n0
+        except Exception as ex:
+            sys.stderr.write("bench.py: CUDA-graph capture of the model step failed (%s); eager launches\n" % ex)
+            graph = None
+        torch.cuda.synchronize()
+
     def step_resident():
-        return train_step(net, resident, crit, opt, ema, autocast_dtype=torch.bfloat16)
+        if graph is not None:
+            graph.replay()
+            return graph_loss
+        return step_eager()
 
+    # e2e: one pinned-host -> device batch copy (94 MB) per step into preallocated, double-buffered staging tensors on a
+    # copy stream, overlapped with the previous step's compute; the step then reads the staged batch (graph mode: after a
+    # device-to-device move into the graph's static input tensors)
     copy_stream = torch.cuda.Stream()
-    nxt = {"b": None, "ev": None}
+    flat = lambda b: list(b[0]) + list(b[1]) + list(b[2]) + list(b[3:5])
+    host_flat = flat(host)
+    stage = [[torch.empty_like(t, device=dev) for t in host_flat] for _ in range(2)]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    e2e_k = [0, False]
 
-    def prefetch():
+    def unflat(ts):
+        return ts[0:S], ts[S:2 * S], ts[2 * S:3 * S], ts[3 * S], ts[3 * S + 1], None
+
+    def prefetch(i):
         with torch.cuda.stream(copy_stream):
-            nxt["b"] = to_dev(host)
-            nxt["ev"] = torch.cuda.Event()
-            nxt["ev"].record(copy_stream)
+            copy_stream.wait_event(ev_free[i])
+            for d, h in zip(stage[i], host_flat):
+                d.copy_(h, non_blocking=True)
+            ev_ready[i].record(copy_stream)
 
     def step_e2e():
-        if nxt["b"] is None:
-            prefetch()
-        torch.cuda.current_stream().wait_event(nxt["ev"])
-        b = nxt["b"]
-        for t in b[0] + b[1] + b[2] + list(b[3:]):
-            t.record_stream(torch.cuda.current_stream())
-        prefetch()  # next step's batch (94 MB pinned-host -> device) overlaps this step's compute
-        loss_h.copy_(train_step(net, b, crit, opt, ema, autocast_dtype=torch.bfloat16).detach(), non_blocking=True)
+        i = e2e_k[0] & 1
+        if not e2e_k[1]:
+            prefetch(i)
+            e2e_k[1] = True
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev_ready[i])
+        if graph is not None:
+            with torch.no_grad():
+                for dst, src in zip(flat(resident), stage[i]):
+                    dst.copy_(src, non_blocking=True)
+            ev_free[i].record(cur)
+            prefetch(i ^ 1)
+            graph.replay()
+            loss_h.copy_(graph_loss.detach(), non_blocking=True)
+        else:
+            prefetch(i ^ 1)
+            loss_h.copy_(step_eager(unflat(stage[i])).detach(), non_blocking=True)
+            ev_free[i].record(cur)
+        e2e_k[0] += 1
 
     def barrier():
         torch.cuda.synchronize()
@@ -603,7 +656,7 @@ def run_model(args, rank, world, local_rank):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, _capi.launch_count() - n0
+        return ms, (_capi.launch_count() - n0) + (graph_launches * steps if graph is not None else 0)
 
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -611,7 +664,7 @@ def run_model(args, rank, world, local_rank):
         sampler.start()
     ms, launches = timed(step_resident, steps, warmup)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, _ = timed(step_e2e, steps, 2, finalize=lambda: torch.cuda.current_stream().wait_event(nxt["ev"]))
+    ms_e2e, _ = timed(step_e2e, steps, 2, finalize=lambda: torch.cuda.current_stream().wait_event(ev_ready[e2e_k[0] & 1]))
     loss_val = float(loss_h)
     if rank != 0:
         return
@@ -624,7 +677,7 @@ def run_model(args, rank, world, local_rank):
         "config": {"workload": "full model2_seq TransFuser training step: fwd + focal loss + bwd + fused AdamW + EMA, batch 12/GPU, seq_len 5, "
                                "256x256 inputs, dropout 0.1, %d parameters, ResNet trunks in stock PyTorch (channels_last, bf16 autocast), "
                                "4 fusion stages on dsfuse kernels" % n_params,
-                   "global_batch": BATCH * world, "seq_len": S, "parallelism": "dp%d" % world, "launch": "eager launches, PDL " + ("on" if args.pdl else "off"),
+                   "global_batch": BATCH * world, "seq_len": S, "parallelism": "dp%d" % world, "launch": launch_note + ", PDL " + ("on" if args.pdl else "off"),
                    "l2": "per-step working set (activations of 3 ResNets + 4 fusion stages) >> 126 MB L2; no explicit flush",
                    "grad_allreduce": "torch DistributedDataParallel (NCCL, bucketed, overlapped)" if world > 1 else "none (1 GPU)"},
         "e2e": {"value": BATCH * world * steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -150,10 +150,17 @@ class GPT(nn.Module):
 
 
 # --------------------------------------------------------------------------------------------- trunks
+_IMAGENET_STATS = {}
+
+
 def normalize_imagenet(x):
-    """ImageNet mean/std on 0-255 input (model2_seq.py:36-45)."""
-    mean = x.new_tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
-    std = x.new_tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    """ImageNet mean/std on 0-255 input (model2_seq.py:36-45).  The constants are cached per (device, dtype): building
+    them from Python lists on every call is a host-to-device copy, which a CUDA-graph capture of the step forbids."""
+    key = (x.device, x.dtype)
+    if key not in _IMAGENET_STATS:
+        _IMAGENET_STATS[key] = (torch.tensor([0.485, 0.456, 0.406], dtype=x.dtype).view(1, 3, 1, 1).to(x.device),
+                                torch.tensor([0.229, 0.224, 0.225], dtype=x.dtype).view(1, 3, 1, 1).to(x.device))
+    mean, std = _IMAGENET_STATS[key]
     return (x / 255.0 - mean) / std
 
 
