@@ -60,6 +60,17 @@ tokens_fwd_nchw_kernel(dsf_geom g, const void* __restrict__ img, const void* __r
   const int kh = g.H / g.A_h, kw = g.W / g.A_w;
   const float inv = 1.0f / (float)(kh * kw);
   const bool vec = (kw % 4 == 0) && (g.W % 4 == 0);
+  if (kh == 1 && kw == 1 && cells % 4 == 0) {
+    // stage 4 (feature map == anchor grid): the (channel tile x cells) block is contiguous -> 16-byte loads, transposed
+    // into shared memory
+    for (int i = tid; i < nct * cells / 4; i += TOK_THREADS) {
+      float v[4];
+      Vec4<FT>::load(plane0 + 4 * i, v);
+      const int cl = (4 * i) / cells, cell = (4 * i) % cells;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sm[(cell + k) * (TOK_CT + 1) + cl] = v[k];
+    }
+  } else
   for (int o = tid; o < nct * cells; o += TOK_THREADS) {
     const int cl = o / cells, cell = o % cells;
     const int cy = cell / g.A_w, cx = cell % g.A_w;
@@ -81,6 +92,18 @@ tokens_fwd_nchw_kernel(dsf_geom g, const void* __restrict__ img, const void* __r
   }
   __syncthreads();
   const int tok0 = sl * cells;
+  if (nct == TOK_CT && g.C % 4 == 0) {  // 16-byte stores: 8 lanes cover the 32 channels of one token
+    for (int o = tid; o < cells * (TOK_CT / 4); o += TOK_THREADS) {
+      const int cell = o / (TOK_CT / 4), cl = (o % (TOK_CT / 4)) * 4;
+      const int tok = tok0 + cell;
+      float pe[4], v[4];
+      Vec4<float>::load(pos_emb + (size_t)tok * g.C + c0 + cl, pe);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = sm[cell * (TOK_CT + 1) + cl + k] + pe[k];
+      Vec4<float>::store(x + ((size_t)b * T + tok) * g.C + c0 + cl, v);
+    }
+    return;
+  }
   for (int o = tid; o < cells * nct; o += TOK_THREADS) {
     const int cell = o / nct, cl = o % nct;
     const int tok = tok0 + cell;
@@ -159,9 +182,19 @@ tokens_bwd_nchw_kernel(dsf_geom g, const float* __restrict__ dx, const void* __r
   const int kh = g.H / g.A_h, kw = g.W / g.A_w;
   const float inv = 1.0f / (float)(kh * kw);
   const int tok0 = sl * cells;
-  for (int o = tid; o < cells * nct; o += TOK_THREADS) {
-    const int cell = o / nct, cl = o % nct;
-    sm[cell * (TOK_CT + 1) + cl] = dx[((size_t)b * T + tok0 + cell) * g.C + c0 + cl] * inv;
+  if (nct == TOK_CT && g.C % 4 == 0) {  // 16-byte loads: 8 lanes cover the 32 channels of one token
+    for (int o = tid; o < cells * (TOK_CT / 4); o += TOK_THREADS) {
+      const int cell = o / (TOK_CT / 4), cl = (o % (TOK_CT / 4)) * 4;
+      float v[4];
+      Vec4<float>::load(dx + ((size_t)b * T + tok0 + cell) * g.C + c0 + cl, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sm[cell * (TOK_CT + 1) + cl + k] = v[k] * inv;
+    }
+  } else {
+    for (int o = tid; o < cells * nct; o += TOK_THREADS) {
+      const int cell = o / nct, cl = o % nct;
+      sm[cell * (TOK_CT + 1) + cl] = dx[((size_t)b * T + tok0 + cell) * g.C + c0 + cl] * inv;
+    }
   }
   __syncthreads();
   const void* resv; int n;

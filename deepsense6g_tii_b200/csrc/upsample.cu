@@ -47,9 +47,19 @@ upsample_add_fwd_nchw_kernel(dsf_geom g, const float* __restrict__ y, Ptr3 feat,
   const int nct = min(UP_CT, g.C - c0);
   const int tid = threadIdx.x;
   const int b = f / slots, sl = f % slots;
-  for (int o = tid; o < cells * nct; o += UP_THREADS) {
-    const int cell = o / nct, cl = o % nct;
-    sm[cell * (UP_CT + 1) + cl] = y[((size_t)b * T + sl * cells + cell) * g.C + c0 + cl];
+  if (nct == UP_CT && g.C % 4 == 0) {  // 16-byte loads: 8 lanes cover the 32 channels of one token
+    for (int o = tid; o < cells * (UP_CT / 4); o += UP_THREADS) {
+      const int cell = o / (UP_CT / 4), cl = (o % (UP_CT / 4)) * 4;
+      float v[4];
+      Vec4<float>::load(y + ((size_t)b * T + sl * cells + cell) * g.C + c0 + cl, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sm[cell * (UP_CT + 1) + cl + k] = v[k];
+    }
+  } else {
+    for (int o = tid; o < cells * nct; o += UP_THREADS) {
+      const int cell = o / nct, cl = o % nct;
+      sm[cell * (UP_CT + 1) + cl] = y[((size_t)b * T + sl * cells + cell) * g.C + c0 + cl];
+    }
   }
   __syncthreads();
   int which, n;
@@ -164,6 +174,16 @@ upsample_add_bwd_nchw_kernel(dsf_geom g, Ptr3 dout, const float* __restrict__ dg
   const FT* src = reinterpret_cast<const FT*>(dout.p[which]) + ((size_t)n * g.C + c0) * HW;
   const float rsh = (float)g.A_h / (float)g.H, rsw = (float)g.A_w / (float)g.W;
   const int sw = g.W / g.A_w;
+  if (g.H == g.A_h && g.W == g.A_w && cells % 4 == 0) {
+    // stage 4 (no upsampling): plain transpose of the contiguous (channel tile x cells) block, 16-byte loads
+    for (int i = tid; i < nct * cells / 4; i += UP_THREADS) {
+      float v[4];
+      Vec4<FT>::load(src + 4 * i, v);
+      const int cl = (4 * i) / cells, cell = (4 * i) % cells;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) outT[(cell + k) * (UP_CT + 1) + cl] = v[k];
+    }
+  } else
   for (int cl = warp; cl < nct; cl += UP_WARPS) {
     for (int i = lane; i < g.A_h * g.W; i += 32) tmp[i] = 0.f;
     __syncwarp();
@@ -194,6 +214,16 @@ upsample_add_bwd_nchw_kernel(dsf_geom g, Ptr3 dout, const float* __restrict__ dg
     __syncwarp();
   }
   __syncthreads();
+  if (nct == UP_CT && g.C % 4 == 0) {  // 16-byte stores
+    for (int o = tid; o < cells * (UP_CT / 4); o += UP_THREADS) {
+      const int cell = o / (UP_CT / 4), cl = (o % (UP_CT / 4)) * 4;
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = outT[cell * (UP_CT + 1) + cl + k];
+      Vec4<float>::store(dy + ((size_t)b * T + sl * cells + cell) * g.C + c0 + cl, v);
+    }
+    return;
+  }
   for (int o = tid; o < cells * nct; o += UP_THREADS) {
     const int cell = o / nct, cl = o % nct;
     dy[((size_t)b * T + sl * cells + cell) * g.C + c0 + cl] = outT[cell * (UP_CT + 1) + cl];
