@@ -62,15 +62,24 @@ class OverlappedGradReducer:
         self.active = dist.is_initialized() and dist.get_world_size() > 1
         self._works = []
 
+    def _start(self, t):
+        if dist.get_backend() == "nccl":
+            self._works.append((dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=True), None))
+        else:  # gloo (CPU tests) has no AVG: sum now, divide once the collective has completed
+            self._works.append((dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True), t))
+
     def block_ready(self, index, flat):
         if self.active:
-            self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.AVG, async_op=True))
+            self._start(flat)
 
     def finish(self, tensors=()):
         if not self.active:
             return
         for t in tensors:
-            self._works.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=True))
-        for w in self._works:
+            self._start(t)
+        world = dist.get_world_size()
+        for w, t in self._works:
             w.wait()
+            if t is not None:
+                t.div_(world)
         self._works = []

@@ -51,3 +51,39 @@ def test_broadcast_and_grad_allreduce_world2():
     assert reuse_a and reuse_b
     for ga, gb, ra, rb in zip(loc_a, loc_b, red_a, red_b):
         assert np.allclose(ra, (ga + gb) / 2, atol=1e-6) and np.array_equal(ra, rb)
+
+
+def _reducer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deepsense6g_tii_b200 import dist as D
+    red = D.OverlappedGradReducer()
+    # the fused backward hands over one flat bucket per transformer block (last block first), then the leftovers
+    buckets = [torch.full((16,), float(10 * i + rank + 1)) for i in range(3)]
+    tail = [torch.full((4,), float(100 + rank)), torch.full((2,), float(200 + rank))]
+    for i in reversed(range(3)):
+        red.block_ready(i, buckets[i])
+    red.finish(tail)
+    q.put((rank, [b.numpy().copy() for b in buckets], [t.numpy().copy() for t in tail], red.active))
+    dist.destroy_process_group()
+
+
+def test_overlapped_grad_reducer_averages_block_buckets_world2():
+    """dist.OverlappedGradReducer (the per-block all-reduce bench.py --gpus N runs inside the backward): every bucket and
+    the leftover tensors end up as the mean over ranks on every rank."""
+    import numpy as np
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, buckets, tail, active in res:
+        assert active
+        for i, b in enumerate(buckets):
+            assert np.allclose(b, 10 * i + 1.5)          # mean of (10i + 1) and (10i + 2)
+        assert np.allclose(tail[0], 100.5) and np.allclose(tail[1], 200.5)
