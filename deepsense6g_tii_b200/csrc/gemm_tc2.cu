@@ -342,6 +342,10 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_des
       : "memory");
 }
 
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 template <int BN, int STAGES>
 struct G3Smem {
   static constexpr int A_BYTES = G2_BM * G2_BK * 2;        // this CTA's 128 rows of A
@@ -359,7 +363,7 @@ struct G3Smem {
 template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                EpiArgs2 epi, int M, int N, int K, int m_tiles, int n_tiles) {
+                EpiArgs2 epi, int M, int N, int K, int m_tiles, int n_tiles, int tail_start, int tail_split) {
   using L = G3Smem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -369,7 +373,19 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int num_k = K / G2_BK;
-  const int total = m_tiles * n_tiles;  // 256 x BN tiles
+  // Work units: units < tail_start are whole 256 x BN tiles (unit = tile).  The tiles left over after the last full
+  // round of the pairs (tail_start .. ) are each split tail_split ways along K so that the last round is short: a split
+  // unit covers k-blocks [kb0, kb1) of its tile and ADDS its partial product to the fp32 output with vector reductions
+  // (the host zero-fills those tiles first; split 0 also adds bias / residual).  tail_split == 1: no splitting.
+  const int total = tail_start + (m_tiles * n_tiles - tail_start) * tail_split;
+  auto unit_of = [&](int u, int& tile, int& kb0, int& kb1, int& part) {
+    if (u < tail_start || tail_split == 1) { tile = u; kb0 = 0; kb1 = num_k; part = 0; return; }
+    const int j = u - tail_start, sp = j % tail_split;
+    tile = tail_start + j / tail_split;
+    kb0 = sp * num_k / tail_split;
+    kb1 = (sp + 1) * num_k / tail_split;
+    part = 1 + (sp == 0 ? 0 : 1);  // 1 = first split (carries bias / residual), 2 = the others
+  };
   pdl_trigger();
 
   if (warp == 0 && lane == 0) {
@@ -391,9 +407,11 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       const uint32_t full0 = mapa_u32(bar_full, 0);  // the leader's full barriers
       int it = 0;
-      for (int tile = pair; tile < total; tile += n_pairs) {
+      for (int u = pair; u < total; u += n_pairs) {
+        int tile, kb0, kb1, part;
+        unit_of(u, tile, kb0, kb1, part);
         const int m0 = (tile % m_tiles) * 256 + (int)rank * G2_BM, n0 = (tile / m_tiles) * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < num_k; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
           if (epi.ablate & 2) { if (rank == 0) mbar_arrive(bar_full + s * 8); continue; }
@@ -408,19 +426,21 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (rank == 0) {  // MMA issuer of the pair: all 32 lanes walk the schedule, one elected lane issues
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
       int it = 0, i = 0;
-      for (int tile = pair; tile < total; tile += n_pairs, ++i) {
+      for (int u = pair; u < total; u += n_pairs, ++i) {
+        int tile, kb0, kb1, part;
+        unit_of(u, tile, kb0, kb1, part);
         const int ab = i & 1;
         mbar_wait(acc_empty + ab * 8, ((i >> 1) & 1) ^ 1);  // the epilogues of both CTAs have drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem_base + ab * BN;
-        for (int kb = 0; kb < num_k; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
           tc_fence_after();
           const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
           const uint64_t da = make_smem_desc(sa, 16, 1024, SWZ_128B);
           const uint64_t db = make_smem_desc(sb, 16, 1024, SWZ_128B);
-          const uint32_t first = kb != 0 ? 1u : 0u;
+          const uint32_t first = kb != kb0 ? 1u : 0u;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < G2_BK / 16; ++k) tc_mma_bf16_pair(acc, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, k == 0 ? first : 1u);
@@ -439,11 +459,35 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int HALF = BN / 2;
     const uint32_t acc_empty0 = mapa_u32(acc_empty, 0);
     int i = 0, nbox = 0;
-    for (int tile = pair; tile < total; tile += n_pairs, ++i) {
+    for (int u = pair; u < total; u += n_pairs, ++i) {
+      int tile, kb0, kb1, part;
+      unit_of(u, tile, kb0, kb1, part);
       const int ab = i & 1;
       const int m0 = (tile % m_tiles) * 256 + (int)rank * G2_BM, n0 = (tile / m_tiles) * BN;
       mbar_wait(acc_full + ab * 8, (i >> 1) & 1);
       tc_fence_after();
+      if (part != 0) {  // split-K unit: fp32 partial sums are reduced straight into C (zero-filled by the host)
+        const int row = m0 + q * 32 + lane;
+        const uint32_t tacc = tmem_base + ab * BN + ((uint32_t)(q * 32) << 16) + ch * HALF;
+        EpiArgs2 e2 = epi;
+        if (part == 2) e2.flags &= ~(DSF_EPI_BIAS | DSF_EPI_RESIDUAL);
+        if (m0 + q * 32 < M) {
+#pragma unroll 1
+          for (int c = 0; c < HALF; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c, r);
+            tmem_wait_ld();
+            float v[32];
+            const int ncol = n0 + ch * HALF + c;
+            epi_math32(e2, row, ncol, r, v, row < M);
+            if (row < M) {
+              float* cp = reinterpret_cast<float*>(epi.C) + (size_t)row * epi.ldc + ncol;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) red_add_v4(cp + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          }
+        }
+      } else
       if (m0 + q * 32 < M && !(epi.ablate & 1)) {
         const int row = m0 + q * 32 + lane;
         const uint32_t tacc = tmem_base + ab * BN + ((uint32_t)(q * 32) << 16) + ch * HALF;
@@ -502,9 +546,6 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------- TN (wgrad), split contraction
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(G2_THREADS, 1)
@@ -638,6 +679,12 @@ static int launch_tn2(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, 
   return check_launch("gemm_tn2");
 }
 
+// Split the leftover tiles of the pair kernel along K.  OFF by default: measured on B200 it loses — N = 512, K = 2048,
+// fp32 output + residual runs 35.7 us unsplit (92 tiles on 74 pairs, 2 rounds) and 43.7 us with the 18 leftover tiles
+// split 4 ways (zero-fill node + 19 MB of fp32 vector reductions cost more than the idle half round they remove); the
+// whole step goes from 4.39 to 4.62 ms.  DSF_GEMM_TAIL_SPLIT=1 enables it for experiments.
+static const bool g_nt_tail_split = getenv("DSF_GEMM_TAIL_SPLIT") ? atoi(getenv("DSF_GEMM_TAIL_SPLIT")) != 0 : false;
+
 template <int BN, int STAGES>
 static int launch_nt3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const EpiArgs2& epi, int M, int N, int K,
                       cudaStream_t st) {
@@ -649,8 +696,27 @@ static int launch_nt3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
     configured = true;
   }
   const int m_tiles = cdiv(M, 256), n_tiles = N / BN;
-  const int pairs = std::min(m_tiles * n_tiles, num_sms() / 2);
-  launch_pdl(gemm_nt3_kernel<BN, STAGES>, dim3(2 * pairs), dim3(G2_THREADS), L::DYN, st, tmA, tmB, tmC, epi, M, N, K, m_tiles, n_tiles);
+  const int tiles = m_tiles * n_tiles;
+  const int pairs = std::min(tiles, num_sms() / 2);
+  // Tail splitting (see the kernel): only for plain fp32 outputs (linear epilogue, reductions need fp32), when the
+  // leftover tiles fill at most half of the pairs and sit in one column of tiles (one rectangle to zero-fill).
+  int tail_start = tiles, tail_split = 1;
+  const int rem = tiles % pairs, num_k = K / G2_BK;
+  if (g_nt_tail_split && rem > 0 && 2 * rem <= pairs && epi.c_dtype == DSF_F32 && !(epi.flags & DSF_EPI_RELU) && epi.relu_src == nullptr &&
+      epi.residual != epi.C && num_k >= 2) {
+    const int t0 = tiles - rem;
+    if (t0 / m_tiles == (tiles - 1) / m_tiles) {
+      tail_start = t0;
+      tail_split = std::min(std::min(pairs / rem, num_k), 8);
+      const int row0 = (t0 % m_tiles) * 256, col0 = (t0 / m_tiles) * BN;
+      const int rows = std::min(M, ((tiles - 1) % m_tiles + 1) * 256) - row0;
+      if (cudaMemset2DAsync(reinterpret_cast<float*>(epi.C) + (size_t)row0 * epi.ldc + col0, (size_t)epi.ldc * 4, 0, (size_t)BN * 4, (size_t)rows,
+                            st) != cudaSuccess)
+        return check_launch("gemm_nt3/memset");
+    }
+  }
+  launch_pdl(gemm_nt3_kernel<BN, STAGES>, dim3(2 * pairs), dim3(G2_THREADS), L::DYN, st, tmA, tmB, tmC, epi, M, N, K, m_tiles, n_tiles, tail_start,
+             tail_split);
   return check_launch("gemm_nt3");
 }
 

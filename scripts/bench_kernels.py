@@ -46,7 +46,7 @@ if "attn" in what or "attn512" in what:
 
 if "gemm" in what:
     M = 11544
-    for (N, Kd) in [(1536, 512), (512, 512), (2048, 512), (512, 2048), (768, 256), (1024, 256), (256, 1024), (192, 64)]:
+    for (N, Kd) in [(1536, 512), (512, 512), (2048, 512), (512, 2048), (512, 1536), (768, 256), (1024, 256), (256, 1024), (192, 64)]:
         a = torch.randn(M, Kd, device=dev).to(torch.bfloat16)
         w = torch.randn(N, Kd, device=dev).to(torch.bfloat16)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
@@ -64,6 +64,11 @@ if "gemm" in what:
                 t2 = timeit(lambda: K.gemm_bf16_tn(dy, a, dw))
                 line += " tn %.4f ms (%.0f TF/s)" % (t2, fl / t2 / 1e9)
         K.gemm_set_impl(0)
+        if N == 512:  # the residual-stream GEMMs of the step: fp32 output + bias + fp32 residual (tail tiles split along K)
+            out32 = torch.empty(M, N, device=dev)
+            res = torch.randn(M, N, device=dev)
+            t = timeit(lambda: K.gemm_bf16_nt(a, w, out32, bias=bias, residual=res))
+            line += " | v3 f32+bias+residual %.4f ms (%.0f TF/s)" % (t, fl / t / 1e9)
         print(line)
 
 if "elem" in what:
