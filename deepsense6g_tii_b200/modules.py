@@ -18,6 +18,7 @@ Extra, optional config attributes (duck-typed ``config`` object, config_seq.py:3
   ``fusion_dtype``            torch.bfloat16 (default, tensor-core mode) or torch.float32 (parity mode)
   ``modality_missing``        None | 'image' | 'lidar' | 'radar' | 'lidar_radar'  (mambafuser_seq.py:361-391)
   ``modality_missing_type``   'zerolike' | 'randlike'
+  ``missing_fast_path``       bool (default True): eval-mode cache of the stem output of a zeroed branch
   ``pretrained``              bool; torchvision ImageNet weights for the trunks (needs a local cache)
 """
 import torch
@@ -236,10 +237,35 @@ class Encoder(nn.Module):
                        embd_pdrop=config.embd_pdrop, attn_pdrop=config.attn_pdrop, resid_pdrop=config.resid_pdrop,
                        config=config)
 
+        self._stem_cache = {}  # missing-modality fast path, see _stem()
         self.transformer1 = gpt(64)
         self.transformer2 = gpt(128)
         self.transformer3 = gpt(256)
         self.transformer4 = gpt(512)
+
+    def _stem(self, name, m, x):
+        """conv1 -> bn1 -> relu -> maxpool -> layer1 of one trunk (model2_seq.py:495-512).  Missing-modality fast path
+        (SURVEY.md §8f item 3): in eval mode a branch whose input was replaced by zeros (mambafuser_seq.py:418-420) yields
+        the same feature map for every frame, so it is computed once for ONE frame, cached until any parameter or
+        buffer of that stem changes, and broadcast — two of the three stems drop out of the missing-modality sweep."""
+        def run(t):
+            return m.layer1(m.maxpool(m.relu(m.bn1(m.conv1(t)))))
+
+        cfg = self.config
+        if (self.training or not _missing(cfg, name) or getattr(cfg, "modality_missing_type", "zerolike") != "zerolike"
+                or not getattr(cfg, "missing_fast_path", True)):
+            return run(x)
+        parts = [m.conv1, m.bn1, m.layer1]
+        version = sum(int(t._version) for mod in parts for t in list(mod.parameters()) + list(mod.buffers()))
+        key = (name, tuple(x.shape[1:]), x.dtype, x.device, x.is_contiguous(memory_format=torch.channels_last), torch.is_autocast_enabled())
+        hit = self._stem_cache.get(key)
+        if hit is None or hit[0] != version:
+            with torch.no_grad():
+                hit = (version, run(x[:1]))
+            self._stem_cache[key] = hit
+        one = hit[1]
+        nhwc = one.is_contiguous(memory_format=torch.channels_last) and not one.is_contiguous()
+        return one.expand(x.shape[0], *one.shape[1:]).contiguous(memory_format=torch.channels_last if nhwc else torch.contiguous_format)
 
     def _apply_missing(self, name, t):
         # semantics of mambafuser_seq.py:361-391, 418-420: replace the stacked input ahead of conv1
@@ -264,10 +290,7 @@ class Encoder(nn.Module):
 
         ie, le, re_ = self.image_encoder.features, self.lidar_encoder._model, self.radar_encoder._model
 
-        def stem(m, x):
-            return m.layer1(m.maxpool(m.relu(m.bn1(m.conv1(x)))))
-
-        f_img, f_lid, f_rad = stem(ie, img), stem(le, lid), stem(re_, rad)
+        f_img, f_lid, f_rad = self._stem("image", ie, img), self._stem("lidar", le, lid), self._stem("radar", re_, rad)
         g = self.vel_emb1(gps)
         f_img, f_lid, f_rad, g = self.transformer1.fuse(f_img, f_lid, f_rad, g)
         f_img, f_lid, f_rad = ie.layer2(f_img), le.layer2(f_lid), re_.layer2(f_rad)

@@ -112,3 +112,31 @@ def test_missing_modality_zeroes_inputs_ahead_of_conv1(cuda_dev):
         m.config.modality_missing = "lidar_radar"
         got = m(imgs, lids, rads, gps)
     assert rel_err(got, ref) < 1e-6
+
+
+def test_missing_modality_fast_path_caches_the_zeroed_stems(cuda_dev):
+    """Eval mode, lidar and radar zeroed ahead of conv1: the stem output of a zeroed branch is input-independent, so the
+    drop-in computes it for one frame, caches it and broadcasts.  Same logits as the uncached path; the cache follows
+    in-place weight updates; train() mode never uses it."""
+    m = _build(cuda_dev, torch.float32, n_layer=1, modality_missing="lidar_radar").eval()
+    ins = _inputs(2, cuda_dev, seed=6)
+    with torch.no_grad():
+        m.config.missing_fast_path = False
+        ref = m(*ins)
+        m.config.missing_fast_path = True
+        got = m(*ins)
+        assert set(k[0] for k in m.encoder._stem_cache) == {"lidar", "radar"}
+        assert rel_err(got, ref) < 1e-6
+        again = m(*ins)
+        assert torch.equal(again, got)
+        # an in-place parameter update invalidates the cached stem
+        m.encoder.lidar_encoder._model.bn1.bias.add_(0.5)
+        m.config.missing_fast_path = False
+        ref2 = m(*ins)
+        m.config.missing_fast_path = True
+        got2 = m(*ins)
+        assert rel_err(got2, ref2) < 1e-6 and rel_err(got2, got) > 1e-6
+    m.train()
+    m.encoder._stem_cache.clear()
+    m(*ins)
+    assert not m.encoder._stem_cache
