@@ -697,7 +697,15 @@ def main():
                     help="stage = BASELINE.json configs[1] (default, the driver's line); model = configs[2], the full training step")
     ap.add_argument("--quick", action="store_true", help="profiling runs: skip the e2e leg, the instrumented step and the CPU baseline")
     ap.add_argument("--no-pdl", dest="pdl", action="store_false", help="disable programmatic dependent launch of the hot kernels")
+    ap.add_argument("--anchors", type=int, default=8, choices=[8, 16],
+                    help="16 = BASELINE.json configs[4], the scaled fusion stage: 16x16 anchors -> T = 3842 tokens (not the driver's line)")
     args = ap.parse_args()
+    if args.anchors != 8:
+        global A, T, WORKLOAD, FWD_FLOPS_PER_SAMPLE
+        A = args.anchors
+        T = (V + 2) * S * A * A + 2
+        WORKLOAD = "gpt_fusion_stage n_embd=512 n_layer=8 n_head=4 anchors=%dx%d seq_len=5 T=%d batch=12/GPU fwd+bwd (scaled config)" % (A, A, T)
+        FWD_FLOPS_PER_SAMPLE = L * (24.0 * T * C * C + 4.0 * T * T * C)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -189,6 +189,54 @@ def test_stage_scaled_config_16x16_anchors(cuda_dev):
         assert_close(x.float(), y, 2e-2, 1e-4, "scaled")
 
 
+def test_stage_scaled_config_backward_c512(cuda_dev):
+    """configs[4] at the stage-4 width: C = 512, 16x16 anchors on a 16x16 feature map (512x512 input), T = 3842, fwd+bwd in
+    bf16 against the fp32 oracle on the same device (2 layers, B = 1); gradients at the calibrated bf16 bounds."""
+    from conftest import rel_err
+    from deepsense6g_tii_b200.functional import fusion_stage, param_names
+    S, A, nh, C, L, B, H = 5, 16, 4, 512, 2, 1, 16
+    T = 3 * S * A * A + 2
+    gen = torch.Generator().manual_seed(9)
+    p0 = R.init_gpt_params(C, nh, 4, L, T, generator=gen, pos_std=0.02)
+    p0 = {k: (v + 0.01 * torch.randn(v.shape, generator=gen)).to(cuda_dev) for k, v in p0.items()}
+    feats = [torch.randn(B * S, C, H, H, generator=gen).to(cuda_dev) for _ in range(3)]
+    gps = torch.randn(B, 2, C, generator=gen).to(cuda_dev)
+    probes = [torch.randn(f.shape, generator=gen).to(cuda_dev) for f in feats] + [torch.randn(B, 2, C, generator=gen).to(cuda_dev)]
+    names = param_names(L)
+
+    def leafs():
+        return ({k: v.clone().requires_grad_(True) for k, v in p0.items()},
+                [f.clone().requires_grad_(True) for f in feats] + [gps.clone().requires_grad_(True)])
+
+    def oracle(autocast):
+        po, io = leafs()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            (a, b, c), gout = R.fusion_stage(po, io[:3], io[3], nh, S, A, A)
+        sum((o.float() * pr).sum() for o, pr in zip((a, b, c, gout), probes)).backward()
+        return (a, b, c, gout), po, io
+
+    ref, po, io = oracle(False)
+    cref, cpo, cio = oracle(True)
+    pk, ik = leafs()
+    cfg = dict(seq_len=S, n_views=1, vert_anchors=A, horz_anchors=A, n_head=nh, n_layer=L, compute_dtype=torch.bfloat16)
+    got = fusion_stage(cfg, ik[0], ik[1], ik[2], ik[3], [pk[n] for n in names])
+    sum((o.float() * pr).sum() for o, pr in zip(got, probes)).backward()
+    for x, y in zip(got, ref):
+        assert_close(x.float(), y, 1e-2, 1e-5, "scaled out")
+    for i, (x, y) in enumerate(zip(ik, io)):
+        assert_close(x.grad, y.grad, max(2e-2, 1.25 * rel_err(cio[i].grad, y.grad)), 1e-5, "scaled gin%d" % i)
+    bad = []
+    for n in names:
+        g_ref = po[n].grad
+        if n.endswith("attn.key.bias"):
+            continue
+        floor = 2e-2 if g_ref.dim() > 1 else 3e-2
+        err, bnd = rel_err(pk[n].grad, g_ref), max(floor, 1.25 * rel_err(cpo[n].grad, g_ref))
+        if err > bnd:
+            bad.append("%s: %.3e > %.3e" % (n, err, bnd))
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("B,C,H,L", [(2, 64, 32, 2), (1, 512, 8, 2), (2, 128, 32, 8)])
 def test_stage_dropout_matches_oracle_given_the_same_masks(cuda_dev, B, C, H, L):
     """Training-mode dropout (p = 0.1 at all four sites, config_seq.py:39-41).  torch's RNG stream cannot be matched
