@@ -155,12 +155,15 @@ def run_reference(args, rank):
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
+PDROP = 0.0  # --dropout: embd/attn/resid probability of the stage workload (the reference trains with 0.1)
+
+
 def build_gpt(device):
     import types
     from deepsense6g_tii_b200 import GPT
     cfg = types.SimpleNamespace(n_views=V, fusion_dtype=torch.bfloat16)
     torch.manual_seed(100)  # the reference's seed (train2_seq.py:430-434)
-    m = GPT(C, NH, 4, L, A, A, S, 0.0, 0.0, 0.0, cfg)
+    m = GPT(C, NH, 4, L, A, A, S, PDROP, PDROP, PDROP, cfg)
     with torch.no_grad():
         m.pos_emb.normal_(0, 0.02)
     return m.to(device)
@@ -506,7 +509,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": "train samples/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "seq_len": S, "parallelism": "dp%d" % world,
-                   "launch": graph_note + pdl_note,
+                   "launch": graph_note + pdl_note, "dropout": PDROP,
                    "l2": "per-step working set ~1.5 GB of saved activations > 126 MB L2; no explicit flush",
                    "grad_allreduce": "NCCL all-reduce (avg) of 25.7 M fp32 grads per step, one bucket per block, overlapped with backward" if world > 1 else "none (1 GPU)",
                    "grads_identical_across_ranks": synced},
@@ -697,9 +700,14 @@ def main():
                     help="stage = BASELINE.json configs[1] (default, the driver's line); model = configs[2], the full training step")
     ap.add_argument("--quick", action="store_true", help="profiling runs: skip the e2e leg, the instrumented step and the CPU baseline")
     ap.add_argument("--no-pdl", dest="pdl", action="store_false", help="disable programmatic dependent launch of the hot kernels")
+    ap.add_argument("--dropout", type=float, default=0.0,
+                    help="stage workload: embd/attn/resid dropout probability (default 0 = the parity configuration; the reference trains with 0.1)")
     ap.add_argument("--anchors", type=int, default=8, choices=[8, 16],
                     help="16 = BASELINE.json configs[4], the scaled fusion stage: 16x16 anchors -> T = 3842 tokens (not the driver's line)")
     args = ap.parse_args()
+    if args.dropout > 0:
+        global PDROP
+        PDROP = args.dropout
     if args.anchors != 8:
         global A, T, WORKLOAD, FWD_FLOPS_PER_SAMPLE
         A = args.anchors

@@ -30,7 +30,7 @@ __device__ __forceinline__ float ex2_approx(float x) {  // 2^x, MUFU.EX2 without
   return y;
 }
 // Attention-probability dropout (attn_drop, model2_seq.py:104).  Decisions use 8-bit thresholds (p is quantised to
-// k/256, scale = 256/(256-k)) so that one Philox4x32-10 call yields 16 of them; the forward kernel writes the keep
+// k/256, scale = 256/(256-k)) so that one Philox4x32 call yields 16 of them; the forward kernel writes the keep
 // bits of every (b, h, q) row to a bitmap (Tw 32-bit words per row) and the backward kernels read them back.
 struct AttnDrop {
   uint32_t thresh8;  // drop iff random byte < thresh8; 0 = disabled
@@ -46,7 +46,7 @@ __device__ __forceinline__ uint32_t attn_keep_word(const AttnDrop& a, uint64_t r
   const uint32_t t4 = a.thresh8 * 0x01010101u;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    const uint4 r = philox4x32_10(a.k0, a.k1, (uint32_t)rowid, (uint32_t)(rowid >> 32), word * 2 + c, a.site);
+    const uint4 r = philox4x32(a.k0, a.k1, (uint32_t)rowid, (uint32_t)(rowid >> 32), word * 2 + c, a.site);
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {

@@ -100,20 +100,24 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // ---------------------------------------------------------------- counter-based dropout (Philox4x32-10)
 // nn.Dropout sites of the path (model2_seq.py:104,109,125,272).  The mask of element e of a site is a pure function of
-// (seed, site, step, e): component e%4 of philox(key = seed, counter = (e/4, site, step)); keep iff value >= p * 2^32,
-// kept values are scaled by 1/(1-p).  Forward and backward kernels recompute it, nothing is stored (attention excepted).
+// (seed, site, step, e): 16-bit lane e%8 of philox(key = seed, counter = (e/8, site, step)); keep iff lane >= t16 with
+// t16 = round(p * 65536), kept values are scaled by 65536 / (65536 - t16) (= 1/(1-p) to 1.5e-5).  One Philox call
+// decides 8 elements.  Forward and backward kernels recompute it, nothing is stored (attention excepted).
+// Philox4x32 with 7 rounds (the Random123 "Crush-resistant" minimum; 10 is the library default with safety margin):
+// the masks only have to be uncorrelated, and the generator runs inside GEMM epilogues and the softmax loop.
 struct DropArgs {
-  uint32_t thresh;  // drop iff random < thresh  (0 = dropout disabled)
-  float scale;      // 1 / (1 - p)
+  uint32_t thresh;  // 16-bit threshold: drop iff lane < thresh  (0 = dropout disabled)
+  float scale;      // 65536 / (65536 - thresh)
   uint32_t seed_lo, seed_hi, site, step;
   const unsigned long long* seed_dev;  // nullable device word XOR-ed into the seed (graph-safe reseeding)
 };
 __host__ __device__ inline DropArgs make_drop(const dsf_dropout* d) {
   DropArgs a{0u, 1.0f, 0u, 0u, 0u, 0u, nullptr};
   if (d && d->p > 0.f) {
-    const double t = (double)d->p * 4294967296.0;
-    a.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
-    a.scale = 1.0f / (1.0f - d->p);
+    long t = lrint((double)d->p * 65536.0);
+    t = t < 1 ? 1 : (t > 65535 ? 65535 : t);
+    a.thresh = (uint32_t)t;
+    a.scale = 65536.0f / (65536.0f - (float)t);
     a.seed_lo = (uint32_t)(d->seed & 0xFFFFFFFFull);
     a.seed_hi = (uint32_t)(d->seed >> 32);
     a.site = d->site;
@@ -131,9 +135,10 @@ __device__ __forceinline__ DropArgs resolve_drop(DropArgs a) {
   }
   return a;
 }
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+constexpr int PHILOX_ROUNDS = 7;
+__device__ __forceinline__ uint4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < PHILOX_ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
@@ -141,13 +146,23 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// scale factors (0 or 1/(1-p)) of the 4 consecutive elements e4*4 .. e4*4+3
+// scale factors (0 or scale) of the 8 consecutive elements e8*8 .. e8*8+7
+__device__ __forceinline__ void drop_scale8(const DropArgs& a, uint64_t e8, float (&m)[8]) {
+  const uint4 r = philox4x32(a.seed_lo, a.seed_hi, (uint32_t)e8, (uint32_t)(e8 >> 32), a.site, a.step);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    m[2 * k] = (w[k] & 0xFFFFu) >= a.thresh ? a.scale : 0.f;
+    m[2 * k + 1] = (w[k] >> 16) >= a.thresh ? a.scale : 0.f;
+  }
+}
+// the 4 consecutive elements e4*4 .. e4*4+3 (half of one 8-element group)
 __device__ __forceinline__ void drop_scale4(const DropArgs& a, uint64_t e4, float (&m)[4]) {
-  const uint4 r = philox4x32_10(a.seed_lo, a.seed_hi, (uint32_t)e4, (uint32_t)(e4 >> 32), a.site, a.step);
-  m[0] = r.x >= a.thresh ? a.scale : 0.f;
-  m[1] = r.y >= a.thresh ? a.scale : 0.f;
-  m[2] = r.z >= a.thresh ? a.scale : 0.f;
-  m[3] = r.w >= a.thresh ? a.scale : 0.f;
+  float m8[8];
+  drop_scale8(a, e4 >> 1, m8);
+  const int h = (int)(e4 & 1) * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) m[k] = m8[h + k];
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

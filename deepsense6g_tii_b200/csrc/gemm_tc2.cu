@@ -99,12 +99,13 @@ __device__ __forceinline__ void epi_math32(const EpiArgs2& e, int row, int n, co
     }
   }
   if (e.drop.thresh) {
-    const uint64_t e4 = ((uint64_t)row * e.N + n) >> 2;
+    const uint64_t e8 = ((uint64_t)row * e.N + n) >> 3;  // N and n are multiples of 8
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float m[4];
-      drop_scale4(e.drop, e4 + (j >> 2), m);
-      v[j] *= m[0]; v[j + 1] *= m[1]; v[j + 2] *= m[2]; v[j + 3] *= m[3];
+    for (int j = 0; j < 32; j += 8) {
+      float m[8];
+      drop_scale8(e.drop, e8 + (j >> 3), m);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[j + k] *= m[k];
     }
   }
   if ((e.flags & DSF_EPI_RESIDUAL) && row_ok) {

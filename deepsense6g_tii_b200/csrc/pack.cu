@@ -139,29 +139,31 @@ extern "C" int dsf_relu_bwd_colsum(void* dy, const void* h, float* out, int32_t 
 
 // ---------------------------------------------------------------- embedding dropout (model2_seq.py:272) and its backward
 namespace dsf {
-__global__ void __launch_bounds__(256) dropout_inplace_kernel(float* __restrict__ x, int64_t n4, DropArgs a) {
+__global__ void __launch_bounds__(256) dropout_inplace_kernel(float* __restrict__ x, int64_t n8, DropArgs a) {
   pdl_trigger();
   pdl_wait();
   a = resolve_drop(a);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float v[4], m[4];
-    Vec4<float>::load(x + i * 4, v);
-    drop_scale4(a, (uint64_t)i, m);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float v0[4], v1[4], m[8];
+    Vec4<float>::load(x + i * 8, v0);
+    Vec4<float>::load(x + i * 8 + 4, v1);
+    drop_scale8(a, (uint64_t)i, m);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] *= m[k];
-    Vec4<float>::store(x + i * 4, v);
+    for (int k = 0; k < 4; ++k) { v0[k] *= m[k]; v1[k] *= m[4 + k]; }
+    Vec4<float>::store(x + i * 8, v0);
+    Vec4<float>::store(x + i * 8 + 4, v1);
   }
 }
 }  // namespace dsf
 
 extern "C" int dsf_dropout_inplace(float* x, int64_t n, const dsf_dropout* d, void* stream) {
-  DSF_REQUIRE(x && n > 0 && n % 4 == 0, "dropout_inplace: bad arguments (n must be a positive multiple of 4)");
+  DSF_REQUIRE(x && n > 0 && n % 8 == 0, "dropout_inplace: bad arguments (n must be a positive multiple of 8)");
   DSF_REQUIRE(aligned16(x), "dropout_inplace: 16-byte alignment required");
   DSF_REQUIRE(!d || (d->p >= 0.f && d->p < 1.f), "dropout_inplace: p must be in [0, 1)");
   const dsf::DropArgs a = dsf::make_drop(d);
   if (a.thresh == 0) return DSF_OK;
-  const int64_t n4 = n / 4;
-  const int blocks = (int)std::min<int64_t>(dsf::cdiv64(n4, 256), (int64_t)dsf::num_sms() * 16);
-  dsf::launch_pdl(dsf::dropout_inplace_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, n4, a);
+  const int64_t n8 = n / 8;
+  const int blocks = (int)std::min<int64_t>(dsf::cdiv64(n8, 256), (int64_t)dsf::num_sms() * 16);
+  dsf::launch_pdl(dsf::dropout_inplace_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, n8, a);
   return dsf::check_launch("dropout_inplace");
 }

@@ -18,7 +18,7 @@ kernels (no ATen math on the path).  Two compute modes:
 
 Dropout (model2_seq.py:104,109,125,272; bf16 mode only): ``cfg["dropout"] = dict(embd=p, attn=p, resid=p,
 seed=int, step=int[, seed_dev=int64 device tensor][, capture=dict])``; with ``seed_dev`` the kernels use
-``seed ^ seed_dev[0]`` read on the device, so a CUDA-graph replay draws new masks whenever that word was bumped.  Masks are counter-based (Philox4x32-10 of (seed, site, step, element)),
+``seed ^ seed_dev[0]`` read on the device, so a CUDA-graph replay draws new masks whenever that word was bumped.  Masks are counter-based (Philox4x32, 7 rounds, of (seed, site, step, element)),
 recomputed by the backward kernels; sites are numbered ``drop_site(...)``.  torch's own RNG stream cannot be
 reproduced bit for bit, so parity with dropout is tested by feeding the oracle the masks the kernels drew
 (``capture`` receives the attention keep-bitmaps; the elementwise masks are regenerated with

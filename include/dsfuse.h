@@ -63,8 +63,9 @@ int dsf_set_pdl(int32_t on);
 int dsf_set_sm_margin(int32_t sms);
 
 /* One nn.Dropout site (model2_seq.py:104 attn_drop, :109/:125 resid_drop, :272 embd drop).  The keep/drop decision
- * of element e is a pure function of (seed, site, step, e) (Philox4x32-10), so forward and backward kernels agree
- * without storing masks; kept elements are scaled by 1/(1-p).  NULL or p == 0 disables dropout.               */
+ * of element e is a pure function of (seed, site, step, e) (Philox4x32, 7 rounds, one call per 8 elements), so forward
+ * and backward kernels agree without storing masks.  p is quantised to t/65536 (t/256 for the attention
+ * probabilities); kept elements are scaled by 65536/(65536-t).  NULL or p == 0 disables dropout.               */
 typedef struct {
   float p;        /* drop probability in [0, 1) */
   uint64_t seed;  /* per-run seed */
@@ -74,7 +75,7 @@ typedef struct {
                              * captured step draw fresh masks at every replay (the caller bumps the word on the device) */
 } dsf_dropout;
 
-/* x[e] *= mask(e)/(1-p), e in [0, n): embedding dropout on the token tensor (:272) and its backward. */
+/* x[e] *= mask(e)/(1-p), e in [0, n), n a multiple of 8: embedding dropout on the token tensor (:272) and its backward. */
 int dsf_dropout_inplace(float* x, int64_t n, const dsf_dropout* d, void* stream);
 
 /* Geometry shared by the token kernels. */

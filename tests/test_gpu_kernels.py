@@ -374,14 +374,15 @@ def _mask_of(K, cuda_dev, shape, drop):
 
 
 def test_dropout_elementwise_mask_properties(K, cuda_dev):
-    """Counter-based masks: values are exactly 0 or 1/(1-p); the keep rate is 1-p within 5 sigma; the mask is a pure
+    """Counter-based masks: values are exactly 0 or 65536/(65536 - round(65536 p)) (= 1/(1-p) to 1.5e-5); the keep rate is 1-p within 5 sigma; the mask is a pure
     function of (seed, site, step) and changes with each of them."""
     n = 962 * 512 * 4
     for p in (0.1, 0.5):
         d = K.Dropout(p, 1234, 3, 7)
         m = _mask_of(K, cuda_dev, (n,), d)
         kept = m != 0
-        assert torch.all(m[kept] == torch.tensor(1.0 / (1.0 - p), dtype=torch.float32).to(cuda_dev))
+        t16 = round(p * 65536)  # p is quantised to t16 / 65536; kept values carry exactly 65536 / (65536 - t16)
+        assert torch.all(m[kept] == torch.tensor(65536.0 / (65536.0 - t16), dtype=torch.float32).to(cuda_dev))
         rate = float(kept.float().mean())
         assert abs(rate - (1 - p)) < 5 * math.sqrt(p * (1 - p) / n), rate
         assert torch.equal(m, _mask_of(K, cuda_dev, (n,), K.Dropout(p, 1234, 3, 7)))
