@@ -743,7 +743,13 @@ bool g_nt_pairs = true;  // dsf_gemm_set_impl(3) = on (default), (2) = single-CT
 
 int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, const float* bias, const float* residual, int M,
                int N, int K, int flags, const dsf_dropout* drop, const void* relu_src, cudaStream_t st) {
-  static const int ablate = getenv("DSF_GEMM_ABLATE") ? atoi(getenv("DSF_GEMM_ABLATE")) : 0;
+  // kernel-timing diagnostics only (DESIGN.md "What bounds the tensor-core kernels"): any non-zero value makes the
+  // GEMM results WRONG on purpose (skipped loads / epilogue), hence the loud warning
+  static const int ablate = [] {
+    const int v = getenv("DSF_GEMM_ABLATE") ? atoi(getenv("DSF_GEMM_ABLATE")) : 0;
+    if (v) fprintf(stderr, "dsfuse: DSF_GEMM_ABLATE=%d is set: tensor-core GEMM results are INVALID (timing diagnostics only)\n", v);
+    return v;
+  }();
   CUtensorMap tmA, tmB;
   if (g_nt_pairs && N % 128 == 0 && M > 128) {
     // CTA-pair kernel: 256 x BN tiles, each CTA loads BN/2 rows of B.  BN = 256 whenever N allows: one tcgen05.mma costs
