@@ -101,6 +101,22 @@ class GPT(nn.Module):
             module.bias.data.zero_()
             module.weight.data.fill_(1.0)
 
+    def configure_optimizers(self):
+        """Same contract as the reference method (model2_seq.py:216-246): two optimizer parameter groups — weights of
+        Linear layers with weight decay 0.01; every bias, the LayerNorm weights and ``pos_emb`` with weight decay 0 —
+        each group in sorted parameter-name order."""
+        decay, no_decay = [], ["pos_emb"]
+        for mod_name, mod in self.named_modules():
+            for p_name, _ in mod.named_parameters(recurse=False):
+                full = "%s.%s" % (mod_name, p_name) if mod_name else p_name
+                if p_name == "bias" or (p_name == "weight" and isinstance(mod, (nn.LayerNorm, nn.BatchNorm2d))):
+                    no_decay.append(full)
+                elif p_name == "weight" and isinstance(mod, (nn.Linear, nn.Conv2d)):
+                    decay.append(full)
+        table = dict(self.named_parameters())
+        return [{"params": [table[n] for n in sorted(decay)], "weight_decay": 0.01},
+                {"params": [table[n] for n in sorted(set(no_decay))], "weight_decay": 0.0}]
+
     def _flat_params(self):
         table = dict(self.named_parameters())
         return [table[n] for n in self._names]

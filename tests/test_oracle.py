@@ -148,3 +148,20 @@ def test_encoder_restatement_matches_reference_live():
         got = model_ref.encoder_forward(enc, imgs, lids, rads, gps)
     assert got.shape == ref.shape == (1, 512)
     assert rel_err(got, ref) < 1e-4
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree absent (GPU box)")
+def test_configure_optimizers_groups_match_reference():
+    """GPT.configure_optimizers (model2_seq.py:216-246, dead code in the reference but part of the class API): the drop-in
+    returns the same two parameter groups (names, order, weight decay)."""
+    from deepsense6g_tii_b200.modules import GPT
+    M, _ = ref_import.load_reference()
+    cfg = ref_import.make_config()
+    ref = M.GPT(64, 4, 4, 2, 8, 8, 5, 0., 0., 0., cfg)
+    ours = GPT(64, 4, 4, 2, 8, 8, 5, 0., 0., 0., cfg)
+
+    def named_groups(m):
+        inv = {id(p): n for n, p in m.named_parameters()}
+        return [([inv[id(p)] for p in g["params"]], g["weight_decay"]) for g in m.configure_optimizers()]
+
+    assert named_groups(ours) == named_groups(ref)
