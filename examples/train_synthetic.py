@@ -54,7 +54,7 @@ def main():
         batch = synthetic_batch(args.batch_size, 5, 256, generator=gen, device=dev)
         loss = train_step(net, batch, criterion, optimizer, ema, autocast_dtype=torch.bfloat16)
         if rank == 0 and (step % 5 == 0 or step == args.steps - 1):
-            print("step %3d  loss %.5f" % (step, float(loss)))
+            print("step %3d  loss %.5f" % (step, float(loss.detach())))
     if ema:  # validate with the shadow weights as Engine.validate does (train2_seq.py:159-160, 220-221)
         ema.apply_shadow()
         model.eval()

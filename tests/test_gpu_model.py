@@ -140,3 +140,26 @@ def test_missing_modality_fast_path_caches_the_zeroed_stems(cuda_dev):
     m.encoder._stem_cache.clear()
     m(*ins)
     assert not m.encoder._stem_cache
+
+
+def test_training_steps_with_dropout_reduce_the_focal_loss(cuda_dev):
+    """The reference's training recipe on the drop-in model (train2_seq.py:105-134): dropout 0.1 at all four sites, bf16
+    autocast trunks, focal loss on the soft beam target, AdamW, EMA.  A handful of steps on one fixed synthetic batch must
+    drive the loss down and keep every parameter / EMA shadow finite."""
+    from deepsense6g_tii_b200.train import EMA, FocalLoss, synthetic_batch, train_step
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        m = _build(cuda_dev, torch.bfloat16, n_layer=2, embd_pdrop=0.1, attn_pdrop=0.1, resid_pdrop=0.1).train()
+        opt = torch.optim.AdamW(m.parameters(), lr=1e-4)
+        ema = EMA(m, 0.999)
+        ema.register()
+        crit = FocalLoss()
+        batch = synthetic_batch(2, 5, 256, generator=torch.Generator().manual_seed(3), device=cuda_dev)
+        losses = [float(train_step(m, batch, crit, opt, ema, autocast_dtype=torch.bfloat16).detach()) for _ in range(6)]
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert all(l == l and l < 1e3 for l in losses), losses
+    assert losses[-1] < 0.6 * losses[0], losses
+    assert all(torch.isfinite(p).all() for p in m.parameters())
+    assert all(torch.isfinite(t).all() for t in ema.shadow.values())
