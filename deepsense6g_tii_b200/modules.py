@@ -139,6 +139,11 @@ class GPT(nn.Module):
             else:
                 seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
                 seed_dev = None
+            # data-parallel replicas share torch.manual_seed (train2_seq.py:430-434): fold the rank in so that each replica
+            # draws its own masks, like independent per-device generators do under nn.DataParallel
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                seed ^= ((dist.get_rank() + 1) * 0x9E3779B97F4A7C15) & ((1 << 62) - 1)
             dropout = dict(embd=self._pdrop[0], attn=self._pdrop[1], resid=self._pdrop[2], seed=seed, step=0, seed_dev=seed_dev)
             if self._drop_capture is not None:
                 self._drop_capture.clear()
