@@ -589,6 +589,7 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
 int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st);
 int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem,
                 cudaStream_t st);
+int attn_fwd_v5(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, cudaStream_t st);
 int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
                 const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem, int parts, cudaStream_t st);
 
@@ -607,7 +608,7 @@ static int g_attn_impl = 0;
 using namespace dsf;
 
 extern "C" int dsf_attn_set_impl(int32_t impl) {
-  DSF_REQUIRE(impl >= 0 && impl <= 4, "attn_set_impl: impl must be 0 (default), 1, 2, 3 or 4");
+  DSF_REQUIRE(impl >= 0 && impl <= 5, "attn_set_impl: impl must be 0 (default) or 1 .. 5");
   g_attn_impl = impl;
   return DSF_OK;
 }
@@ -638,6 +639,7 @@ extern "C" int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int
   const int hs = C / nh;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_attn_impl == 2) return attn_fwd_v2(qkv, y, lse, B, T, C, nh, st);
+  if (g_attn_impl == 5) return attn_fwd_v5(qkv, y, lse, B, T, C, nh, drop_on ? drop : nullptr, drop_bits, st);
   if (g_attn_impl != 1) return attn_fwd_v3(qkv, y, lse, B, T, C, nh, drop_on ? drop : nullptr, drop_bits, g_attn_impl == 4 || g_attn_impl == 0, st);
   switch (hs) {
     case 16: return launch_attn_fwd<16, 128>(qkv, y, lse, B, T, C, nh, st);
@@ -677,7 +679,7 @@ static int attn_bwd_impl(const void* qkv, const void* y, const void* dy, const f
   const int hs = C / nh;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_attn_impl != 1)
-    return attn_bwd_v2(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop_on ? drop : nullptr, const_cast<uint32_t*>(drop_bits), g_attn_impl == 4 || g_attn_impl == 0, parts, st);
+    return attn_bwd_v2(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop_on ? drop : nullptr, const_cast<uint32_t*>(drop_bits), g_attn_impl == 4 || g_attn_impl == 0 || g_attn_impl == 5, parts, st);
   switch (hs) {
     case 16: return launch_attn_bwd<16, 128>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
     case 32: return launch_attn_bwd<32, 128>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);

@@ -942,6 +942,226 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
+// =============================================================================================== forward (v5: four softmax warpgroups)
+// Same pipeline and TMEM layout as the v4 forward (P kept in tensor memory), but every 128-row query tile is served by TWO
+// warpgroups that split the 64 key columns of each S tile (TMEM lane rule: a warp only reaches lanes 32*(warp%4).., so two
+// warpgroups can share the rows and take 32 columns each).  16 softmax warps instead of 8 double the exp/issue
+// throughput a CTA can bring to bear; the two halves of a row agree on the running maximum through shared memory and one
+// 256-thread named barrier per tile and iteration, keep partial row sums, and each rescales / drains half of O's columns.
+template <int HS, int KST, int VST>
+struct Fwd5 {
+  static constexpr int BKV = 64;
+  static constexpr int Q_BYTES = 128 * HS * 2, KV_BYTES = BKV * HS * 2;
+  static constexpr int Q_OFF = 0, K_OFF = 2 * Q_BYTES, V_OFF = K_OFF + KST * KV_BYTES, X_OFF = V_OFF + VST * KV_BYTES;
+  static constexpr int X_BYTES = (2 * 2 * 2 * 128 + 2 * 2 * 128) * 4;  // max exchange [tile][parity][half][row] + row-sum exchange [tile][half][row]
+  static constexpr int BAR_OFF = X_OFF + X_BYTES;
+  static constexpr int NBAR = 1 + 2 * KST + 2 * VST + 12;
+  static constexpr int DYN = BAR_OFF + NBAR * 8 + 16 + 1024;
+  static constexpr int THREADS = 576;  // 16 softmax warps, 1 MMA warp, 1 TMA warp
+  static_assert(4 * BKV + 2 * HS <= 512, "TMEM budget");
+  static_assert(DYN <= 232448, "shared memory budget");
+};
+
+template <int HS, int KST, int VST>
+__global__ void __launch_bounds__(576, 1)
+attn_fwd5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, __nv_bfloat16* __restrict__ y,
+                 float* __restrict__ lse, int T, int C, int nh, float scale_log2, AttnDrop ad) {
+  using L = Fwd5<HS, KST, VST>;
+  constexpr int BKV = L::BKV;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar0 = sbase + L::BAR_OFF;
+  const uint32_t q_full = bar0, k_full = bar0 + 8, k_empty = k_full + 8 * KST, v_full = k_empty + 8 * KST, v_empty = v_full + 8 * VST,
+                 s_full = v_empty + 8 * VST, p_full = s_full + 32, p_empty = p_full + 32, tmem_slot = p_empty + 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (T + BKV - 1) / BKV;
+  constexpr int MMA_WARP = 16, TMA_WARP = 17;
+
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KST; ++s) { mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1); }
+    for (int s = 0; s < VST; ++s) { mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(p_full + 8 * i, 256); mbar_init(p_empty + 8 * i, 1); }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == TMA_WARP && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
+  if (ad.thresh8 && ad.seed_dev != nullptr) {
+    const unsigned long long sd = __ldg(ad.seed_dev);
+    ad.k0 ^= (uint32_t)(sd & 0xFFFFFFFFull);
+    ad.k1 ^= (uint32_t)(sd >> 32);
+  }
+
+  if (warp == TMA_WARP) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * L::Q_BYTES);
+      for (int w = 0; w < 2; ++w) tma_tile<HS>(sbase + L::Q_OFF + w * L::Q_BYTES, &tmQ, q_full, h * HS, q0 + 128 * w, b, 128);
+      for (int j = 0; j < n_kv; ++j) {
+        const int ks = j % KST, vs = j % VST;
+        if (j >= KST) mbar_wait(k_empty + 8 * ks, ((j / KST) - 1) & 1);
+        mbar_expect_tx(k_full + 8 * ks, L::KV_BYTES);
+        tma_tile<HS>(sbase + L::K_OFF + ks * L::KV_BYTES, &tmKV, k_full + 8 * ks, C + h * HS, j * BKV, b, BKV);
+        if (j >= VST) mbar_wait(v_empty + 8 * vs, ((j / VST) - 1) & 1);
+        mbar_expect_tx(v_full + 8 * vs, L::KV_BYTES);
+        tma_tile<HS>(sbase + L::V_OFF + vs * L::KV_BYTES, &tmKV, v_full + 8 * vs, 2 * C + h * HS, j * BKV, b, BKV);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, HS, 0, 1);
+    mbar_wait(q_full, 0);
+    for (int jj = 0; jj < 2 && jj < n_kv; ++jj) {
+      mbar_wait(k_full + 8 * (jj % KST), (jj / KST) & 1);
+      tc_fence_after();
+      for (int w = 0; w < 2; ++w) {
+        mma_over_head<HS>(tmem_base + (w * 2 + jj) * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + (jj % KST) * L::KV_BYTES,
+                          BKV, idesc_s);
+        tc_commit_elect(s_full + 8 * (w * 2 + jj));
+      }
+      tc_commit_elect(k_empty + 8 * (jj % KST));
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int buf = j & 1, vs = j % VST;
+      mbar_wait(v_full + 8 * vs, (j / VST) & 1);
+      for (int w = 0; w < 2; ++w) {
+        const int sb = w * 2 + buf;
+        mbar_wait(p_full + 8 * sb, (j >> 1) & 1);
+        tc_fence_after();
+        mma_over_rows_ts<HS, BKV, true>(tmem_base + 4 * BKV + w * HS, tmem_base + sb * BKV, sbase + L::V_OFF + vs * L::KV_BYTES, idesc_o, j > 0);
+        tc_commit_elect(p_empty + 8 * sb);
+        if (w == 1) tc_commit_elect(v_empty + 8 * vs);
+        if (j + 2 < n_kv) {
+          const int ks = (j + 2) % KST;
+          if (w == 0) { mbar_wait(k_full + 8 * ks, ((j + 2) / KST) & 1); tc_fence_after(); }
+          mma_over_head<HS>(tmem_base + sb * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + ks * L::KV_BYTES, BKV, idesc_s);
+          tc_commit_elect(s_full + 8 * sb);
+          if (w == 1) tc_commit_elect(k_empty + 8 * ks);
+        }
+      }
+    }
+  } else {
+    const int w = warp >> 3;          // 128-row query tile of this warpgroup pair
+    const int hf = (warp >> 2) & 1;   // which 32 of the 64 key columns
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    // O columns rescaled / drained by this half (head size 16: the first half handles all 16)
+    constexpr int OC = HS >= 32 ? HS / 2 : HS;
+    const int o_lo = HS >= 32 ? hf * OC : 0;
+    const bool o_mine = HS >= 32 || hf == 0;
+    const uint32_t tm_o = tmem_base + 4 * BKV + w * HS + lane_off;
+    float* xmax = reinterpret_cast<float*>(smem + L::X_OFF) + w * (2 * 2 * 128);  // [parity][half][row]
+    float* xsum = reinterpret_cast<float*>(smem + L::X_OFF) + 2 * 2 * 2 * 128 + w * (2 * 128);  // [half][row]
+    float m_run = -INFINITY, l_run = 0.f;
+    const int qrow = q0 + 128 * w + row;
+    const uint64_t rowid = ((uint64_t)b * nh + h) * T + qrow;
+    for (int j = 0; j < n_kv; ++j) {
+      const int kv0 = j * BKV, buf = j & 1, sb = w * 2 + buf;
+      const uint32_t tm_s = tmem_base + sb * BKV + lane_off + hf * 32;
+      mbar_wait(s_full + 8 * sb, (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(tm_s, r);
+      tmem_wait_ld();
+      const int k_lo = kv0 + hf * 32;  // first key of this half
+      float p_max = -INFINITY;
+      if (k_lo + 32 <= T) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) p_max = fmaxf(p_max, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (k_lo + i < T) p_max = fmaxf(p_max, __uint_as_float(r[i]));
+      }
+      p_max *= scale_log2;
+      xmax[(j & 1) * 256 + hf * 128 + row] = p_max;
+      named_bar_sync(1 + w, 256);
+      p_max = fmaxf(p_max, xmax[(j & 1) * 256 + (hf ^ 1) * 128 + row]);
+      const bool need = p_max > m_run + 8.f;  // lazy rescale; both halves of a row see the same p_max and m_run
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = need ? p_max : m_run;
+        const float alpha = ex2_approx(m_run - m_new);
+        if (j > 0) {
+          mbar_wait(p_empty + 8 * (w * 2 + ((j - 1) & 1)), ((j - 1) >> 1) & 1);  // P.V(j-1) retired: O is stable
+          tc_fence_after();
+          if (o_mine) {
+#pragma unroll 1
+            for (int c = 0; c < OC; c += 16) {
+              uint32_t o[16];
+              tmem_ld16(tm_o + o_lo + c, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tm_o + o_lo + c, o);
+            }
+            tmem_wait_st();
+          }
+        }
+        l_run *= alpha;
+        m_run = m_new;
+      }
+      if (j >= 2) mbar_wait(p_empty + 8 * sb, ((j >> 1) - 1) & 1);
+      uint32_t keepw = 0xFFFFFFFFu;
+      if (ad.thresh8) {
+        keepw = attn_keep_word(ad, rowid, (uint32_t)(kv0 / 32 + hf));
+        if (qrow < T) ad.bits[rowid * ad.Tw + kv0 / 32 + hf] = keepw;
+      }
+      const bool full = k_lo + 32 <= T;
+      float l_add = 0.f;
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2, -m_run));
+        float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_run));
+        if (!full) {
+          if (k_lo + i >= T) p0 = 0.f;
+          if (k_lo + i + 1 >= T) p1 = 0.f;
+        }
+        l_add += p0 + p1;
+        if (ad.thresh8) {
+          p0 *= (keepw >> i) & 1u ? ad.scale : 0.f;
+          p1 *= (keepw >> (i + 1)) & 1u ? ad.scale : 0.f;
+        }
+        pk[i / 2] = pack_bf16x2(p0, p1);
+      }
+      tmem_st16(tm_s, pk);  // packed over the first 16 columns of this half's own 32-column region (SPLIT layout)
+      l_run += l_add;
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_full + 8 * sb);
+    }
+    // total row sum = the two halves' partial sums
+    xsum[hf * 128 + row] = l_run;
+    named_bar_sync(1 + w, 256);
+    const float l_tot = l_run + xsum[(hf ^ 1) * 128 + row];
+    mbar_wait(p_empty + 8 * (w * 2 + ((n_kv - 1) & 1)), ((n_kv - 1) >> 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_tot;
+    __nv_bfloat16* yrow = y + ((size_t)b * T + qrow) * C + h * HS;
+    if (o_mine) {
+#pragma unroll 1
+      for (int c = 0; c < OC; c += 16) {
+        uint32_t o[16];
+        tmem_ld16(tm_o + o_lo + c, o);
+        tmem_wait_ld();
+        if (qrow < T) store_row16_bf16(yrow + o_lo + c, o, inv_l);
+      }
+    }
+    if (hf == 0 && qrow < T) lse[((size_t)b * nh + h) * T + qrow] = (m_run + log2f(l_tot)) * 0.6931471805599453f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, 512);
+}
+
 // =============================================================================================== host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1008,6 +1228,25 @@ static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C
   dim3 grid(cdiv(T, 256), nh, B);
   launch_pdl(attn_fwd3_kernel<HS, KST, VST, PT>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
   return check_launch("attn_fwd3");
+}
+
+template <int HS, int KST, int VST>
+static int launch_fwd5(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const AttnDrop& ad, cudaStream_t st) {
+  using L = Fwd5<HS, KST, VST>;
+  using H = HeadCfg<HS>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_fwd5_kernel<HS, KST, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
+      return check_launch("attn_fwd5/attr");
+    configured = true;
+  }
+  CUtensorMap tmQ, tmKV;
+  if (int e = make_tmap3(&tmQ, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
+  if (int e = make_tmap3(&tmKV, qkv, 3 * C, T, B, H::BOXC, L::BKV)) return e;
+  const float scale_log2 = (1.0f / sqrtf((float)HS)) * 1.4426950408889634f;
+  dim3 grid(cdiv(T, 256), nh, B);
+  launch_pdl(attn_fwd5_kernel<HS, KST, VST>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
+  return check_launch("attn_fwd5");
 }
 
 int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, int C, int nh, cudaStream_t st);  // attn_tc.cu
@@ -1114,6 +1353,18 @@ int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse
     case 128: return launch_bwd2<128, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
   }
   set_error("attn_bwd: head size %d not supported (16, 32, 64, 128)", C / nh);
+  return DSF_EUNSUPPORTED;
+}
+
+int attn_fwd_v5(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, cudaStream_t st) {
+  const AttnDrop ad = make_attn_drop(drop, bits, T);
+  switch (C / nh) {
+    case 16: return launch_fwd5<16, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 32: return launch_fwd5<32, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 64: return launch_fwd5<64, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 128: return launch_fwd5<128, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
+  }
+  set_error("attn_fwd: head size %d not supported (16, 32, 64, 128)", C / nh);
   return DSF_EUNSUPPORTED;
 }
 

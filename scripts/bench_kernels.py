@@ -36,7 +36,7 @@ if "attn" in what or "attn512" in what:
         delta = torch.empty(B, nh, T, device=dev)
         dqkv = torch.empty_like(qkv)
         fl = 4.0 * T * T * C * B
-        for impl in ((3, 4) if "attn" in what else (3,)):
+        for impl in ((4, 5) if "attn" in what else (3,)):
             K.attn_set_impl(impl)
             tf = timeit(lambda: K.attn_fwd(qkv, y, lse, B, T, C, nh))
             tb = timeit(lambda: K.attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh))

@@ -306,7 +306,7 @@ def _attn_ref(qkv, B, T, C, nh):
 @pytest.mark.parametrize("B,T,C,nh", [(1, 128, 64, 4), (2, 64, 128, 4), (2, 130, 256, 4), (1, 962, 512, 4), (2, 962, 64, 4),
                                       (1, 962, 128, 4), (1, 962, 256, 4), (1, 300, 128, 1), (1, 3842, 64, 4),
                                       (3, 257, 512, 4), (2, 1, 64, 4), (1, 513, 64, 1)])
-@pytest.mark.parametrize("impl", [1, 2, 3, 4], ids=["v1", "v2", "v3", "v4_p_in_tmem"])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4, 5], ids=["v1", "v2", "v3", "v4_p_in_tmem", "v5_fwd_4wg"])
 def test_attention_fwd_bwd(K, cuda_dev, B, T, C, nh, impl):
     K.attn_set_impl(impl)
     try:
