@@ -11,6 +11,7 @@
 // ROWB (128/64/32 B for head sizes >=64/32/16); the same image is read as a K-major operand (rows = M/N)
 // or an MN-major operand (rows = K).  P / dS tiles written by threads use the no-swizzle core-matrix layout.
 #include <algorithm>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -141,6 +142,21 @@ __device__ __forceinline__ void mma_over_rows_ts(uint32_t tmem_d, uint32_t p_tme
     for (int kk = 0; kk < KC / 16; ++kk) {
       const uint32_t col = SPLIT ? (uint32_t)((kk / 2) * 32 + (kk % 2) * 8) : (uint32_t)(kk * 8);
       tc_mma_bf16_ts(tmem_d, p_tmem + col, db + (uint32_t)((kk * 16 * H::ROWB) >> 4), idesc, kk == 0 ? acc : 1u);
+    }
+  }
+  __syncwarp();
+}
+
+// D[128 x NB] (+)= A(tensor memory: 128 rows x HS bf16, packed two per column at a_tmem) . B(tile, RB rows, K-major)^T
+template <int HS>
+__device__ __forceinline__ void mma_over_head_ts(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_tile, int RB, uint32_t idesc) {
+  using H = HeadCfg<HS>;
+  const uint64_t db = make_smem_desc(b_tile, 16, 8 * H::ROWB, H::SWZ);
+  if (elect_one()) {
+#pragma unroll
+    for (int kk = 0; kk < HS / 16; ++kk) {
+      const uint32_t ob = (uint32_t)(kk / H::KPH) * RB * H::ROWB + (uint32_t)(kk % H::KPH) * 32;
+      tc_mma_bf16_ts(tmem_d, a_tmem + (uint32_t)(kk * 8), db + (ob >> 4), idesc, kk != 0);
     }
   }
   __syncwarp();
@@ -570,11 +586,15 @@ struct BwdQ2 {
   static_assert(4 * BKV + HS <= 512, "TMEM budget");
 };
 
-template <int HS, int ST, bool PT>
+// AT = true: the two stationary operands of this kernel, the Q and dO rows of the CTA's 128 queries, live in tensor memory
+// (written once by the math warps straight from global memory) and feed the S = Q K^T and dP = dO V^T MMAs as TS-mode A
+// operands.  A tcgen05.mma whose A operand comes from shared memory spends ~128 cycles fetching its 128 x 16 slice whatever
+// N is, so the 64-wide S / dP MMAs ran at a quarter of the tensor pipe's rate; from tensor memory they are N-bound.
+template <int HS, int ST, bool PT, bool AT>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmKV,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
-                   float scale, AttnDrop ad) {
+                   float scale, AttnDrop ad, const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dy) {
   using L = BwdQ2<HS, ST>;
   constexpr int BKV = L::BKV;
   extern __shared__ uint8_t smem_raw[];
@@ -586,11 +606,12 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (T + BKV - 1) / BKV;
-  constexpr uint32_t TMEM_COLS = (4 * BKV + HS) <= 256 ? 256 : 512;
+  constexpr uint32_t TMEM_COLS = (4 * BKV + HS + (AT ? (HS >= 32 ? HS : 32) : 0)) <= 256 ? 256 : 512;
+  static_assert(4 * BKV + 2 * HS <= 512, "TMEM budget (S/dP double-buffered, dQ, Q and dO rows)");
 
   pdl_trigger();
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
+    mbar_init(q_full, AT ? 256 : 1);
     mbar_init(acc_done, 1);
     for (int s = 0; s < ST; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
     for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256); mbar_init(ds_empty + 8 * w, 1); }
@@ -605,12 +626,15 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_wait();  // set-up above overlaps the previous kernel's tail
   const uint32_t tm_dq = tmem_base + 4 * BKV;
+  const uint32_t tm_q = tm_dq + HS, tm_do = tm_q + (HS >= 32 ? HS / 2 : 16);  // AT: packed Q / dO rows (HS/2 columns each, >= 16 apart)
 
   if (warp == 9) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * L::Q_BYTES);
-      tma_tile<HS>(sbase + L::Q_OFF, &tmQ, q_full, h * HS, q0, b, 128);
-      tma_tile<HS>(sbase + L::DO_OFF, &tmDO, q_full, h * HS, q0, b, 128);
+      if (!AT) {
+        mbar_expect_tx(q_full, 2 * L::Q_BYTES);
+        tma_tile<HS>(sbase + L::Q_OFF, &tmQ, q_full, h * HS, q0, b, 128);
+        tma_tile<HS>(sbase + L::DO_OFF, &tmDO, q_full, h * HS, q0, b, 128);
+      }
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % ST;
         if (j >= ST) mbar_wait(kv_empty + 8 * st, ((j / ST) - 1) & 1);
@@ -626,8 +650,13 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(q_full, 0);
       mbar_wait(kv_full, 0);
       tc_fence_after();
-      mma_over_head<HS>(tmem_base, sbase + L::Q_OFF, 128, sbase + L::K_OFF, BKV, idesc_s);
-      mma_over_head<HS>(tmem_base + BKV, sbase + L::DO_OFF, 128, sbase + L::V_OFF, BKV, idesc_s);
+      if (AT) {
+        mma_over_head_ts<HS>(tmem_base, tm_q, sbase + L::K_OFF, BKV, idesc_s);
+        mma_over_head_ts<HS>(tmem_base + BKV, tm_do, sbase + L::V_OFF, BKV, idesc_s);
+      } else {
+        mma_over_head<HS>(tmem_base, sbase + L::Q_OFF, 128, sbase + L::K_OFF, BKV, idesc_s);
+        mma_over_head<HS>(tmem_base + BKV, sbase + L::DO_OFF, 128, sbase + L::V_OFF, BKV, idesc_s);
+      }
       tc_commit_elect(s_full);
       for (int j = 0; j < n_kv; ++j) {
         const int bf = j & 1, st = j % ST;
@@ -635,8 +664,13 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const int sn = (j + 1) % ST, bn = (j + 1) & 1;
           mbar_wait(kv_full + 8 * sn, ((j + 1) / ST) & 1);
           tc_fence_after();
-          mma_over_head<HS>(tmem_base + bn * 2 * BKV, sbase + L::Q_OFF, 128, sbase + L::K_OFF + sn * L::KV_BYTES, BKV, idesc_s);
-          mma_over_head<HS>(tmem_base + bn * 2 * BKV + BKV, sbase + L::DO_OFF, 128, sbase + L::V_OFF + sn * L::KV_BYTES, BKV, idesc_s);
+          if (AT) {
+            mma_over_head_ts<HS>(tmem_base + bn * 2 * BKV, tm_q, sbase + L::K_OFF + sn * L::KV_BYTES, BKV, idesc_s);
+            mma_over_head_ts<HS>(tmem_base + bn * 2 * BKV + BKV, tm_do, sbase + L::V_OFF + sn * L::KV_BYTES, BKV, idesc_s);
+          } else {
+            mma_over_head<HS>(tmem_base + bn * 2 * BKV, sbase + L::Q_OFF, 128, sbase + L::K_OFF + sn * L::KV_BYTES, BKV, idesc_s);
+            mma_over_head<HS>(tmem_base + bn * 2 * BKV + BKV, sbase + L::DO_OFF, 128, sbase + L::V_OFF + sn * L::KV_BYTES, BKV, idesc_s);
+          }
           tc_commit_elect(s_full + 8 * bn);
         }
         mbar_wait(ds_full + 8 * bf, (j >> 1) & 1);
@@ -657,6 +691,24 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float scale_log2 = scale * 1.4426950408889634f;
     const float my_lse = q_ok ? lse[((size_t)b * nh + h) * T + q] * 1.4426950408889634f : INFINITY;
     const float my_delta = q_ok ? delta[((size_t)b * nh + h) * T + q] : 0.f;
+    if (AT) {  // warpgroup 0 parks the Q row of its query in tensor memory, warpgroup 1 the dO row (two bf16 per column)
+      const __nv_bfloat16* src = wg == 0 ? qkv + ((size_t)b * T + q) * (3 * C) + h * HS : dy + ((size_t)b * T + q) * C + h * HS;
+      const uint32_t dst = (wg == 0 ? tm_q : tm_do) + lane_off;
+#pragma unroll 1
+      for (int c = 0; c < HS; c += 32) {
+        uint32_t wds[16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // head size 16: the row is only 32 bytes (2 x 16 B); the upper 8 columns are padding
+          const bool real = q_ok && (HS >= 32 || k < 2);
+          const uint4 v = real ? __ldg(reinterpret_cast<const uint4*>(src + c) + k) : make_uint4(0u, 0u, 0u, 0u);
+          wds[4 * k] = v.x; wds[4 * k + 1] = v.y; wds[4 * k + 2] = v.z; wds[4 * k + 3] = v.w;
+        }
+        tmem_st16(dst + c / 2, wds);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(q_full);
+    }
     static_assert(BKV == 64, "the math warps split a 64-key tile in two 32-column halves");
     // attn-dropout keep word of (my query row, keys 32*(2j + wg) ..), fetched one tile ahead
     const uint32_t* my_bits = (ad.thresh8 && q_ok) ? ad.bits + (((size_t)b * nh + h) * T + q) * ad.Tw + wg : nullptr;
@@ -1251,6 +1303,8 @@ static int launch_fwd5(const void* qkv, void* y, float* lse, int B, int T, int C
 
 int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, int C, int nh, cudaStream_t st);  // attn_tc.cu
 
+static const bool g_attn_a_in_tmem = getenv("DSF_ATTN_A_TMEM") ? atoi(getenv("DSF_ATTN_A_TMEM")) != 0 : true;
+
 template <int HS, int BQ, int STA, int STB, bool PT>
 static int launch_bwd2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
                        const AttnDrop& ad, int parts, cudaStream_t st) {
@@ -1260,7 +1314,8 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
+        cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, PT, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
       return check_launch("attn_bwd2/attr");
     configured = true;
   }
@@ -1281,7 +1336,12 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
     if (int e = check_launch("attn_bwd2/kv")) return e;
   }
   if (parts & 4) {
-    launch_pdl(attn_bwd_q2_kernel<HS, STB, PT>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
+    if (PT && g_attn_a_in_tmem)
+      launch_pdl(attn_bwd_q2_kernel<HS, STB, PT, PT>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta, (__nv_bfloat16*)dqkv,
+                 T, C, nh, scale, ad, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dy);
+    else
+      launch_pdl(attn_bwd_q2_kernel<HS, STB, PT, false>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta,
+                 (__nv_bfloat16*)dqkv, T, C, nh, scale, ad, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dy);
     if (int e = check_launch("attn_bwd2/q")) return e;
   }
   return DSF_OK;
