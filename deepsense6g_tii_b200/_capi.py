@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdsfuse.so")
+LIB_PATH = os.environ.get("DSF_LIB") or os.path.join(_HERE, "libdsfuse.so")  # DSF_LIB: diagnostics builds (make trace)
 
 DSF_F32, DSF_BF16 = 0, 1
 DSF_NCHW, DSF_NHWC = 0, 1

@@ -25,6 +25,19 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// ---- optional in-kernel timeline (make trace -> libdsfuse_trace.so, scripts/attn_trace.py): CTA (0,0,0) of the forward
+// kernel stamps clock64() at the hand-over points of its MMA warp and of one softmax warp per warpgroup.
+#ifdef DSF_ATTN_TRACE
+__device__ long long g_attn_trace[3][64][6];
+#define TRACE(who, it, slot)                                                                               \
+  do {                                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0 && (it) < 64)     \
+      g_attn_trace[who][it][slot] = clock64();                                                             \
+  } while (0)
+#else
+#define TRACE(who, it, slot) do {} while (0)
+#endif
+
 __device__ __forceinline__ float ex2_approx(float x) {  // 2^x, MUFU.EX2 without the denormal fix-up of exp2f()
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -59,6 +72,9 @@ __device__ __forceinline__ uint32_t attn_keep_word(const AttnDrop& a, uint64_t r
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 template <int HS>
@@ -797,7 +813,9 @@ struct Fwd3 {
 
 // PT = true: the bf16 probabilities never touch shared memory — the softmax warps write them back (packed two per column)
 // over the S tile they came from and P.V runs with its A operand in tensor memory (tcgen05.mma [d], [a], b-desc).
-template <int HS, int KST, int VST, bool PT>
+// PP = true (experiment, DSF_ATTN_PINGPONG=1): the two softmax warpgroups take turns in the exponential phase (named
+// barriers 3 / 4) so that one warpgroup's MUFU.EX2 work runs under the other's max / rescale bookkeeping.
+template <int HS, int KST, int VST, bool PT, bool PP>
 __global__ void __launch_bounds__(320, 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, __nv_bfloat16* __restrict__ y,
                  float* __restrict__ lse, int T, int C, int nh, float scale_log2, AttnDrop ad) {
@@ -866,10 +884,13 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       for (int j = 0; j < n_kv; ++j) {
         const int buf = j & 1, vs = j % VST;
+        TRACE(2, j, 0);
         mbar_wait(v_full + 8 * vs, (j / VST) & 1);
         for (int w = 0; w < 2; ++w) {
           const int sb = w * 2 + buf;
+          TRACE(2, j, 1 + 2 * w);
           mbar_wait(p_full + 8 * sb, (j >> 1) & 1);
+          TRACE(2, j, 2 + 2 * w);
           tc_fence_after();
           if (PT)
             mma_over_rows_ts<HS, BKV>(tmem_base + 4 * BKV + w * HS, tmem_base + sb * BKV, sbase + L::V_OFF + vs * L::KV_BYTES, idesc_o, j > 0);
@@ -894,16 +915,20 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tm_o = tmem_base + 4 * BKV + w * HS + lane_off;
     float m_run = -INFINITY, l_run = 0.f;
+    if (PP && w == 1) named_bar_arrive(3, 256);  // warpgroup 0 goes first
     for (int j = 0; j < n_kv; ++j) {
       const int kv0 = j * BKV, buf = j & 1, sb = w * 2 + buf;
       const uint32_t tm_s = tmem_base + sb * BKV + lane_off;
       uint8_t* p_tile = smem + L::P_OFF + sb * L::P_BYTES;
+      if ((warp & 3) == 0) TRACE(w, j, 0);
       mbar_wait(s_full + 8 * sb, (j >> 1) & 1);
+      if ((warp & 3) == 0) TRACE(w, j, 1);
       tc_fence_after();
       uint32_t r0[32], r1[32];
       tmem_ld32(tm_s, r0);
       tmem_ld32(tm_s + 32, r1);
       tmem_wait_ld();
+      if ((warp & 3) == 0) TRACE(w, j, 2);
       float p_max = -INFINITY;
       if (kv0 + BKV <= T) {
 #pragma unroll
@@ -937,7 +962,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         l_run *= alpha;
         m_run = m_new;
       }
+      if ((warp & 3) == 0) TRACE(w, j, 3);
       if (j >= 2) mbar_wait(p_empty + 8 * sb, ((j >> 1) - 1) & 1);  // P.V(j-2) retired: this P buffer is free
+      if (PP) named_bar_sync(3 + w, 256);  // my turn on the exponential unit
+      if ((warp & 3) == 0) TRACE(w, j, 4);
       float l_add = 0.f;
       const bool full = kv0 + BKV <= T;
       const int qrow = q0 + 128 * w + row;
@@ -969,11 +997,13 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (PT) tmem_st16(tm_s + half * 16, pk);  // keys 32*half .. +31 -> packed columns 16*half .. +15 of the S tile
         else store_p32<BKV>(p_tile, row, half * 32, pk);
       }
+      if (PP) named_bar_arrive(4 - w, 256);  // hand the exponential unit to the other warpgroup
       l_run += l_add;
       if (PT) tmem_wait_st();
       else fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full + 8 * sb);
+      if ((warp & 3) == 0) TRACE(w, j, 5);
     }
     mbar_wait(p_empty + 8 * (w * 2 + ((n_kv - 1) & 1)), ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
@@ -1263,13 +1293,18 @@ static int launch_fwd2(const void* qkv, void* y, float* lse, int B, int T, int C
   return check_launch("attn_fwd2");
 }
 
+// off by default: measured neutral (2110 vs 2150 cycles per iteration) — a softmax warp needs ~1300 cycles for its 64
+// exponentials + packing even when it has the SFU to itself, so the phase is bound by single-warp issue, not by contention
+static const bool g_attn_pingpong = getenv("DSF_ATTN_PINGPONG") ? atoi(getenv("DSF_ATTN_PINGPONG")) != 0 : false;
+
 template <int HS, int KST, int VST, bool PT>
 static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const AttnDrop& ad, cudaStream_t st) {
   using L = Fwd3<HS, KST, VST>;
   using H = HeadCfg<HS>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("attn_fwd3/attr");
     configured = true;
   }
@@ -1278,7 +1313,10 @@ static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C
   if (int e = make_tmap3(&tmKV, qkv, 3 * C, T, B, H::BOXC, L::BKV)) return e;
   const float scale_log2 = (1.0f / sqrtf((float)HS)) * 1.4426950408889634f;
   dim3 grid(cdiv(T, 256), nh, B);
-  launch_pdl(attn_fwd3_kernel<HS, KST, VST, PT>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
+  if (PT && g_attn_pingpong)
+    launch_pdl(attn_fwd3_kernel<HS, KST, VST, PT, true>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
+  else
+    launch_pdl(attn_fwd3_kernel<HS, KST, VST, PT, false>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
   return check_launch("attn_fwd3");
 }
 
@@ -1346,6 +1384,14 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   }
   return DSF_OK;
 }
+
+#ifdef DSF_ATTN_TRACE
+}  // namespace dsf
+extern "C" int dsf_debug_attn_trace(long long* host_out) {  // 3 x 64 x 6 clock64 stamps of the last forward launch
+  return cudaMemcpyFromSymbol(host_out, dsf::g_attn_trace, sizeof(dsf::g_attn_trace)) == cudaSuccess ? 0 : 2;
+}
+namespace dsf {
+#endif
 
 int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st) {
   switch (C / nh) {
