@@ -58,9 +58,10 @@ class _Ctx:
 _SIDE_STREAMS = {}
 
 
-def _side_stream(device):
-    """One extra stream per device for the weight-gradient GEMMs of the backward (see ``_backward_bf16``)."""
-    key = (device.type, device.index)
+def _side_stream(device, which=0):
+    """Extra streams per device: 0 carries the weight-gradient GEMMs / bias sums of the backward and the weight packs of
+    the forward, 1 the dQ attention kernel (see ``_backward_bf16``)."""
+    key = (device.type, device.index, which)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
@@ -374,36 +375,53 @@ class _Runner:
         use_side = (env == "1") if env in ("0", "1") else torch.cuda.is_current_stream_capturing()
         main = torch.cuda.current_stream()
         side = _side_stream(dev) if use_side else None
+        side_q = _side_stream(dev, 1) if use_side else None
 
-        def fork(fn):
-            if side is None:
+        def fork(fn, stream=None):
+            stream = stream or side
+            if stream is None:
                 fn()
                 return
             ev = torch.cuda.Event()
             ev.record(main)
-            side.wait_event(ev)
-            with torch.cuda.stream(side):
+            stream.wait_event(ev)
+            with torch.cuda.stream(stream):
                 fn()
 
-        def join():
-            if side is not None:
+        def join(stream=None):
+            stream = stream or side
+            if stream is not None:
                 ev = torch.cuda.Event()
-                ev.record(side)
+                ev.record(stream)
                 main.wait_event(ev)
+
+        # The weight-gradient work of block i is only joined one block later (before anything it reads can be overwritten
+        # or released): the side stream gets a whole block of slack instead of having to finish inside its own block.
+        pending = None  # (event recorded on the side stream after block i's last fork, block index, references kept alive)
+
+        def join_pending():
+            nonlocal pending
+            if pending is not None:
+                ev, blk, _keep = pending
+                main.wait_event(ev)
+                pending = None
+                if self.grad_hook is not None:  # data parallel: average this block's bucket while the other blocks compute
+                    self.grad_hook.block_ready(blk, gbuf[blk * per_block:(blk + 1) * per_block])
 
         dgf, dbf = gbuf[L * per_block:L * per_block + C], gbuf[L * per_block + C:]
         dx = torch.empty(M, C, device=dev, dtype=f32)
-        dxa = torch.empty(M, C, device=dev, dtype=bf)
+        dxa_bufs = [torch.empty(M, C, device=dev, dtype=bf), torch.empty(M, C, device=dev, dtype=bf)]  # block i reads [i & 1]
         # ln_f backward; by-products: bf16 copy of dx and db2 of the last block
         last = block_views(L - 1) if L > 0 else None
         K.layernorm_bwd(dyf, saved.x_last, params[-2], saved.mean_f, saved.rstd_f, None, dx, dgf, dbf,
-                        dx_bf16=dxa if L > 0 else None, dx_colsum=last[7] if L > 0 else None,
+                        dx_bf16=dxa_bufs[(L - 1) & 1] if L > 0 else None, dx_colsum=last[7] if L > 0 else None,
                         byprod_drop=self._drop("mlp", L - 1) if L > 0 else None)
         grads[-2], grads[-1] = dgf, dbf
         for i in reversed(range(L)):
             base = 1 + 16 * i
             (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[base: base + 16]
             st = saved.layers[i]
+            dxa = dxa_bufs[i & 1]
             dwqkv, dwp, dw1, dw2, dbqkv, dbp, db1, db2, dg1, dbt1, dg2, dbt2 = block_views(i)
             dwqkv, dwp, dw1, dw2 = dwqkv.view(3 * C, C), dwp.view(C, C), dw1.view(F, C), dw2.view(C, F)
             # ---- MLP:  x_out = x_mid + relu(h2 W1^T + b1) W2^T + b2     (model2_seq.py:121-126,132)
@@ -432,9 +450,9 @@ class _Runner:
             else:  # the dQ kernel runs next to the dK/dV kernel: together they leave one partly filled round instead of two
                 adrop = self._drop("attn", i)
                 K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, adrop, st.drop_bits, parts=1)
-                fork(lambda: K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, adrop, st.drop_bits, parts=4))
+                fork(lambda: K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, adrop, st.drop_bits, parts=4), side_q)
                 K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, adrop, st.drop_bits, parts=2)
-                join()
+                join(side_q)
 
             def qkv_grads():
                 K.colsum(dqkv, dbqkv)
@@ -442,18 +460,25 @@ class _Runner:
             fork(qkv_grads)
             dh1 = torch.empty(M, C, device=dev, dtype=f32)
             K.gemm_bf16_nt(dqkv, st.wqkv_t, dh1)
-            join()  # the next kernel overwrites dxa (read by this block's first wgrad); the block's buffers are released below
+            # block i+1's weight-gradient work must be complete now: the next kernel overwrites the bf16 buffer its first wgrad
+            # read, and its activations / gradient operands are released here
+            join_pending()
+            if side is not None:
+                ev_blk = torch.cuda.Event()
+                ev_blk.record(side)
+                pending = (ev_blk, i, (st, da, dxm, dqkv))
             dx = torch.empty(M, C, device=dev, dtype=f32)
             prev = block_views(i - 1) if i > 0 else None
             K.layernorm_bwd(dh1, st.x_in, ln1w, st.mean1, st.rstd1, dx_mid, dx, dg1, dbt1,
-                            dx_bf16=dxa if i > 0 else None, dx_colsum=prev[7] if i > 0 else None,
+                            dx_bf16=dxa_bufs[(i - 1) & 1] if i > 0 else None, dx_colsum=prev[7] if i > 0 else None,
                             byprod_drop=self._drop("mlp", i - 1) if i > 0 else None)
             grads[base: base + 16] = [dg1, dbt1, dg2, dbt2,
                                       dwqkv[C:2 * C], dbqkv[C:2 * C], dwqkv[:C], dbqkv[:C], dwqkv[2 * C:], dbqkv[2 * C:],
                                       dwp, dbp, dw1, db1, dw2, db2]
-            saved.layers[i] = None  # release this block's activations early
-            if self.grad_hook is not None:  # data parallel: start averaging this block's bucket while blocks i-1..0 compute
+            saved.layers[i] = None  # release this block's activations early (with the side stream: once `pending` lets go)
+            if side is None and self.grad_hook is not None:  # data parallel: average this block's bucket while blocks i-1..0 compute
                 self.grad_hook.block_ready(i, gbuf[i * per_block:(i + 1) * per_block])
+        join_pending()
         dfeats = [torch.empty_like(d) for d in douts]
         dgps = torch.empty(self.B, 2, C, device=dev, dtype=f32)
         dpos = torch.empty(1, self.T, C, device=dev, dtype=f32)
