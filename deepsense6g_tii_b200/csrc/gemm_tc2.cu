@@ -364,7 +364,8 @@ struct G3Smem {
 template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                EpiArgs2 epi, int M, int N, int K, int m_tiles, int n_tiles, int tail_start, int tail_split) {
+                const __grid_constant__ CUtensorMap tmBt, EpiArgs2 epi, int M, int N, int K, int m_tiles, int n_tiles, int tail_start,
+                int tail_split, int n_split) {
   using L = G3Smem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -378,9 +379,24 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // round of the pairs (tail_start .. ) are each split tail_split ways along K so that the last round is short: a split
   // unit covers k-blocks [kb0, kb1) of its tile and ADDS its partial product to the fp32 output with vector reductions
   // (the host zero-fills those tiles first; split 0 also adds bias / residual).  tail_split == 1: no splitting.
-  const int total = tail_start + (m_tiles * n_tiles - tail_start) * tail_split;
+  // n_split > 1 (needs tail_split == 1): the leftover tiles are instead split n_split ways along N — a unit is a
+  // 256 x (BN / n_split) sub-tile with its own, narrower MMA shape and B box (tmBt); nothing is reduced across units, so
+  // any epilogue works.  The short last round costs ~BN/n_split columns of epilogue and a cheaper MMA stream.
+  const int total = tail_start + (m_tiles * n_tiles - tail_start) * tail_split * n_split;
+  auto nsub_of = [&](int u, int& tile, int& n_off, int& width) {  // N-split view of unit u
+    if (u < tail_start || n_split == 1) { tile = u; n_off = 0; width = BN; return; }
+    const int j = u - tail_start;
+    tile = tail_start + j / n_split;
+    width = BN / n_split;
+    n_off = (j % n_split) * width;
+  };
   auto unit_of = [&](int u, int& tile, int& kb0, int& kb1, int& part) {
-    if (u < tail_start || tail_split == 1) { tile = u; kb0 = 0; kb1 = num_k; part = 0; return; }
+    if (u < tail_start || tail_split == 1) {
+      int n_off, width;
+      nsub_of(u, tile, n_off, width);
+      kb0 = 0; kb1 = num_k; part = 0;
+      return;
+    }
     const int j = u - tail_start, sp = j % tail_split;
     tile = tail_start + j / tail_split;
     kb0 = sp * num_k / tail_split;
@@ -411,25 +427,33 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int u = pair; u < total; u += n_pairs) {
         int tile, kb0, kb1, part;
         unit_of(u, tile, kb0, kb1, part);
-        const int m0 = (tile % m_tiles) * 256 + (int)rank * G2_BM, n0 = (tile / m_tiles) * BN + (int)rank * (BN / 2);
+        int n_off, width;
+        if (n_split > 1) nsub_of(u, tile, n_off, width);
+        else { n_off = 0; width = BN; }
+        const bool narrow = width != BN;
+        const int m0 = (tile % m_tiles) * 256 + (int)rank * G2_BM, n0 = (tile / m_tiles) * BN + n_off + (int)rank * (width / 2);
+        const uint32_t tx = 2u * (uint32_t)(L::A_BYTES + (width / 2) * G2_BK * 2);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
           if (epi.ablate & 2) { if (rank == 0) mbar_arrive(bar_full + s * 8); continue; }
-          if (rank == 0) mbar_expect_tx(bar_full + s * 8, 2 * L::STAGE_BYTES);
+          if (rank == 0) mbar_expect_tx(bar_full + s * 8, tx);
           const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
           tma_load_2d_pair(sa, &tmA, full0 + s * 8, kb * G2_BK, m0);
-          tma_load_2d_pair(sb, &tmB, full0 + s * 8, kb * G2_BK, n0);
+          tma_load_2d_pair(sb, narrow ? &tmBt : &tmB, full0 + s * 8, kb * G2_BK, n0);
         }
       }
     }
   } else if (warp == 1) {
     if (rank == 0) {  // MMA issuer of the pair: all 32 lanes walk the schedule, one elected lane issues
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
       int it = 0, i = 0;
       for (int u = pair; u < total; u += n_pairs, ++i) {
         int tile, kb0, kb1, part;
         unit_of(u, tile, kb0, kb1, part);
+        int n_off, width;
+        if (n_split > 1) nsub_of(u, tile, n_off, width);
+        else { n_off = 0; width = BN; }
+        const uint32_t idesc = make_idesc_bf16(256, width, 0, 0);
         const int ab = i & 1;
         mbar_wait(acc_empty + ab * 8, ((i >> 1) & 1) ^ 1);  // the epilogues of both CTAs have drained this accumulator
         tc_fence_after();
@@ -463,8 +487,11 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int u = pair; u < total; u += n_pairs, ++i) {
       int tile, kb0, kb1, part;
       unit_of(u, tile, kb0, kb1, part);
+      int n_off, width;
+      if (n_split > 1) nsub_of(u, tile, n_off, width);
+      else { n_off = 0; width = BN; }
       const int ab = i & 1;
-      const int m0 = (tile % m_tiles) * 256 + (int)rank * G2_BM, n0 = (tile / m_tiles) * BN;
+      const int m0 = (tile % m_tiles) * 256 + (int)rank * G2_BM, n0 = (tile / m_tiles) * BN + n_off;
       mbar_wait(acc_full + ab * 8, (i >> 1) & 1);
       tc_fence_after();
       if (part != 0) {  // split-K unit: fp32 partial sums are reduced straight into C (zero-filled by the host)
@@ -491,15 +518,20 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       } else
       if (m0 + q * 32 < M && !(epi.ablate & 1)) {
         const int row = m0 + q * 32 + lane;
-        const uint32_t tacc = tmem_base + ab * BN + ((uint32_t)(q * 32) << 16) + ch * HALF;
+        const uint32_t tacc = tmem_base + ab * BN + ((uint32_t)(q * 32) << 16);
         const uint32_t stg = base + L::STAGING_OFF + (warp - 2) * 8192;
         const int CW = epi.c_dtype == DSF_F32 ? 32 : 64;  // columns per 128-byte staged row
+        // columns of this unit drained by this warp: its column half, or (narrow unit, half narrower than one staged
+        // box) the whole unit for column-half 0 and nothing for column-half 1
+        const int half_u = width / 2;
+        const int c_lo = half_u >= CW ? ch * half_u : 0;
+        const int c_hi = half_u >= CW ? c_lo + half_u : (ch == 0 ? width : 0);
 #pragma unroll 1
-        for (int c = 0; c < HALF; c += CW, ++nbox) {
+        for (int c = c_lo; c < c_hi; c += CW, ++nbox) {
           const uint32_t sbuf = stg + (nbox & 1) * 4096;
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
-          const int ncol = n0 + ch * HALF + c;
+          const int ncol = n0 + c;
           uint32_t w[32];
           if (epi.c_dtype == DSF_F32) {
             uint32_t r[32];
@@ -686,9 +718,13 @@ static int launch_tn2(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, 
 // whole step goes from 4.39 to 4.62 ms.  DSF_GEMM_TAIL_SPLIT=1 enables it for experiments.
 static const bool g_nt_tail_split = getenv("DSF_GEMM_TAIL_SPLIT") ? atoi(getenv("DSF_GEMM_TAIL_SPLIT")) != 0 : false;
 
+// Split the leftover tiles of the pair kernel along N instead (256 x 128 or 256 x 64 units, see the kernel): no partial
+// sums, works with every epilogue.  DSF_GEMM_TAIL_NSPLIT=0 disables it.
+static const bool g_nt_tail_nsplit = getenv("DSF_GEMM_TAIL_NSPLIT") ? atoi(getenv("DSF_GEMM_TAIL_NSPLIT")) != 0 : true;
+
 template <int BN, int STAGES>
 static int launch_nt3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const EpiArgs2& epi, int M, int N, int K,
-                      cudaStream_t st) {
+                      cudaStream_t st, const void* Bptr = nullptr, int ldb = 0) {
   using L = G3Smem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -716,8 +752,19 @@ static int launch_nt3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
         return check_launch("gemm_nt3/memset");
     }
   }
-  launch_pdl(gemm_nt3_kernel<BN, STAGES>, dim3(2 * pairs), dim3(G2_THREADS), L::DYN, st, tmA, tmB, tmC, epi, M, N, K, m_tiles, n_tiles, tail_start,
-             tail_split);
+  int n_split = 1;
+  CUtensorMap tmBt = tmB;
+  if (g_nt_tail_nsplit && tail_split == 1 && BN == 256 && Bptr != nullptr && rem > 0 && tiles > pairs) {
+    for (int ns = 4; ns >= 2; ns >>= 1) {
+      if (rem * ns <= pairs) { n_split = ns; break; }
+    }
+    if (n_split > 1) {
+      tail_start = tiles - rem;
+      if (int e = make_tmap_bf16(&tmBt, Bptr, N, K, ldb, BN / n_split / 2)) return e;
+    }
+  }
+  launch_pdl(gemm_nt3_kernel<BN, STAGES>, dim3(2 * pairs), dim3(G2_THREADS), L::DYN, st, tmA, tmB, tmC, tmBt, epi, M, N, K, m_tiles, n_tiles,
+             tail_start, tail_split, n_split);
   return check_launch("gemm_nt3");
 }
 
@@ -762,7 +809,7 @@ int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc,
     CUtensorMap tmC3;
     if (int e = make_tmap_2d(&tmC3, C, c_dtype, M, N, ldc, c_dtype == DSF_F32 ? 32 : 64, 32)) return e;
     EpiArgs2 epi3{C, ldc, c_dtype, bias, residual, flags, N, reinterpret_cast<const __nv_bfloat16*>(relu_src), ablate, make_drop(drop)};
-    if (BN3 == 256) return launch_nt3<256, 5>(tmA, tmB, tmC3, epi3, M, N, K, st);
+    if (BN3 == 256) return launch_nt3<256, 5>(tmA, tmB, tmC3, epi3, M, N, K, st, B, ldb);
     return launch_nt3<128, 6>(tmA, tmB, tmC3, epi3, M, N, K, st);
   }
   const int BN = pick_bn_nt(M, N);

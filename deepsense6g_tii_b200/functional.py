@@ -409,6 +409,9 @@ class _Runner:
                     self.grad_hook.block_ready(blk, gbuf[blk * per_block:(blk + 1) * per_block])
 
         dgf, dbf = gbuf[L * per_block:L * per_block + C], gbuf[L * per_block + C:]
+        # dtype in which the fc1 / QKV data-gradient GEMMs hand dL/d(LayerNorm output) to the LayerNorm backward kernels:
+        # fp32 (default) or bf16 (DSF_LN_DY_BF16=1: what stock autocast does; halves that tensor's write + read traffic)
+        dh_dt = bf if os.environ.get("DSF_LN_DY_BF16", "0") == "1" else f32
         dx = torch.empty(M, C, device=dev, dtype=f32)
         dxa_bufs = [torch.empty(M, C, device=dev, dtype=bf), torch.empty(M, C, device=dev, dtype=bf)]  # block i reads [i & 1]
         # ln_f backward; by-products: bf16 copy of dx and db2 of the last block
@@ -433,7 +436,7 @@ class _Runner:
                 K.colsum(da, db1)
                 K.gemm_bf16_tn(da, st.h2, dw1)
             fork(mlp0_grads)
-            dh2 = torch.empty(M, C, device=dev, dtype=f32)  # fp32: feeds LayerNorm backward, not a GEMM
+            dh2 = torch.empty(M, C, device=dev, dtype=dh_dt)  # feeds LayerNorm backward, not a GEMM
             K.gemm_bf16_nt(da, st.w1_t, dh2)
             dx_mid = torch.empty(M, C, device=dev, dtype=f32)
             dxm = torch.empty(M, C, device=dev, dtype=bf)
@@ -458,7 +461,7 @@ class _Runner:
                 K.colsum(dqkv, dbqkv)
                 K.gemm_bf16_tn(dqkv, st.h1, dwqkv)
             fork(qkv_grads)
-            dh1 = torch.empty(M, C, device=dev, dtype=f32)
+            dh1 = torch.empty(M, C, device=dev, dtype=dh_dt)
             K.gemm_bf16_nt(dqkv, st.wqkv_t, dh1)
             # block i+1's weight-gradient work must be complete now: the next kernel overwrites the bf16 buffer its first wgrad
             # read, and its activations / gradient operands are released here

@@ -259,7 +259,10 @@ def gemm_impl(request, K):
     K.gemm_set_impl(0)
 
 
-@pytest.mark.parametrize("M,N,Kd", GEMM_SHAPES + [(11544, 2048, 512), (11544, 512, 2048), (300, 1536, 128), (5, 256, 64)])
+@pytest.mark.parametrize("M,N,Kd", GEMM_SHAPES + [(11544, 2048, 512), (11544, 512, 2048), (300, 1536, 128), (5, 256, 64),
+                                                  # leftover tiles of the pair kernel split along N: 4 ways (18 of 92 tiles),
+                                                  # 2 ways (36 of 184 tiles)
+                                                  (11544, 512, 1536), (11544, 1024, 256)])
 def test_gemm_bf16_nt(K, cuda_dev, gemm_impl, M, N, Kd):
     g = _gen(6)
     a = torch.randn(M, Kd, generator=g).to(cuda_dev).to(torch.bfloat16)
