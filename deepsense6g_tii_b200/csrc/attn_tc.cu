@@ -588,7 +588,7 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
 // v2 (warp-specialised, TMA-fed) implementations, attn_tc2.cu
 int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st);
 int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem,
-                cudaStream_t st);
+                int force_nwg, cudaStream_t st);
 int attn_fwd_v5(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, cudaStream_t st);
 int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
                 const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem, int parts, cudaStream_t st);
@@ -600,7 +600,8 @@ int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, in
 }
 
 // 0 = default (= 4), 1 = v1 (simple synchronous), 2 = v2 (pipelined), 3 = v3 (fwd: double-buffered S/P, P through shared memory),
-// 4 = v4 (v3 schedule with P / dS kept in tensor memory: TS-mode tcgen05.mma, no shared-memory round trip)
+// 4 = v4 (v3 schedule with P / dS kept in tensor memory: TS-mode tcgen05.mma, no shared-memory round trip),
+// 5 = v4 with the four-warpgroup forward, 6 / 7 = v4 with the forward forced to 128-row CTAs (two per SM) / 256-row CTAs
 static int g_attn_impl = 0;
 
 }  // namespace dsf
@@ -608,7 +609,7 @@ static int g_attn_impl = 0;
 using namespace dsf;
 
 extern "C" int dsf_attn_set_impl(int32_t impl) {
-  DSF_REQUIRE(impl >= 0 && impl <= 5, "attn_set_impl: impl must be 0 (default) or 1 .. 5");
+  DSF_REQUIRE(impl >= 0 && impl <= 7, "attn_set_impl: impl must be 0 (default) or 1 .. 7");
   g_attn_impl = impl;
   return DSF_OK;
 }
@@ -640,7 +641,8 @@ extern "C" int dsf_attn_fwd(const void* qkv, void* y, float* lse, int32_t B, int
   cudaStream_t st = (cudaStream_t)stream;
   if (g_attn_impl == 2) return attn_fwd_v2(qkv, y, lse, B, T, C, nh, st);
   if (g_attn_impl == 5) return attn_fwd_v5(qkv, y, lse, B, T, C, nh, drop_on ? drop : nullptr, drop_bits, st);
-  if (g_attn_impl != 1) return attn_fwd_v3(qkv, y, lse, B, T, C, nh, drop_on ? drop : nullptr, drop_bits, g_attn_impl == 4 || g_attn_impl == 0, st);
+  if (g_attn_impl != 1)
+    return attn_fwd_v3(qkv, y, lse, B, T, C, nh, drop_on ? drop : nullptr, drop_bits, g_attn_impl != 3, g_attn_impl == 6 ? 1 : (g_attn_impl == 7 ? 2 : 0), st);
   switch (hs) {
     case 16: return launch_attn_fwd<16, 128>(qkv, y, lse, B, T, C, nh, st);
     case 32: return launch_attn_fwd<32, 128>(qkv, y, lse, B, T, C, nh, st);
@@ -679,7 +681,7 @@ static int attn_bwd_impl(const void* qkv, const void* y, const void* dy, const f
   const int hs = C / nh;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_attn_impl != 1)
-    return attn_bwd_v2(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop_on ? drop : nullptr, const_cast<uint32_t*>(drop_bits), g_attn_impl == 4 || g_attn_impl == 0 || g_attn_impl == 5, parts, st);
+    return attn_bwd_v2(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop_on ? drop : nullptr, const_cast<uint32_t*>(drop_bits), g_attn_impl != 3 && g_attn_impl != 2, parts, st);
   switch (hs) {
     case 16: return launch_attn_bwd<16, 128>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);
     case 32: return launch_attn_bwd<32, 128>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, st);

@@ -798,29 +798,38 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // wait for the tensor pipe: S_w(j+2) is issued as soon as softmax_w(j) has drained its S buffer, and
 // softmax_w(j+1) may write its P tile while P.V_w(j) is still reading the other one.  K and V ride in
 // separate TMA rings because K(j+2) is consumed two iterations ahead of V(j).  BKV = 64.
-template <int HS, int KST, int VST>
+// NWG = softmax warpgroups (128 query rows each) per CTA.  NWG = 2: one CTA per SM, the two warpgroups share every K/V
+// tile.  NWG = 1: a CTA is half as big in every resource (192 threads, 256 TMEM columns, <= 113 KB of shared memory), TWO
+// of them share an SM: the same MUFU / tensor-pipe mix per SM, but the grid is scheduled in 128-row units, which matters
+// when the 256-row grid does not fill the 148 SMs evenly (T = 962, 48 heads: 192 CTAs = 2 rounds at 65 %; 384 half-size
+// CTAs on 296 slots = 1.3 rounds).
+template <int HS, int KST, int VST, int NWG = 2, bool PT = false>
 struct Fwd3 {
   static constexpr int BKV = 64;
   static constexpr int Q_BYTES = 128 * HS * 2, KV_BYTES = BKV * HS * 2, P_BYTES = 128 * BKV * 2;
-  static constexpr int Q_OFF = 0, K_OFF = 2 * Q_BYTES, V_OFF = K_OFF + KST * KV_BYTES, P_OFF = V_OFF + VST * KV_BYTES;
-  static constexpr int BAR_OFF = P_OFF + 4 * P_BYTES;
+  static constexpr int Q_OFF = 0, K_OFF = NWG * Q_BYTES, V_OFF = K_OFF + KST * KV_BYTES, P_OFF = V_OFF + VST * KV_BYTES;
+  static constexpr int BAR_OFF = P_OFF + (PT ? 0 : 2 * NWG * P_BYTES);  // P tiles live in tensor memory when PT
   static constexpr int NBAR = 1 + 2 * KST + 2 * VST + 12;
   static constexpr int DYN = BAR_OFF + NBAR * 8 + 16 + 1024;
-  static constexpr int THREADS = 320;
-  static_assert(4 * BKV + 2 * HS <= 512, "TMEM budget");
-  static_assert(DYN <= 232448, "shared memory budget");
+  static constexpr int THREADS = 128 * NWG + 64;
+  static constexpr int MIN_CTAS = NWG == 1 ? 2 : 1;
+  static constexpr uint32_t TMEM_COLS = NWG == 1 ? 256 : 512;
+  static_assert(2 * NWG * BKV + NWG * HS <= (int)TMEM_COLS, "TMEM budget");
+  static_assert(DYN <= 232448 / MIN_CTAS - 1024 * (MIN_CTAS - 1), "shared memory budget");
 };
 
 // PT = true: the bf16 probabilities never touch shared memory — the softmax warps write them back (packed two per column)
 // over the S tile they came from and P.V runs with its A operand in tensor memory (tcgen05.mma [d], [a], b-desc).
 // PP = true (experiment, DSF_ATTN_PINGPONG=1): the two softmax warpgroups take turns in the exponential phase (named
 // barriers 3 / 4) so that one warpgroup's MUFU.EX2 work runs under the other's max / rescale bookkeeping.
-template <int HS, int KST, int VST, bool PT, bool PP>
-__global__ void __launch_bounds__(320, 1)
+template <int HS, int KST, int VST, bool PT, bool PP, int NWG = 2>
+__global__ void __launch_bounds__(128 * NWG + 64, NWG == 1 ? 2 : 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, __nv_bfloat16* __restrict__ y,
                  float* __restrict__ lse, int T, int C, int nh, float scale_log2, AttnDrop ad) {
-  using L = Fwd3<HS, KST, VST>;
+  using L = Fwd3<HS, KST, VST, NWG, PT>;
   constexpr int BKV = L::BKV;
+  constexpr int MMAW = 4 * NWG, TMAW = 4 * NWG + 1;  // warp roles: 0 .. 4*NWG-1 softmax, then MMA issuer, TMA producer
+  static_assert(!PP || NWG == 2, "ping-pong needs two warpgroups");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -828,7 +837,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t q_full = bar0, k_full = bar0 + 8, k_empty = k_full + 8 * KST, v_full = k_empty + 8 * KST, v_empty = v_full + 8 * VST,
                  s_full = v_empty + 8 * VST, p_full = s_full + 32, p_empty = p_full + 32, tmem_slot = p_empty + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * (128 * NWG), h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (T + BKV - 1) / BKV;
 
   pdl_trigger();
@@ -836,11 +845,11 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_init(q_full, 1);
     for (int s = 0; s < KST; ++s) { mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1); }
     for (int s = 0; s < VST; ++s) { mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(p_full + 8 * i, 128); mbar_init(p_empty + 8 * i, 1); }
+    for (int i = 0; i < 2 * NWG; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(p_full + 8 * i, 128); mbar_init(p_empty + 8 * i, 1); }
     fence_barrier_init();
   }
-  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  if (warp == 9 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); }
+  if (warp == MMAW) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
+  if (warp == TMAW && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -853,10 +862,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     ad.k1 ^= (uint32_t)(sd >> 32);
   }
 
-  if (warp == 9) {
+  if (warp == TMAW) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * L::Q_BYTES);
-      for (int w = 0; w < 2; ++w) tma_tile<HS>(sbase + L::Q_OFF + w * L::Q_BYTES, &tmQ, q_full, h * HS, q0 + 128 * w, b, 128);
+      mbar_expect_tx(q_full, NWG * L::Q_BYTES);
+      for (int w = 0; w < NWG; ++w) tma_tile<HS>(sbase + L::Q_OFF + w * L::Q_BYTES, &tmQ, q_full, h * HS, q0 + 128 * w, b, 128);
       for (int j = 0; j < n_kv; ++j) {
         const int ks = j % KST, vs = j % VST;
         if (j >= KST) mbar_wait(k_empty + 8 * ks, ((j / KST) - 1) & 1);
@@ -867,7 +876,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_tile<HS>(sbase + L::V_OFF + vs * L::KV_BYTES, &tmKV, v_full + 8 * vs, 2 * C + h * HS, j * BKV, b, BKV);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == MMAW) {
     {  // MMA issuer: all 32 lanes walk the schedule (uniform control flow); single lanes are elected per instruction
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, HS, 0, 1);
@@ -875,7 +884,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int jj = 0; jj < 2 && jj < n_kv; ++jj) {
         mbar_wait(k_full + 8 * (jj % KST), (jj / KST) & 1);
         tc_fence_after();
-        for (int w = 0; w < 2; ++w) {
+        for (int w = 0; w < NWG; ++w) {
           mma_over_head<HS>(tmem_base + (w * 2 + jj) * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + (jj % KST) * L::KV_BYTES,
                             BKV, idesc_s);
           tc_commit_elect(s_full + 8 * (w * 2 + jj));
@@ -886,25 +895,25 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int buf = j & 1, vs = j % VST;
         TRACE(2, j, 0);
         mbar_wait(v_full + 8 * vs, (j / VST) & 1);
-        for (int w = 0; w < 2; ++w) {
+        for (int w = 0; w < NWG; ++w) {
           const int sb = w * 2 + buf;
           TRACE(2, j, 1 + 2 * w);
           mbar_wait(p_full + 8 * sb, (j >> 1) & 1);
           TRACE(2, j, 2 + 2 * w);
           tc_fence_after();
           if (PT)
-            mma_over_rows_ts<HS, BKV>(tmem_base + 4 * BKV + w * HS, tmem_base + sb * BKV, sbase + L::V_OFF + vs * L::KV_BYTES, idesc_o, j > 0);
+            mma_over_rows_ts<HS, BKV>(tmem_base + 2 * NWG * BKV + w * HS, tmem_base + sb * BKV, sbase + L::V_OFF + vs * L::KV_BYTES, idesc_o, j > 0);
           else
-            mma_over_rows<HS, BKV>(tmem_base + 4 * BKV + w * HS, sbase + L::P_OFF + sb * L::P_BYTES, sbase + L::V_OFF + vs * L::KV_BYTES, idesc_o,
+            mma_over_rows<HS, BKV>(tmem_base + 2 * NWG * BKV + w * HS, sbase + L::P_OFF + sb * L::P_BYTES, sbase + L::V_OFF + vs * L::KV_BYTES, idesc_o,
                                    j > 0);
           tc_commit_elect(p_empty + 8 * sb);
-          if (w == 1) tc_commit_elect(v_empty + 8 * vs);
+          if (w == NWG - 1) tc_commit_elect(v_empty + 8 * vs);
           if (j + 2 < n_kv) {
             const int ks = (j + 2) % KST;
             if (w == 0) { mbar_wait(k_full + 8 * ks, ((j + 2) / KST) & 1); tc_fence_after(); }
             mma_over_head<HS>(tmem_base + sb * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + ks * L::KV_BYTES, BKV, idesc_s);
             tc_commit_elect(s_full + 8 * sb);
-            if (w == 1) tc_commit_elect(k_empty + 8 * ks);
+            if (w == NWG - 1) tc_commit_elect(k_empty + 8 * ks);
           }
         }
       }
@@ -913,7 +922,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int w = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tm_o = tmem_base + 4 * BKV + w * HS + lane_off;
+    const uint32_t tm_o = tmem_base + 2 * NWG * BKV + w * HS + lane_off;
     float m_run = -INFINITY, l_run = 0.f;
     if (PP && w == 1) named_bar_arrive(3, 256);  // warpgroup 0 goes first
     for (int j = 0; j < n_kv; ++j) {
@@ -1021,7 +1030,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == MMAW) tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
 // =============================================================================================== forward (v5: four softmax warpgroups)
@@ -1297,14 +1306,15 @@ static int launch_fwd2(const void* qkv, void* y, float* lse, int B, int T, int C
 // exponentials + packing even when it has the SFU to itself, so the phase is bound by single-warp issue, not by contention
 static const bool g_attn_pingpong = getenv("DSF_ATTN_PINGPONG") ? atoi(getenv("DSF_ATTN_PINGPONG")) != 0 : false;
 
-template <int HS, int KST, int VST, bool PT>
+template <int HS, int KST, int VST, bool PT, int NWG = 2>
 static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const AttnDrop& ad, cudaStream_t st) {
-  using L = Fwd3<HS, KST, VST>;
+  using L = Fwd3<HS, KST, VST, NWG, PT>;
   using H = HeadCfg<HS>;
+  constexpr bool PPOK = PT && NWG == 2;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, PT, false, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, PT, PPOK, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("attn_fwd3/attr");
     configured = true;
   }
@@ -1312,12 +1322,25 @@ static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C
   if (int e = make_tmap3(&tmQ, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
   if (int e = make_tmap3(&tmKV, qkv, 3 * C, T, B, H::BOXC, L::BKV)) return e;
   const float scale_log2 = (1.0f / sqrtf((float)HS)) * 1.4426950408889634f;
-  dim3 grid(cdiv(T, 256), nh, B);
-  if (PT && g_attn_pingpong)
-    launch_pdl(attn_fwd3_kernel<HS, KST, VST, PT, true>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
+  dim3 grid(cdiv(T, 128 * NWG), nh, B);
+  if (PPOK && g_attn_pingpong)
+    launch_pdl(attn_fwd3_kernel<HS, KST, VST, PT, PPOK, NWG>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2,
+               ad);
   else
-    launch_pdl(attn_fwd3_kernel<HS, KST, VST, PT, false>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
+    launch_pdl(attn_fwd3_kernel<HS, KST, VST, PT, false, NWG>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2,
+               ad);
   return check_launch("attn_fwd3");
+}
+
+// Forward CTA size (see Fwd3): 2 = 256-row CTAs, one per SM; 1 = 128-row CTAs, two per SM; 0 / unset = pick the one whose
+// grid fills the SMs better (a 256-row grid runs in ceil(ctas / SMs) rounds, the half-size grid in ~ctas / (2 SMs)).
+static int attn_fwd_nwg(int B, int T, int nh) {
+  static const int forced = getenv("DSF_ATTN_FWD_NWG") ? atoi(getenv("DSF_ATTN_FWD_NWG")) : 0;
+  if (forced == 1 || forced == 2) return forced;
+  const int sms = num_sms();
+  const double cost2 = (double)cdiv(cdiv(T, 256) * nh * B, sms);
+  const double cost1 = std::max(1.0, (double)(cdiv(T, 128) * nh * B) / (2.0 * sms));
+  return cost1 < 0.85 * cost2 ? 1 : 2;
 }
 
 template <int HS, int KST, int VST>
@@ -1421,8 +1444,16 @@ static AttnDrop make_attn_drop(const dsf_dropout* d, uint32_t* bits, int T) {
 }
 
 int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem,
-                cudaStream_t st) {
+                int force_nwg, cudaStream_t st) {
   const AttnDrop ad = make_attn_drop(drop, bits, T);
+  if (p_in_tmem && (force_nwg ? force_nwg : attn_fwd_nwg(B, T, nh)) == 1) {
+    switch (C / nh) {
+      case 16: return launch_fwd3<16, 3, 2, true, 1>(qkv, y, lse, B, T, C, nh, ad, st);
+      case 32: return launch_fwd3<32, 3, 2, true, 1>(qkv, y, lse, B, T, C, nh, ad, st);
+      case 64: return launch_fwd3<64, 3, 2, true, 1>(qkv, y, lse, B, T, C, nh, ad, st);
+      case 128: return launch_fwd3<128, 2, 2, true, 1>(qkv, y, lse, B, T, C, nh, ad, st);
+    }
+  }
   if (p_in_tmem) {
     switch (C / nh) {
       case 16: return launch_fwd3<16, 3, 2, true>(qkv, y, lse, B, T, C, nh, ad, st);

@@ -425,6 +425,10 @@ static int ln_impl() {
   static const int v = getenv("DSF_LN_IMPL") ? atoi(getenv("DSF_LN_IMPL")) : 2;
   return v;
 }
+static int ln_fwd_impl() {  // the forward can be switched on its own (DSF_LN_FWD_IMPL)
+  static const int v = getenv("DSF_LN_FWD_IMPL") ? atoi(getenv("DSF_LN_FWD_IMPL")) : ln_impl();
+  return v;
+}
 
 template <typename K>
 static bool ln2_configure(K kernel, int smem) {
@@ -465,7 +469,7 @@ template <typename TY>
 int launch_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int C,
                   float eps, cudaStream_t st) {
   TY* yy = reinterpret_cast<TY*>(y);
-  if (ln_impl() == 2 && C % 128 == 0) {
+  if (ln_fwd_impl() == 2 && C % 128 == 0) {
     switch (C / 128) {
       case 1: return launch_ln_fwd2<TY, 1>(x, gamma, beta, yy, mean, rstd, M, eps, st);
       case 2: return launch_ln_fwd2<TY, 2>(x, gamma, beta, yy, mean, rstd, M, eps, st);

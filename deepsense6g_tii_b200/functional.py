@@ -410,8 +410,9 @@ class _Runner:
 
         dgf, dbf = gbuf[L * per_block:L * per_block + C], gbuf[L * per_block + C:]
         # dtype in which the fc1 / QKV data-gradient GEMMs hand dL/d(LayerNorm output) to the LayerNorm backward kernels:
-        # fp32 (default) or bf16 (DSF_LN_DY_BF16=1: what stock autocast does; halves that tensor's write + read traffic)
-        dh_dt = bf if os.environ.get("DSF_LN_DY_BF16", "0") == "1" else f32
+        # bf16 (default: what stock autocast does; halves that tensor's write + read traffic, -0.06 ms per step) or fp32
+        # (DSF_LN_DY_BF16=0)
+        dh_dt = bf if os.environ.get("DSF_LN_DY_BF16", "1") == "1" else f32
         dx = torch.empty(M, C, device=dev, dtype=f32)
         dxa_bufs = [torch.empty(M, C, device=dev, dtype=bf), torch.empty(M, C, device=dev, dtype=bf)]  # block i reads [i & 1]
         # ln_f backward; by-products: bf16 copy of dx and db2 of the last block

@@ -202,7 +202,9 @@ int dsf_attn_bwd_parts(const void* qkv, const void* y, const void* dy, const flo
 /* Selects the attention implementation (process-wide; for tests and A/B timing): 0 = default (= 4),
  * 1 = v1 (simple synchronous kernels), 2 = v2 (warp-specialised, TMA-fed, pipelined),
  * 3 = v3 (v2 + per-warpgroup double-buffered S/P in the forward), 4 = v4 (v3 schedule, the bf16 P / dS tiles
- * stay in tensor memory and feed tcgen05.mma as its A operand instead of going through shared memory). */
+ * stay in tensor memory and feed tcgen05.mma as its A operand instead of going through shared memory),
+ * 5 = v4 with the four-warpgroup forward, 6 / 7 = v4 with the forward forced to 128-row CTAs (two per SM) /
+ * 256-row CTAs (one per SM); by default v4 picks whichever grid fills the SMs better. */
 int dsf_attn_set_impl(int32_t impl);
 
 /* K7 forward.  Replaces slice/view/permute/contiguous (model2_seq.py:275-286) + F.interpolate

@@ -26,9 +26,9 @@ def timeit(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
-if "attn" in what or "attn512" in what:
+if "attn" in what or "attn512" in what or "attnq" in what:
     shapes = [(12, 962, 512, 4), (12, 962, 256, 4), (12, 962, 128, 4), (12, 962, 64, 4), (2, 3842, 512, 4)]
-    for (B, T, C, nh) in (shapes if "attn" in what else shapes[:1]):
+    for (B, T, C, nh) in (shapes if ("attn" in what or "attnq" in what) else shapes[:1]):
         qkv = torch.randn(B * T, 3 * C, device=dev).to(torch.bfloat16)
         y = torch.empty(B * T, C, device=dev, dtype=torch.bfloat16)
         dy = torch.randn(B * T, C, device=dev).to(torch.bfloat16)
@@ -36,7 +36,7 @@ if "attn" in what or "attn512" in what:
         delta = torch.empty(B, nh, T, device=dev)
         dqkv = torch.empty_like(qkv)
         fl = 4.0 * T * T * C * B
-        for impl in ((4, 5) if "attn" in what else (3,)):
+        for impl in ((4, 5) if "attn" in what else ((7, 6) if "attnq" in what else (3,))):  # 7 / 6: forward with 256- / 128-row CTAs
             K.attn_set_impl(impl)
             tf = timeit(lambda: K.attn_fwd(qkv, y, lse, B, T, C, nh))
             tb = timeit(lambda: K.attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh))

@@ -309,7 +309,7 @@ def _attn_ref(qkv, B, T, C, nh):
 @pytest.mark.parametrize("B,T,C,nh", [(1, 128, 64, 4), (2, 64, 128, 4), (2, 130, 256, 4), (1, 962, 512, 4), (2, 962, 64, 4),
                                       (1, 962, 128, 4), (1, 962, 256, 4), (1, 300, 128, 1), (1, 3842, 64, 4),
                                       (3, 257, 512, 4), (2, 1, 64, 4), (1, 513, 64, 1)])
-@pytest.mark.parametrize("impl", [1, 2, 3, 4, 5], ids=["v1", "v2", "v3", "v4_p_in_tmem", "v5_fwd_4wg"])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4, 5, 6, 7], ids=["v1", "v2", "v3", "v4_p_in_tmem", "v5_fwd_4wg", "v4_fwd_128row_ctas", "v4_fwd_256row_ctas"])
 def test_attention_fwd_bwd(K, cuda_dev, B, T, C, nh, impl):
     K.attn_set_impl(impl)
     try:
@@ -448,7 +448,16 @@ def _unpack_bits(bits, B, nh, T, dev):
 
 
 @pytest.mark.parametrize("B,T,C,nh", [(1, 128, 64, 4), (2, 130, 256, 4), (1, 962, 512, 4), (2, 962, 64, 4), (1, 962, 128, 4), (1, 513, 64, 1)])
-def test_attention_dropout_fwd_bwd(K, cuda_dev, B, T, C, nh):
+@pytest.mark.parametrize("impl", [0, 6], ids=["default", "fwd_128row_ctas"])
+def test_attention_dropout_fwd_bwd(K, cuda_dev, B, T, C, nh, impl):
+    K.attn_set_impl(impl)
+    try:
+        _attention_dropout_case(K, cuda_dev, B, T, C, nh)
+    finally:
+        K.attn_set_impl(0)
+
+
+def _attention_dropout_case(K, cuda_dev, B, T, C, nh):
     """attn_drop (:104): softmax -> dropout -> @v.  The kernel's keep-bitmap is fed to a plain torch evaluation."""
     from deepsense6g_tii_b200.functional import attn_drop_scale
     g = _gen(18)
