@@ -1332,15 +1332,15 @@ static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C
   return check_launch("attn_fwd3");
 }
 
-// Forward CTA size (see Fwd3): 2 = 256-row CTAs, one per SM; 1 = 128-row CTAs, two per SM; 0 / unset = pick the one whose
-// grid fills the SMs better (a 256-row grid runs in ceil(ctas / SMs) rounds, the half-size grid in ~ctas / (2 SMs)).
+// Forward CTA size (see Fwd3): 1 = 128-row CTAs, two per SM (default), 2 = 256-row CTAs, one per SM (DSF_ATTN_FWD_NWG=2).
+// Measured on B200 (scripts/bench_kernels.py attnq, batch 12, T = 962): 42 vs 48 us at hs = 128, 36 vs 43 (hs = 64), 34 vs
+// 41 (hs = 32), 33 vs 40 us (hs = 16); T = 3842, batch 2, hs = 128: 68 vs 80 us (891 vs 760 TF/s) — the half-size CTAs win
+// even where the 256-row grid fills the SMs in one round: two independent MMA / TMA / softmax pipelines per SM overlap
+// better than one pipeline with two softmax warpgroups, and the grid is scheduled in finer units.
 static int attn_fwd_nwg(int B, int T, int nh) {
   static const int forced = getenv("DSF_ATTN_FWD_NWG") ? atoi(getenv("DSF_ATTN_FWD_NWG")) : 0;
-  if (forced == 1 || forced == 2) return forced;
-  const int sms = num_sms();
-  const double cost2 = (double)cdiv(cdiv(T, 256) * nh * B, sms);
-  const double cost1 = std::max(1.0, (double)(cdiv(T, 128) * nh * B) / (2.0 * sms));
-  return cost1 < 0.85 * cost2 ? 1 : 2;
+  (void)B; (void)T; (void)nh;
+  return forced == 2 ? 2 : 1;
 }
 
 template <int HS, int KST, int VST>
