@@ -490,7 +490,9 @@ def run_ours(args, rank, world, local_rank):
     dom = max(tc, key=lambda k: tc[k]["ms"])
     achieved = tc[dom]["flops"] / (tc[dom]["ms"] * 1e-3) / 1e12
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01p_traffic.json")
+    import glob
+    tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))  # newest committed capture (tags sort by round)
+    tp = tps[-1] if tps else ""
     if dom == "gemm_bf16_nt" and os.path.isfile(tp):  # dram bytes per launch of the dominant kernel, from the committed ncu capture
         tj = json.load(open(tp))
         traffic, traffic_src = tj["avg_dram_bytes_per_launch"], tj["source"]

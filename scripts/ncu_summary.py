@@ -1,6 +1,7 @@
 """Summarise ncu artefacts into small text files for profiles/.
   python scripts/ncu_summary.py launches <launches.csv>        -> per-kernel share of the captured window
   python scripts/ncu_summary.py full <file.ncu-rep>            -> key counters of each captured launch
+  python scripts/ncu_summary.py traffic <fwd.ncu-rep> <tag>    -> profiles/<tag>_traffic.json (DRAM bytes per NT GEMM launch)
 """
 import collections
 import csv
@@ -52,5 +53,39 @@ def full(path):
                 print("  %-78s %14s %s" % (k, d[k], units[hdr.index(k)]))
 
 
+def traffic(path, tag):
+    """DRAM bytes per launch of the dominant kernel family (pair NT GEMM) from a --set full capture -> profiles/<tag>_traffic.json
+    (read by bench.py for roofline.traffic).  The forward capture holds block 0's QKV, proj, fc1, fc2 launches in that order."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    names = ["QKV N=1536 K=512", "proj N=512 K=512 (+fp32 residual)", "fc1 N=2048 K=512", "fc2 N=512 K=2048 (+fp32 residual)"]
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    ls = []
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        if "gemm_nt3" not in d.get("Kernel Name", ""):
+            continue
+        rd = float(d["dram__bytes_read.sum"].replace(",", "")) * mult[units[hdr.index("dram__bytes_read.sum")]]
+        wr = float(d["dram__bytes_write.sum"].replace(",", "")) * mult[units[hdr.index("dram__bytes_write.sum")]]
+        ls.append({"what": names[len(ls)] if len(ls) < len(names) else "?", "dram_read_mb": rd / 1e6, "dram_write_mb": wr / 1e6,
+                   "duration_us": float(d["gpu__time_duration.sum"].replace(",", ""))})
+    ls = ls[:4]
+    res = {"kernel": "gemm_nt3_kernel<256, 5>",
+           "source": "profiles/%s_top_kernels_full.txt (ncu --set full, cold cache, bench.py --no-graph --quick --steps 1)" % tag,
+           "launches": ls,
+           "avg_dram_bytes_per_launch": int(sum((x["dram_read_mb"] + x["dram_write_mb"]) * 1e6 for x in ls) / max(1, len(ls))),
+           "note": "the first four NT GEMM launches of the step (block 0 forward); writes mostly stay in the 126 MB L2 for the duration "
+                   "of one launch, so dram__bytes_write under-counts the output traffic"}
+    dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "%s_traffic.json" % tag)
+    json.dump(res, open(dst, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
