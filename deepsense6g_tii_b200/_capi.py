@@ -22,7 +22,7 @@ EPI_BIAS, EPI_RELU, EPI_RESIDUAL, EPI_ACCUM = 1, 2, 4, 8
 SYMBOLS = [
     "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_set_pdl", "dsf_set_sm_margin", "dsf_dropout_inplace", "dsf_tokens_fwd", "dsf_tokens_bwd",
     "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_set_impl", "dsf_gemm_f32",
-    "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_bwd_parts", "dsf_attn_set_impl", "dsf_attn_drop_words",
+    "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_bwd_parts", "dsf_attn_set_impl", "dsf_attn_drop_words", "dsf_gemm_bf16_nt_ln",
     "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16",
 ]
 
@@ -76,6 +76,8 @@ def lib():
             "dsf_pack_block_weights": [P] * 9 + [c_int32, c_int32] + [P] * 10,
             "dsf_gemm_bf16_nt": [P, c_int32, P, c_int32, P, c_int32, c_int32, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P, P],
             "dsf_gemm_bf16_tn": [P, c_int32, P, c_int32, P, c_int32, c_int32, c_int32, c_int32, P],
+            "dsf_gemm_bf16_nt_ln": [P, c_int32, P, c_int32, P, c_int32, P, P, P, c_int32, P, P, P, P, c_float, c_int32, c_int32, c_int32,
+                                    POINTER(Dropout), P],
             "dsf_gemm_f32": [POINTER(GemmF32Desc), P, P, P, P, P, P],
             "dsf_colsum": [P, c_int32, c_int32, P, c_int32, c_int32, P],
             "dsf_relu_bwd": [P, P, c_int32, c_int64, P],
@@ -191,6 +193,15 @@ def gemm_bf16_nt(A, B, C, bias=None, residual=None, relu=False, drop=None, relu_
     flags = (EPI_BIAS if bias is not None else 0) | (EPI_RELU if relu else 0) | (EPI_RESIDUAL if residual is not None else 0)
     _chk(lib().dsf_gemm_bf16_nt(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), _dt(C), _p(bias), _p(residual),
                                 M, N, K, flags, _dp(drop), _p(relu_src), _stream()), "dsf_gemm_bf16_nt")
+
+
+def gemm_bf16_nt_ln(A, B, C, bias, residual, H, gamma, beta, mean, rstd, eps=1e-5, drop=None):
+    """C[M,512] (fp32) = A[M,K] @ B[512,K]^T + bias (dropout) + residual; H (bf16) = LayerNorm(C) * gamma + beta; mean / rstd (M)
+    saved for the backward.  One launch (a CTA pair owns full rows); N = 512 only."""
+    M, K = A.shape
+    N = B.shape[0]
+    _chk(lib().dsf_gemm_bf16_nt_ln(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), _p(bias), _p(residual), _p(H), H.stride(0),
+                                   _p(gamma), _p(beta), _p(mean), _p(rstd), eps, M, N, K, _dp(drop), _stream()), "dsf_gemm_bf16_nt_ln")
 
 
 def gemm_bf16_tn(A, B, C):

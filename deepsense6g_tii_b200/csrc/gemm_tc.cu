@@ -335,6 +335,9 @@ int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc,
 int gemm_tn_v2(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st);
 extern bool g_nt_pairs;      // gemm_tc2.cu: NT GEMMs on CTA pairs (cta_group::2) where the shape allows
 static int g_gemm_impl = 0;  // 0 = default (v3), 1 = v1 (one CTA per 128 x 128 tile), 2 = v2 (persistent single CTA), 3 = v3 (CTA pairs)
+int gemm_nt_ln(const void* A, int lda, const void* B, int ldb, float* C, int ldc, const float* bias, const float* residual, void* H, int ldh,
+               const float* gamma, const float* beta, float* mean, float* rstd, float eps, int M, int K, const dsf_dropout* drop,
+               cudaStream_t st);  // gemm_tc2.cu
 }  // namespace dsf
 
 using namespace dsf;
@@ -371,6 +374,22 @@ extern "C" int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32
   cudaStream_t st = (cudaStream_t)stream;
   if (BN == 128) return launch_nt<128, 3>(tmA, tmB, epi, M, N, K, st);
   return launch_nt<64, 4>(tmA, tmB, epi, M, N, K, st);
+}
+
+extern "C" int dsf_gemm_bf16_nt_ln(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc, const float* bias,
+                                   const float* residual, void* H, int32_t ldh, const float* gamma, const float* beta, float* mean,
+                                   float* rstd, float eps, int32_t M, int32_t N, int32_t K, const dsf_dropout* drop, void* stream) {
+  DSF_REQUIRE(A && B && C && H && gamma && beta && mean && rstd, "gemm_bf16_nt_ln: NULL pointer");
+  DSF_REQUIRE(M > 0 && K > 0, "gemm_bf16_nt_ln: non-positive extent");
+  DSF_REQUIRE(N == 512, "gemm_bf16_nt_ln: the fused LayerNorm epilogue needs N = 512 (one CTA pair owns full rows); got N=%d", N);
+  DSF_REQUIRE(K % GT_BK == 0, "gemm_bf16_nt_ln: K=%d must be a multiple of 64", K);
+  DSF_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && ldh % 8 == 0 && lda >= K && ldb >= K && ldc >= N && ldh >= N,
+              "gemm_bf16_nt_ln: bad leading dimensions");
+  DSF_REQUIRE(aligned16(A) && aligned16(B) && aligned16(C) && aligned16(H) && aligned16(bias) && aligned16(residual) && aligned16(gamma) &&
+                  aligned16(beta),
+              "gemm_bf16_nt_ln: 16-byte alignment required");
+  DSF_REQUIRE(!drop || (drop->p >= 0.f && drop->p < 1.f), "gemm_bf16_nt_ln: dropout p must be in [0, 1)");
+  return gemm_nt_ln(A, lda, B, ldb, C, ldc, bias, residual, H, ldh, gamma, beta, mean, rstd, eps, M, K, drop, (cudaStream_t)stream);
 }
 
 extern "C" int dsf_gemm_bf16_tn(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc, int32_t M,

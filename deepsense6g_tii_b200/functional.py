@@ -286,6 +286,10 @@ class _Runner:
         K.tokens_fwd(self.geom, feats[0], feats[1], feats[2], gps_emb, params[0], x)
         if self._drop("embd") is not None:
             K.dropout_inplace(x, self._drop("embd"))
+        # n_embd = 512: the proj / mlp.2 GEMMs also run the LayerNorm that follows them (dsf_gemm_bf16_nt_ln); DSF_GEMM_LN_FUSE=0
+        # keeps the separate GEMM + LayerNorm launches
+        fuse_ln = C == 512 and os.environ.get("DSF_GEMM_LN_FUSE", "1") == "1"
+        nxt = None
         for i in range(L):
             (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[1 + 16 * i: 17 + 16 * i]
             if side is not None:
@@ -298,8 +302,12 @@ class _Runner:
             st.x_in = x
             stats = torch.empty(4, M, device=dev, dtype=f32)
             st.mean1, st.rstd1, st.mean2, st.rstd2 = stats[0], stats[1], stats[2], stats[3]
-            st.h1 = torch.empty(M, C, device=dev, dtype=bf)
-            K.layernorm_fwd(x, ln1w, ln1b, st.h1, st.mean1, st.rstd1)
+            if nxt is not None:  # ln1 of this block was computed by the previous block's mlp.2 GEMM epilogue
+                st.h1, st.mean1, st.rstd1 = nxt
+                nxt = None
+            else:
+                st.h1 = torch.empty(M, C, device=dev, dtype=bf)
+                K.layernorm_fwd(x, ln1w, ln1b, st.h1, st.mean1, st.rstd1)
             st.qkv = torch.empty(M, 3 * C, device=dev, dtype=bf)
             K.gemm_bf16_nt(st.h1, st.wqkv, st.qkv, bias=bqkv)
             st.y = torch.empty(M, C, device=dev, dtype=bf)
@@ -311,13 +319,23 @@ class _Runner:
                     self.dropout["capture"]["attn_bits.%d" % i] = st.drop_bits
             K.attn_fwd(st.qkv, st.y, st.lse, self.B, self.T, C, self.nh, self._drop("attn", i), st.drop_bits)
             st.x_mid = torch.empty(M, C, device=dev, dtype=f32)
-            K.gemm_bf16_nt(st.y, st.wp, st.x_mid, bias=pb, residual=x, drop=self._drop("proj", i))
             st.h2 = torch.empty(M, C, device=dev, dtype=bf)
-            K.layernorm_fwd(st.x_mid, ln2w, ln2b, st.h2, st.mean2, st.rstd2)
+            if fuse_ln:  # proj + residual + ln2 in one launch (a CTA pair owns full rows)
+                K.gemm_bf16_nt_ln(st.y, st.wp, st.x_mid, pb, x, st.h2, ln2w, ln2b, st.mean2, st.rstd2, drop=self._drop("proj", i))
+            else:
+                K.gemm_bf16_nt(st.y, st.wp, st.x_mid, bias=pb, residual=x, drop=self._drop("proj", i))
+                K.layernorm_fwd(st.x_mid, ln2w, ln2b, st.h2, st.mean2, st.rstd2)
             st.a = torch.empty(M, F, device=dev, dtype=bf)
             K.gemm_bf16_nt(st.h2, st.w1, st.a, bias=b1, relu=True)
             x = torch.empty(M, C, device=dev, dtype=f32)
-            K.gemm_bf16_nt(st.a, st.w2, x, bias=b2, residual=st.x_mid, drop=self._drop("mlp", i))
+            if fuse_ln and i + 1 < L:  # mlp.2 + residual + the NEXT block's ln1
+                h1n = torch.empty(M, C, device=dev, dtype=bf)
+                statn = torch.empty(2, M, device=dev, dtype=f32)
+                K.gemm_bf16_nt_ln(st.a, st.w2, x, b2, st.x_mid, h1n, params[1 + 16 * (i + 1)], params[2 + 16 * (i + 1)], statn[0], statn[1],
+                                  drop=self._drop("mlp", i))
+                nxt = (h1n, statn[0], statn[1])
+            else:
+                K.gemm_bf16_nt(st.a, st.w2, x, bias=b2, residual=st.x_mid, drop=self._drop("mlp", i))
             saved.layers.append(st)
         saved.x_last = x
         saved.mean_f = torch.empty(M, device=dev, dtype=f32)

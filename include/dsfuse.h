@@ -138,6 +138,14 @@ int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32_t ldb, voi
                      void* stream);
 int dsf_gemm_bf16_tn(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc,
                      int32_t M, int32_t Nout, int32_t Kout, void* stream);
+/* NT GEMM + residual + the FOLLOWING LayerNorm in one launch (N = 512 only; a CTA pair owns full rows):
+ *   C[M,512] (fp32) = A W^T + bias (dropout) + residual     -- proj / mlp.2 + residual add (model2_seq.py:109,124-126,131-132)
+ *   H[M,512] (bf16) = LayerNorm(C) * gamma + beta, mean / rstd (fp32, M) saved for the backward  (:118-119, eps as given)
+ * Replaces dsf_gemm_bf16_nt(..., residual) followed by dsf_layernorm_fwd on its output.                        */
+int dsf_gemm_bf16_nt_ln(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc,
+                        const float* bias, const float* residual, void* H, int32_t ldh, const float* gamma,
+                        const float* beta, float* mean, float* rstd, float eps, int32_t M, int32_t N, int32_t K,
+                        const dsf_dropout* drop, void* stream);
 /* Selects the tensor-core GEMM implementation (process-wide; tests and A/B timing): 0 = default (= 3),
  * 1 = v1 (one CTA per 128x128 tile), 2 = v2 (persistent, 128x256 tiles, double-buffered TMEM),
  * 3 = v3 (NT: CTA pairs, tcgen05.mma.cta_group::2 on 256x256 tiles where N % 256 == 0; otherwise v2). */

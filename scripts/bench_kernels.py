@@ -135,3 +135,24 @@ if "ln" in what:
         K.colsum(big[it[0] % 8], o)
     t = timeit(runc, iters=40, warm=8)
     print("colsum bf16 M x 1536 (HBM-resident): %.4f ms (%.0f GB/s)" % (t, M * 3 * C * 2 / t / 1e6))
+
+if "lnfuse" in what:
+    # proj / mlp.2 + residual followed by LayerNorm: separate launches vs the fused full-row epilogue (dsf_gemm_bf16_nt_ln)
+    M, N = 11544, 512
+    for Kd in (512, 2048):
+        a = torch.randn(M, Kd, device=dev).to(torch.bfloat16)
+        w = torch.randn(N, Kd, device=dev).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev)
+        res = torch.randn(M, N, device=dev)
+        g = torch.ones(N, device=dev)
+        b = torch.zeros(N, device=dev)
+        x = torch.empty(M, N, device=dev)
+        h = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
+
+        def sep():
+            K.gemm_bf16_nt(a, w, x, bias=bias, residual=res)
+            K.layernorm_fwd(x, g, b, h, mean, rstd)
+        t1 = timeit(sep)
+        t2 = timeit(lambda: K.gemm_bf16_nt_ln(a, w, x, bias, res, h, g, b, mean, rstd))
+        print("N=512 K=%d fp32+bias+residual then LayerNorm: separate %.4f ms, fused %.4f ms" % (Kd, t1, t2))

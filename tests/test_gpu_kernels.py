@@ -283,6 +283,43 @@ def test_gemm_bf16_nt(K, cuda_dev, gemm_impl, M, N, Kd):
     assert_close(out32, 2 * ref + bias + res, 1e-5, 1e-5, "residual aliasing a copy")
 
 
+@pytest.mark.parametrize("M,Kd", [(11544, 512), (11544, 2048), (300, 512), (257, 128), (5, 64), (46104, 512)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_gemm_bf16_nt_ln_fused(K, cuda_dev, M, Kd, p):
+    """proj / mlp.2 + residual + the following LayerNorm in one launch (dsf_gemm_bf16_nt_ln, N = 512) against the separate
+    GEMM and LayerNorm kernels and against plain torch."""
+    g = _gen(23)
+    N = 512
+    a = torch.randn(M, Kd, generator=g).to(cuda_dev).to(torch.bfloat16)
+    w = (0.05 * torch.randn(N, Kd, generator=g)).to(cuda_dev).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    res = (2.0 * torch.randn(M, N, generator=g) + 0.5).to(cuda_dev)
+    gamma = (1 + 0.1 * torch.randn(N, generator=g)).to(cuda_dev)
+    beta = (0.1 * torch.randn(N, generator=g)).to(cuda_dev)
+    d = K.Dropout(p, 7, 3, 1) if p > 0 else None
+    x = torch.full((M, N), float("nan"), device=cuda_dev)
+    h = torch.full((M, N), float("nan"), device=cuda_dev, dtype=torch.bfloat16)
+    mean = torch.full((M,), float("nan"), device=cuda_dev)
+    rstd = torch.full((M,), float("nan"), device=cuda_dev)
+    K.gemm_bf16_nt_ln(a, w, x, bias, res, h, gamma, beta, mean, rstd, drop=d)
+    torch.cuda.synchronize()
+    # the separate kernels
+    x2 = torch.empty(M, N, device=cuda_dev)
+    K.gemm_bf16_nt(a, w, x2, bias=bias, residual=res, drop=d)
+    h2 = torch.empty(M, N, device=cuda_dev, dtype=torch.bfloat16)
+    mean2, rstd2 = torch.empty(M, device=cuda_dev), torch.empty(M, device=cuda_dev)
+    K.layernorm_fwd(x2, gamma, beta, h2, mean2, rstd2)
+    assert_close(x, x2, 1e-6, 1e-6, "x_out vs separate GEMM")
+    assert_close(mean, mean2, 1e-5, 1e-6, "mean vs separate LN")
+    assert_close(rstd, rstd2, 1e-5, 1e-6, "rstd vs separate LN")
+    assert_close(h.float(), h2.float(), 8e-3, 1e-3, "h vs separate LN")
+    # plain torch
+    mask = _mask_of(K, cuda_dev, (M, N), d) if d is not None else 1.0
+    xr = (a.float() @ w.float().t() + bias) * mask + res
+    assert_close(x, xr, 1e-5, 1e-5, "x_out vs torch")
+    assert_close(h.float(), R.layer_norm(xr, gamma, beta), 8e-3, 1e-3, "h vs torch")
+
+
 @pytest.mark.parametrize("M,No,Ko", [(64, 64, 64), (128, 128, 128), (200, 64, 192), (962, 192, 64), (1924, 512, 512),
                                      (11544, 512, 2048), (11544, 2048, 512), (5000, 1536, 512), (77, 128, 64)])
 def test_gemm_bf16_tn(K, cuda_dev, gemm_impl, M, No, Ko):
