@@ -286,9 +286,11 @@ class _Runner:
         K.tokens_fwd(self.geom, feats[0], feats[1], feats[2], gps_emb, params[0], x)
         if self._drop("embd") is not None:
             K.dropout_inplace(x, self._drop("embd"))
-        # n_embd = 512: the proj / mlp.2 GEMMs also run the LayerNorm that follows them (dsf_gemm_bf16_nt_ln); DSF_GEMM_LN_FUSE=0
-        # keeps the separate GEMM + LayerNorm launches
-        fuse_ln = C == 512 and os.environ.get("DSF_GEMM_LN_FUSE", "1") == "1"
+        # n_embd = 512, DSF_GEMM_LN_FUSE=1: the proj / mlp.2 GEMMs also run the LayerNorm that follows them
+        # (dsf_gemm_bf16_nt_ln).  Correct but OFF by default: measured on B200 the full-row epilogue (not overlapped with a
+        # next tile, its fp32 residual reads exposed) costs more than the launch it removes: 29.5 vs 27.2 us (K = 512),
+        # 50.6 vs 40.0 us (K = 2048) for GEMM + LayerNorm, 4.11 vs 4.05 ms per step.
+        fuse_ln = C == 512 and os.environ.get("DSF_GEMM_LN_FUSE", "0") == "1"
         nxt = None
         for i in range(L):
             (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[1 + 16 * i: 17 + 16 * i]
