@@ -347,26 +347,32 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool RTMA = false>
 struct G3Smem {
   static constexpr int A_BYTES = G2_BM * G2_BK * 2;        // this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * G2_BK * 2;     // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;
   static constexpr int STAGING_BYTES = 8 * 2 * 4096;
-  static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;
-  static constexpr int DYN = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr int RES_OFF = STAGING_OFF + STAGING_BYTES;  // RTMA: one 32 x 32 fp32 residual box per epilogue warp
+  static constexpr int RES_BYTES = RTMA ? 8 * 4096 : 0;
+  static constexpr int BAR_OFF = RES_OFF + RES_BYTES;
+  static constexpr int RBAR_OFF = BAR_OFF + (2 * STAGES + 4) * 8 + 16;  // 8 mbarriers (one per epilogue warp) when RTMA
+  static constexpr int DYN = RBAR_OFF + (RTMA ? 64 : 0) + 1024;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
   static_assert(DYN <= 232448, "shared memory budget");
   static_assert(TMEM_COLS == 512 || TMEM_COLS == 256, "TMEM columns must be a power of two");
 };
 
-template <int BN, int STAGES>
+// RTMA (fp32 output + residual only): the residual tile is not read by the epilogue threads from global memory (one
+// uncoalesced 128-byte row piece per lane and chunk, ~1 us of exposed latency per chunk) but prefetched by TMA, one
+// 32 x 32 box per epilogue warp, one chunk ahead — the first box of a tile while its main loop is still running.
+template <int BN, int STAGES, bool RTMA = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                const __grid_constant__ CUtensorMap tmBt, EpiArgs2 epi, int M, int N, int K, int m_tiles, int n_tiles, int tail_start,
-                int tail_split, int n_split) {
-  using L = G3Smem<BN, STAGES>;
+                const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ CUtensorMap tmR, EpiArgs2 epi, int M, int N, int K,
+                int m_tiles, int n_tiles, int tail_start, int tail_split, int n_split) {
+  using L = G3Smem<BN, STAGES, RTMA>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = base + L::BAR_OFF, bar_empty = bar_full + STAGES * 8, acc_full = bar_empty + STAGES * 8,
@@ -410,6 +416,9 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a * 8, 1); mbar_init(acc_empty + a * 8, 16); }
+    if (RTMA) {
+      for (int w = 0; w < 8; ++w) mbar_init(base + L::RBAR_OFF + w * 8, 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc_pair(tmem_slot, L::TMEM_COLS); tmem_relinquish_pair(); }
@@ -484,6 +493,35 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int HALF = BN / 2;
     const uint32_t acc_empty0 = mapa_u32(acc_empty, 0);
     int i = 0, nbox = 0;
+    // RTMA: residual boxes of this warp.  chunks_of() mirrors exactly the conditions under which the chunk loop below
+    // runs for a unit (every issued box is consumed, every consumed box was issued); r_inflight is warp-uniform.
+    const uint32_t rbuf = base + L::RES_OFF + (warp - 2) * 4096, rbar = base + L::RBAR_OFF + (warp - 2) * 8;
+    int nres = 0;
+    bool r_inflight = false;
+    auto chunks_of = [&](int uu, int& cm0, int& cn0, int& clo, int& chi) -> bool {
+      int t2, a0, a1, p2, off2, w2;
+      unit_of(uu, t2, a0, a1, p2);
+      if (n_split > 1) nsub_of(uu, t2, off2, w2);
+      else { off2 = 0; w2 = BN; }
+      cm0 = (t2 % m_tiles) * 256 + (int)rank * G2_BM;
+      cn0 = (t2 / m_tiles) * BN + off2;
+      const int hu = w2 / 2;
+      clo = hu >= 32 ? ch * hu : 0;
+      chi = hu >= 32 ? clo + hu : (ch == 0 ? w2 : 0);
+      return p2 == 0 && cm0 + q * 32 < M && !(epi.ablate & 1) && clo < chi;
+    };
+    auto issue_res = [&](int ncol, int row0) {
+      if (lane == 0) {
+        fence_proxy_async();  // the box is re-filled after generic-proxy reads of the previous one
+        mbar_expect_tx(rbar, 4096);
+        tma_load_2d(rbuf, &tmR, rbar, ncol, row0);
+      }
+      r_inflight = true;
+    };
+    if (RTMA && pair < total) {
+      int cm0, cn0, clo, chi;
+      if (chunks_of(pair, cm0, cn0, clo, chi)) issue_res(cn0 + clo, cm0 + q * 32);
+    }
     for (int u = pair; u < total; u += n_pairs, ++i) {
       int tile, kb0, kb1, part;
       unit_of(u, tile, kb0, kb1, part);
@@ -533,7 +571,34 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           const int ncol = n0 + c;
           uint32_t w[32];
-          if (epi.c_dtype == DSF_F32) {
+          if (RTMA) {  // fp32 output + residual: the residual box of this chunk was requested one chunk (or one tile) ago
+            if (!r_inflight) issue_res(ncol, m0 + q * 32);
+            mbar_wait(rbar, nres & 1);
+            ++nres;
+            float rr[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t src = rbuf + lane * 128 + ((j ^ (lane & 7)) << 4);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(rr[4 * j]), "=f"(rr[4 * j + 1]), "=f"(rr[4 * j + 2]), "=f"(rr[4 * j + 3]) : "r"(src) : "memory");
+            }
+            __syncwarp();  // every lane has read the box: it can be re-filled
+            r_inflight = false;
+            if (c + CW < c_hi) {
+              issue_res(ncol + CW, m0 + q * 32);
+            } else if (u + n_pairs < total) {
+              int cm0, cn0, clo, chi;
+              if (chunks_of(u + n_pairs, cm0, cn0, clo, chi)) issue_res(cn0 + clo, cm0 + q * 32);
+            }
+            uint32_t r[32];
+            tmem_ld32(tacc + c, r);
+            tmem_wait_ld();
+            float v[32];
+            EpiArgs2 e2 = epi;
+            e2.flags &= ~DSF_EPI_RESIDUAL;
+            epi_math32(e2, row, ncol, r, v, row < M);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j] + rr[j]);
+          } else if (epi.c_dtype == DSF_F32) {
             uint32_t r[32];
             tmem_ld32(tacc + c, r);
             tmem_wait_ld();
@@ -953,15 +1018,22 @@ static const bool g_nt_tail_split = getenv("DSF_GEMM_TAIL_SPLIT") ? atoi(getenv(
 // sums, works with every epilogue.  DSF_GEMM_TAIL_NSPLIT=0 disables it.
 static const bool g_nt_tail_nsplit = getenv("DSF_GEMM_TAIL_NSPLIT") ? atoi(getenv("DSF_GEMM_TAIL_NSPLIT")) != 0 : true;
 
-template <int BN, int STAGES>
+// fp32 output + residual: prefetch the residual tile by TMA (see the kernel).  DSF_GEMM_RES_TMA=0 disables it.
+static const bool g_nt_res_tma = getenv("DSF_GEMM_RES_TMA") ? atoi(getenv("DSF_GEMM_RES_TMA")) != 0 : true;
+
+template <int BN, int STAGES, bool RTMA = false>
 static int launch_nt3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const EpiArgs2& epi, int M, int N, int K,
                       cudaStream_t st, const void* Bptr = nullptr, int ldb = 0) {
-  using L = G3Smem<BN, STAGES>;
+  using L = G3Smem<BN, STAGES, RTMA>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_nt3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_nt3_kernel<BN, STAGES, RTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("gemm_nt3/attr");
     configured = true;
+  }
+  CUtensorMap tmR = tmC;
+  if (RTMA) {
+    if (int e = make_tmap_2d(&tmR, epi.residual, DSF_F32, M, N, epi.ldc, 32, 32)) return e;
   }
   const int m_tiles = cdiv(M, 256), n_tiles = N / BN;
   const int tiles = m_tiles * n_tiles;
@@ -970,7 +1042,7 @@ static int launch_nt3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   // leftover tiles fill at most half of the pairs and sit in one column of tiles (one rectangle to zero-fill).
   int tail_start = tiles, tail_split = 1;
   const int rem = tiles % pairs, num_k = K / G2_BK;
-  if (g_nt_tail_split && rem > 0 && 2 * rem <= pairs && epi.c_dtype == DSF_F32 && !(epi.flags & DSF_EPI_RELU) && epi.relu_src == nullptr &&
+  if (!RTMA && g_nt_tail_split && rem > 0 && 2 * rem <= pairs && epi.c_dtype == DSF_F32 && !(epi.flags & DSF_EPI_RELU) && epi.relu_src == nullptr &&
       epi.residual != epi.C && num_k >= 2) {
     const int t0 = tiles - rem;
     if (t0 / m_tiles == (tiles - 1) / m_tiles) {
@@ -994,8 +1066,8 @@ static int launch_nt3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
       if (int e = make_tmap_bf16(&tmBt, Bptr, N, K, ldb, BN / n_split / 2)) return e;
     }
   }
-  launch_pdl(gemm_nt3_kernel<BN, STAGES>, dim3(2 * pairs), dim3(G2_THREADS), L::DYN, st, tmA, tmB, tmC, tmBt, epi, M, N, K, m_tiles, n_tiles,
-             tail_start, tail_split, n_split);
+  launch_pdl(gemm_nt3_kernel<BN, STAGES, RTMA>, dim3(2 * pairs), dim3(G2_THREADS), L::DYN, st, tmA, tmB, tmC, tmBt, tmR, epi, M, N, K, m_tiles,
+             n_tiles, tail_start, tail_split, n_split);
   return check_launch("gemm_nt3");
 }
 
@@ -1040,6 +1112,8 @@ int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc,
     CUtensorMap tmC3;
     if (int e = make_tmap_2d(&tmC3, C, c_dtype, M, N, ldc, c_dtype == DSF_F32 ? 32 : 64, 32)) return e;
     EpiArgs2 epi3{C, ldc, c_dtype, bias, residual, flags, N, reinterpret_cast<const __nv_bfloat16*>(relu_src), ablate, make_drop(drop)};
+    if (BN3 == 256 && g_nt_res_tma && c_dtype == DSF_F32 && (flags & DSF_EPI_RESIDUAL) && residual != nullptr && !ablate)
+      return launch_nt3<256, 4, true>(tmA, tmB, tmC3, epi3, M, N, K, st, B, ldb);
     if (BN3 == 256) return launch_nt3<256, 5>(tmA, tmB, tmC3, epi3, M, N, K, st, B, ldb);
     return launch_nt3<128, 6>(tmA, tmB, tmC3, epi3, M, N, K, st);
   }
