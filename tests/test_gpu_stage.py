@@ -379,6 +379,8 @@ def test_fused_gemm_layernorm_epilogue_matches_separate_launches(cuda_dev, monke
     for a, b in zip(res[1][0], res[0][0]):
         assert_close(a, b, 2e-3, 1e-5, "stage output")
     for a, b, n in zip(res[1][1], res[0][1], names):
+        if n.endswith("attn.key.bias"):  # mathematically zero (softmax shift invariance): both are rounding noise
+            continue
         assert_close(a, b, 2e-2, 1e-5, n)
 
 
