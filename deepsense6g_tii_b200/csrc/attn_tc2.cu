@@ -459,15 +459,19 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       tc_commit_elect(s_full);
       for (int i = 0; i < n_q; ++i) {
         const int bf = i & 1, st = i % ST;
+        TRACE(2, i, 0);
         if (i + 1 < n_q) {
           const int sn = (i + 1) % ST, bn = (i + 1) & 1;
           mbar_wait(q_full + 8 * sn, ((i + 1) / ST) & 1);
+          TRACE(2, i, 1);
           tc_fence_after();
           mma_over_head<HS>(tmem_base + bn * 2 * BQ, sbase + L::K_OFF, 128, sbase + L::Q_OFF + sn * L::Q_BYTES, BQ, idesc_s);
           mma_over_head<HS>(tmem_base + bn * 2 * BQ + BQ, sbase + L::V_OFF, 128, sbase + L::DO_OFF + sn * L::Q_BYTES, BQ, idesc_s);
           tc_commit_elect(s_full + 8 * bn);
         }
+        TRACE(2, i, 2);
         mbar_wait(ds_full + 8 * bf, (i >> 1) & 1);
+        TRACE(2, i, 3);
         tc_fence_after();
         if (PT) {  // P^T / dS^T were written back over the S^T / dP^T tiles in tensor memory
           mma_over_rows_ts<HS, BQ, true>(tm_dv, tmem_base + bf * 2 * BQ, sbase + L::DO_OFF + st * L::Q_BYTES, idesc_g, i > 0);
@@ -478,6 +482,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         }
         tc_commit_elect(q_empty + 8 * st);
         tc_commit_elect(ds_empty + 8 * bf);
+        TRACE(2, i, 4);
       }
       tc_commit_elect(acc_done);
     }
@@ -516,11 +521,15 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       if (tw < 32) st_lse[wg * 32 + tw] = sv;
       else if (tw < 64) st_delta[wg * 32 + tw - 32] = sv;
       const uint32_t myw = wv;
+      if ((warp & 3) == 0) TRACE(wg, i, 0);
       if (i + 1 < n_q) fetch(i + 1, sv, wv);
       named_bar_sync(1 + wg, 128);
+      if ((warp & 3) == 0) TRACE(wg, i, 1);
       mbar_wait(s_full + 8 * bf, (i >> 1) & 1);
+      if ((warp & 3) == 0) TRACE(wg, i, 2);
       tc_fence_after();
       if (i >= 2) mbar_wait(ds_empty + 8 * bf, ((i >> 1) - 1) & 1);
+      if ((warp & 3) == 0) TRACE(wg, i, 3);
       uint8_t* pt = smem + L::PT_OFF + bf * L::P_BYTES;
       uint8_t* dst = smem + L::DST_OFF + bf * L::P_BYTES;
       const uint32_t tm_s = tmem_base + bf * 2 * BQ + lane_off, tm_dp = tm_s + BQ;
@@ -569,6 +578,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       else fence_proxy_async();
       tc_fence_before();
       mbar_arrive(ds_full + 8 * bf);
+      if ((warp & 3) == 0) TRACE(wg, i, 4);
     }
     mbar_wait(acc_done, 0);
     tc_fence_after();
