@@ -1106,7 +1106,11 @@ int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc,
     // about the same ~85 ns for N = 128 as for N = 256 (operand reads from shared memory bound it), so narrow tiles
     // waste the tensor pipe even when they would balance the 74 pairs better (measured: N = 512, K = 2048 runs 27.0 us
     // with 256-wide and 30.2 us with 128-wide tiles).
-    const int BN3 = N % 256 == 0 ? 256 : 128;
+    // Short contractions with a narrow output (proj and its data gradient: N = 512, K = 512) are epilogue-bound — 2.6 us of
+    // MMAs against ~4 us of epilogue per 256 x 256 tile and only 1.25 tiles per pair — so 128-wide tiles (2.5 per pair)
+    // overlap epilogue and main loop better there (DSF_GEMM_BN128_SMALLK=1; K = 2048 stays on 256-wide tiles, see above).
+    static const bool small_k_bn128 = getenv("DSF_GEMM_BN128_SMALLK") ? atoi(getenv("DSF_GEMM_BN128_SMALLK")) != 0 : false;
+    const int BN3 = (N % 256 == 0 && !(small_k_bn128 && K <= 512 && N <= 512)) ? 256 : 128;
     if (int e = make_tmap_bf16(&tmA, A, M, K, lda, G2_BM)) return e;
     if (int e = make_tmap_bf16(&tmB, B, N, K, ldb, BN3 / 2)) return e;
     CUtensorMap tmC3;
@@ -1115,6 +1119,8 @@ int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc,
     if (BN3 == 256 && g_nt_res_tma && c_dtype == DSF_F32 && (flags & DSF_EPI_RESIDUAL) && residual != nullptr && !ablate)
       return launch_nt3<256, 4, true>(tmA, tmB, tmC3, epi3, M, N, K, st, B, ldb);
     if (BN3 == 256) return launch_nt3<256, 5>(tmA, tmB, tmC3, epi3, M, N, K, st, B, ldb);
+    if (g_nt_res_tma && c_dtype == DSF_F32 && (flags & DSF_EPI_RESIDUAL) && residual != nullptr && !ablate)
+      return launch_nt3<128, 5, true>(tmA, tmB, tmC3, epi3, M, N, K, st);
     return launch_nt3<128, 6>(tmA, tmB, tmC3, epi3, M, N, K, st);
   }
   const int BN = pick_bn_nt(M, N);
