@@ -1,8 +1,8 @@
 """Diagnostic (GPU): per-tensor relative errors of the bf16 fused stage vs the fp32 oracle, next to the
 errors of stock PyTorch bf16 autocast running the oracle code — calibrates what 'bf16 accuracy' means
-for each gradient tensor.  Usage: python scripts/diag_bf16_error.py [B C H L]"""
+for each gradient tensor.  Usage: python tests/tools/diag_bf16_error.py [B C H L]"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import fusion_ref as R
 from deepsense6g_tii_b200.functional import fusion_stage, param_names

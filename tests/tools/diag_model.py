@@ -1,6 +1,6 @@
 """Diagnostic (GPU): per-parameter gradient errors of the drop-in TransFuser vs the oracle forward on the same module."""
 import os, sys, types
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import model_ref
 from deepsense6g_tii_b200 import TransFuser

@@ -1,7 +1,7 @@
 """Diagnostic (GPU): one fusion stage on REALISTIC trunk features (ResNet stem output) with a structured
 upstream gradient, mine (fp32 mode) vs oracle fp32 vs oracle fp64."""
 import os, sys, types
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import fusion_ref as R
 from deepsense6g_tii_b200 import TransFuser
