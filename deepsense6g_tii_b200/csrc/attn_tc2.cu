@@ -400,7 +400,11 @@ struct BwdKV2 {
   static_assert(DYN <= 232448, "shared memory budget");
 };
 
-template <int HS, int BQ, int ST, bool PT>
+// DS = true: the math warps read the per-query statistics (lse, delta) of a tile straight from global memory (broadcast
+// 8-byte loads, L1 / L2 hits: the two vectors of a head are 7.7 KB) instead of staging them in shared memory behind a
+// 128-thread named barrier per iteration.  The in-kernel timeline showed the math warps as the critical path of this kernel
+// (~450 of their ~2200 cycles per iteration in staging + barrier, the MMA warp waiting ~650 cycles for dS).
+template <int HS, int BQ, int ST, bool PT, bool DS = false>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
@@ -518,12 +522,16 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       float* st_lse = reinterpret_cast<float*>(smem + L::STAT_OFF) + bf * 2 * BQ;
       float* st_delta = st_lse + BQ;
       // the stats buffer bf was last read two iterations ago; every thread of the warpgroup has passed the barrier below since
-      if (tw < 32) st_lse[wg * 32 + tw] = sv;
-      else if (tw < 64) st_delta[wg * 32 + tw - 32] = sv;
+      if (!DS) {
+        if (tw < 32) st_lse[wg * 32 + tw] = sv;
+        else if (tw < 64) st_delta[wg * 32 + tw - 32] = sv;
+      }
       const uint32_t myw = wv;
       if ((warp & 3) == 0) TRACE(wg, i, 0);
-      if (i + 1 < n_q) fetch(i + 1, sv, wv);
-      named_bar_sync(1 + wg, 128);
+      if (!DS || ad.thresh8) {
+        if (i + 1 < n_q) fetch(i + 1, sv, wv);
+      }
+      if (!DS) named_bar_sync(1 + wg, 128);
       if ((warp & 3) == 0) TRACE(wg, i, 1);
       mbar_wait(s_full + 8 * bf, (i >> 1) & 1);
       if ((warp & 3) == 0) TRACE(wg, i, 2);
@@ -540,11 +548,31 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         tmem_ld32(tm_dp + c, rp);
         tmem_wait_ld();
         uint32_t pk[16], dk[16];
+        const int qc = i * BQ + c;  // first query of this chunk
+        const bool q_full_chunk = qc + 32 <= T && (T & 1) == 0;  // even T: every head's vectors start 8-byte aligned
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(st_lse + c + e);
-          const float4 d4 = *reinterpret_cast<const float4*>(st_delta + c + e);
-          const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+          float ls[4], dl[4];
+          if (DS) {
+            if (q_full_chunk) {  // T and the chunk start are even: 8-byte aligned pairs
+              const float2 la = __ldg(reinterpret_cast<const float2*>(lse_g + qc + e)), lb = __ldg(reinterpret_cast<const float2*>(lse_g + qc + e + 2));
+              const float2 da = __ldg(reinterpret_cast<const float2*>(delta_g + qc + e)), db = __ldg(reinterpret_cast<const float2*>(delta_g + qc + e + 2));
+              ls[0] = la.x * 1.4426950408889634f; ls[1] = la.y * 1.4426950408889634f; ls[2] = lb.x * 1.4426950408889634f; ls[3] = lb.y * 1.4426950408889634f;
+              dl[0] = da.x; dl[1] = da.y; dl[2] = db.x; dl[3] = db.y;
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int qq = qc + e + u;
+                ls[u] = qq < T ? __ldg(lse_g + qq) * 1.4426950408889634f : INFINITY;
+                dl[u] = qq < T ? __ldg(delta_g + qq) : 0.f;
+              }
+            }
+          } else {
+            const float4 l4 = *reinterpret_cast<const float4*>(st_lse + c + e);
+            const float4 d4 = *reinterpret_cast<const float4*>(st_delta + c + e);
+            ls[0] = l4.x; ls[1] = l4.y; ls[2] = l4.z; ls[3] = l4.w;
+            dl[0] = d4.x; dl[1] = d4.y; dl[2] = d4.z; dl[3] = d4.w;
+          }
           float p[4], d[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -1384,7 +1412,8 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   using H = HeadCfg<HS>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
+    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
         cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess ||
         cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, PT, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
       return check_launch("attn_bwd2/attr");
@@ -1403,7 +1432,14 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
   dim3 grid(cdiv(T, 128), nh, B);
   if (parts & 2) {
-    launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta, (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
+    // DSF_ATTN_KV_DIRECT_STATS=0: stage lse / delta in shared memory behind a named barrier (the original scheme)
+    static const bool direct_stats = getenv("DSF_ATTN_KV_DIRECT_STATS") ? atoi(getenv("DSF_ATTN_KV_DIRECT_STATS")) != 0 : true;
+    if (direct_stats)
+      launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT, true>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta,
+                 (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
+    else
+      launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT, false>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta,
+                 (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
     if (int e = check_launch("attn_bwd2/kv")) return e;
   }
   if (parts & 4) {
