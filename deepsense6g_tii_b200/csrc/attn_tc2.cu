@@ -400,10 +400,10 @@ struct BwdKV2 {
   static_assert(DYN <= 232448, "shared memory budget");
 };
 
-// DS = true: the math warps read the per-query statistics (lse, delta) of a tile straight from global memory (broadcast
-// 8-byte loads, L1 / L2 hits: the two vectors of a head are 7.7 KB) instead of staging them in shared memory behind a
-// 128-thread named barrier per iteration.  The in-kernel timeline showed the math warps as the critical path of this kernel
-// (~450 of their ~2200 cycles per iteration in staging + barrier, the MMA warp waiting ~650 cycles for dS).
+// DS = true (experiment, measured slower, off): the math warps read the per-query statistics (lse, delta) of a tile straight
+// from global memory (broadcast 8-byte loads, L1 / L2 hits) instead of staging them in shared memory behind a 128-thread
+// named barrier per iteration.  The in-kernel timeline shows the math warps as the critical path of this kernel (~450 of
+// their ~2200 cycles per iteration in staging + barrier, the MMA warp waiting ~650 cycles for dS), but the loads cost more.
 template <int HS, int BQ, int ST, bool PT, bool DS = false>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
@@ -1432,8 +1432,10 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
   dim3 grid(cdiv(T, 128), nh, B);
   if (parts & 2) {
-    // DSF_ATTN_KV_DIRECT_STATS=0: stage lse / delta in shared memory behind a named barrier (the original scheme)
-    static const bool direct_stats = getenv("DSF_ATTN_KV_DIRECT_STATS") ? atoi(getenv("DSF_ATTN_KV_DIRECT_STATS")) != 0 : true;
+    // DSF_ATTN_KV_DIRECT_STATS=1: read lse / delta straight from global memory instead of staging them in shared memory
+    // behind a named barrier.  OFF: measured slower on B200 (backward 177 vs 139 us per layer, 4.20 vs 4.00 ms per step) —
+    // 32 broadcast 8-byte loads per thread and iteration cost more LSU time than the barrier they remove.
+    static const bool direct_stats = getenv("DSF_ATTN_KV_DIRECT_STATS") ? atoi(getenv("DSF_ATTN_KV_DIRECT_STATS")) != 0 : false;
     if (direct_stats)
       launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT, true>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta,
                  (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
