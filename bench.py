@@ -301,6 +301,26 @@ def profile_families(gpt, feats, gps, probes):
     return fam
 
 
+def hbm_family_bytes(batch):
+    """Algorithmic bytes per step of the HBM-bound kernel families (elements x dtype size, what each launch must
+    read and write once): M = batch*T token rows, E_f = feature-map elements of the three branches."""
+    M = batch * T
+    e_t = M * C
+    e_f = 3 * batch * S * C * (A * SCALE) * (A * SCALE)
+    F = 4 * C
+    per_block_w = 4 * C * C + 2 * F * C  # q, k, v, proj + mlp.0 + mlp.2 weights
+    return {
+        "tokens_fwd": e_f * 4 + e_t * 4 + T * C * 4,
+        "tokens_bwd": e_t * 4 + 2 * e_f * 4 + T * C * 4,                     # dx in; d(out) in for the residual branch, d(feat) out; dpos out
+        "layernorm_fwd": (2 * L) * e_t * (4 + 2) + e_t * (4 + 4),           # 16 x (fp32 in, bf16 out) + ln_f (fp32 out)
+        "layernorm_bwd": (2 * L) * e_t * (2 + 4 + 4 + 4 + 2) + e_t * (4 + 4 + 4 + 2),  # dy bf16, x, dx_add in; dx fp32 + bf16 copy out
+        "colsum": L * M * (F + 3 * C) * 2,                                   # bf16 dL/d(mlp.0 out) and dqkv
+        "pack_block_weights": L * per_block_w * (4 + 2 * 2),                 # fp32 in, plain + transposed bf16 out
+        "upsample_add_fwd": e_t * 4 + 2 * e_f * 4,
+        "upsample_add_bwd": e_f * 4 + e_t * 4,
+    }
+
+
 def one_step(gpt, feats, gps, probes):
     for p in gpt.parameters():
         p.grad = None
@@ -503,6 +523,15 @@ def run_ours(args, rank, world, local_rank):
                 "share_of_step": tc[dom]["ms"] / total_ms, "timing": how,
                 "families": {k: {"ms": round(d["ms"], 4), "calls": d["launch_calls"],
                                  "tflops": (d["flops"] / (d["ms"] * 1e-3) / 1e12) if d["flops"] else None} for k, d in fam.items()}}
+    try:  # HBM-bound families: algorithmic GB/s against the measured copy bandwidth (launch-bound at 10-25 us per launch)
+        hb = hbm_family_bytes(feats[0].shape[0] // S)
+        for k, d in roofline["families"].items():
+            if k in hb and d["ms"] > 0:
+                d["gbps"] = round(hb[k] / (d["ms"] * 1e-3) / 1e9, 1)
+                d["frac_of_hbm_peak"] = round(d["gbps"] / pk["hbm"], 3)
+        roofline["hbm_peak_gbps"] = pk["hbm"]
+    except Exception as ex:  # never lose the bench line over a diagnostic
+        sys.stderr.write("bench.py: HBM family roofline skipped (%s)\n" % ex)
     cpu_v, cpu_ms = time_cpu(2, 1)
     cores = torch.get_num_threads()
     h2d = sum(t.numel() * t.element_size() for t in feats_h) + gps_h.numel() * gps_h.element_size()
