@@ -292,7 +292,17 @@ class _Runner:
         # 50.6 vs 40.0 us (K = 2048) for GEMM + LayerNorm, 4.11 vs 4.05 ms per step.
         fuse_ln = C == 512 and os.environ.get("DSF_GEMM_LN_FUSE", "0") == "1"
         nxt = None
-        for i in range(L):
+        # Forward micro-batching (DSF_FWD_MICROBATCH=1; default: on while the step is being captured, like the side streams):
+        # the forward is a chain of short kernels that leave SMs idle in their partly filled last rounds and ramps, and it has
+        # no independent work to overlap with.  The two halves of the batch are independent, so their chains run on two
+        # streams (parallel branches of the captured graph) into the SAME full-batch buffers (row ranges): one half's
+        # kernels fill the SMs the other half's leave idle.  The backward stays full-batch (it is throughput-bound already).
+        env_mb = os.environ.get("DSF_FWD_MICROBATCH")
+        micro = ((env_mb == "1") if env_mb in ("0", "1") else False) and self.dropout is None and not fuse_ln \
+            and self.B >= 2 and self.B % 2 == 0 and L > 0
+        if micro:
+            x = self._forward_blocks_microbatched(x, params, packed, pack, main, side, saved)
+        for i in range(0 if micro else L):
             (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[1 + 16 * i: 17 + 16 * i]
             if side is not None:
                 st = packed[i]
@@ -348,6 +358,60 @@ class _Runner:
         K.upsample_add_fwd(self.geom, yf, feats if residual else [torch.zeros_like(f) for f in feats], outs)
         gps_out = yf.view(self.B, self.T, C)[:, self.Tm:, :].contiguous()
         return outs, gps_out, saved
+
+    def _forward_blocks_microbatched(self, x, params, packed, pack, main, side, saved):
+        """The L transformer blocks of the bf16 forward with the batch split in two halves on two streams (see
+        ``_forward_bf16``).  Buffers are allocated full-batch on the main stream; each half's kernels work on its row range."""
+        dev = x.device
+        M, C, L, T = self.M, self.C, self.L, self.T
+        f32, bf = torch.float32, torch.bfloat16
+        F = params[13].shape[0]
+        mb = _side_stream(dev, 2)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        mb.wait_event(ev)
+        Mh = (self.B // 2) * T
+        halves = ((0, Mh, main), (Mh, M, mb))
+        for i in range(L):
+            (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[1 + 16 * i: 17 + 16 * i]
+            if side is not None:
+                st = packed[i]
+                main.wait_event(st.packed_ev)
+                mb.wait_event(st.packed_ev)
+                st.packed_ev = None
+            else:
+                st = pack(i)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                mb.wait_event(ev)
+            st.x_in = x
+            stats = torch.empty(4, M, device=dev, dtype=f32)
+            st.mean1, st.rstd1, st.mean2, st.rstd2 = stats[0], stats[1], stats[2], stats[3]
+            st.h1 = torch.empty(M, C, device=dev, dtype=bf)
+            st.qkv = torch.empty(M, 3 * C, device=dev, dtype=bf)
+            st.y = torch.empty(M, C, device=dev, dtype=bf)
+            st.lse = torch.empty(self.B, self.nh, T, device=dev, dtype=f32)
+            st.drop_bits = None
+            st.x_mid = torch.empty(M, C, device=dev, dtype=f32)
+            st.h2 = torch.empty(M, C, device=dev, dtype=bf)
+            st.a = torch.empty(M, F, device=dev, dtype=bf)
+            x_new = torch.empty(M, C, device=dev, dtype=f32)
+            for r0, r1, stream in halves:
+                b0, bh = r0 // T, (r1 - r0) // T
+                with torch.cuda.stream(stream):
+                    K.layernorm_fwd(x[r0:r1], ln1w, ln1b, st.h1[r0:r1], st.mean1[r0:r1], st.rstd1[r0:r1])
+                    K.gemm_bf16_nt(st.h1[r0:r1], st.wqkv, st.qkv[r0:r1], bias=st.bqkv)
+                    K.attn_fwd(st.qkv[r0:r1], st.y[r0:r1], st.lse[b0:b0 + bh], bh, T, C, self.nh, None, None)
+                    K.gemm_bf16_nt(st.y[r0:r1], st.wp, st.x_mid[r0:r1], bias=pb, residual=x[r0:r1])
+                    K.layernorm_fwd(st.x_mid[r0:r1], ln2w, ln2b, st.h2[r0:r1], st.mean2[r0:r1], st.rstd2[r0:r1])
+                    K.gemm_bf16_nt(st.h2[r0:r1], st.w1, st.a[r0:r1], bias=b1, relu=True)
+                    K.gemm_bf16_nt(st.a[r0:r1], st.w2, x_new[r0:r1], bias=b2, residual=st.x_mid[r0:r1])
+            x = x_new
+            saved.layers.append(st)
+        ev = torch.cuda.Event()
+        ev.record(mb)
+        main.wait_event(ev)
+        return x
 
     def _drop(self, kind, block=0):
         """``_capi.Dropout`` of one site, or None when that probability is 0 / dropout is off."""
