@@ -292,7 +292,7 @@ class _Runner:
         # 50.6 vs 40.0 us (K = 2048) for GEMM + LayerNorm, 4.11 vs 4.05 ms per step.
         fuse_ln = C == 512 and os.environ.get("DSF_GEMM_LN_FUSE", "0") == "1"
         nxt = None
-        # Forward micro-batching (DSF_FWD_MICROBATCH=1; default: on while the step is being captured, like the side streams):
+        # Forward micro-batching (experiment, DSF_FWD_MICROBATCH=1; OFF by default: measured 4.11 vs 4.02 ms per step on B200):
         # the forward is a chain of short kernels that leave SMs idle in their partly filled last rounds and ramps, and it has
         # no independent work to overlap with.  The two halves of the batch are independent, so their chains run on two
         # streams (parallel branches of the captured graph) into the SAME full-batch buffers (row ranges): one half's
