@@ -29,3 +29,21 @@ def test_gpu_arm_refuses_to_run_without_a_gpu():
         return
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)
+
+
+def test_hbm_family_bytes_follow_the_per_sample_figures_of_the_measurement_plan():
+    """bench.py's algorithmic bytes of the HBM-bound families (roofline.families[*].gbps) against SURVEY.md §8(d) / BASELINE.md §3:
+    E_t = T*C = 492 544 token elements and E_f = 3*5*C*H^2 = 491 520 feature elements per sample at stage 4 (C = 512, H = 8)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    b = 12
+    hb = bench.hbm_family_bytes(b)
+    e_t, e_f = 962 * 512 * b, 3 * 5 * 512 * 8 * 8 * b
+    assert hb["tokens_fwd"] == e_f * 4 + e_t * 4 + 962 * 512 * 4          # read features, write tokens (+ pos_emb once)
+    assert hb["upsample_add_fwd"] == e_t * 4 + 2 * e_f * 4                # read tokens + features, write features
+    assert hb["upsample_add_bwd"] == e_f * 4 + e_t * 4
+    assert hb["layernorm_fwd"] == 16 * e_t * 6 + e_t * 8                  # 16 x (fp32 in, bf16 out) + ln_f (fp32 out)
+    assert hb["layernorm_bwd"] == 16 * e_t * 16 + e_t * 14
+    assert hb["colsum"] == 8 * (962 * b) * (2048 + 1536) * 2
+    assert hb["pack_block_weights"] == 8 * (4 * 512 * 512 + 2 * 2048 * 512) * 8
+    assert all(v > 0 for v in hb.values())
