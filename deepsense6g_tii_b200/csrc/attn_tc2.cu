@@ -404,7 +404,10 @@ struct BwdKV2 {
 // from global memory (broadcast 8-byte loads, L1 / L2 hits) instead of staging them in shared memory behind a 128-thread
 // named barrier per iteration.  The in-kernel timeline shows the math warps as the critical path of this kernel (~450 of
 // their ~2200 cycles per iteration in staging + barrier, the MMA warp waiting ~650 cycles for dS), but the loads cost more.
-template <int HS, int BQ, int ST, bool PT, bool DS = false>
+// WS = true (needs PT: the staging lives in the then unused P^T region of shared memory): every math WARP stages the 32 lse +
+// 32 delta values of its warpgroup's query columns for itself (each lane fetches one pair a tile ahead) and only needs a
+// __syncwarp — the four warps of a warpgroup no longer rendezvous at a named barrier every iteration.
+template <int HS, int BQ, int ST, bool PT, bool DS = false, bool WS = false>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
@@ -514,24 +517,43 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         wv = qd < T ? ad.bits[(bh * T + qd) * ad.Tw + kw] : 0u;
       }
     };
+    static_assert(!WS || (PT && !DS), "warp-local statistics staging lives in the P^T region, which only PT leaves unused");
     float sv;
     uint32_t wv;
     fetch(0, sv, wv);
+    float wl = 0.f, wd = 0.f;  // WS: this lane's lse (log2 units) / delta of query (tile * BQ + wg * 32 + lane), one tile ahead
+    auto fetch_w = [&](int it) {
+      const int qq = it * BQ + wg * 32 + lane;
+      wl = qq < T ? lse_g[qq] * 1.4426950408889634f : INFINITY;
+      wd = qq < T ? delta_g[qq] : 0.f;
+    };
+    if (WS) fetch_w(0);
     for (int i = 0; i < n_q; ++i) {
       const int bf = i & 1;
       float* st_lse = reinterpret_cast<float*>(smem + L::STAT_OFF) + bf * 2 * BQ;
       float* st_delta = st_lse + BQ;
+      if (WS) {  // per-warp buffers [warp][bf][lse 32 | delta 32]; indexed below with the warpgroup's column offset removed
+        float* wst = reinterpret_cast<float*>(smem + L::PT_OFF) + (warp * 2 + bf) * 64;
+        wst[lane] = wl;
+        wst[32 + lane] = wd;
+        st_lse = wst - wg * 32;
+        st_delta = wst + 32 - wg * 32;
+      }
       // the stats buffer bf was last read two iterations ago; every thread of the warpgroup has passed the barrier below since
-      if (!DS) {
+      if (!DS && !WS) {
         if (tw < 32) st_lse[wg * 32 + tw] = sv;
         else if (tw < 64) st_delta[wg * 32 + tw - 32] = sv;
       }
       const uint32_t myw = wv;
       if ((warp & 3) == 0) TRACE(wg, i, 0);
-      if (!DS || ad.thresh8) {
+      if ((!DS && !WS) || ad.thresh8) {
         if (i + 1 < n_q) fetch(i + 1, sv, wv);
       }
-      if (!DS) named_bar_sync(1 + wg, 128);
+      if (WS) {
+        if (i + 1 < n_q) fetch_w(i + 1);
+        __syncwarp();  // this warp's staging is visible to its lanes; buffer bf was last read two iterations (two __syncwarps) ago
+      }
+      if (!DS && !WS) named_bar_sync(1 + wg, 128);
       if ((warp & 3) == 0) TRACE(wg, i, 1);
       mbar_wait(s_full + 8 * bf, (i >> 1) & 1);
       if ((warp & 3) == 0) TRACE(wg, i, 2);
@@ -1414,6 +1436,7 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   if (!configured) {
     if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
         cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT, false, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
         cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess ||
         cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, PT, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
       return check_launch("attn_bwd2/attr");
@@ -1436,7 +1459,12 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
     // behind a named barrier.  OFF: measured slower on B200 (backward 177 vs 139 us per layer, 4.20 vs 4.00 ms per step) —
     // 32 broadcast 8-byte loads per thread and iteration cost more LSU time than the barrier they remove.
     static const bool direct_stats = getenv("DSF_ATTN_KV_DIRECT_STATS") ? atoi(getenv("DSF_ATTN_KV_DIRECT_STATS")) != 0 : false;
-    if (direct_stats)
+    // DSF_ATTN_KV_WARP_STATS=1 (P kept in tensor memory only): warp-local statistics staging, no named barrier per iteration
+    static const bool warp_stats = getenv("DSF_ATTN_KV_WARP_STATS") ? atoi(getenv("DSF_ATTN_KV_WARP_STATS")) != 0 : false;
+    if (PT && warp_stats)
+      launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT, false, PT>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta,
+                 (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
+    else if (direct_stats)
       launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT, true>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta,
                  (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
     else
