@@ -1459,8 +1459,9 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
     // behind a named barrier.  OFF: measured slower on B200 (backward 177 vs 139 us per layer, 4.20 vs 4.00 ms per step) —
     // 32 broadcast 8-byte loads per thread and iteration cost more LSU time than the barrier they remove.
     static const bool direct_stats = getenv("DSF_ATTN_KV_DIRECT_STATS") ? atoi(getenv("DSF_ATTN_KV_DIRECT_STATS")) != 0 : false;
-    // DSF_ATTN_KV_WARP_STATS=1 (P kept in tensor memory only): warp-local statistics staging, no named barrier per iteration
-    static const bool warp_stats = getenv("DSF_ATTN_KV_WARP_STATS") ? atoi(getenv("DSF_ATTN_KV_WARP_STATS")) != 0 : false;
+    // warp-local statistics staging, no named barrier per iteration (P kept in tensor memory only); measured 124 vs 127 us per
+    // layer for the whole backward, 3.99 vs 4.02 ms per step.  DSF_ATTN_KV_WARP_STATS=0: warpgroup staging + named barrier
+    static const bool warp_stats = getenv("DSF_ATTN_KV_WARP_STATS") ? atoi(getenv("DSF_ATTN_KV_WARP_STATS")) != 0 : true;
     if (PT && warp_stats)
       launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT, false, PT>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta,
                  (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
