@@ -1,20 +1,21 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200-native GPT fusion stage.
+"""bench.py — headline benchmark of the B200-native GPT fusion path of model2_seq.py.
 
-Metric (BASELINE.json): train samples/sec (fwd+bwd).  Workload at every N: BASELINE.json configs[1],
-"single GPT fusion stage microbench (n_embd 512, 8 layers, 4 heads, 8x8 anchors, ~960 tokens) fwd+bwd,
-bf16" = the stage-4 fusion stage of model2_seq.py (Encoder.forward:571-579 + GPT:175-287) at per-GPU
-batch 12, seq_len 5 -> T = 962 tokens, synthetic (60, 512, 8, 8) feature maps per modality.
+Metric (BASELINE.json): train samples/sec (fwd+bwd).  Default workload (``--workload fusion4``): the WHOLE hot path north_star
+names — the four fusion stages of the 256x256 model back to back (Encoder.forward:515-526, 533-544, 552-563, 571-579 + GPT
+:175-287; n_embd 64/128/256/512 on 64/32/16/8-pixel feature maps, 8 layers, 4 heads, 8x8 anchors, seq_len 5 -> T = 962
+tokens), fwd+bwd, bf16, per-GPU batch 12, synthetic trunk features.  BASELINE.json configs[1] (the n_embd 512 stage alone)
+is measured in the same run and reported as the sub-record ``stage4`` (``--workload stage4`` makes it the whole line).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload fusion4|stage4|model] [--anchors 8|16]
 
-N > 1 is launched by torchrun (one rank per GPU): every rank runs its own batch-12 shard (weak scaling)
-and the GPT gradients are all-reduced over NCCL every step (DDP semantics of train2_seq.py:538 replaced
-by one-process-per-GPU).  Rank 0 prints ONE JSON line.
+N > 1 is launched by torchrun (one rank per GPU): every rank runs its own batch-12 shard (weak scaling) and the GPT gradients
+are all-reduced over NCCL every step (DDP semantics of train2_seq.py:538 replaced by one-process-per-GPU).  Rank 0 prints
+ONE JSON line.
 
---impl reference times the reference's own CPU implementation of the same path (the oracle port of
-model2_seq.py in oracle/fusion_ref.py — /root/reference does not exist on the GPU box) on the host
-cores, on a bounded sample (batch 2) of the same workload.
+--impl reference times the reference's own implementation of the same path on the host cores, fp32, batch 12: the unmodified
+reference ``GPT`` class (oracle/_ref/model2_seq.py, placed there by ``__graft_entry__.build()`` where /root/reference exists)
+inside the pool / interpolate / add calls of Encoder.forward; when oracle/_ref is absent, the oracle port (oracle/fusion_ref.py).
 """
 import argparse
 import json
@@ -30,19 +31,37 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-C, L, NH, A, S, V, BATCH, SCALE = 512, 8, 4, 8, 5, 1, 12, 1
-T = (V + 2) * S * A * A + 2
-WORKLOAD = "gpt_fusion_stage n_embd=512 n_layer=8 n_head=4 anchors=8x8 seq_len=5 T=962 batch=12/GPU fwd+bwd"
-FWD_FLOPS_PER_SAMPLE = L * (24.0 * T * C * C + 4.0 * T * T * C)  # 63.58 GF
-CPU_SAMPLE_BATCH = 2
+L, NH, S, V, BATCH = 8, 4, 5, 1, 12
+A = 8
+STAGES4 = ((64, 8), (128, 4), (256, 2), (512, 1))   # (n_embd, feature-map side / anchors) of the four fusion stages
+SPEC = STAGES4                                      # stages of the selected workload
+PDROP = 0.0  # --dropout: embd/attn/resid probability (the reference trains with 0.1; 0 = the parity configuration)
+
+
+def n_tokens():
+    return (V + 2) * S * A * A + 2
+
+
+def fwd_flops_per_sample(c):
+    """L * (24 T C^2 + 4 T^2 C); backward = 2x (flash-attention recompute not counted)."""
+    t = n_tokens()
+    return L * (24.0 * t * c * c + 4.0 * t * t * c)
+
+
+def workload_name():
+    t = n_tokens()
+    if len(SPEC) == 1:
+        return "gpt_fusion_stage n_embd=%d n_layer=8 n_head=4 anchors=%dx%d seq_len=5 T=%d batch=12/GPU fwd+bwd" % (SPEC[0][0], A, A, t)
+    return ("gpt_fusion_path: the 4 fusion stages of model2_seq back to back (n_embd %s on %s-pixel feature maps), n_layer=8 n_head=4 "
+            "anchors=%dx%d seq_len=5 T=%d batch=12/GPU fwd+bwd" % ("/".join(str(c) for c, _ in SPEC), "/".join(str(A * s) for _, s in SPEC), A, A, t))
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
         d = json.load(open(p))
-        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
-    return dict(hbm=6650.0, tc_burst=1590.0, tc_sust=1400.0, src="fallback")
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sust=1400.0, src="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
@@ -56,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -83,49 +102,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synth_inputs(gen, batch, device="cpu", pin=False):
-    """Synthetic stage-4 inputs: post-ReLU-like trunk features (non-negative, ~unit scale) and GPS embeddings."""
-    feats = [torch.randn(batch * S, C, A * SCALE, A * SCALE, generator=gen).abs_() for _ in range(3)]
-    gps = torch.randn(batch, 2, C, generator=gen)
-    probes = [torch.randn(f.shape, generator=gen) * 1e-3 for f in feats] + [torch.randn(batch, 2, C, generator=gen) * 1e-3]
+def synth_inputs(gen, batch, c, scale, pin=False):
+    """Synthetic inputs of one stage: post-ReLU-like trunk features (non-negative, ~unit scale), GPS embeddings, loss probes."""
+    h = A * scale
+    feats = [torch.randn(batch * S, c, h, h, generator=gen).abs_() for _ in range(3)]
+    gps = torch.randn(batch, 2, c, generator=gen)
+    probes = [torch.randn(f.shape, generator=gen) * 1e-3 for f in feats] + [torch.randn(batch, 2, c, generator=gen) * 1e-3]
     ts = feats + [gps] + probes
     if pin:
         ts = [t.pin_memory() for t in ts]
-    if device != "cpu":
-        ts = [t.to(device) for t in ts]
     return ts[:3], ts[3], ts[4:]
-
-
-# ----------------------------------------------------------------------------------------- CPU arm
-def cpu_step_fn():
-    from oracle import fusion_ref as R
-    gen = torch.Generator().manual_seed(0)
-    p = R.init_gpt_params(C, NH, 4, L, T, generator=gen, pos_std=0.02)
-    p = {k: v.requires_grad_(True) for k, v in p.items()}
-    feats, gps, probes = synth_inputs(gen, CPU_SAMPLE_BATCH)
-    feats = [f.requires_grad_(True) for f in feats]
-    gps.requires_grad_(True)
-
-    def step():
-        for t in list(p.values()) + feats + [gps]:
-            t.grad = None
-        (a, b, c), g = R.fusion_stage(p, feats, gps, NH, S, A, A)
-        loss = sum((o * pr).sum() for o, pr in zip((a, b, c, g), probes))
-        loss.backward()
-        return float(loss.detach())
-    return step
-
-
-def time_cpu(steps, warmup):
-    torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_step_fn()
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    return CPU_SAMPLE_BATCH * steps / dt, dt / steps * 1e3
 
 
 def cpu_model():
@@ -138,52 +124,195 @@ def cpu_model():
     return "unknown"
 
 
+# ----------------------------------------------------------------------------------------- reference arm (CPU) / stock-PyTorch GPU baseline
+def _load_reference_gpt():
+    """The reference's own GPT class, imported from the git-ignored copy build() places under oracle/_ref (SURVEY §8c shims:
+    stub ``mamba_ssm``).  Returns (model2_seq module, GlobalConfig) or None when the copy is absent."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isfile(os.path.join(ref, "model2_seq.py")):
+        return None
+    os.environ.setdefault("DSF_REFERENCE_ROOT", ref)
+    try:
+        from oracle import ref_import
+        ref_import.REFERENCE_ROOT = ref
+        return ref_import.load_reference()
+    except Exception as ex:
+        sys.stderr.write("bench.py: oracle/_ref present but not importable (%s); using the oracle port\n" % ex)
+        return None
+
+
+def reference_step_fn(device, batch, autocast=False):
+    """fwd+bwd of the selected workload through the reference code (stock PyTorch ops) on ``device``.  Returns (step, kind)."""
+    ref = _load_reference_gpt()
+    dev = torch.device(device)
+    gen = torch.Generator().manual_seed(0)
+    units = []
+    for c, scale in SPEC:
+        feats, gps, probes = synth_inputs(gen, batch, c, scale)
+        feats = [f.to(dev).requires_grad_(True) for f in feats]
+        gps = gps.to(dev).requires_grad_(True)
+        probes = [p.to(dev) for p in probes]
+        if ref is not None:
+            M, GlobalConfig = ref
+            torch.manual_seed(100)
+            cfg = GlobalConfig(add_velocity=1, embd_pdrop=PDROP, attn_pdrop=PDROP, resid_pdrop=PDROP)
+            cfg.vert_anchors = cfg.horz_anchors = A
+            gpt = M.GPT(c, NH, 4, L, A, A, S, PDROP, PDROP, PDROP, cfg).to(dev).train()
+            pool = torch.nn.AdaptiveAvgPool2d((A, A))
+            params = list(gpt.parameters())
+
+            def fwd(feats=feats, gps=gps, gpt=gpt, pool=pool, scale=scale):   # Encoder.forward, model2_seq.py:515-526
+                o = gpt(pool(feats[0]), pool(feats[1]), pool(feats[2]), gps)
+                ups = [o[k] if scale == 1 else torch.nn.functional.interpolate(o[k], scale_factor=scale, mode="bilinear") for k in range(3)]
+                return [f + u for f, u in zip(feats, ups)] + [o[3]]
+        else:
+            from oracle import fusion_ref as R
+            p = R.init_gpt_params(c, NH, 4, L, n_tokens(), generator=gen, pos_std=0.02)
+            p = {k: v.to(dev).requires_grad_(True) for k, v in p.items()}
+            params = list(p.values())
+
+            def fwd(feats=feats, gps=gps, p=p):
+                (a, b, cc), g = R.fusion_stage(p, feats, gps, NH, S, A, A)
+                return [a, b, cc, g]
+        units.append((fwd, params, feats, gps, probes))
+
+    def step():
+        total = 0.0
+        for fwd, params, feats, gps, probes in units:
+            for t in params + feats + [gps]:
+                t.grad = None
+            with torch.autocast(dev.type, dtype=torch.bfloat16, enabled=autocast):
+                outs = fwd()
+            loss = sum((o.float() * pr).sum() for o, pr in zip(outs, probes))
+            loss.backward()
+            total = total + loss.detach()
+        return total
+    return step, ("reference" if ref is not None else "port")
+
+
+def time_cpu(steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, kind = reference_step_fn("cpu", BATCH)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return BATCH * steps / dt, dt / steps * 1e3, kind
+
+
+def cpu_sample_note(kind, cores, steps, warmup):
+    what = ("the reference's own GPT class (oracle/_ref/model2_seq.py, unmodified) inside the pool/interpolate/add of Encoder.forward"
+            if kind == "reference" else "oracle port (oracle/fusion_ref.py)")
+    return "%s, same workload, fp32, batch %d per step, %d warm-up + %d timed steps, %d threads, %s" % (what, BATCH, warmup, steps, cores, cpu_model())
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
-    v, ms = time_cpu(steps, warmup)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    v, ms, kind = time_cpu(steps, warmup)
     cores = torch.get_num_threads()
-    sample = "oracle port (oracle/fusion_ref.py) of the same stage, fp32, batch %d per step, %d threads, %s" % (CPU_SAMPLE_BATCH, cores, cpu_model())
     print(json.dumps({
         "impl": "reference", "metric": "train samples/sec (fwd+bwd)", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample_batch": CPU_SAMPLE_BATCH},
-        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "sample": cpu_sample_note(kind, cores, steps, warmup)},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+def workload_config(world):
+    """The part of ``config`` both arms share (the driver compares them)."""
+    return {"workload": workload_name(), "global_batch": BATCH * world, "seq_len": S, "parallelism": "dp%d" % world}
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
-PDROP = 0.0  # --dropout: embd/attn/resid probability of the stage workload (the reference trains with 0.1)
-
-
-def build_gpt(device):
+def build_gpt(device, c):
     import types
     from deepsense6g_tii_b200 import GPT
     cfg = types.SimpleNamespace(n_views=V, fusion_dtype=torch.bfloat16)
     torch.manual_seed(100)  # the reference's seed (train2_seq.py:430-434)
-    m = GPT(C, NH, 4, L, A, A, S, PDROP, PDROP, PDROP, cfg)
+    m = GPT(c, NH, 4, L, A, A, S, PDROP, PDROP, PDROP, cfg)
     with torch.no_grad():
         m.pos_emb.normal_(0, 0.02)
     return m.to(device)
 
 
-def profile_families_graph(gpt, feats, gps, probes):
-    """Per-call device times INSIDE a CUDA graph: the instrumented step is captured with `external` CUDA events (event-record
-    nodes) around every C-ABI call and replayed; the events then bracket the kernels exactly as the graph-launched timed
-    region runs them (no host launch latency between a record and its kernel).  The side stream is switched off for this
-    capture so that every family is timed alone on the GPU.  Returns None when external events are unavailable."""
+class StageWork:
+    """One fusion stage of the workload: its GPT, its device-resident inputs and the pinned host copies of them."""
+
+    def __init__(self, c, scale, dev, gen, pin=True):
+        self.c, self.scale = c, scale
+        self.gpt = build_gpt(dev, c)
+        self.feats_h, self.gps_h, probes_h = synth_inputs(gen, BATCH, c, scale, pin=pin)
+        self.feats = [f.to(dev).requires_grad_(True) for f in self.feats_h]
+        self.gps = self.gps_h.to(dev).requires_grad_(True)
+        self.probes = [p.to(dev) for p in probes_h]
+
+    def step(self):
+        for p in self.gpt.parameters():
+            p.grad = None
+        for t in self.feats:
+            t.grad = None
+        self.gps.grad = None
+        outs = self.gpt.fuse(self.feats[0], self.feats[1], self.feats[2], self.gps)
+        loss = sum((o.float() * pr).sum() for o, pr in zip(outs, self.probes))
+        loss.backward()
+        return loss.detach()
+
+
+def one_step(works):
+    total = None
+    for w in works:
+        l = w.step()
+        total = l if total is None else total + l
+    return total
+
+
+def capture_step(fn, warm=3):
+    """Warm ``fn`` up on a side stream, then capture it into ONE CUDA graph (the launch sequence is static: fixed shapes, torch's
+    caching allocator keeps the captured addresses alive).  Under capture ``functional`` moves the weight-gradient GEMMs, bias
+    sums, weight packs and the dQ attention kernel to side streams (fork/join events = graph edges).  Returns
+    (graph, value returned by the captured call, dsfuse launches per replay)."""
+    from deepsense6g_tii_b200 import _capi
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warm):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    n0 = _capi.launch_count()
+    with torch.cuda.graph(graph):
+        out = fn()
+    n = _capi.launch_count() - n0
+    torch.cuda.synchronize()
+    return graph, out, n
+
+
+FAMILIES = ["tokens_fwd", "tokens_bwd", "layernorm_fwd", "layernorm_bwd", "gemm_bf16_nt", "gemm_bf16_tn", "colsum", "attn_fwd", "attn_bwd",
+            "upsample_add_fwd", "upsample_add_bwd", "pack_block_weights", "dropout_inplace"]
+
+
+def profile_families_graph(work):
+    """Per-call device times of ONE stage INSIDE a CUDA graph: the instrumented step is captured with `external` CUDA events
+    (event-record nodes) around every C-ABI call and replayed; the events bracket the kernels exactly as a graph-launched step
+    runs them (no host launch latency).  The side streams are switched off for this capture, so every call is timed as an
+    isolated launch (an event between two kernels forces a drain): per-family times are conservative and the roofline of a
+    family is taken against the BURST peak.  Returns {family: {launch_calls, ms, flops, bytes}} or None."""
     from deepsense6g_tii_b200 import _capi
     import deepsense6g_tii_b200.functional as Fn
     try:
         torch.cuda.Event(enable_timing=True, external=True)
     except TypeError:
         return None
-    names = ["tokens_fwd", "tokens_bwd", "layernorm_fwd", "layernorm_bwd", "gemm_bf16_nt", "gemm_bf16_tn", "colsum", "attn_fwd", "attn_bwd",
-             "upsample_add_fwd", "upsample_add_bwd", "pack_block_weights", "dropout_inplace"]
     rec, orig = [], {}
-    for n in names:
+    for n in FAMILIES:
+        if not hasattr(_capi, n):
+            continue
         f = getattr(_capi, n)
         orig[n] = f
 
@@ -192,37 +321,36 @@ def profile_families_graph(gpt, feats, gps, probes):
             e0.record()
             _f(*a, **k)
             e1.record()
-            shape = None
-            if _n == "gemm_bf16_nt":
-                shape = (a[0].shape[0], a[1].shape[0], a[0].shape[1])
-            elif _n == "gemm_bf16_tn":
-                shape = (a[0].shape[0], a[0].shape[1], a[1].shape[1])
-            rec.append((_n, e0, e1, shape))
+            flops = nbytes = 0.0
+            if _n == "gemm_bf16_nt":      # a (M,K) bf16, w (N,K) bf16, out (M,N) bf16|fp32 [+ fp32 residual]
+                m, kk, nn_ = a[0].shape[0], a[0].shape[1], a[1].shape[0]
+                flops = 2.0 * m * nn_ * kk
+                nbytes = 2.0 * (m * kk + nn_ * kk) + m * nn_ * a[2].element_size() + (4.0 * m * nn_ if k.get("residual") is not None else 0.0) \
+                    + (2.0 * m * nn_ if k.get("relu_src") is not None else 0.0)
+            elif _n == "gemm_bf16_tn":    # dy (M,N) bf16, x (M,K) bf16 -> dw (N,K) fp32
+                m, nn_, kk = a[0].shape[0], a[0].shape[1], a[1].shape[1]
+                flops = 2.0 * m * nn_ * kk
+                nbytes = 2.0 * (m * nn_ + m * kk) + 4.0 * nn_ * kk
+            rec.append((_n, e0, e1, flops, nbytes))
         setattr(_capi, n, wrap)
     old_env = os.environ.get("DSF_WGRAD_STREAM")
     os.environ["DSF_WGRAD_STREAM"] = "0"
     runs = []
     try:
         Fn.K = _capi
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            one_step(gpt, feats, gps, probes)
-        torch.cuda.current_stream().wait_stream(side)
+        work.step()
         torch.cuda.synchronize()
-        for p in gpt.parameters():
-            p.grad = None
         del rec[:]
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            one_step(gpt, feats, gps, probes)
+            work.step()
         for _ in range(4):
             g.replay()
             torch.cuda.synchronize()
-            runs.append([(n, e0.elapsed_time(e1), shape) for n, e0, e1, shape in rec])
+            runs.append([e0.elapsed_time(e1) for _, e0, e1, _, _ in rec])
         runs = runs[1:]
-    except Exception as ex:  # keep the bench line alive: fall back to the eager instrumentation
-        sys.stderr.write("bench.py: graph-instrumented profile failed (%s); using eager events\n" % ex)
+    except Exception as ex:  # keep the bench line alive
+        sys.stderr.write("bench.py: graph-instrumented profile failed (%s)\n" % ex)
         return None
     finally:
         for n, f in orig.items():
@@ -232,105 +360,51 @@ def profile_families_graph(gpt, feats, gps, probes):
         else:
             os.environ["DSF_WGRAD_STREAM"] = old_env
     fam = {}
-    for i, (n, _, shape) in enumerate(runs[0]):
-        d = fam.setdefault(n, {"launch_calls": 0, "ms": 0.0, "flops": 0.0})
+    for i, (n, _, _, flops, nbytes) in enumerate(rec):
+        d = fam.setdefault(n, {"launch_calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
         d["launch_calls"] += 1
-        d["ms"] += statistics.median(r[i][1] for r in runs)
-        if shape is not None:
-            d["flops"] += 2.0 * shape[0] * shape[1] * shape[2]
-    b = feats[0].shape[0] // S
-    if "attn_fwd" in fam:
-        fam["attn_fwd"]["flops"] = L * 4.0 * T * T * C * b
-    if "attn_bwd" in fam:
-        fam["attn_bwd"]["flops"] = L * 2 * 4.0 * T * T * C * b  # 2x forward (recompute not counted)
-    return fam
-
-
-def profile_families(gpt, feats, gps, probes):
-    """One instrumented fwd+bwd: CUDA events around every C-ABI call, summed per kernel family."""
-    from deepsense6g_tii_b200 import _capi
-    names = ["tokens_fwd", "tokens_bwd", "layernorm_fwd", "layernorm_bwd", "gemm_bf16_nt", "gemm_bf16_tn", "colsum", "relu_bwd",
-             "attn_fwd", "attn_bwd", "upsample_add_fwd", "upsample_add_bwd", "cast_f32_bf16", "relu_bwd_colsum",
-             "pack_block_weights"]
-    rec, orig = [], {}
-    for n in names:
-        f = getattr(_capi, n)
-        orig[n] = f
-
-        def wrap(*a, _f=f, _n=n, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _f(*a, **k)
-            e1.record()
-            shape = None
-            if _n == "gemm_bf16_nt":
-                shape = (a[0].shape[0], a[1].shape[0], a[0].shape[1])
-            elif _n == "gemm_bf16_tn":
-                shape = (a[0].shape[0], a[0].shape[1], a[1].shape[1])
-            rec.append((_n, e0, e1, shape))
-        setattr(_capi, n, wrap)
-    REPS = 3
-    runs = []
-    try:
-        import deepsense6g_tii_b200.functional as Fn
-        Fn.K = _capi
-        for _ in range(REPS):
-            del rec[:]
-            torch.cuda.synchronize()
-            # keep the GPU busy (~15 ms spin) while the host enqueues the whole instrumented step, so that the events
-            # bracket back-to-back kernel execution and not host launch latency
-            torch.cuda._sleep(30_000_000)
-            one_step(gpt, feats, gps, probes)
-            torch.cuda.synchronize()
-            runs.append([(n, e0.elapsed_time(e1), shape) for n, e0, e1, shape in rec])
-    finally:
-        for n, f in orig.items():
-            setattr(_capi, n, f)
-    fam = {}
-    for i, (n, _, shape) in enumerate(runs[0]):  # per-call median over the repetitions
-        d = fam.setdefault(n, {"launch_calls": 0, "ms": 0.0, "flops": 0.0})
-        d["launch_calls"] += 1
-        d["ms"] += statistics.median(r[i][1] for r in runs)
-        if shape is not None:
-            d["flops"] += 2.0 * shape[0] * shape[1] * shape[2]
-    b = feats[0].shape[0] // S
-    if "attn_fwd" in fam:
-        fam["attn_fwd"]["flops"] = L * 4.0 * T * T * C * b
-    if "attn_bwd" in fam:
-        fam["attn_bwd"]["flops"] = L * 2 * 4.0 * T * T * C * b  # 2x forward (recompute not counted)
-    return fam
-
-
-def hbm_family_bytes(batch):
-    """Algorithmic bytes per step of the HBM-bound kernel families (elements x dtype size, what each launch must
-    read and write once): M = batch*T token rows, E_f = feature-map elements of the three branches."""
-    M = batch * T
-    e_t = M * C
-    e_f = 3 * batch * S * C * (A * SCALE) * (A * SCALE)
-    F = 4 * C
-    per_block_w = 4 * C * C + 2 * F * C  # q, k, v, proj + mlp.0 + mlp.2 weights
-    return {
-        "tokens_fwd": e_f * 4 + e_t * 4 + T * C * 4,
-        "tokens_bwd": e_t * 4 + 2 * e_f * 4 + T * C * 4,                     # dx in; d(out) in for the residual branch, d(feat) out; dpos out
-        "layernorm_fwd": (2 * L) * e_t * (4 + 2) + e_t * (4 + 4),           # 16 x (fp32 in, bf16 out) + ln_f (fp32 out)
-        "layernorm_bwd": (2 * L) * e_t * (2 + 4 + 4 + 4 + 2) + e_t * (4 + 4 + 4 + 2),  # dy bf16, x, dx_add in; dx fp32 + bf16 copy out
-        "colsum": L * M * (F + 3 * C) * 2,                                   # bf16 dL/d(mlp.0 out) and dqkv
-        "pack_block_weights": L * per_block_w * (4 + 2 * 2),                 # fp32 in, plain + transposed bf16 out
-        "upsample_add_fwd": e_t * 4 + 2 * e_f * 4,
-        "upsample_add_bwd": e_f * 4 + e_t * 4,
+        d["ms"] += statistics.median(r[i] for r in runs)
+        d["flops"] += flops
+        d["bytes"] += nbytes
+    c, t = work.c, n_tokens()
+    m = BATCH * t
+    e_t, e_f, F = m * c, 3 * BATCH * S * c * (A * work.scale) ** 2, 4 * c
+    per_block_w = 4 * c * c + 2 * F * c
+    # algorithmic work of the non-GEMM families (elements x dtype size, each operand read / written once)
+    extra = {
+        "attn_fwd": (L * 4.0 * t * t * c * BATCH, L * (m * 3 * c * 2 + e_t * 2)),
+        "attn_bwd": (L * 8.0 * t * t * c * BATCH, L * (m * 3 * c * 2 * 2 + e_t * 2 * 2)),                 # recompute not counted
+        "tokens_fwd": (0, e_f * 4 + e_t * 4 + t * c * 4),
+        "tokens_bwd": (0, e_t * 4 + 2 * e_f * 4 + t * c * 4),
+        "layernorm_fwd": (0, (2 * L) * e_t * (4 + 2) + e_t * (4 + 4)),
+        "layernorm_bwd": (0, (2 * L) * e_t * (2 + 4 + 4 + 4 + 2) + e_t * (4 + 4 + 4 + 2)),
+        "colsum": (0, L * m * (F + 3 * c) * 2),
+        "pack_block_weights": (0, L * per_block_w * (4 + 2 * 2)),
+        "upsample_add_fwd": (0, e_t * 4 + 2 * e_f * 4),
+        "upsample_add_bwd": (0, e_f * 4 + e_t * 4),
     }
+    for k, (fl, by) in extra.items():
+        if k in fam:
+            fam[k]["flops"], fam[k]["bytes"] = float(fl), float(by)
+    return fam
 
 
-def one_step(gpt, feats, gps, probes):
-    for p in gpt.parameters():
-        p.grad = None
-    for t in feats:
-        t.grad = None
-    gps.grad = None
-    outs = gpt.fuse(feats[0], feats[1], feats[2], gps)
-    loss = sum((o.float() * pr).sum() for o, pr in zip(outs, probes))
-    loss.backward()
-    return loss
+def family_rooflines(fam, pk):
+    """Per family: achieved TFLOP/s and GB/s of the algorithmic work, and the fraction of min(TC, HBM) — roof time =
+    max(flops / burst bf16 peak, bytes / HBM copy peak) over the measured time (stage 1-2 GEMMs sit below the ridge)."""
+    out = {}
+    for k, d in fam.items():
+        ms = d["ms"]
+        if ms <= 0:
+            continue
+        t_tc = d["flops"] / (pk["tc_burst"] * 1e12) * 1e3
+        t_hbm = d["bytes"] / (pk["hbm"] * 1e9) * 1e3
+        out[k] = {"ms": round(ms, 4), "calls": d["launch_calls"],
+                  "tflops": round(d["flops"] / (ms * 1e-3) / 1e12, 1) if d["flops"] else None,
+                  "gbps": round(d["bytes"] / (ms * 1e-3) / 1e9, 1) if d["bytes"] else None,
+                  "bound": "tensor" if t_tc >= t_hbm else "hbm", "roof_ms": round(max(t_tc, t_hbm), 4),
+                  "frac_of_roof": round(max(t_tc, t_hbm) / ms, 3)}
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
@@ -341,55 +415,26 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     _capi.check_device()
     _capi.set_pdl(args.pdl)
-    sm_margin = int(os.environ.get("DSF_SM_MARGIN", "0")) if world > 1 else 0
-    _capi.set_sm_margin(sm_margin)
-    gpt = build_gpt(dev)
-    model = gpt
-    if world > 1:
-        # same initial weights on every rank; gradients all-reduced (mean) over NCCL every step
-        D.broadcast_params(gpt.parameters())
+    _capi.set_sm_margin(int(os.environ.get("DSF_SM_MARGIN", "0")) if world > 1 else 0)
     gen = torch.Generator().manual_seed(rank)  # data generator seed 0 + rank
-    feats_h, gps_h, probes_h = synth_inputs(gen, BATCH, pin=True)
-    feats = [f.to(dev).requires_grad_(True) for f in feats_h]
-    gps = gps_h.to(dev).requires_grad_(True)
-    probes = [p.to(dev) for p in probes_h]
+    works = [StageWork(c, scale, dev, gen) for c, scale in SPEC]
+    n_params = sum(p.numel() for w in works for p in w.gpt.parameters())
     if world > 1:
-        # gradients are averaged bucket-by-bucket (one bucket per transformer block) while backward is still running
-        gpt.set_grad_reducer(D.OverlappedGradReducer())
-
-    def allreduce_grads():
-        pass  # done inside backward by the overlapped reducer
+        for w in works:
+            D.broadcast_params(w.gpt.parameters())   # same initial weights on every rank
+            # gradients are averaged bucket-by-bucket (one bucket per transformer block) while backward is still running
+            w.gpt.set_grad_reducer(D.OverlappedGradReducer())
 
     def step_eager():
-        loss = one_step(model, feats, gps, probes)
-        allreduce_grads()
-        return loss
+        return one_step(works)
 
     loss_h = torch.empty((), pin_memory=True)
-
-    # The whole fwd+bwd step (~190 kernel launches through the C ABI) is captured ONCE into a CUDA graph and replayed:
-    # the launch sequence is static (fixed shapes, torch's caching allocator keeps the captured addresses alive), so
-    # replay removes the per-launch host cost and the launch gaps between dependent kernels.
-    graph, graph_launches, graph_note = None, 0, "eager launches"
-    pdl_note = ", programmatic dependent launch on" if args.pdl else ", programmatic dependent launch off"
+    graph, graph_loss, graph_launches, graph_note = None, None, 0, "eager launches"
+    pdl_note = ", programmatic dependent launch " + ("on" if args.pdl else "off")
     # (N > 1: the bucketed NCCL all-reduces issued from inside the backward are captured too; DSF_GRAPH_DDP=0 opts out)
-    use_graph = args.graph and (world == 1 or os.environ.get("DSF_GRAPH_DDP", "1") == "1")
-    if use_graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                step_eager()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        for p in gpt.parameters():
-            p.grad = None
-        graph = torch.cuda.CUDAGraph()
-        n0 = _capi.launch_count()
+    if args.graph and (world == 1 or os.environ.get("DSF_GRAPH_DDP", "1") == "1"):
         try:
-            with torch.cuda.graph(graph):
-                graph_loss = step_eager()
-            graph_launches = _capi.launch_count() - n0
+            graph, graph_loss, graph_launches = capture_step(step_eager)
             graph_note = "whole step captured in one CUDA graph (%d dsfuse kernels per replay)" % graph_launches
         except Exception as ex:  # e.g. a collective that cannot be captured: keep the bench line alive with eager launches
             sys.stderr.write("bench.py: CUDA-graph capture failed on rank %d (%s); falling back to eager launches\n" % (rank, ex))
@@ -407,12 +452,13 @@ def run_ours(args, rank, world, local_rank):
         else:
             step_eager()
 
-    # e2e pipeline: every step copies ONE batch of inputs pinned-host -> device (23.6 MB) and reads the loss back.  The
-    # copy of step k+1's batch runs on a copy stream into a double-buffered staging area while step k computes (what a
-    # training data loader with pinned-memory prefetch does); the compute stream then moves the staged batch into the
-    # step's input tensors (device-to-device, ~10 us) and runs the step.
+    # e2e pipeline: every step copies ONE batch of inputs (all stages' feature maps + GPS embeddings) pinned-host -> device and
+    # reads the loss back.  The copy of step k+1's batch runs on a copy stream into a double-buffered staging area while step k
+    # computes (what a training data loader with pinned-memory prefetch does); the compute stream then moves the staged batch
+    # into the step's input tensors (device-to-device) and runs the step.
     copy_stream = torch.cuda.Stream()
-    host_in = feats_h + [gps_h]
+    host_in = [t for w in works for t in w.feats_h + [w.gps_h]]
+    dev_in = [t for w in works for t in w.feats + [w.gps]]
     stage = [[torch.empty_like(t, device=dev) for t in host_in] for _ in range(2)]
     ev_ready = [torch.cuda.Event() for _ in range(2)]  # batch landed in stage[i]
     ev_free = [torch.cuda.Event() for _ in range(2)]   # the compute stream has consumed stage[i]
@@ -433,16 +479,16 @@ def run_ours(args, rank, world, local_rank):
         cur = torch.cuda.current_stream()
         cur.wait_event(ev_ready[i])
         with torch.no_grad():
-            for d, st_ in zip(feats + [gps], stage[i]):
+            for d, st_ in zip(dev_in, stage[i]):
                 d.copy_(st_, non_blocking=True)
         ev_free[i].record(cur)
         prefetch(i ^ 1)  # next step's batch: overlaps this step's compute
         e2e_k[0] += 1
         if graph is not None:
             graph.replay()
-            loss_h.copy_(graph_loss.detach(), non_blocking=True)
+            loss_h.copy_(graph_loss, non_blocking=True)
         else:
-            loss_h.copy_(step_eager().detach(), non_blocking=True)
+            loss_h.copy_(step_eager(), non_blocking=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -489,68 +535,128 @@ def run_ours(args, rank, world, local_rank):
     # the K-th prefetch issued inside the region must also complete inside it: K steps <-> K host-to-device batch copies
     ms_e2e, _, _ = timed(step_e2e, steps, 2, finalize=lambda: torch.cuda.current_stream().wait_event(ev_ready[e2e_k[0] & 1]))
     e2e_value = BATCH * world * steps / (ms_e2e * 1e-3)
+    # sustained behaviour: the same step replayed back to back for >= 2 s (clocks drop under sustained tensor load)
+    sustained = None
+    if args.sustained > 0:
+        n_s = max(steps, int(args.sustained * 1e3 / (ms / steps)))
+        smp = ClockSampler(local_rank) if rank == 0 else None
+        ms_s, _, clk_s = timed(step_resident, n_s, 1, smp)
+        sustained = {"seconds": round(ms_s * 1e-3, 2), "steps": n_s, "ms_per_step": ms_s / n_s, "value": BATCH * world * n_s / (ms_s * 1e-3), "clocks": clk_s}
 
     synced = None
     if world > 1:  # the replayed / eager steps really exchanged gradients: every rank holds the same averaged pos_emb gradient
-        g = gpt.pos_emb.grad.detach().reshape(-1)[:4096].contiguous()
+        g = works[-1].gpt.pos_emb.grad.detach().reshape(-1)[:4096].contiguous()
         gs = [torch.empty_like(g) for _ in range(world)]
         dist.all_gather(gs, g)
         synced = all(torch.equal(gs[0], t) for t in gs[1:]) and bool(torch.isfinite(g).all()) and float(g.abs().sum()) > 0
     if rank != 0:
         return
     pk = peaks()
-    gpt.set_grad_reducer(None)  # the instrumented step runs on rank 0 only: no collectives in it
-    fam = profile_families_graph(gpt, feats, gps, probes) if graph is not None else None
-    how = "external CUDA events captured around every kernel of a graph-replayed step (median of 3 replays, side stream off)"
-    if fam is None:
-        fam = profile_families(gpt, feats, gps, probes)
-        how = "CUDA events around every kernel of an eager step (median of 3; adds ~3 us per call)"
-    total_ms = sum(d["ms"] for d in fam.values())
-    tc = {k: d for k, d in fam.items() if d["flops"] > 0}
-    dom = max(tc, key=lambda k: tc[k]["ms"])
-    achieved = tc[dom]["flops"] / (tc[dom]["ms"] * 1e-3) / 1e12
-    traffic, traffic_src = None, None
-    import glob
-    tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))  # newest committed capture (tags sort by round)
-    tp = tps[-1] if tps else ""
-    if dom == "gemm_bf16_nt" and os.path.isfile(tp):  # dram bytes per launch of the dominant kernel, from the committed ncu capture
-        tj = json.load(open(tp))
-        traffic, traffic_src = tj["avg_dram_bytes_per_launch"], tj["source"]
-    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tc_sust"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tc_sust"], "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": pk["src"] + " bf16_tflops_sustained",
-                "launches_per_step": tc[dom]["launch_calls"], "avg_launch_ms": tc[dom]["ms"] / tc[dom]["launch_calls"],
-                "share_of_step": tc[dom]["ms"] / total_ms, "timing": how,
-                "families": {k: {"ms": round(d["ms"], 4), "calls": d["launch_calls"],
-                                 "tflops": (d["flops"] / (d["ms"] * 1e-3) / 1e12) if d["flops"] else None} for k, d in fam.items()}}
-    try:  # HBM-bound families: algorithmic GB/s against the measured copy bandwidth (launch-bound at 10-25 us per launch)
-        hb = hbm_family_bytes(feats[0].shape[0] // S)
-        for k, d in roofline["families"].items():
-            if k in hb and d["ms"] > 0:
-                d["gbps"] = round(hb[k] / (d["ms"] * 1e-3) / 1e9, 1)
-                d["frac_of_hbm_peak"] = round(d["gbps"] / pk["hbm"], 3)
-        roofline["hbm_peak_gbps"] = pk["hbm"]
-    except Exception as ex:  # never lose the bench line over a diagnostic
-        sys.stderr.write("bench.py: HBM family roofline skipped (%s)\n" % ex)
-    cpu_v, cpu_ms = time_cpu(2, 1)
+    for w in works:
+        w.gpt.set_grad_reducer(None)  # everything below runs on rank 0 only: no collectives in it
+    # ---- per stage: graph-replayed time of the stage alone + instrumented per-family times
+    stages = {}
+    for w in works:
+        rec = {"n_embd": w.c, "feature_map": A * w.scale, "flops_per_step": 3.0 * fwd_flops_per_sample(w.c) * BATCH}
+        try:
+            g_s, _, n_s = capture_step(w.step, warm=1)
+            for _ in range(3):
+                g_s.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                g_s.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            rec["ms_per_step"] = e0.elapsed_time(e1) / steps
+            rec["samples_per_s"] = BATCH / (rec["ms_per_step"] * 1e-3)
+            rec["tflops"] = rec["flops_per_step"] / (rec["ms_per_step"] * 1e-3) / 1e12
+            rec["dsfuse_launches"] = n_s
+            del g_s
+        except Exception as ex:
+            sys.stderr.write("bench.py: per-stage graph of C=%d failed (%s)\n" % (w.c, ex))
+        fam = profile_families_graph(w)
+        if fam:
+            fr = family_rooflines(fam, pk)
+            rec["families"] = fr
+            rec["sum_family_ms"] = round(sum(d["ms"] for d in fr.values()), 4)
+            rec["roof_ms"] = round(sum(d["roof_ms"] for d in fr.values()), 4)
+            if "ms_per_step" in rec:
+                rec["frac_of_roof"] = round(rec["roof_ms"] / rec["ms_per_step"], 3)   # min(TC, HBM) roof of the stage / its measured time
+        stages["C%d" % w.c] = rec
+    # ---- headline roofline: the dominant tensor-core family of the whole workload
+    tot = {}
+    for rec in stages.values():
+        for k, d in rec.get("families", {}).items():
+            t = tot.setdefault(k, {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
+            t["ms"] += d["ms"]; t["calls"] += d["calls"]
+            t["flops"] += (d["tflops"] or 0.0) * 1e12 * d["ms"] * 1e-3
+            t["bytes"] += (d["gbps"] or 0.0) * 1e9 * d["ms"] * 1e-3
+    roofline = None
+    if tot:
+        total_ms = sum(d["ms"] for d in tot.values())
+        tcf = {k: d for k, d in tot.items() if d["flops"] > 0}
+        dom = max(tcf, key=lambda k: tcf[k]["ms"])
+        achieved = tcf[dom]["flops"] / (tcf[dom]["ms"] * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        import glob
+        for tp in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+            tj = json.load(open(tp))
+            if tj.get("family", "gemm_bf16_nt") == dom:
+                traffic, traffic_src = tj["avg_dram_bytes_per_launch"], tj["source"]
+                break
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tc_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tc_burst"],
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": pk["src"] + " bf16_tflops (burst: every family is timed as isolated launches)",
+                    "launches_per_step": tcf[dom]["calls"], "avg_launch_ms": tcf[dom]["ms"] / tcf[dom]["calls"], "share_of_step": tcf[dom]["ms"] / total_ms,
+                    "timing": "external CUDA events captured around every kernel of a graph-replayed step, stage by stage (median of 3 replays, side streams off)",
+                    "families": {k: {"ms": round(d["ms"], 4), "calls": d["calls"], "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1) if d["flops"] else None,
+                                     "gbps": round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1) if d["bytes"] else None} for k, d in tot.items()},
+                    "hbm_peak_gbps": pk["hbm"], "tc_peak_sustained": pk["tc_sust"]}
+    # ---- baselines
+    gpu_base = None
+    if args.gpu_baseline:
+        try:
+            gstep, gkind = reference_step_fn(dev, BATCH, autocast=True)
+            for _ in range(2):
+                gstep()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                gstep()
+            e1.record()
+            torch.cuda.synchronize()
+            gms = e0.elapsed_time(e1) / 5
+            gpu_base = {"value": BATCH / (gms * 1e-3), "unit": "samples/s", "ms_per_step": gms, "kind": gkind,
+                        "what": "stock PyTorch eager, torch.autocast(bf16), same workload and batch on the same GPU (cuBLAS / ATen kernels; 2 warm-up + 5 timed steps)"}
+            del gstep
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            sys.stderr.write("bench.py: gpu_baseline skipped (%s)\n" % ex)
+    cpu_v, cpu_ms, cpu_kind = time_cpu(2, 1)
     cores = torch.get_num_threads()
-    h2d = sum(t.numel() * t.element_size() for t in feats_h) + gps_h.numel() * gps_h.element_size()
-    step_flops = 3.0 * FWD_FLOPS_PER_SAMPLE * BATCH
+    h2d = sum(t.numel() * t.element_size() for t in host_in)
+    step_flops = sum(3.0 * fwd_flops_per_sample(c) * BATCH for c, _ in SPEC)
+    cfg = workload_config(world)
+    cfg.update({"launch": graph_note + pdl_note, "dropout": PDROP, "gpt_parameters": n_params,
+                "l2": "per-step working set (saved activations of 8 blocks per stage, > 1 GB) > 126 MB L2; no explicit flush",
+                "grad_allreduce": ("NCCL all-reduce (avg) of %.1f M fp32 grads per step, one bucket per transformer block, overlapped with backward" % (n_params / 1e6)) if world > 1 else "none (1 GPU)",
+                "grads_identical_across_ranks": synced})
     out = {
         "metric": "train samples/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "seq_len": S, "parallelism": "dp%d" % world,
-                   "launch": graph_note + pdl_note, "dropout": PDROP,
-                   "l2": "per-step working set ~1.5 GB of saved activations > 126 MB L2; no explicit flush",
-                   "grad_allreduce": "NCCL all-reduce (avg) of 25.7 M fp32 grads per step, one bucket per block, overlapped with backward" if world > 1 else "none (1 GPU)",
-                   "grads_identical_across_ranks": synced},
-        "stage_tflops": step_flops * world / (ms / steps * 1e-3) / 1e12,
+        "config": cfg, "path_tflops": step_flops * world / (ms / steps * 1e-3) / 1e12,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps,
                 "pipeline": "one pinned-host -> device batch copy per step on a copy stream (double-buffered), overlapped with the previous step's compute; loss read back every step"},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-        "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": "oracle port fp32, batch %d, 1 warm-up + 2 timed steps, %s" % (CPU_SAMPLE_BATCH, cpu_model())},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "stages": stages,
+        "stage4": stages.get("C512"), "sustained": sustained, "gpu_baseline": gpu_base,
+        "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": cpu_kind, "sample": cpu_sample_note(cpu_kind, cores, 2, 1)},
     }
+    if "C512" in stages and len(SPEC) > 1:
+        out["stage4"] = dict(stages["C512"], note="BASELINE.json configs[1] (the n_embd 512 stage alone), same run")
+        out["stage4"].pop("families", None)
     print(json.dumps(out))
 
 
@@ -599,20 +705,9 @@ def run_model(args, rank, world, local_rank):
     # AdamW, multi-tensor EMA) is captured in one CUDA graph on static input tensors and replayed.
     graph, graph_loss, launch_note, graph_launches = None, None, "eager launches", 0
     if use_graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                step_eager()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        n0 = _capi.launch_count()
         try:
-            with torch.cuda.graph(graph):
-                graph_loss = step_eager()
-            launch_note = "whole training step captured in one CUDA graph (%d dsfuse kernels per replay)" % (_capi.launch_count() - n0)
-            graph_launches = _capi.launch_count() - n0
+            graph, graph_loss, graph_launches = capture_step(step_eager)
+            launch_note = "whole training step captured in one CUDA graph (%d dsfuse kernels per replay)" % graph_launches
         except Exception as ex:
             sys.stderr.write("bench.py: CUDA-graph capture of the model step failed (%s); eager launches\n" % ex)
             graph = None
@@ -713,7 +808,7 @@ def run_model(args, rank, world, local_rank):
                                "4 fusion stages on dsfuse kernels" % n_params,
                    "global_batch": BATCH * world, "seq_len": S, "parallelism": "dp%d" % world, "launch": launch_note + ", PDL " + ("on" if args.pdl else "off"),
                    "l2": "per-step working set (activations of 3 ResNets + 4 fusion stages) >> 126 MB L2; no explicit flush",
-                   "grad_allreduce": "torch DistributedDataParallel (NCCL, bucketed, overlapped)" if world > 1 else "none (1 GPU)"},
+                   "grad_allreduce": "torch DistributedDataParallel (NCCL, bucketed, overlapped) of %.1f M fp32 gradients" % (n_params / 1e6) if world > 1 else "none (1 GPU)"},
         "e2e": {"value": BATCH * world * steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / steps, "pipeline": "next batch copied pinned-host -> device on a copy stream during the current step"},
         "gpu_launches": launches, "clocks": clocks, "final_loss": loss_val,
@@ -727,24 +822,26 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--workload", default="stage", choices=["stage", "model"],
-                    help="stage = BASELINE.json configs[1] (default, the driver's line); model = configs[2], the full training step")
-    ap.add_argument("--quick", action="store_true", help="profiling runs: skip the e2e leg, the instrumented step and the CPU baseline")
+    ap.add_argument("--workload", default="fusion4", choices=["fusion4", "stage4", "stage", "model"],
+                    help="fusion4 = the four fusion stages back to back (default: the whole hot path); stage4 = BASELINE.json configs[1], the "
+                         "n_embd 512 stage alone ('stage' is an alias); model = configs[2], the full training step")
+    ap.add_argument("--stage", type=int, default=0, choices=[0, 1, 2, 3, 4], help="bench ONE fusion stage (1-4) alone")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: skip the e2e leg, the instrumented steps and the baselines")
     ap.add_argument("--no-pdl", dest="pdl", action="store_false", help="disable programmatic dependent launch of the hot kernels")
+    ap.add_argument("--no-gpu-baseline", dest="gpu_baseline", action="store_false", help="skip the stock-PyTorch-autocast leg on the GPU")
+    ap.add_argument("--sustained", type=float, default=2.0, help="seconds of back-to-back replays for the `sustained` sub-record (0 = skip)")
     ap.add_argument("--dropout", type=float, default=0.0,
-                    help="stage workload: embd/attn/resid dropout probability (default 0 = the parity configuration; the reference trains with 0.1)")
+                    help="embd/attn/resid dropout probability (default 0 = the parity configuration; the reference trains with 0.1)")
     ap.add_argument("--anchors", type=int, default=8, choices=[8, 16],
-                    help="16 = BASELINE.json configs[4], the scaled fusion stage: 16x16 anchors -> T = 3842 tokens (not the driver's line)")
+                    help="16 = BASELINE.json configs[4], the scaled fusion path: 512x512 inputs, 16x16 anchors -> T = 3842 tokens")
     args = ap.parse_args()
-    if args.dropout > 0:
-        global PDROP
-        PDROP = args.dropout
-    if args.anchors != 8:
-        global A, T, WORKLOAD, FWD_FLOPS_PER_SAMPLE
-        A = args.anchors
-        T = (V + 2) * S * A * A + 2
-        WORKLOAD = "gpt_fusion_stage n_embd=512 n_layer=8 n_head=4 anchors=%dx%d seq_len=5 T=%d batch=12/GPU fwd+bwd (scaled config)" % (A, A, T)
-        FWD_FLOPS_PER_SAMPLE = L * (24.0 * T * C * C + 4.0 * T * T * C)
+    global PDROP, A, SPEC
+    PDROP = args.dropout
+    A = args.anchors
+    if args.stage:
+        SPEC = (STAGES4[args.stage - 1],)
+    elif args.workload in ("stage4", "stage"):
+        SPEC = (STAGES4[3],)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -223,7 +223,8 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 template <int HS, int BKV>
 int launch_attn_fwd(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st) {
   using L = AttnFwdSmem<HS, BKV>;
-  static bool configured = false;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
   if (!configured) {
     if (cudaFuncSetAttribute(attn_fwd_kernel<HS, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("attn_fwd/attr");
@@ -564,7 +565,8 @@ int launch_attn_bwd(const void* qkv, const void* y, const void* dy, const float*
                     int nh, cudaStream_t st) {
   using LA = AttnBwdKVSmem<HS, BQ>;
   using LB = AttnBwdQSmem<HS>;
-  static bool configured = false;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
   if (!configured) {
     if (cudaFuncSetAttribute(attn_bwd_kv_kernel<HS, BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
         cudaFuncSetAttribute(attn_bwd_q_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)

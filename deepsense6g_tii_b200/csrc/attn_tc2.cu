@@ -1347,7 +1347,8 @@ template <int HS, int BKV, int ST>
 static int launch_fwd2(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st) {
   using L = Fwd2<HS, BKV, ST>;
   using H = HeadCfg<HS>;
-  static bool configured = false;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
   if (!configured) {
     if (cudaFuncSetAttribute(attn_fwd2_kernel<HS, BKV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("attn_fwd2/attr");
@@ -1371,7 +1372,8 @@ static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C
   using L = Fwd3<HS, KST, VST, NWG, PT>;
   using H = HeadCfg<HS>;
   constexpr bool PPOK = PT && NWG == 2;
-  static bool configured = false;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
   if (!configured) {
     if (cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, PT, false, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess ||
         cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, PT, PPOK, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
@@ -1407,7 +1409,8 @@ template <int HS, int KST, int VST>
 static int launch_fwd5(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const AttnDrop& ad, cudaStream_t st) {
   using L = Fwd5<HS, KST, VST>;
   using H = HeadCfg<HS>;
-  static bool configured = false;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
   if (!configured) {
     if (cudaFuncSetAttribute(attn_fwd5_kernel<HS, KST, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("attn_fwd5/attr");
@@ -1432,7 +1435,8 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   using LA = BwdKV2<HS, BQ, STA>;
   using LB = BwdQ2<HS, STB>;
   using H = HeadCfg<HS>;
-  static bool configured = false;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
   if (!configured) {
     if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
         cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||

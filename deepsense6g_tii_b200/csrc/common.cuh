@@ -26,6 +26,14 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int num_sms();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device (per-context) setting: a kernel's launcher keeps one
+// "configured" flag per device, so a process that drives several GPUs (nn.DataParallel threads, cuda:1 without
+// set_device(0)) configures the kernel on each of them.  Flags are only ever set (benign if two threads race).
+inline bool& per_device_flag(bool (&flags)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return flags[dev & 63];
+}
 
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // The hot kernels of the bf16 path are launched with cudaLaunchAttributeProgrammaticStreamSerialization: every kernel

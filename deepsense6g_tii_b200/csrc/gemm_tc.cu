@@ -296,7 +296,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 template <int BN, int STAGES>
 int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiArgs& epi, int M, int N, int K, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
-  static bool configured = false;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_bf16_nt_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("gemm_bf16_nt/attr");
@@ -310,7 +311,8 @@ int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiArgs& epi
 template <int BN, int STAGES>
 int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
-  static bool configured = false;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("gemm_bf16_tn/attr");

@@ -977,7 +977,8 @@ template <int BN, int STAGES>
 static int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const EpiArgs2& epi, int M, int N, int K,
                       cudaStream_t st) {
   using L = G2Smem<BN, STAGES>;
-  static bool configured = false;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_nt2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("gemm_nt2/attr");
@@ -992,7 +993,8 @@ static int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
 template <int BN, int STAGES>
 static int launch_tn2(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st) {
   using L = G2Smem<BN, STAGES, false>;
-  static bool configured = false;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_tn2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("gemm_tn2/attr");
@@ -1025,7 +1027,8 @@ template <int BN, int STAGES, bool RTMA = false>
 static int launch_nt3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const EpiArgs2& epi, int M, int N, int K,
                       cudaStream_t st, const void* Bptr = nullptr, int ldb = 0) {
   using L = G3Smem<BN, STAGES, RTMA>;
-  static bool configured = false;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_nt3_kernel<BN, STAGES, RTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("gemm_nt3/attr");
@@ -1139,7 +1142,8 @@ int gemm_nt_ln(const void* A, int lda, const void* B, int ldb, float* C, int ldc
                cudaStream_t st) {
   constexpr int STAGES = 5;
   using L = G3LnSmem<STAGES>;
-  static bool configured = false;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_nt3_ln_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("gemm_nt3_ln/attr");

@@ -28,6 +28,7 @@ import math
 import os
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _capi as K
 from ._capi import EPI_ACCUM, EPI_BIAS, EPI_RELU, EPI_RESIDUAL, GemmF32Desc
@@ -86,6 +87,7 @@ class _Runner:
         self.act = torch.bfloat16 if self.bf16 else torch.float32
         self.grad_hook = None  # optional dist.OverlappedGradReducer (bf16 path)
         self.dropout = None    # cfg["dropout"] dict (bf16 path)
+        self.capture = None    # cfg["capture"] dict: receives the mlp.0 outputs ("relu.{i}", the ReLU decisions) of every block
         if self.bf16:
             if C % 64 != 0 or self.hs not in (16, 32, 64, 128):
                 raise RuntimeError("bf16 tensor-core mode needs n_embd %% 64 == 0 and head size in {16,32,64,128}; "
@@ -222,6 +224,8 @@ class _Runner:
             st.h2 = torch.empty(M, C, device=dev, dtype=self.act)
             K.layernorm_fwd(x_mid, ln2w, ln2b, st.h2, st.mean2, st.rstd2)
             st.a = self._linear_fwd(st.h2, w1, b1, self.act, relu=True, w_shadow=sh.w1)
+            if self.capture is not None:
+                self.capture["relu.%d" % i] = st.a
             x = self._linear_fwd(st.a, w2, b2, f32, residual=x_mid, w_shadow=sh.w2)
             saved.layers.append(st)
         saved.x_last = x
@@ -339,6 +343,8 @@ class _Runner:
                 K.layernorm_fwd(st.x_mid, ln2w, ln2b, st.h2, st.mean2, st.rstd2)
             st.a = torch.empty(M, F, device=dev, dtype=bf)
             K.gemm_bf16_nt(st.h2, st.w1, st.a, bias=b1, relu=True)
+            if self.capture is not None:
+                self.capture["relu.%d" % i] = st.a
             x = torch.empty(M, C, device=dev, dtype=f32)
             if fuse_ln and i + 1 < L:  # mlp.2 + residual + the NEXT block's ln1
                 h1n = torch.empty(M, C, device=dev, dtype=bf)
@@ -693,10 +699,21 @@ class FusionStageFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, img, lidar, radar, gps_emb, *params):
-        K.check_device()
         for t, n in ((img, "image features"), (lidar, "lidar features"), (radar, "radar features")):
             if not t.is_cuda:
                 raise RuntimeError("%s must be CUDA tensors (the fusion stage has no CPU path)" % n)
+        # Every launch goes to the CURRENT device's stream with raw pointers: all operands must live on one device, and that
+        # device is made current for the whole call (tensors on cuda:1 while cuda:0 is current — nn.DataParallel replicas,
+        # TransFuser(cfg, 'cuda:1') without set_device — would otherwise fault instead of raising).
+        for t in (lidar, radar, gps_emb) + tuple(params):
+            if t.device != img.device:
+                raise RuntimeError("fusion stage: all inputs and parameters must be on %s, found a tensor on %s" % (img.device, t.device))
+        with torch.cuda.device(img.device):
+            return FusionStageFn._forward(ctx, cfg, img, lidar, radar, gps_emb, *params)
+
+    @staticmethod
+    def _forward(ctx, cfg, img, lidar, radar, gps_emb, *params):
+        K.check_device()
         layout = _layout_of(img)
         if _layout_of(lidar) != layout or _layout_of(radar) != layout:
             lidar = lidar.contiguous(memory_format=torch.channels_last if layout == K.DSF_NHWC else torch.contiguous_format)
@@ -718,6 +735,7 @@ class FusionStageFn(torch.autograd.Function):
         residual = bool(cfg.get("residual", True))
         r.grad_hook = cfg.get("grad_hook")
         r.dropout = cfg.get("dropout")
+        r.capture = cfg.get("capture")
         if r.dropout is not None and any(float(r.dropout.get(k, 0.0)) > 0.0 for k in ("embd", "attn", "resid")):
             if not r.bf16:
                 raise NotImplementedError("dropout is implemented in the bf16 tensor-core mode only (the fp32 mode is the "
@@ -726,12 +744,27 @@ class FusionStageFn(torch.autograd.Function):
             r.dropout = None
         outs, gps_out, saved = r.forward([img.detach(), lidar.detach(), radar.detach()], gps_emb.detach(), plist, residual)
         ctx.runner, ctx.saved_state, ctx.plist, ctx.residual = r, saved, plist, residual
+        ctx.device = img.device
+        ctx.param_versions = [p._version for p in params]
+        ctx.params_ref = params
         ctx.feat_mf = torch.channels_last if layout == K.DSF_NHWC else torch.contiguous_format
         ctx.gps_dtype = gps_emb.dtype
         return outs[0], outs[1], outs[2], gps_out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, d_img, d_lidar, d_radar, d_gps):
+        if ctx.saved_state is None:
+            raise RuntimeError("fusion stage: backward called a second time — the saved activations are released block by block "
+                               "during the first backward (retain_graph is not supported; call forward again)")
+        if any(p._version != v for p, v in zip(ctx.params_ref, ctx.param_versions)):
+            raise RuntimeError("fusion stage: a GPT parameter was modified in place between forward and backward (the bf16 weight "
+                               "shadows saved by the forward would no longer match the parameters)")
+        with torch.cuda.device(ctx.device):
+            return FusionStageFn._backward(ctx, d_img, d_lidar, d_radar, d_gps)
+
+    @staticmethod
+    def _backward(ctx, d_img, d_lidar, d_radar, d_gps):
         r = ctx.runner
         mf = ctx.feat_mf
 
@@ -747,5 +780,7 @@ class FusionStageFn(torch.autograd.Function):
 
 
 def fusion_stage(cfg, img, lidar, radar, gps_emb, params):
-    """cfg: dict(seq_len, n_views, vert_anchors, horz_anchors, n_head, n_layer, compute_dtype[, residual])."""
+    """cfg: dict(seq_len, n_views, vert_anchors, horz_anchors, n_head, n_layer, compute_dtype[, residual][, dropout][, grad_hook]
+    [, capture]).  ``capture`` (a dict, diagnostics / tests) receives ``relu.{i}``: the (B*T, 4C) mlp.0 output of block i, whose
+    sign pattern is the set of ReLU decisions this evaluation took (see tests/tools/bf16_error_model.py)."""
     return FusionStageFn.apply(cfg, img, lidar, radar, gps_emb, *params)

@@ -99,13 +99,17 @@ def self_attention(x: Tensor, p: Dict[str, Tensor], prefix: str, n_head: int, at
 
 def block(x: Tensor, p: Dict[str, Tensor], i: int, n_head: int, masks: Dict[str, Tensor] = None) -> Tensor:
     """``Block.forward`` (model2_seq.py:128-134): pre-LN attention and ReLU MLP, both residual.
-    ``masks``: optional dropout masks ``attn.{i}`` (B,nh,T,T), ``proj.{i}``, ``mlp.{i}`` (B,T,C)."""
+    ``masks``: optional dropout masks ``attn.{i}`` (B,nh,T,T), ``proj.{i}``, ``mlp.{i}`` (B,T,C).
+    ``relu.{i}`` (B,T,4C) of 0/1, if present, replaces ``nn.ReLU`` (:123) by a multiplication with THAT decision pattern:
+    where it equals ``z > 0`` this is ReLU itself; tests use it to evaluate the reference math with the decisions another
+    evaluation took (pre-activations within rounding distance of 0 may land on either side)."""
     pre = "blocks.%d." % i
     m = masks or {}
     x = x + self_attention(layer_norm(x, p[pre + "ln1.weight"], p[pre + "ln1.bias"]), p, pre + "attn.", n_head,
                            m.get("attn.%d" % i), m.get("proj.%d" % i))
     h = layer_norm(x, p[pre + "ln2.weight"], p[pre + "ln2.bias"])
-    h = torch.relu(linear(h, p[pre + "mlp.0.weight"], p[pre + "mlp.0.bias"]))
+    h = linear(h, p[pre + "mlp.0.weight"], p[pre + "mlp.0.bias"])
+    h = torch.relu(h) if ("relu.%d" % i) not in m else h * m["relu.%d" % i]
     h = linear(h, p[pre + "mlp.2.weight"], p[pre + "mlp.2.bias"])
     if ("mlp.%d" % i) in m:  # nn.Dropout(resid_pdrop), model2_seq.py:125
         h = h * m["mlp.%d" % i]

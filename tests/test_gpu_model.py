@@ -91,6 +91,44 @@ def test_transfuser_forward_backward_vs_oracle(cuda_dev, mode):
     assert rel_err(out.float(), ref) <= max(tol / 4, 1.5 * rel_err(cal.float(), ref)), "logits no worse than the stock path"
 
 
+def test_top1_beam_agreement_over_64_samples(cuda_dev):
+    """north_star: top-1 beam-index agreement on the logits.  4 model seeds x 16 samples = 64 samples, bf16 fusion stages against the
+    float64 oracle model (shared weights, train-mode BatchNorm statistics of the same batch, dropout 0).  Random-init logits can
+    be nearly tied, so the check is margin-aware: a sample whose float64 top-1 / top-2 margin exceeds twice the largest logit
+    error of that sample MUST agree; the others are counted and reported."""
+    import copy
+    from deepsense6g_tii_b200 import TransFuser
+    n_agree = n_total = n_decided = 0
+    worst_rel, min_margin, worst_err = 0.0, 1e30, 0.0
+    for seed in (100, 101, 102, 103):
+        torch.manual_seed(seed)
+        m = TransFuser(_cfg(torch.bfloat16), cuda_dev).train()
+        with torch.no_grad():
+            for k in (1, 2, 3, 4):
+                getattr(m.encoder, "transformer%d" % k).pos_emb.normal_(0, 0.02)
+        m64 = copy.deepcopy(m).double()
+        for chunk in range(2):
+            ins = _inputs(8, cuda_dev, seed=seed * 10 + chunk)
+            with torch.no_grad():
+                out = m(*ins).double()
+                ins64 = ([t.double() for t in ins[0]], [t.double() for t in ins[1]], [t.double() for t in ins[2]], ins[3].double())
+                ref = model_ref.transfuser_forward(m64, *ins64)
+            top2 = ref.topk(2, dim=-1).values
+            margin = top2[:, 0] - top2[:, 1]
+            err = (out - ref).abs().amax(dim=-1)
+            agree = out.argmax(-1) == ref.argmax(-1)
+            decided = margin > 2 * err
+            assert bool(agree[decided].all()), "top-1 differs on a sample whose margin exceeds twice the logit error"
+            n_agree += int(agree.sum()); n_total += agree.numel(); n_decided += int(decided.sum())
+            worst_rel = max(worst_rel, rel_err(out, ref)); min_margin = min(min_margin, float(margin.min())); worst_err = max(worst_err, float(err.max()))
+        del m, m64
+        torch.cuda.empty_cache()
+    print("top-1 agreement %d / %d samples (%d with margin > 2 x logit error); worst logits rel. error %.2e, max |logit error| %.2e, "
+          "smallest top-1/top-2 margin %.2e" % (n_agree, n_total, n_decided, worst_rel, worst_err, min_margin))
+    assert n_total >= 64 and worst_rel <= 2e-2
+    assert n_agree >= n_decided and n_agree >= int(0.9 * n_total)
+
+
 def test_channels_last_trunks_use_nhwc_kernels(cuda_dev):
     """Trunks in channels_last hand NHWC storage to the fusion stage; results equal the NCHW run."""
     m = _build(cuda_dev, torch.float32, n_layer=2).eval()
