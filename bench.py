@@ -183,9 +183,8 @@ def reference_step_fn(device, batch, autocast=False):
                 t.grad = None
             with torch.autocast(dev.type, dtype=torch.bfloat16, enabled=autocast):
                 outs = fwd()
-            loss = sum((o.float() * pr).sum() for o, pr in zip(outs, probes))
-            loss.backward()
-            total = total + loss.detach()
+            torch.autograd.backward(outs, [pr.to(o.dtype) for o, pr in zip(outs, probes)])   # probes = upstream gradients, as in the GPU arm
+            total = total + outs[3].detach().float().sum()
         return total
     return step, ("reference" if ref is not None else "port")
 
@@ -243,9 +242,16 @@ def build_gpt(device, c):
 class StageWork:
     """One fusion stage of the workload: its GPT, its device-resident inputs and the pinned host copies of them."""
 
-    def __init__(self, c, scale, dev, gen, pin=True):
+    def __init__(self, c, scale, dev, gen, pin=True, optimizer=False):
         self.c, self.scale = c, scale
         self.gpt = build_gpt(dev, c)
+        self.opt = self.ema = None
+        if optimizer:   # --optimizer: AdamW + EMA + bf16 repack as one dsfuse launch per stage (the forward then packs nothing)
+            from deepsense6g_tii_b200.optim import FusedAdamWEMA
+            from deepsense6g_tii_b200.train import EMA
+            self.ema = EMA(self.gpt, 0.999)
+            self.ema.register()
+            self.opt = FusedAdamWEMA(self.gpt.parameters(), lr=1e-4, ema=self.ema, gpts=[self.gpt])
         self.feats_h, self.gps_h, probes_h = synth_inputs(gen, BATCH, c, scale, pin=pin)
         self.feats = [f.to(dev).requires_grad_(True) for f in self.feats_h]
         self.gps = self.gps_h.to(dev).requires_grad_(True)
@@ -258,9 +264,13 @@ class StageWork:
             t.grad = None
         self.gps.grad = None
         outs = self.gpt.fuse(self.feats[0], self.feats[1], self.feats[2], self.gps)
-        loss = sum((o.float() * pr).sum() for o, pr in zip(outs, self.probes))
-        loss.backward()
-        return loss.detach()
+        # the probes are the upstream gradients (in the model they come from the ResNet layers that follow the stage); the step's
+        # scalar result is the sum of the two GPS output tokens (a 12 x 2 x C reduction: the only non-dsfuse kernel of the step)
+        torch.autograd.backward(outs, self.probes)
+        if self.opt is not None:
+            self.opt.step()
+            self.ema.update()
+        return outs[3].detach().sum()
 
 
 def one_step(works):
@@ -417,7 +427,7 @@ def run_ours(args, rank, world, local_rank):
     _capi.set_pdl(args.pdl)
     _capi.set_sm_margin(int(os.environ.get("DSF_SM_MARGIN", "0")) if world > 1 else 0)
     gen = torch.Generator().manual_seed(rank)  # data generator seed 0 + rank
-    works = [StageWork(c, scale, dev, gen) for c, scale in SPEC]
+    works = [StageWork(c, scale, dev, gen, optimizer=args.optimizer) for c, scale in SPEC]
     n_params = sum(p.numel() for w in works for p in w.gpt.parameters())
     if world > 1:
         for w in works:
@@ -641,6 +651,8 @@ def run_ours(args, rank, world, local_rank):
     step_flops = sum(3.0 * fwd_flops_per_sample(c) * BATCH for c, _ in SPEC)
     cfg = workload_config(world)
     cfg.update({"launch": graph_note + pdl_note, "dropout": PDROP, "gpt_parameters": n_params,
+                "optimizer": "fused AdamW + EMA + bf16 weight repack in the step (dsf_adamw_ema_pack, one launch per stage; no pack launches in the forward)"
+                if args.optimizer else "none (fwd+bwd only; bf16 weight shadows re-packed at the start of every forward)",
                 "l2": "per-step working set (saved activations of 8 blocks per stage, > 1 GB) > 126 MB L2; no explicit flush",
                 "grad_allreduce": ("NCCL all-reduce (avg) of %.1f M fp32 grads per step, one bucket per transformer block, overlapped with backward" % (n_params / 1e6)) if world > 1 else "none (1 GPU)",
                 "grads_identical_across_ranks": synced})
@@ -683,9 +695,16 @@ def run_model(args, rank, world, local_rank):
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
     crit = FocalLoss()
     use_graph = args.graph and world == 1
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
     ema = EMA(model, 0.999)
     ema.register()
+    if args.torch_optimizer:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
+        opt_note = "torch.optim.AdamW(fused, capturable) + multi-tensor EMA lerp"
+    else:   # AdamW + EMA + the bf16 repack of the four GPTs' weights in one dsfuse launch (train2_seq.py:131-134, 315-320, 539)
+        from deepsense6g_tii_b200.optim import FusedAdamWEMA
+        enc = model.encoder
+        opt = FusedAdamWEMA(model.parameters(), lr=1e-4, ema=ema, gpts=[enc.transformer1, enc.transformer2, enc.transformer3, enc.transformer4])
+        opt_note = "dsf_adamw_ema_pack: AdamW + EMA + bf16 weight repack of the 4 GPTs in one launch"
     gen = torch.Generator().manual_seed(rank)
     host = synthetic_batch(BATCH, S, 256, generator=gen, pin=True)
 
@@ -807,6 +826,7 @@ def run_model(args, rank, world, local_rank):
                                "256x256 inputs, dropout 0.1, %d parameters, ResNet trunks in stock PyTorch (channels_last, bf16 autocast), "
                                "4 fusion stages on dsfuse kernels" % n_params,
                    "global_batch": BATCH * world, "seq_len": S, "parallelism": "dp%d" % world, "launch": launch_note + ", PDL " + ("on" if args.pdl else "off"),
+                   "optimizer": opt_note,
                    "l2": "per-step working set (activations of 3 ResNets + 4 fusion stages) >> 126 MB L2; no explicit flush",
                    "grad_allreduce": "torch DistributedDataParallel (NCCL, bucketed, overlapped) of %.1f M fp32 gradients" % (n_params / 1e6) if world > 1 else "none (1 GPU)"},
         "e2e": {"value": BATCH * world * steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -830,6 +850,8 @@ def main():
     ap.add_argument("--no-pdl", dest="pdl", action="store_false", help="disable programmatic dependent launch of the hot kernels")
     ap.add_argument("--no-gpu-baseline", dest="gpu_baseline", action="store_false", help="skip the stock-PyTorch-autocast leg on the GPU")
     ap.add_argument("--sustained", type=float, default=2.0, help="seconds of back-to-back replays for the `sustained` sub-record (0 = skip)")
+    ap.add_argument("--optimizer", action="store_true", help="stage workloads: add the fused AdamW + EMA + weight-repack launch to every step")
+    ap.add_argument("--torch-optimizer", action="store_true", help="model workload: stock torch AdamW(fused) + multi-tensor EMA instead of dsf_adamw_ema_pack")
     ap.add_argument("--dropout", type=float, default=0.0,
                     help="embd/attn/resid dropout probability (default 0 = the parity configuration; the reference trains with 0.1)")
     ap.add_argument("--anchors", type=int, default=8, choices=[8, 16],

@@ -22,8 +22,8 @@ EPI_BIAS, EPI_RELU, EPI_RESIDUAL, EPI_ACCUM = 1, 2, 4, 8
 SYMBOLS = [
     "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_set_pdl", "dsf_set_sm_margin", "dsf_dropout_inplace", "dsf_tokens_fwd", "dsf_tokens_bwd",
     "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_set_impl", "dsf_gemm_f32",
-    "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_bwd_parts", "dsf_attn_set_impl", "dsf_attn_drop_words", "dsf_gemm_bf16_nt_ln",
-    "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16",
+    "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_bwd_parts", "dsf_attn_set_impl", "dsf_attn_drop_words",
+    "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16", "dsf_opt_tiles", "dsf_adamw_ema_pack",
 ]
 
 
@@ -48,6 +48,12 @@ class GemmF32Desc(ctypes.Structure):
                 [(n, c_int64) for n in ("a_b1", "a_b2", "a_m", "a_k", "b_b1", "b_b2", "b_n", "b_k",
                                         "c_b1", "c_b2", "c_m", "c_n")] +
                 [("alpha", c_float), ("epi_flags", c_int32)])
+
+
+class OptTensor(ctypes.Structure):
+    """``dsf_opt_tensor`` (include/dsfuse.h): one parameter tensor of the fused AdamW + EMA + bf16-repack step."""
+    _fields_ = ([(n, c_void_p) for n in ("p", "g", "m", "v", "ema", "shadow", "shadow_t", "copy_f32")] +
+                [(n, c_int32) for n in ("rows", "cols", "row_off", "ld_t")] + [("weight_decay", c_float), ("reserved", c_int32)])
 
 
 _lib = None
@@ -76,8 +82,6 @@ def lib():
             "dsf_pack_block_weights": [P] * 9 + [c_int32, c_int32] + [P] * 10,
             "dsf_gemm_bf16_nt": [P, c_int32, P, c_int32, P, c_int32, c_int32, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P, P],
             "dsf_gemm_bf16_tn": [P, c_int32, P, c_int32, P, c_int32, c_int32, c_int32, c_int32, P],
-            "dsf_gemm_bf16_nt_ln": [P, c_int32, P, c_int32, P, c_int32, P, P, P, c_int32, P, P, P, P, c_float, c_int32, c_int32, c_int32,
-                                    POINTER(Dropout), P],
             "dsf_gemm_f32": [POINTER(GemmF32Desc), P, P, P, P, P, P],
             "dsf_colsum": [P, c_int32, c_int32, P, c_int32, c_int32, P],
             "dsf_relu_bwd": [P, P, c_int32, c_int64, P],
@@ -93,6 +97,8 @@ def lib():
             "dsf_upsample_add_fwd": [POINTER(Geom), P, P, P, P, P, P, P, P],
             "dsf_upsample_add_bwd": [POINTER(Geom), P, P, P, P, P, P],
             "dsf_cast_f32_bf16": [P, P, c_int64, P],
+            "dsf_opt_tiles": [c_int32, c_int32, c_int32],
+            "dsf_adamw_ema_pack": [P, P, c_int32, c_int32, c_float, c_float, c_float, c_float, c_float, P, c_float, P],
         }
         for name, argtypes in sig.items():
             fn = getattr(L, name)
@@ -195,15 +201,6 @@ def gemm_bf16_nt(A, B, C, bias=None, residual=None, relu=False, drop=None, relu_
                                 M, N, K, flags, _dp(drop), _p(relu_src), _stream()), "dsf_gemm_bf16_nt")
 
 
-def gemm_bf16_nt_ln(A, B, C, bias, residual, H, gamma, beta, mean, rstd, eps=1e-5, drop=None):
-    """C[M,512] (fp32) = A[M,K] @ B[512,K]^T + bias (dropout) + residual; H (bf16) = LayerNorm(C) * gamma + beta; mean / rstd (M)
-    saved for the backward.  One launch (a CTA pair owns full rows); N = 512 only."""
-    M, K = A.shape
-    N = B.shape[0]
-    _chk(lib().dsf_gemm_bf16_nt_ln(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), _p(bias), _p(residual), _p(H), H.stride(0),
-                                   _p(gamma), _p(beta), _p(mean), _p(rstd), eps, M, N, K, _dp(drop), _stream()), "dsf_gemm_bf16_nt_ln")
-
-
 def gemm_bf16_tn(A, B, C):
     """C[N',K'] += A[M,N']^T @ B[M,K'] (fp32 atomics; C must be pre-zeroed or hold a running sum)."""
     M, Nout = A.shape
@@ -248,7 +245,7 @@ def attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, drop=None, drop_bits=Non
 
 
 def gemm_set_impl(impl):
-    """0 = default (= 3), 1 = v1 (CTA per tile), 2 = v2 (persistent), 3 = v3 (NT on CTA pairs, cta_group::2); process-wide."""
+    """0 = default (NT on CTA pairs, cta_group::2, where the shape allows), 2 = single-CTA persistent tiles only; process-wide."""
     _chk(lib().dsf_gemm_set_impl(impl), "dsf_gemm_set_impl")
 
 
@@ -263,7 +260,7 @@ def set_sm_margin(sms):
 
 
 def attn_set_impl(impl):
-    """0 = default, 1 = v1 (simple), 2 = v2 (pipelined); process-wide."""
+    """Forward CTA shape: 0 = default (128-row CTAs, two per SM), 1 = force 128-row CTAs, 2 = force 256-row CTAs; process-wide."""
     _chk(lib().dsf_attn_set_impl(impl), "dsf_attn_set_impl")
 
 
@@ -278,3 +275,17 @@ def upsample_add_bwd(g, douts, dgps_out, dy):
 
 def cast_f32_bf16(src, dst):
     _chk(lib().dsf_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()), "dsf_cast_f32_bf16")
+
+
+def opt_tiles(rows, cols, transposed_shadow):
+    """CTAs the fused optimizer kernel spends on one (rows, cols) tensor (32 x 32 tiles with a transposed shadow, else 1024-element chunks)."""
+    n = int(lib().dsf_opt_tiles(rows, cols, 1 if transposed_shadow else 0))
+    if n < 0:
+        raise RuntimeError("dsf_opt_tiles: a tensor with a transposed shadow needs rows and cols that are multiples of 32, got %d x %d" % (rows, cols))
+    return n
+
+
+def adamw_ema_pack(table_dev, tile0_dev, n_tensors, n_tiles, lr, beta1, beta2, eps, ema_decay, step_dev, grad_scale=1.0):
+    """One launch: AdamW update + EMA lerp + bf16 repack over every tensor of the device-resident table (see include/dsfuse.h)."""
+    _chk(lib().dsf_adamw_ema_pack(_p(table_dev), _p(tile0_dev), n_tensors, n_tiles, lr, beta1, beta2, eps, ema_decay, _p(step_dev),
+                                  grad_scale, _stream()), "dsf_adamw_ema_pack")

@@ -206,184 +206,6 @@ __device__ __forceinline__ void store_row16_bf16(__nv_bfloat16* dst, const uint3
 }
 
 // =============================================================================================== forward
-template <int HS, int BKV, int ST>
-struct Fwd2 {
-  static constexpr int Q_BYTES = 128 * HS * 2, KV_BYTES = BKV * HS * 2, P_BYTES = 128 * BKV * 2;
-  static constexpr int Q_OFF = 0, K_OFF = 2 * Q_BYTES, V_OFF = K_OFF + ST * KV_BYTES, P_OFF = V_OFF + ST * KV_BYTES;
-  static constexpr int BAR_OFF = P_OFF + 2 * P_BYTES;
-  static constexpr int NBAR = 1 + 2 * ST + 6;
-  static constexpr int DYN = BAR_OFF + NBAR * 8 + 16 + 1024;
-  static constexpr int THREADS = 320;  // 8 softmax warps, 1 MMA warp, 1 TMA warp
-  static_assert(2 * BKV + 2 * HS <= 512, "TMEM budget");
-};
-
-template <int HS, int BKV, int ST>
-__global__ void __launch_bounds__(320, 1)
-attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, __nv_bfloat16* __restrict__ y,
-                 float* __restrict__ lse, int T, int C, int nh, float scale_log2) {
-  using L = Fwd2<HS, BKV, ST>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t bar0 = sbase + L::BAR_OFF;
-  const uint32_t q_full = bar0, kv_full = bar0 + 8, kv_empty = kv_full + 8 * ST, s_full = kv_empty + 8 * ST, p_full = s_full + 16,
-                 o_done = p_full + 16, tmem_slot = o_done + 16;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
-  const int n_kv = (T + BKV - 1) / BKV;
-
-  if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < ST; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(p_full + 8 * w, 128); mbar_init(o_done + 8 * w, 1); }
-    fence_barrier_init();
-  }
-  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  if (warp == 9 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  if (warp == 9) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * L::Q_BYTES);
-      for (int w = 0; w < 2; ++w) tma_tile<HS>(sbase + L::Q_OFF + w * L::Q_BYTES, &tmQ, q_full, h * HS, q0 + 128 * w, b, 128);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % ST;
-        if (j >= ST) mbar_wait(kv_empty + 8 * st, ((j / ST) - 1) & 1);
-        mbar_expect_tx(kv_full + 8 * st, 2 * L::KV_BYTES);
-        tma_tile<HS>(sbase + L::K_OFF + st * L::KV_BYTES, &tmKV, kv_full + 8 * st, C + h * HS, j * BKV, b, BKV);
-        tma_tile<HS>(sbase + L::V_OFF + st * L::KV_BYTES, &tmKV, kv_full + 8 * st, 2 * C + h * HS, j * BKV, b, BKV);
-      }
-    }
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer (all lanes, see mma_over_head)
-    {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, HS, 0, 1);
-      mbar_wait(q_full, 0);
-      mbar_wait(kv_full, 0);
-      tc_fence_after();
-      for (int w = 0; w < 2; ++w) {
-        mma_over_head<HS>(tmem_base + w * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF, BKV, idesc_s);
-        tc_commit_elect(s_full + 8 * w);
-      }
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j % ST;
-        for (int w = 0; w < 2; ++w) {
-          mbar_wait(p_full + 8 * w, j & 1);
-          tc_fence_after();
-          mma_over_rows<HS, BKV>(tmem_base + 2 * BKV + w * HS, sbase + L::P_OFF + w * L::P_BYTES, sbase + L::V_OFF + st * L::KV_BYTES,
-                                 idesc_o, j > 0);
-          tc_commit_elect(o_done + 8 * w);
-          if (w == 1) tc_commit_elect(kv_empty + 8 * st);
-          if (j + 1 < n_kv) {
-            const int sn = (j + 1) % ST;
-            if (w == 0) { mbar_wait(kv_full + 8 * sn, ((j + 1) / ST) & 1); tc_fence_after(); }
-            mma_over_head<HS>(tmem_base + w * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + sn * L::KV_BYTES, BKV, idesc_s);
-            tc_commit_elect(s_full + 8 * w);
-          }
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax warpgroups
-    const int w = warp >> 2;
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tm_s = tmem_base + w * BKV + lane_off, tm_o = tmem_base + 2 * BKV + w * HS + lane_off;
-    uint8_t* p_tile = smem + L::P_OFF + w * L::P_BYTES;
-    float m_run = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      const int kv0 = j * BKV;
-      mbar_wait(s_full + 8 * w, j & 1);
-      tc_fence_after();
-      float p_max = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tm_s + c, r);
-        tmem_wait_ld();
-        if (kv0 + c + 32 <= T) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) p_max = fmaxf(p_max, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kv0 + c + i < T) p_max = fmaxf(p_max, __uint_as_float(r[i]));
-        }
-      }
-      p_max *= scale_log2;
-      if (j > 0) mbar_wait(o_done + 8 * w, (j - 1) & 1);  // P.V(j-1) retired: O is stable, the P buffer is free
-      const bool need = p_max > m_run + 8.f;               // lazy rescale (exact: m only has to bound the exponent)
-      if (__any_sync(0xffffffffu, need)) {
-        const float m_new = need ? p_max : m_run;
-        const float alpha = exp2f(m_run - m_new);
-        if (j > 0) {
-          tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < HS; c += 16) {
-            uint32_t o[16];
-            tmem_ld16(tm_o + c, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tm_o + c, o);
-          }
-          tmem_wait_st();
-        }
-        l_run *= alpha;
-        m_run = m_new;
-      }
-      float l_add = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tm_s + c, r);
-        tmem_wait_ld();
-        uint32_t pk[16];
-        const bool full = kv0 + c + 32 <= T;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2f(__uint_as_float(r[i]) * scale_log2 - m_run);
-          float p1 = exp2f(__uint_as_float(r[i + 1]) * scale_log2 - m_run);
-          if (!full) {
-            if (kv0 + c + i >= T) p0 = 0.f;
-            if (kv0 + c + i + 1 >= T) p1 = 0.f;
-          }
-          __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);  // the row sum uses what the P.V MMA will see
-          l_add += __low2float(pb) + __high2float(pb);
-          pk[i / 2] = *reinterpret_cast<uint32_t*>(&pb);
-        }
-        store_p32<BKV>(p_tile, row, c, pk);
-      }
-      l_run += l_add;
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(p_full + 8 * w);
-    }
-    mbar_wait(o_done + 8 * w, (n_kv - 1) & 1);
-    tc_fence_after();
-    const int q = q0 + 128 * w + row;
-    const float inv_l = 1.0f / l_run;
-    __nv_bfloat16* yrow = y + ((size_t)b * T + q) * C + h * HS;
-#pragma unroll 1
-    for (int c = 0; c < HS; c += 16) {
-      uint32_t o[16];
-      tmem_ld16(tm_o + c, o);
-      tmem_wait_ld();
-      if (q < T) store_row16_bf16(yrow + c, o, inv_l);
-    }
-    if (q < T) lse[((size_t)b * nh + h) * T + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
-}
-
 // =============================================================================================== backward: dK, dV
 // CTA = 128 keys (K, V resident); loop over BQ-query tiles.  Threads own key rows:
 //   S^T = K Q^T, dP^T = V dO^T -> P^T = exp2(S^T*c - lse), dS^T = P^T (dP^T - delta) * scale -> dV += P^T dO, dK += dS^T Q
@@ -1093,226 +915,6 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == MMAW) tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
-// =============================================================================================== forward (v5: four softmax warpgroups)
-// Same pipeline and TMEM layout as the v4 forward (P kept in tensor memory), but every 128-row query tile is served by TWO
-// warpgroups that split the 64 key columns of each S tile (TMEM lane rule: a warp only reaches lanes 32*(warp%4).., so two
-// warpgroups can share the rows and take 32 columns each).  16 softmax warps instead of 8 double the exp/issue
-// throughput a CTA can bring to bear; the two halves of a row agree on the running maximum through shared memory and one
-// 256-thread named barrier per tile and iteration, keep partial row sums, and each rescales / drains half of O's columns.
-template <int HS, int KST, int VST>
-struct Fwd5 {
-  static constexpr int BKV = 64;
-  static constexpr int Q_BYTES = 128 * HS * 2, KV_BYTES = BKV * HS * 2;
-  static constexpr int Q_OFF = 0, K_OFF = 2 * Q_BYTES, V_OFF = K_OFF + KST * KV_BYTES, X_OFF = V_OFF + VST * KV_BYTES;
-  static constexpr int X_BYTES = (2 * 2 * 2 * 128 + 2 * 2 * 128) * 4;  // max exchange [tile][parity][half][row] + row-sum exchange [tile][half][row]
-  static constexpr int BAR_OFF = X_OFF + X_BYTES;
-  static constexpr int NBAR = 1 + 2 * KST + 2 * VST + 12;
-  static constexpr int DYN = BAR_OFF + NBAR * 8 + 16 + 1024;
-  static constexpr int THREADS = 576;  // 16 softmax warps, 1 MMA warp, 1 TMA warp
-  static_assert(4 * BKV + 2 * HS <= 512, "TMEM budget");
-  static_assert(DYN <= 232448, "shared memory budget");
-};
-
-template <int HS, int KST, int VST>
-__global__ void __launch_bounds__(576, 1)
-attn_fwd5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, __nv_bfloat16* __restrict__ y,
-                 float* __restrict__ lse, int T, int C, int nh, float scale_log2, AttnDrop ad) {
-  using L = Fwd5<HS, KST, VST>;
-  constexpr int BKV = L::BKV;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t bar0 = sbase + L::BAR_OFF;
-  const uint32_t q_full = bar0, k_full = bar0 + 8, k_empty = k_full + 8 * KST, v_full = k_empty + 8 * KST, v_empty = v_full + 8 * VST,
-                 s_full = v_empty + 8 * VST, p_full = s_full + 32, p_empty = p_full + 32, tmem_slot = p_empty + 32;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
-  const int n_kv = (T + BKV - 1) / BKV;
-  constexpr int MMA_WARP = 16, TMA_WARP = 17;
-
-  pdl_trigger();
-  if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KST; ++s) { mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1); }
-    for (int s = 0; s < VST; ++s) { mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(p_full + 8 * i, 256); mbar_init(p_empty + 8 * i, 1); }
-    fence_barrier_init();
-  }
-  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  if (warp == TMA_WARP && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_wait();
-  if (ad.thresh8 && ad.seed_dev != nullptr) {
-    const unsigned long long sd = __ldg(ad.seed_dev);
-    ad.k0 ^= (uint32_t)(sd & 0xFFFFFFFFull);
-    ad.k1 ^= (uint32_t)(sd >> 32);
-  }
-
-  if (warp == TMA_WARP) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * L::Q_BYTES);
-      for (int w = 0; w < 2; ++w) tma_tile<HS>(sbase + L::Q_OFF + w * L::Q_BYTES, &tmQ, q_full, h * HS, q0 + 128 * w, b, 128);
-      for (int j = 0; j < n_kv; ++j) {
-        const int ks = j % KST, vs = j % VST;
-        if (j >= KST) mbar_wait(k_empty + 8 * ks, ((j / KST) - 1) & 1);
-        mbar_expect_tx(k_full + 8 * ks, L::KV_BYTES);
-        tma_tile<HS>(sbase + L::K_OFF + ks * L::KV_BYTES, &tmKV, k_full + 8 * ks, C + h * HS, j * BKV, b, BKV);
-        if (j >= VST) mbar_wait(v_empty + 8 * vs, ((j / VST) - 1) & 1);
-        mbar_expect_tx(v_full + 8 * vs, L::KV_BYTES);
-        tma_tile<HS>(sbase + L::V_OFF + vs * L::KV_BYTES, &tmKV, v_full + 8 * vs, 2 * C + h * HS, j * BKV, b, BKV);
-      }
-    }
-  } else if (warp == MMA_WARP) {
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
-    constexpr uint32_t idesc_o = make_idesc_bf16(128, HS, 0, 1);
-    mbar_wait(q_full, 0);
-    for (int jj = 0; jj < 2 && jj < n_kv; ++jj) {
-      mbar_wait(k_full + 8 * (jj % KST), (jj / KST) & 1);
-      tc_fence_after();
-      for (int w = 0; w < 2; ++w) {
-        mma_over_head<HS>(tmem_base + (w * 2 + jj) * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + (jj % KST) * L::KV_BYTES,
-                          BKV, idesc_s);
-        tc_commit_elect(s_full + 8 * (w * 2 + jj));
-      }
-      tc_commit_elect(k_empty + 8 * (jj % KST));
-    }
-    for (int j = 0; j < n_kv; ++j) {
-      const int buf = j & 1, vs = j % VST;
-      mbar_wait(v_full + 8 * vs, (j / VST) & 1);
-      for (int w = 0; w < 2; ++w) {
-        const int sb = w * 2 + buf;
-        mbar_wait(p_full + 8 * sb, (j >> 1) & 1);
-        tc_fence_after();
-        mma_over_rows_ts<HS, BKV, true>(tmem_base + 4 * BKV + w * HS, tmem_base + sb * BKV, sbase + L::V_OFF + vs * L::KV_BYTES, idesc_o, j > 0);
-        tc_commit_elect(p_empty + 8 * sb);
-        if (w == 1) tc_commit_elect(v_empty + 8 * vs);
-        if (j + 2 < n_kv) {
-          const int ks = (j + 2) % KST;
-          if (w == 0) { mbar_wait(k_full + 8 * ks, ((j + 2) / KST) & 1); tc_fence_after(); }
-          mma_over_head<HS>(tmem_base + sb * BKV, sbase + L::Q_OFF + w * L::Q_BYTES, 128, sbase + L::K_OFF + ks * L::KV_BYTES, BKV, idesc_s);
-          tc_commit_elect(s_full + 8 * sb);
-          if (w == 1) tc_commit_elect(k_empty + 8 * ks);
-        }
-      }
-    }
-  } else {
-    const int w = warp >> 3;          // 128-row query tile of this warpgroup pair
-    const int hf = (warp >> 2) & 1;   // which 32 of the 64 key columns
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    // O columns rescaled / drained by this half (head size 16: the first half handles all 16)
-    constexpr int OC = HS >= 32 ? HS / 2 : HS;
-    const int o_lo = HS >= 32 ? hf * OC : 0;
-    const bool o_mine = HS >= 32 || hf == 0;
-    const uint32_t tm_o = tmem_base + 4 * BKV + w * HS + lane_off;
-    float* xmax = reinterpret_cast<float*>(smem + L::X_OFF) + w * (2 * 2 * 128);  // [parity][half][row]
-    float* xsum = reinterpret_cast<float*>(smem + L::X_OFF) + 2 * 2 * 2 * 128 + w * (2 * 128);  // [half][row]
-    float m_run = -INFINITY, l_run = 0.f;
-    const int qrow = q0 + 128 * w + row;
-    const uint64_t rowid = ((uint64_t)b * nh + h) * T + qrow;
-    for (int j = 0; j < n_kv; ++j) {
-      const int kv0 = j * BKV, buf = j & 1, sb = w * 2 + buf;
-      const uint32_t tm_s = tmem_base + sb * BKV + lane_off + hf * 32;
-      mbar_wait(s_full + 8 * sb, (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(tm_s, r);
-      tmem_wait_ld();
-      const int k_lo = kv0 + hf * 32;  // first key of this half
-      float p_max = -INFINITY;
-      if (k_lo + 32 <= T) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) p_max = fmaxf(p_max, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (k_lo + i < T) p_max = fmaxf(p_max, __uint_as_float(r[i]));
-      }
-      p_max *= scale_log2;
-      xmax[(j & 1) * 256 + hf * 128 + row] = p_max;
-      named_bar_sync(1 + w, 256);
-      p_max = fmaxf(p_max, xmax[(j & 1) * 256 + (hf ^ 1) * 128 + row]);
-      const bool need = p_max > m_run + 8.f;  // lazy rescale; both halves of a row see the same p_max and m_run
-      if (__any_sync(0xffffffffu, need)) {
-        const float m_new = need ? p_max : m_run;
-        const float alpha = ex2_approx(m_run - m_new);
-        if (j > 0) {
-          mbar_wait(p_empty + 8 * (w * 2 + ((j - 1) & 1)), ((j - 1) >> 1) & 1);  // P.V(j-1) retired: O is stable
-          tc_fence_after();
-          if (o_mine) {
-#pragma unroll 1
-            for (int c = 0; c < OC; c += 16) {
-              uint32_t o[16];
-              tmem_ld16(tm_o + o_lo + c, o);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st16(tm_o + o_lo + c, o);
-            }
-            tmem_wait_st();
-          }
-        }
-        l_run *= alpha;
-        m_run = m_new;
-      }
-      if (j >= 2) mbar_wait(p_empty + 8 * sb, ((j >> 1) - 1) & 1);
-      uint32_t keepw = 0xFFFFFFFFu;
-      if (ad.thresh8) {
-        keepw = attn_keep_word(ad, rowid, (uint32_t)(kv0 / 32 + hf));
-        if (qrow < T) ad.bits[rowid * ad.Tw + kv0 / 32 + hf] = keepw;
-      }
-      const bool full = k_lo + 32 <= T;
-      float l_add = 0.f;
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2, -m_run));
-        float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_run));
-        if (!full) {
-          if (k_lo + i >= T) p0 = 0.f;
-          if (k_lo + i + 1 >= T) p1 = 0.f;
-        }
-        l_add += p0 + p1;
-        if (ad.thresh8) {
-          p0 *= (keepw >> i) & 1u ? ad.scale : 0.f;
-          p1 *= (keepw >> (i + 1)) & 1u ? ad.scale : 0.f;
-        }
-        pk[i / 2] = pack_bf16x2(p0, p1);
-      }
-      tmem_st16(tm_s, pk);  // packed over the first 16 columns of this half's own 32-column region (SPLIT layout)
-      l_run += l_add;
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(p_full + 8 * sb);
-    }
-    // total row sum = the two halves' partial sums
-    xsum[hf * 128 + row] = l_run;
-    named_bar_sync(1 + w, 256);
-    const float l_tot = l_run + xsum[(hf ^ 1) * 128 + row];
-    mbar_wait(p_empty + 8 * (w * 2 + ((n_kv - 1) & 1)), ((n_kv - 1) >> 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_tot;
-    __nv_bfloat16* yrow = y + ((size_t)b * T + qrow) * C + h * HS;
-    if (o_mine) {
-#pragma unroll 1
-      for (int c = 0; c < OC; c += 16) {
-        uint32_t o[16];
-        tmem_ld16(tm_o + o_lo + c, o);
-        tmem_wait_ld();
-        if (qrow < T) store_row16_bf16(yrow + o_lo + c, o, inv_l);
-      }
-    }
-    if (hf == 0 && qrow < T) lse[((size_t)b * nh + h) * T + qrow] = (m_run + log2f(l_tot)) * 0.6931471805599453f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == MMA_WARP) tmem_dealloc(tmem_base, 512);
-}
-
 // =============================================================================================== host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1343,40 +945,14 @@ static int make_tmap3(CUtensorMap* m, const void* base, int ncols, int T, int B,
   return DSF_OK;
 }
 
-template <int HS, int BKV, int ST>
-static int launch_fwd2(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st) {
-  using L = Fwd2<HS, BKV, ST>;
-  using H = HeadCfg<HS>;
-  static bool configured_on[64] = {};
-  bool& configured = per_device_flag(configured_on);
-  if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd2_kernel<HS, BKV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
-      return check_launch("attn_fwd2/attr");
-    configured = true;
-  }
-  CUtensorMap tmQ, tmKV;
-  if (int e = make_tmap3(&tmQ, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
-  if (int e = make_tmap3(&tmKV, qkv, 3 * C, T, B, H::BOXC, BKV)) return e;
-  const float scale_log2 = (1.0f / sqrtf((float)HS)) * 1.4426950408889634f;
-  dim3 grid(cdiv(T, 256), nh, B);
-  attn_fwd2_kernel<HS, BKV, ST><<<grid, L::THREADS, L::DYN, st>>>(tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2);
-  return check_launch("attn_fwd2");
-}
-
-// off by default: measured neutral (2110 vs 2150 cycles per iteration) — a softmax warp needs ~1300 cycles for its 64
-// exponentials + packing even when it has the SFU to itself, so the phase is bound by single-warp issue, not by contention
-static const bool g_attn_pingpong = getenv("DSF_ATTN_PINGPONG") ? atoi(getenv("DSF_ATTN_PINGPONG")) != 0 : false;
-
-template <int HS, int KST, int VST, bool PT, int NWG = 2>
+template <int HS, int KST, int VST, int NWG>
 static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const AttnDrop& ad, cudaStream_t st) {
-  using L = Fwd3<HS, KST, VST, NWG, PT>;
+  using L = Fwd3<HS, KST, VST, NWG, true>;
   using H = HeadCfg<HS>;
-  constexpr bool PPOK = PT && NWG == 2;
   static bool configured_on[64] = {};
   bool& configured = per_device_flag(configured_on);
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, PT, false, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, PT, PPOK, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, true, false, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("attn_fwd3/attr");
     configured = true;
   }
@@ -1385,51 +961,17 @@ static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C
   if (int e = make_tmap3(&tmKV, qkv, 3 * C, T, B, H::BOXC, L::BKV)) return e;
   const float scale_log2 = (1.0f / sqrtf((float)HS)) * 1.4426950408889634f;
   dim3 grid(cdiv(T, 128 * NWG), nh, B);
-  if (PPOK && g_attn_pingpong)
-    launch_pdl(attn_fwd3_kernel<HS, KST, VST, PT, PPOK, NWG>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2,
-               ad);
-  else
-    launch_pdl(attn_fwd3_kernel<HS, KST, VST, PT, false, NWG>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2,
-               ad);
+  launch_pdl(attn_fwd3_kernel<HS, KST, VST, true, false, NWG>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2,
+             ad);
   return check_launch("attn_fwd3");
 }
 
-// Forward CTA size (see Fwd3): 1 = 128-row CTAs, two per SM (default), 2 = 256-row CTAs, one per SM (DSF_ATTN_FWD_NWG=2).
-// Measured on B200 (scripts/bench_kernels.py attnq, batch 12, T = 962): 42 vs 48 us at hs = 128, 36 vs 43 (hs = 64), 34 vs
-// 41 (hs = 32), 33 vs 40 us (hs = 16); T = 3842, batch 2, hs = 128: 68 vs 80 us (891 vs 760 TF/s) — the half-size CTAs win
-// even where the 256-row grid fills the SMs in one round: two independent MMA / TMA / softmax pipelines per SM overlap
-// better than one pipeline with two softmax warpgroups, and the grid is scheduled in finer units.
-static int attn_fwd_nwg(int B, int T, int nh) {
-  static const int forced = getenv("DSF_ATTN_FWD_NWG") ? atoi(getenv("DSF_ATTN_FWD_NWG")) : 0;
-  (void)B; (void)T; (void)nh;
-  return forced == 2 ? 2 : 1;
-}
+int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, int C, int nh, cudaStream_t st);  // attn_api.cu
 
-template <int HS, int KST, int VST>
-static int launch_fwd5(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const AttnDrop& ad, cudaStream_t st) {
-  using L = Fwd5<HS, KST, VST>;
-  using H = HeadCfg<HS>;
-  static bool configured_on[64] = {};
-  bool& configured = per_device_flag(configured_on);
-  if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd5_kernel<HS, KST, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
-      return check_launch("attn_fwd5/attr");
-    configured = true;
-  }
-  CUtensorMap tmQ, tmKV;
-  if (int e = make_tmap3(&tmQ, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
-  if (int e = make_tmap3(&tmKV, qkv, 3 * C, T, B, H::BOXC, L::BKV)) return e;
-  const float scale_log2 = (1.0f / sqrtf((float)HS)) * 1.4426950408889634f;
-  dim3 grid(cdiv(T, 256), nh, B);
-  launch_pdl(attn_fwd5_kernel<HS, KST, VST>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2, ad);
-  return check_launch("attn_fwd5");
-}
-
-int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, int C, int nh, cudaStream_t st);  // attn_tc.cu
-
+// Q / dO rows of the dQ kernel parked in tensor memory as TS-mode A operands (default on: +-0 at T = 962, +6 % at T = 3842)
 static const bool g_attn_a_in_tmem = getenv("DSF_ATTN_A_TMEM") ? atoi(getenv("DSF_ATTN_A_TMEM")) != 0 : true;
 
-template <int HS, int BQ, int STA, int STB, bool PT>
+template <int HS, int BQ, int STA, int STB>
 static int launch_bwd2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
                        const AttnDrop& ad, int parts, cudaStream_t st) {
   using LA = BwdKV2<HS, BQ, STA>;
@@ -1438,11 +980,9 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   static bool configured_on[64] = {};
   bool& configured = per_device_flag(configured_on);
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, PT, false, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, PT, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
       return check_launch("attn_bwd2/attr");
     configured = true;
   }
@@ -1459,30 +999,17 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
   if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
   dim3 grid(cdiv(T, 128), nh, B);
   if (parts & 2) {
-    // DSF_ATTN_KV_DIRECT_STATS=1: read lse / delta straight from global memory instead of staging them in shared memory
-    // behind a named barrier.  OFF: measured slower on B200 (backward 177 vs 139 us per layer, 4.20 vs 4.00 ms per step) —
-    // 32 broadcast 8-byte loads per thread and iteration cost more LSU time than the barrier they remove.
-    static const bool direct_stats = getenv("DSF_ATTN_KV_DIRECT_STATS") ? atoi(getenv("DSF_ATTN_KV_DIRECT_STATS")) != 0 : false;
-    // warp-local statistics staging, no named barrier per iteration (P kept in tensor memory only); measured 124 vs 127 us per
-    // layer for the whole backward, 3.99 vs 4.02 ms per step.  DSF_ATTN_KV_WARP_STATS=0: warpgroup staging + named barrier
-    static const bool warp_stats = getenv("DSF_ATTN_KV_WARP_STATS") ? atoi(getenv("DSF_ATTN_KV_WARP_STATS")) != 0 : true;
-    if (PT && warp_stats)
-      launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT, false, PT>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta,
-                 (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
-    else if (direct_stats)
-      launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT, true>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta,
-                 (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
-    else
-      launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, PT, false>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta,
-                 (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
+    // dK/dV kernel: P^T / dS^T stay in tensor memory, lse / delta staged per warp (no named barrier per iteration)
+    launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, true, false, true>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta,
+               (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
     if (int e = check_launch("attn_bwd2/kv")) return e;
   }
   if (parts & 4) {
-    if (PT && g_attn_a_in_tmem)
-      launch_pdl(attn_bwd_q2_kernel<HS, STB, PT, PT>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta, (__nv_bfloat16*)dqkv,
+    if (g_attn_a_in_tmem)
+      launch_pdl(attn_bwd_q2_kernel<HS, STB, true, true>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta, (__nv_bfloat16*)dqkv,
                  T, C, nh, scale, ad, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dy);
     else
-      launch_pdl(attn_bwd_q2_kernel<HS, STB, PT, false>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta,
+      launch_pdl(attn_bwd_q2_kernel<HS, STB, true, false>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta,
                  (__nv_bfloat16*)dqkv, T, C, nh, scale, ad, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dy);
     if (int e = check_launch("attn_bwd2/q")) return e;
   }
@@ -1496,17 +1023,6 @@ extern "C" int dsf_debug_attn_trace(long long* host_out) {  // 3 x 64 x 6 clock6
 }
 namespace dsf {
 #endif
-
-int attn_fwd_v2(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, cudaStream_t st) {
-  switch (C / nh) {
-    case 16: return launch_fwd2<16, 128, 3>(qkv, y, lse, B, T, C, nh, st);
-    case 32: return launch_fwd2<32, 128, 3>(qkv, y, lse, B, T, C, nh, st);
-    case 64: return launch_fwd2<64, 128, 3>(qkv, y, lse, B, T, C, nh, st);
-    case 128: return launch_fwd2<128, 64, 3>(qkv, y, lse, B, T, C, nh, st);
-  }
-  set_error("attn_fwd: head size %d not supported (16, 32, 64, 128)", C / nh);
-  return DSF_EUNSUPPORTED;
-}
 
 // attn_drop arguments: 8-bit threshold (p quantised to k/256), bitmap of T_words = 2*ceil(T/64) words per (b, h, q) row
 static AttnDrop make_attn_drop(const dsf_dropout* d, uint32_t* bits, int T) {
@@ -1524,65 +1040,42 @@ static AttnDrop make_attn_drop(const dsf_dropout* d, uint32_t* bits, int T) {
   return a;
 }
 
-int attn_fwd_v3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem,
-                int force_nwg, cudaStream_t st) {
+// Forward CTA shape (see Fwd3): force_nwg 0 / 1 = 128-row CTAs, two per SM (default); 2 = 256-row CTAs, one per SM.  Measured on
+// B200 (scripts/bench_kernels.py attnq, batch 12, T = 962): 42 vs 48 us at hs = 128, 36 vs 43 (hs = 64), 34 vs 41 (hs = 32), 33 vs
+// 40 us (hs = 16); T = 3842, batch 2, hs = 128: 68 vs 80 us (891 vs 760 TF/s) — the half-size CTAs win even where the 256-row
+// grid fills the SMs in one round: two independent MMA / TMA / softmax pipelines per SM overlap better than one pipeline with
+// two softmax warpgroups, and the grid is scheduled in finer units.
+int attn_fwd_run(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, int force_nwg,
+                 cudaStream_t st) {
   const AttnDrop ad = make_attn_drop(drop, bits, T);
-  if (p_in_tmem && (force_nwg ? force_nwg : attn_fwd_nwg(B, T, nh)) == 1) {
+  if (force_nwg != 2) {
     switch (C / nh) {
-      case 16: return launch_fwd3<16, 3, 2, true, 1>(qkv, y, lse, B, T, C, nh, ad, st);
-      case 32: return launch_fwd3<32, 3, 2, true, 1>(qkv, y, lse, B, T, C, nh, ad, st);
-      case 64: return launch_fwd3<64, 3, 2, true, 1>(qkv, y, lse, B, T, C, nh, ad, st);
-      case 128: return launch_fwd3<128, 2, 2, true, 1>(qkv, y, lse, B, T, C, nh, ad, st);
-    }
-  }
-  if (p_in_tmem) {
-    switch (C / nh) {
-      case 16: return launch_fwd3<16, 3, 2, true>(qkv, y, lse, B, T, C, nh, ad, st);
-      case 32: return launch_fwd3<32, 3, 2, true>(qkv, y, lse, B, T, C, nh, ad, st);
-      case 64: return launch_fwd3<64, 3, 2, true>(qkv, y, lse, B, T, C, nh, ad, st);
-      case 128: return launch_fwd3<128, 3, 2, true>(qkv, y, lse, B, T, C, nh, ad, st);
+      case 16: return launch_fwd3<16, 3, 2, 1>(qkv, y, lse, B, T, C, nh, ad, st);
+      case 32: return launch_fwd3<32, 3, 2, 1>(qkv, y, lse, B, T, C, nh, ad, st);
+      case 64: return launch_fwd3<64, 3, 2, 1>(qkv, y, lse, B, T, C, nh, ad, st);
+      case 128: return launch_fwd3<128, 2, 2, 1>(qkv, y, lse, B, T, C, nh, ad, st);
     }
   }
   switch (C / nh) {
-    case 16: return launch_fwd3<16, 3, 2, false>(qkv, y, lse, B, T, C, nh, ad, st);
-    case 32: return launch_fwd3<32, 3, 2, false>(qkv, y, lse, B, T, C, nh, ad, st);
-    case 64: return launch_fwd3<64, 3, 2, false>(qkv, y, lse, B, T, C, nh, ad, st);
-    case 128: return launch_fwd3<128, 3, 2, false>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 16: return launch_fwd3<16, 3, 2, 2>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 32: return launch_fwd3<32, 3, 2, 2>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 64: return launch_fwd3<64, 3, 2, 2>(qkv, y, lse, B, T, C, nh, ad, st);
+    case 128: return launch_fwd3<128, 3, 2, 2>(qkv, y, lse, B, T, C, nh, ad, st);
   }
   set_error("attn_fwd: head size %d not supported (16, 32, 64, 128)", C / nh);
   return DSF_EUNSUPPORTED;
 }
 
-int attn_bwd_v2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
-                const dsf_dropout* drop, uint32_t* bits, bool p_in_tmem, int parts, cudaStream_t st) {
+int attn_bwd_run(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
+                 const dsf_dropout* drop, uint32_t* bits, int parts, cudaStream_t st) {
   const AttnDrop ad = make_attn_drop(drop, bits, T);
-  if (p_in_tmem) {
-    switch (C / nh) {
-      case 16: return launch_bwd2<16, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
-      case 32: return launch_bwd2<32, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
-      case 64: return launch_bwd2<64, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
-      case 128: return launch_bwd2<128, 64, 3, 3, true>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
-    }
-  }
   switch (C / nh) {
-    case 16: return launch_bwd2<16, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
-    case 32: return launch_bwd2<32, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
-    case 64: return launch_bwd2<64, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
-    case 128: return launch_bwd2<128, 64, 3, 3, false>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
+    case 16: return launch_bwd2<16, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
+    case 32: return launch_bwd2<32, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
+    case 64: return launch_bwd2<64, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
+    case 128: return launch_bwd2<128, 64, 3, 3>(qkv, y, dy, lse, delta, dqkv, B, T, C, nh, ad, parts, st);
   }
   set_error("attn_bwd: head size %d not supported (16, 32, 64, 128)", C / nh);
-  return DSF_EUNSUPPORTED;
-}
-
-int attn_fwd_v5(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const dsf_dropout* drop, uint32_t* bits, cudaStream_t st) {
-  const AttnDrop ad = make_attn_drop(drop, bits, T);
-  switch (C / nh) {
-    case 16: return launch_fwd5<16, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
-    case 32: return launch_fwd5<32, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
-    case 64: return launch_fwd5<64, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
-    case 128: return launch_fwd5<128, 3, 2>(qkv, y, lse, B, T, C, nh, ad, st);
-  }
-  set_error("attn_fwd: head size %d not supported (16, 32, 64, 128)", C / nh);
   return DSF_EUNSUPPORTED;
 }
 

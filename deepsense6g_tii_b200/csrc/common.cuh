@@ -26,6 +26,8 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int num_sms();
+// channel tile of the NCHW token / upsample kernels: 8 for planes of >= 1024 pixels (stages 1-2: 4x the CTAs), else 32
+inline int nchw_channel_tile(const dsf_geom* g) { return (g->H * g->W >= 1024 && g->C % 8 == 0) ? 8 : 32; }
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device (per-context) setting: a kernel's launcher keeps one
 // "configured" flag per device, so a process that drives several GPUs (nn.DataParallel threads, cuda:1 without
 // set_device(0)) configures the kernel on each of them.  Flags are only ever set (benign if two threads race).

@@ -643,236 +643,6 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) tmem_dealloc_pair(tmem_base, L::TMEM_COLS);
 }
 
-// ---------------------------------------------------------------------------------- NT + LayerNorm (full-row epilogue)
-// x_out = A W^T + bias (dropout) + residual  AND  h = LayerNorm(x_out) * gamma + beta  in one launch, for N = 512:
-// proj / mlp.2 of a block (model2_seq.py:109,124-126 + residual :131-132) followed by the next LayerNorm (:118-119 via
-// :131-132).  A CTA pair owns FULL rows: the two 256-column halves of its 256 rows go to the two TMEM accumulator buffers
-// (= all 512 columns), so after both main loops every epilogue thread can reach its whole row.  Pass 1 adds bias / dropout /
-// residual, writes x_out (fp32, TMA store) and parks the sums back in tensor memory; passes 2 and 3 re-read them for the
-// centred variance and for the normalised bf16 row (TMA store), statistics exchanged between the two column-half warps of a
-// row quarter through 1 KB of shared memory and 64-thread named barriers.  Removes the separate LayerNorm launch (~5 us
-// of fixed cost + 35 MB of traffic each) and the half-empty second round of the N = 512 GEMMs; the price is that the
-// epilogue no longer overlaps a next tile (46 row units on 74 pairs: there is no next tile).
-constexpr int LN_N = 512;
-
-__device__ __forceinline__ void gemm_named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-
-struct LnEpi {
-  const float* gamma;
-  const float* beta;
-  float* mean;
-  float* rstd;
-  float eps;
-};
-
-template <int STAGES>
-struct G3LnSmem : G3Smem<256, STAGES> {
-  using B = G3Smem<256, STAGES>;
-  static constexpr int XCH_OFF = B::BAR_OFF + (2 * STAGES + 4) * 8 + 16;  // 4 x 2 x 32 floats
-  static constexpr int DYN = XCH_OFF + 1024 + 1024;
-  static_assert(DYN <= 232448, "shared memory budget");
-};
-
-template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
-gemm_nt3_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                   const __grid_constant__ CUtensorMap tmH, EpiArgs2 epi, LnEpi ln, int M, int K, int m_tiles) {
-  constexpr int BN = 256;
-  using L = G3LnSmem<STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_full = base + L::BAR_OFF, bar_empty = bar_full + STAGES * 8, acc_full = bar_empty + STAGES * 8,
-                 acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
-  float* xch = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + L::XCH_OFF);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int num_k = K / G2_BK;
-  pdl_trigger();
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a * 8, 1); mbar_init(acc_empty + a * 8, 16); }
-    fence_barrier_init();
-  }
-  if (warp == 1) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_wait();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t full0 = mapa_u32(bar_full, 0);
-      int it = 0;
-      for (int mt = pair; mt < m_tiles; mt += n_pairs) {
-        const int m0 = mt * 256 + (int)rank * G2_BM;
-        for (int nt = 0; nt < 2; ++nt) {
-          const int n0 = nt * BN + (int)rank * (BN / 2);
-          for (int kb = 0; kb < num_k; ++kb, ++it) {
-            const int s = it % STAGES;
-            mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
-            if (rank == 0) mbar_expect_tx(bar_full + s * 8, 2 * L::STAGE_BYTES);
-            const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
-            tma_load_2d_pair(sa, &tmA, full0 + s * 8, kb * G2_BK, m0);
-            tma_load_2d_pair(sb, &tmB, full0 + s * 8, kb * G2_BK, n0);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
-      int it = 0, i = 0;
-      for (int mt = pair; mt < m_tiles; mt += n_pairs) {
-        for (int nt = 0; nt < 2; ++nt, ++i) {
-          const int ab = nt;  // i & 1
-          mbar_wait(acc_empty + ab * 8, ((i >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t acc = tmem_base + ab * BN;
-          for (int kb = 0; kb < num_k; ++kb, ++it) {
-            const int s = it % STAGES;
-            mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
-            tc_fence_after();
-            const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
-            const uint64_t da = make_smem_desc(sa, 16, 1024, SWZ_128B);
-            const uint64_t db = make_smem_desc(sb, 16, 1024, SWZ_128B);
-            const uint32_t first = kb != 0 ? 1u : 0u;
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < G2_BK / 16; ++k) tc_mma_bf16_pair(acc, da + (uint32_t)(k * 2), db + (uint32_t)(k * 2), idesc, k == 0 ? first : 1u);
-              tc_commit_pair(bar_empty + s * 8);
-            }
-            __syncwarp();
-          }
-          if (elect_one()) tc_commit_pair(acc_full + ab * 8);
-          __syncwarp();
-        }
-      }
-    }
-  } else {
-    const int q = warp & 3;          // TMEM lane quarter (32 rows)
-    const int ch = (warp - 2) >> 2;  // 128-column half of each 256-column accumulator
-    epi.drop = resolve_drop(epi.drop);
-    const uint32_t acc_empty0 = mapa_u32(acc_empty, 0);
-    float* my_x = xch + (q * 2 + ch) * 32 + lane;
-    const float* peer_x = xch + (q * 2 + (ch ^ 1)) * 32 + lane;
-    const uint32_t stg = base + L::STAGING_OFF + (warp - 2) * 8192;
-    constexpr float inv_n = 1.0f / (float)LN_N;
-    int j = 0, nbox = 0;
-    for (int mt = pair; mt < m_tiles; mt += n_pairs, ++j) {
-      const int m0 = mt * 256 + (int)rank * G2_BM;
-      mbar_wait(acc_full, j & 1);
-      mbar_wait(acc_full + 8, j & 1);
-      tc_fence_after();
-      if (m0 + q * 32 < M) {  // same decision in both column-half warps of a quarter: the barriers below stay paired
-        const int row = m0 + q * 32 + lane;
-        const bool row_ok = row < M;
-        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + ch * 128;
-        // ---- pass 1: x_out = acc + bias (dropout) + residual -> global (TMA) and back into tensor memory; row sum
-        float sum = 0.f;
-#pragma unroll 1
-        for (int cc = 0; cc < 8; ++cc, ++nbox) {
-          const int ab = cc >> 2, c = (cc & 3) * 32;
-          const uint32_t sbuf = stg + (nbox & 1) * 4096;
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
-          const int ncol = ab * BN + ch * 128 + c;
-          uint32_t r[32];
-          tmem_ld32(tq + ab * BN + c, r);
-          tmem_wait_ld();
-          float v[32];
-          epi_math32(epi, row, ncol, r, v, row_ok);
-          uint32_t w[32];
-#pragma unroll
-          for (int t = 0; t < 32; ++t) { sum += v[t]; w[t] = __float_as_uint(v[t]); }
-          tmem_st32(tq + ab * BN + c, w);
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const uint32_t dst = sbuf + lane * 128 + ((t ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[4 * t]), "r"(w[4 * t + 1]), "r"(w[4 * t + 2]), "r"(w[4 * t + 3])
-                         : "memory");
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmC, sbuf, ncol, m0 + q * 32);
-            bulk_commit();
-          }
-        }
-        tmem_wait_st();
-        gemm_named_bar(1 + q, 64);  // the peer has read the previous unit's exchange word
-        *my_x = sum;
-        gemm_named_bar(1 + q, 64);
-        const float mu = (sum + *peer_x) * inv_n;
-        // ---- pass 2: centred sum of squares
-        float sq = 0.f;
-#pragma unroll 1
-        for (int cc = 0; cc < 8; ++cc) {
-          const int ab = cc >> 2, c = (cc & 3) * 32;
-          uint32_t r[32];
-          tmem_ld32(tq + ab * BN + c, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int t = 0; t < 32; ++t) { const float d = __uint_as_float(r[t]) - mu; sq = fmaf(d, d, sq); }
-        }
-        gemm_named_bar(1 + q, 64);  // both halves have read the sums
-        *my_x = sq;
-        gemm_named_bar(1 + q, 64);
-        const float rs = rsqrtf((sq + *peer_x) * inv_n + ln.eps);
-        if (ch == 0 && row_ok) { ln.mean[row] = mu; ln.rstd[row] = rs; }
-        // ---- pass 3: h = (x - mu) * rstd * gamma + beta -> bf16 (TMA store, 64 columns per box)
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc, ++nbox) {
-          const int ab = cc >> 1, c = (cc & 1) * 64;
-          const uint32_t sbuf = stg + (nbox & 1) * 4096;
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
-          const int ncol = ab * BN + ch * 128 + c;
-          uint32_t w[32];
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t r[32];
-            tmem_ld32(tq + ab * BN + c + hh * 32, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int t = 0; t < 32; t += 4) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(ln.gamma + ncol + hh * 32 + t));
-              const float4 bt = __ldg(reinterpret_cast<const float4*>(ln.beta + ncol + hh * 32 + t));
-              const float o0 = (__uint_as_float(r[t]) - mu) * rs * g.x + bt.x, o1 = (__uint_as_float(r[t + 1]) - mu) * rs * g.y + bt.y;
-              const float o2 = (__uint_as_float(r[t + 2]) - mu) * rs * g.z + bt.z, o3 = (__uint_as_float(r[t + 3]) - mu) * rs * g.w + bt.w;
-              w[hh * 16 + t / 2] = pack_bf16x2(o0, o1);
-              w[hh * 16 + t / 2 + 1] = pack_bf16x2(o2, o3);
-            }
-          }
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const uint32_t dst = sbuf + lane * 128 + ((t ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[4 * t]), "r"(w[4 * t + 1]), "r"(w[4 * t + 2]), "r"(w[4 * t + 3])
-                         : "memory");
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmH, sbuf, ncol, m0 + q * 32);
-            bulk_commit();
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive_cluster(acc_empty0); mbar_arrive_cluster(acc_empty0 + 8); }
-    }
-    if (lane == 0) bulk_wait<0>();
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
-}
 
 // ---------------------------------------------------------------------------------- TN (wgrad), split contraction
 
@@ -1010,13 +780,7 @@ static int launch_tn2(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, 
   return check_launch("gemm_tn2");
 }
 
-// Split the leftover tiles of the pair kernel along K.  OFF by default: measured on B200 it loses — N = 512, K = 2048,
-// fp32 output + residual runs 35.7 us unsplit (92 tiles on 74 pairs, 2 rounds) and 43.7 us with the 18 leftover tiles
-// split 4 ways (zero-fill node + 19 MB of fp32 vector reductions cost more than the idle half round they remove); the
-// whole step goes from 4.39 to 4.62 ms.  DSF_GEMM_TAIL_SPLIT=1 enables it for experiments.
-static const bool g_nt_tail_split = getenv("DSF_GEMM_TAIL_SPLIT") ? atoi(getenv("DSF_GEMM_TAIL_SPLIT")) != 0 : false;
-
-// Split the leftover tiles of the pair kernel along N instead (256 x 128 or 256 x 64 units, see the kernel): no partial
+// Split the leftover tiles of the pair kernel along N (256 x 128 or 256 x 64 units, see the kernel): no partial
 // sums, works with every epilogue.  DSF_GEMM_TAIL_NSPLIT=0 disables it.
 static const bool g_nt_tail_nsplit = getenv("DSF_GEMM_TAIL_NSPLIT") ? atoi(getenv("DSF_GEMM_TAIL_NSPLIT")) != 0 : true;
 
@@ -1041,23 +805,9 @@ static int launch_nt3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   const int m_tiles = cdiv(M, 256), n_tiles = N / BN;
   const int tiles = m_tiles * n_tiles;
   const int pairs = std::min(tiles, num_sms() / 2);
-  // Tail splitting (see the kernel): only for plain fp32 outputs (linear epilogue, reductions need fp32), when the
-  // leftover tiles fill at most half of the pairs and sit in one column of tiles (one rectangle to zero-fill).
-  int tail_start = tiles, tail_split = 1;
-  const int rem = tiles % pairs, num_k = K / G2_BK;
-  if (!RTMA && g_nt_tail_split && rem > 0 && 2 * rem <= pairs && epi.c_dtype == DSF_F32 && !(epi.flags & DSF_EPI_RELU) && epi.relu_src == nullptr &&
-      epi.residual != epi.C && num_k >= 2) {
-    const int t0 = tiles - rem;
-    if (t0 / m_tiles == (tiles - 1) / m_tiles) {
-      tail_start = t0;
-      tail_split = std::min(std::min(pairs / rem, num_k), 8);
-      const int row0 = (t0 % m_tiles) * 256, col0 = (t0 / m_tiles) * BN;
-      const int rows = std::min(M, ((tiles - 1) % m_tiles + 1) * 256) - row0;
-      if (cudaMemset2DAsync(reinterpret_cast<float*>(epi.C) + (size_t)row0 * epi.ldc + col0, (size_t)epi.ldc * 4, 0, (size_t)BN * 4, (size_t)rows,
-                            st) != cudaSuccess)
-        return check_launch("gemm_nt3/memset");
-    }
-  }
+  int tail_start = tiles;
+  const int tail_split = 1;  // (splitting leftover tiles along K was measured slower and is no longer offered by the host side)
+  const int rem = tiles % pairs;
   int n_split = 1;
   CUtensorMap tmBt = tmB;
   if (g_nt_tail_nsplit && tail_split == 1 && BN == 256 && Bptr != nullptr && rem > 0 && tiles > pairs) {
@@ -1092,10 +842,8 @@ static int pick_bn_nt(int M, int N) {
   return best;
 }
 
-bool g_nt_pairs = true;  // dsf_gemm_set_impl(3) = on (default), (2) = single-CTA v2 only
-
-int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, const float* bias, const float* residual, int M,
-               int N, int K, int flags, const dsf_dropout* drop, const void* relu_src, cudaStream_t st) {
+int gemm_nt_run(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, const float* bias, const float* residual, int M,
+                int N, int K, int flags, const dsf_dropout* drop, const void* relu_src, bool pairs, cudaStream_t st) {
   // kernel-timing diagnostics only (DESIGN.md "What bounds the tensor-core kernels"): any non-zero value makes the
   // GEMM results WRONG on purpose (skipped loads / epilogue), hence the loud warning
   static const int ablate = [] {
@@ -1104,16 +852,12 @@ int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc,
     return v;
   }();
   CUtensorMap tmA, tmB;
-  if (g_nt_pairs && N % 128 == 0 && M > 128) {
+  if (pairs && N % 128 == 0 && M > 128) {
     // CTA-pair kernel: 256 x BN tiles, each CTA loads BN/2 rows of B.  BN = 256 whenever N allows: one tcgen05.mma costs
     // about the same ~85 ns for N = 128 as for N = 256 (operand reads from shared memory bound it), so narrow tiles
     // waste the tensor pipe even when they would balance the 74 pairs better (measured: N = 512, K = 2048 runs 27.0 us
     // with 256-wide and 30.2 us with 128-wide tiles).
-    // Short contractions with a narrow output (proj and its data gradient: N = 512, K = 512) are epilogue-bound — 2.6 us of
-    // MMAs against ~4 us of epilogue per 256 x 256 tile and only 1.25 tiles per pair — so 128-wide tiles (2.5 per pair)
-    // overlap epilogue and main loop better there (DSF_GEMM_BN128_SMALLK=1; K = 2048 stays on 256-wide tiles, see above).
-    static const bool small_k_bn128 = getenv("DSF_GEMM_BN128_SMALLK") ? atoi(getenv("DSF_GEMM_BN128_SMALLK")) != 0 : false;
-    const int BN3 = (N % 256 == 0 && !(small_k_bn128 && K <= 512 && N <= 512)) ? 256 : 128;
+    const int BN3 = (N % 256 == 0) ? 256 : 128;
     if (int e = make_tmap_bf16(&tmA, A, M, K, lda, G2_BM)) return e;
     if (int e = make_tmap_bf16(&tmB, B, N, K, ldb, BN3 / 2)) return e;
     CUtensorMap tmC3;
@@ -1137,33 +881,7 @@ int gemm_nt_v2(const void* A, int lda, const void* B, int ldb, void* C, int ldc,
   return launch_nt2<64, 5>(tmA, tmB, tmC, epi, M, N, K, st);
 }
 
-int gemm_nt_ln(const void* A, int lda, const void* B, int ldb, float* C, int ldc, const float* bias, const float* residual, void* H, int ldh,
-               const float* gamma, const float* beta, float* mean, float* rstd, float eps, int M, int K, const dsf_dropout* drop,
-               cudaStream_t st) {
-  constexpr int STAGES = 5;
-  using L = G3LnSmem<STAGES>;
-  static bool configured_on[64] = {};
-  bool& configured = per_device_flag(configured_on);
-  if (!configured) {
-    if (cudaFuncSetAttribute(gemm_nt3_ln_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
-      return check_launch("gemm_nt3_ln/attr");
-    configured = true;
-  }
-  CUtensorMap tmA, tmB, tmC, tmH;
-  if (int e = make_tmap_bf16(&tmA, A, M, K, lda, G2_BM)) return e;
-  if (int e = make_tmap_bf16(&tmB, B, LN_N, K, ldb, 128)) return e;
-  if (int e = make_tmap_2d(&tmC, C, DSF_F32, M, LN_N, ldc, 32, 32)) return e;
-  if (int e = make_tmap_2d(&tmH, H, DSF_BF16, M, LN_N, ldh, 64, 32)) return e;
-  const int flags = (bias ? DSF_EPI_BIAS : 0) | (residual ? DSF_EPI_RESIDUAL : 0);
-  EpiArgs2 epi{C, ldc, DSF_F32, bias, residual, flags, LN_N, nullptr, 0, make_drop(drop)};
-  LnEpi ln{gamma, beta, mean, rstd, eps};
-  const int m_tiles = cdiv(M, 256);
-  const int pairs = std::min(m_tiles, num_sms() / 2);
-  launch_pdl(gemm_nt3_ln_kernel<STAGES>, dim3(2 * pairs), dim3(G2_THREADS), L::DYN, st, tmA, tmB, tmC, tmH, epi, ln, M, K, m_tiles);
-  return check_launch("gemm_nt3_ln");
-}
-
-int gemm_tn_v2(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st) {
+int gemm_tn_run(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st) {
   const int BN = (Kout % 256 == 0) ? 256 : ((Kout % 128 == 0) ? 128 : 64);
   CUtensorMap tmA, tmB;
   if (int e = make_tmap_bf16(&tmA, A, M, Nout, lda, G2_BK)) return e;

@@ -2,10 +2,11 @@
 // Replaces model2_seq.py:515-517 (AdaptiveAvgPool2d x3) and :256-272 (view/cat/permute/contiguous/
 // cat(gps)/+pos_emb) with one pass over the feature maps; HBM-bound (reads E_f, writes E_t).
 //
-// NCHW: one CTA owns (frame, 32-channel tile).  Lanes run along the contiguous W axis when reading the
-// pooling windows (16-byte vector loads when kw % 4 == 0), the pooled (cell, channel) tile is
-// transposed through shared memory and written channel-contiguous (128 B per warp store) with
-// pos_emb added on the way out.
+// NCHW: one CTA owns (frame, CT-channel tile), CT = 32 for small planes and 8 for planes of >= 1024 pixels (stages 1-2:
+// four times as many CTAs, i.e. enough 16-byte loads in flight to cover the HBM latency).  Lanes run along the contiguous
+// W axis when reading the pooling windows: consecutive lanes load consecutive 16-byte chunks of a row (fully coalesced),
+// the kw/4 lanes of a window combine their partial sums with shuffles; the pooled (cell, channel) tile is transposed
+// through shared memory and written channel-contiguous with pos_emb added on the way out.
 // NHWC: pure streaming; one thread owns 4 channels of one anchor cell.
 #include <algorithm>
 
@@ -13,8 +14,9 @@
 
 namespace dsf {
 
-constexpr int TOK_CT = 32;       // channel tile (NCHW kernels)
+constexpr int TOK_CT = 32;       // largest channel tile (NCHW kernels)
 constexpr int TOK_THREADS = 256;
+
 
 struct FrameRef {
   const void* base;
@@ -30,19 +32,19 @@ __device__ __forceinline__ void frame_of(const dsf_geom& g, int b, int sl, const
 }
 
 // ------------------------------------------------------------------------------------ forward NCHW
-template <typename FT>
+template <typename FT, int CT>
 __global__ void __launch_bounds__(TOK_THREADS)
 tokens_fwd_nchw_kernel(dsf_geom g, const void* __restrict__ img, const void* __restrict__ lidar,
                        const void* __restrict__ radar, const float* __restrict__ gps,
                        const float* __restrict__ pos_emb, float* __restrict__ x) {
-  extern __shared__ float sm[];  // [cells][TOK_CT + 1]
+  extern __shared__ float sm[];  // [cells][CT + 1]
   const int cells = g.A_h * g.A_w;
   const int slots = (g.V + 2) * g.S;
   const int Tm = slots * cells, T = Tm + 2;
   const int F = g.B * slots;
   const int f = blockIdx.x;
-  const int c0 = blockIdx.y * TOK_CT;
-  const int nct = min(TOK_CT, g.C - c0);
+  const int c0 = blockIdx.y * CT;
+  const int nct = min(CT, g.C - c0);
   const int tid = threadIdx.x;
   if (f >= F) {  // GPS tokens of sample b (model2_seq.py:270)
     const int b = f - F;
@@ -68,7 +70,24 @@ tokens_fwd_nchw_kernel(dsf_geom g, const void* __restrict__ img, const void* __r
       Vec4<FT>::load(plane0 + 4 * i, v);
       const int cl = (4 * i) / cells, cell = (4 * i) % cells;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) sm[(cell + k) * (TOK_CT + 1) + cl] = v[k];
+      for (int k = 0; k < 4; ++k) sm[(cell + k) * (CT + 1) + cl] = v[k];
+    }
+  } else if (vec && (kw / 4 == 1 || kw / 4 == 2 || kw / 4 == 4 || kw / 4 == 8) && ((nct * g.A_h * (g.W / 4)) % 32 == 0)) {
+    // lanes along W: item = (channel, anchor row, 16-byte chunk of the row); the LW = kw/4 lanes of one window are adjacent
+    const int W4 = g.W / 4, LW = kw / 4;
+    const int items = nct * g.A_h * W4;
+    for (int o = tid; o < items; o += TOK_THREADS) {
+      const int j = o % W4, cy = (o / W4) % g.A_h, cl = o / (W4 * g.A_h);
+      const FT* p = plane0 + (size_t)cl * HW + (size_t)(cy * kh) * g.W + 4 * j;
+      float acc = 0.f;
+#pragma unroll 4
+      for (int r = 0; r < kh; ++r) {
+        float v[4];
+        Vec4<FT>::load(p + (size_t)r * g.W, v);
+        acc += (v[0] + v[1]) + (v[2] + v[3]);
+      }
+      for (int d = 1; d < LW; d <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+      if (j % LW == 0) sm[(cy * g.A_w + j / LW) * (CT + 1) + cl] = acc * inv;
     }
   } else
   for (int o = tid; o < nct * cells; o += TOK_THREADS) {
@@ -88,18 +107,18 @@ tokens_fwd_nchw_kernel(dsf_geom g, const void* __restrict__ img, const void* __r
       for (int r = 0; r < kh; ++r)
         for (int q = 0; q < kw; ++q) acc += to_f<FT>(p[(size_t)r * g.W + q]);
     }
-    sm[cell * (TOK_CT + 1) + cl] = acc * inv;
+    sm[cell * (CT + 1) + cl] = acc * inv;
   }
   __syncthreads();
   const int tok0 = sl * cells;
-  if (nct == TOK_CT && g.C % 4 == 0) {  // 16-byte stores: 8 lanes cover the 32 channels of one token
-    for (int o = tid; o < cells * (TOK_CT / 4); o += TOK_THREADS) {
-      const int cell = o / (TOK_CT / 4), cl = (o % (TOK_CT / 4)) * 4;
+  if (nct == CT && g.C % 4 == 0) {  // 16-byte stores: 8 lanes cover the 32 channels of one token
+    for (int o = tid; o < cells * (CT / 4); o += TOK_THREADS) {
+      const int cell = o / (CT / 4), cl = (o % (CT / 4)) * 4;
       const int tok = tok0 + cell;
       float pe[4], v[4];
       Vec4<float>::load(pos_emb + (size_t)tok * g.C + c0 + cl, pe);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = sm[cell * (TOK_CT + 1) + cl + k] + pe[k];
+      for (int k = 0; k < 4; ++k) v[k] = sm[cell * (CT + 1) + cl + k] + pe[k];
       Vec4<float>::store(x + ((size_t)b * T + tok) * g.C + c0 + cl, v);
     }
     return;
@@ -107,7 +126,7 @@ tokens_fwd_nchw_kernel(dsf_geom g, const void* __restrict__ img, const void* __r
   for (int o = tid; o < cells * nct; o += TOK_THREADS) {
     const int cell = o / nct, cl = o % nct;
     const int tok = tok0 + cell;
-    x[((size_t)b * T + tok) * g.C + c0 + cl] = sm[cell * (TOK_CT + 1) + cl] + pos_emb[(size_t)tok * g.C + c0 + cl];
+    x[((size_t)b * T + tok) * g.C + c0 + cl] = sm[cell * (CT + 1) + cl] + pos_emb[(size_t)tok * g.C + c0 + cl];
   }
 }
 
@@ -155,20 +174,20 @@ tokens_fwd_nhwc_kernel(dsf_geom g, const void* __restrict__ img, const void* __r
 }
 
 // ------------------------------------------------------------------------------------ backward NCHW
-template <typename FT>
+template <typename FT, int CT>
 __global__ void __launch_bounds__(TOK_THREADS)
 tokens_bwd_nchw_kernel(dsf_geom g, const float* __restrict__ dx, const void* __restrict__ dres_img,
                        const void* __restrict__ dres_lidar, const void* __restrict__ dres_radar,
                        void* __restrict__ dimg, void* __restrict__ dlidar, void* __restrict__ dradar,
                        float* __restrict__ dgps) {
-  extern __shared__ float sm[];  // [cells][TOK_CT + 1]
+  extern __shared__ float sm[];  // [cells][CT + 1]
   const int cells = g.A_h * g.A_w;
   const int slots = (g.V + 2) * g.S;
   const int Tm = slots * cells, T = Tm + 2;
   const int F = g.B * slots;
   const int f = blockIdx.x;
-  const int c0 = blockIdx.y * TOK_CT;
-  const int nct = min(TOK_CT, g.C - c0);
+  const int c0 = blockIdx.y * CT;
+  const int nct = min(CT, g.C - c0);
   const int tid = threadIdx.x;
   if (f >= F) {
     const int b = f - F;
@@ -182,18 +201,18 @@ tokens_bwd_nchw_kernel(dsf_geom g, const float* __restrict__ dx, const void* __r
   const int kh = g.H / g.A_h, kw = g.W / g.A_w;
   const float inv = 1.0f / (float)(kh * kw);
   const int tok0 = sl * cells;
-  if (nct == TOK_CT && g.C % 4 == 0) {  // 16-byte loads: 8 lanes cover the 32 channels of one token
-    for (int o = tid; o < cells * (TOK_CT / 4); o += TOK_THREADS) {
-      const int cell = o / (TOK_CT / 4), cl = (o % (TOK_CT / 4)) * 4;
+  if (nct == CT && g.C % 4 == 0) {  // 16-byte loads: 8 lanes cover the 32 channels of one token
+    for (int o = tid; o < cells * (CT / 4); o += TOK_THREADS) {
+      const int cell = o / (CT / 4), cl = (o % (CT / 4)) * 4;
       float v[4];
       Vec4<float>::load(dx + ((size_t)b * T + tok0 + cell) * g.C + c0 + cl, v);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) sm[cell * (TOK_CT + 1) + cl + k] = v[k] * inv;
+      for (int k = 0; k < 4; ++k) sm[cell * (CT + 1) + cl + k] = v[k] * inv;
     }
   } else {
     for (int o = tid; o < cells * nct; o += TOK_THREADS) {
       const int cell = o / nct, cl = o % nct;
-      sm[cell * (TOK_CT + 1) + cl] = dx[((size_t)b * T + tok0 + cell) * g.C + c0 + cl] * inv;
+      sm[cell * (CT + 1) + cl] = dx[((size_t)b * T + tok0 + cell) * g.C + c0 + cl] * inv;
     }
   }
   __syncthreads();
@@ -207,27 +226,37 @@ tokens_bwd_nchw_kernel(dsf_geom g, const float* __restrict__ dx, const void* __r
   if (g.W % 4 == 0) {
     const int W4 = g.W / 4;
     const int per = g.H * W4;
-    for (int o = tid; o < nct * per; o += TOK_THREADS) {
-      const int cl = o / per, r = o % per;
-      const int h = r / W4, w = (r % W4) * 4;
-      const int cy = h / kh;
-      float v[4];
+    const int total = nct * per;
+    constexpr int U = 4;  // independent 16-byte loads in flight per thread
+    for (int o0 = tid; o0 < total; o0 += U * TOK_THREADS) {
+      float rv[U][4];
+      size_t offs[U];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = sm[(cy * g.A_w + (w + k) / kw) * (TOK_CT + 1) + cl];
-      const size_t off = (size_t)cl * HW + (size_t)h * g.W + w;
-      if (res) {
-        float rv[4];
-        Vec4<FT>::load(res + off, rv);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] += rv[k];
+      for (int u = 0; u < U; ++u) {
+        const int o = o0 + u * TOK_THREADS;
+        const int oc = o < total ? o : o0;
+        const int cl = oc / per, r = oc % per;
+        offs[u] = (size_t)cl * HW + (size_t)(r / W4) * g.W + (r % W4) * 4;
+        if (res) Vec4<FT>::load(res + offs[u], rv[u]);
+        else { rv[u][0] = rv[u][1] = rv[u][2] = rv[u][3] = 0.f; }
       }
-      Vec4<FT>::store(out + off, v);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int o = o0 + u * TOK_THREADS;
+        if (o >= total) break;
+        const int cl = o / per, r = o % per;
+        const int h = r / W4, w = (r % W4) * 4;
+        const int cy = h / kh;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rv[u][k] += sm[(cy * g.A_w + (w + k) / kw) * (CT + 1) + cl];
+        Vec4<FT>::store(out + offs[u], rv[u]);
+      }
     }
   } else {
     for (int o = tid; o < nct * HW; o += TOK_THREADS) {
       const int cl = o / HW, r = o % HW;
       const int h = r / g.W, w = r % g.W;
-      float v = sm[((h / kh) * g.A_w + w / kw) * (TOK_CT + 1) + cl];
+      float v = sm[((h / kh) * g.A_w + w / kw) * (CT + 1) + cl];
       const size_t off = (size_t)cl * HW + r;
       if (res) v += to_f<FT>(res[off]);
       out[off] = from_f<FT>(v);
@@ -327,15 +356,17 @@ extern "C" int dsf_tokens_fwd(const dsf_geom* g, const void* img, const void* li
   const int cells = g->A_h * g->A_w;
   const int slots = (g->V + 2) * g->S;
   if (g->layout == DSF_NCHW) {
-    dim3 grid(g->B * slots + g->B, cdiv(g->C, TOK_CT));
-    size_t smem = (size_t)cells * (TOK_CT + 1) * sizeof(float);
-    if (g->feat_dtype == DSF_F32) {
-      if (smem > 48 * 1024) cudaFuncSetAttribute(tokens_fwd_nchw_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      tokens_fwd_nchw_kernel<float><<<grid, TOK_THREADS, smem, st>>>(*g, img, lidar, radar, gps, pos_emb, x);
-    } else {
-      if (smem > 48 * 1024) cudaFuncSetAttribute(tokens_fwd_nchw_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      tokens_fwd_nchw_kernel<__nv_bfloat16><<<grid, TOK_THREADS, smem, st>>>(*g, img, lidar, radar, gps, pos_emb, x);
-    }
+    const int ct = nchw_channel_tile(g);
+    dim3 grid(g->B * slots + g->B, cdiv(g->C, ct));
+    size_t smem = (size_t)cells * (ct + 1) * sizeof(float);
+#define DSF_TOK_FWD(FT, CT_)                                                                                                       \
+  do {                                                                                                                             \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(tokens_fwd_nchw_kernel<FT, CT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    tokens_fwd_nchw_kernel<FT, CT_><<<grid, TOK_THREADS, smem, st>>>(*g, img, lidar, radar, gps, pos_emb, x);                       \
+  } while (0)
+    if (g->feat_dtype == DSF_F32) { if (ct == 8) DSF_TOK_FWD(float, 8); else DSF_TOK_FWD(float, 32); }
+    else { if (ct == 8) DSF_TOK_FWD(__nv_bfloat16, 8); else DSF_TOK_FWD(__nv_bfloat16, 32); }
+#undef DSF_TOK_FWD
   } else {
     const int64_t total = (int64_t)g->B * (slots * cells + 2) * (g->C / 4);
     int blocks = (int)std::min<int64_t>(cdiv64(total, 256), (int64_t)num_sms() * 16);
@@ -361,15 +392,17 @@ extern "C" int dsf_tokens_bwd(const dsf_geom* g, const float* dx, const void* dr
   const int slots = (g->V + 2) * g->S;
   const int T = slots * cells + 2;
   if (g->layout == DSF_NCHW) {
-    dim3 grid(g->B * slots + g->B, cdiv(g->C, TOK_CT));
-    size_t smem = (size_t)cells * (TOK_CT + 1) * sizeof(float);
-    if (g->feat_dtype == DSF_F32) {
-      if (smem > 48 * 1024) cudaFuncSetAttribute(tokens_bwd_nchw_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      tokens_bwd_nchw_kernel<float><<<grid, TOK_THREADS, smem, st>>>(*g, dx, dres_img, dres_lidar, dres_radar, dimg, dlidar, dradar, dgps);
-    } else {
-      if (smem > 48 * 1024) cudaFuncSetAttribute(tokens_bwd_nchw_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      tokens_bwd_nchw_kernel<__nv_bfloat16><<<grid, TOK_THREADS, smem, st>>>(*g, dx, dres_img, dres_lidar, dres_radar, dimg, dlidar, dradar, dgps);
-    }
+    const int ct = nchw_channel_tile(g);
+    dim3 grid(g->B * slots + g->B, cdiv(g->C, ct));
+    size_t smem = (size_t)cells * (ct + 1) * sizeof(float);
+#define DSF_TOK_BWD(FT, CT_)                                                                                                       \
+  do {                                                                                                                             \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(tokens_bwd_nchw_kernel<FT, CT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    tokens_bwd_nchw_kernel<FT, CT_><<<grid, TOK_THREADS, smem, st>>>(*g, dx, dres_img, dres_lidar, dres_radar, dimg, dlidar, dradar, dgps); \
+  } while (0)
+    if (g->feat_dtype == DSF_F32) { if (ct == 8) DSF_TOK_BWD(float, 8); else DSF_TOK_BWD(float, 32); }
+    else { if (ct == 8) DSF_TOK_BWD(__nv_bfloat16, 8); else DSF_TOK_BWD(__nv_bfloat16, 32); }
+#undef DSF_TOK_BWD
   } else {
     const int64_t total = (int64_t)g->B * slots * g->H * g->W * (g->C / 4) + (int64_t)g->B * 2 * (g->C / 4);
     int blocks = (int)std::min<int64_t>(cdiv64(total, 256), (int64_t)num_sms() * 16);

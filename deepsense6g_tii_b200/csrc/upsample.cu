@@ -11,7 +11,6 @@
 
 namespace dsf {
 
-constexpr int UP_CT = 32;
 constexpr int UP_THREADS = 256;
 constexpr int UP_WARPS = UP_THREADS / 32;
 
@@ -36,7 +35,7 @@ struct Ptr3 { const void* p[3]; };
 struct MPtr3 { void* p[3]; };
 
 // ------------------------------------------------------------------------------------ forward NCHW
-template <typename FT>
+template <typename FT, int UP_CT>
 __global__ void __launch_bounds__(UP_THREADS)
 upsample_add_fwd_nchw_kernel(dsf_geom g, const float* __restrict__ y, Ptr3 feat, MPtr3 out) {
   extern __shared__ float sm[];  // [cells][UP_CT + 1]
@@ -70,24 +69,37 @@ upsample_add_fwd_nchw_kernel(dsf_geom g, const float* __restrict__ y, Ptr3 feat,
   FT* fout = reinterpret_cast<FT*>(out.p[which]) + off0;
   const float rsh = (float)g.A_h / (float)g.H, rsw = (float)g.A_w / (float)g.W;
   if (g.W % 4 == 0) {
-    const int W4 = g.W / 4, per = g.H * W4;
-    for (int o = tid; o < nct * per; o += UP_THREADS) {
-      const int cl = o / per, r = o % per;
-      const int h = r / W4, w = (r % W4) * 4;
-      const Tap ty = tap_of(h, rsh, g.A_h);
-      const float* r0 = sm + (ty.i0 * g.A_w) * (UP_CT + 1) + cl;
-      const float* r1 = sm + (ty.i1 * g.A_w) * (UP_CT + 1) + cl;
-      const size_t off = (size_t)cl * HW + (size_t)h * g.W + w;
-      float v[4];
-      Vec4<FT>::load(fin + off, v);
+    const int W4 = g.W / 4, per = g.H * W4, total = nct * per;
+    constexpr int U = 4;  // independent 16-byte loads in flight per thread
+    for (int o0 = tid; o0 < total; o0 += U * UP_THREADS) {
+      float v[U][4];
+      size_t offs[U];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const Tap tx = tap_of(w + k, rsw, g.A_w);
-        const float top = (1.f - tx.lam) * r0[tx.i0 * (UP_CT + 1)] + tx.lam * r0[tx.i1 * (UP_CT + 1)];
-        const float bot = (1.f - tx.lam) * r1[tx.i0 * (UP_CT + 1)] + tx.lam * r1[tx.i1 * (UP_CT + 1)];
-        v[k] += (1.f - ty.lam) * top + ty.lam * bot;
+      for (int u = 0; u < U; ++u) {
+        const int o = o0 + u * UP_THREADS;
+        const int oc = o < total ? o : o0;
+        const int cl = oc / per, r = oc % per;
+        offs[u] = (size_t)cl * HW + (size_t)(r / W4) * g.W + (r % W4) * 4;
+        Vec4<FT>::load(fin + offs[u], v[u]);
       }
-      Vec4<FT>::store(fout + off, v);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int o = o0 + u * UP_THREADS;
+        if (o >= total) break;
+        const int cl = o / per, r = o % per;
+        const int h = r / W4, w = (r % W4) * 4;
+        const Tap ty = tap_of(h, rsh, g.A_h);
+        const float* r0 = sm + (ty.i0 * g.A_w) * (UP_CT + 1) + cl;
+        const float* r1 = sm + (ty.i1 * g.A_w) * (UP_CT + 1) + cl;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const Tap tx = tap_of(w + k, rsw, g.A_w);
+          const float top = (1.f - tx.lam) * r0[tx.i0 * (UP_CT + 1)] + tx.lam * r0[tx.i1 * (UP_CT + 1)];
+          const float bot = (1.f - tx.lam) * r1[tx.i0 * (UP_CT + 1)] + tx.lam * r1[tx.i1 * (UP_CT + 1)];
+          v[u][k] += (1.f - ty.lam) * top + ty.lam * bot;
+        }
+        Vec4<FT>::store(fout + offs[u], v[u]);
+      }
     }
   } else {
     for (int o = tid; o < nct * HW; o += UP_THREADS) {
@@ -146,7 +158,7 @@ upsample_add_fwd_nhwc_kernel(dsf_geom g, const float* __restrict__ y, Ptr3 feat,
 // Separable adjoint: (1) each warp walks one channel plane with lanes along W and scatters the
 // row-weighted values into its private tmp[A_h][W] tile, (2) the W axis is folded per anchor cell,
 // (3) the (cell, channel) tile is transposed through shared memory and written channel-contiguous.
-template <typename FT>
+template <typename FT, int UP_CT>
 __global__ void __launch_bounds__(UP_THREADS)
 upsample_add_bwd_nchw_kernel(dsf_geom g, Ptr3 dout, const float* __restrict__ dgps_out, float* __restrict__ dy) {
   extern __shared__ float sm[];
@@ -188,6 +200,52 @@ upsample_add_bwd_nchw_kernel(dsf_geom g, Ptr3 dout, const float* __restrict__ dg
     for (int i = lane; i < g.A_h * g.W; i += 32) tmp[i] = 0.f;
     __syncwarp();
     const FT* pl = src + (size_t)cl * HW;
+    const int W4 = g.W / 4, sh = g.H / g.A_h;
+    if (g.W % 4 == 0 && (W4 == 1 || W4 == 2 || W4 == 4 || W4 == 8 || W4 == 16 || W4 == 32)) {
+      // Rows of the plane are streamed with 16-byte loads: lane = (row phase, 16-byte chunk), npar = 32 / W4 rows per load
+      // instruction.  Source rows of anchor block k (k*sh .. k*sh+sh-1) touch anchor rows k-1, k, k+1 only, so a lane keeps
+      // three register accumulators per column and adds them to the shared [A_h][W] tile (shared-memory atomics: lanes of
+      // other row phases own the same columns) whenever its next row belongs to another block.
+      const int npar = 32 / W4, par = lane / W4, w0 = (lane % W4) * 4;
+      float a_prev[4] = {0.f, 0.f, 0.f, 0.f}, a_cur[4] = {0.f, 0.f, 0.f, 0.f}, a_next[4] = {0.f, 0.f, 0.f, 0.f};
+      int blk = -1;
+      auto flush = [&]() {
+        if (blk < 0) return;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (blk > 0) atomicAdd(tmp + (blk - 1) * g.W + w0 + k, a_prev[k]);
+          atomicAdd(tmp + blk * g.W + w0 + k, a_cur[k]);
+          if (blk + 1 < g.A_h) atomicAdd(tmp + (blk + 1) * g.W + w0 + k, a_next[k]);
+          a_prev[k] = a_cur[k] = a_next[k] = 0.f;
+        }
+      };
+      constexpr int U = 4;
+      for (int h0 = par; h0 < g.H; h0 += U * npar) {
+        float v[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int h = h0 + u * npar;
+          if (h < g.H) Vec4<FT>::load(pl + (size_t)h * g.W + w0, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int h = h0 + u * npar;
+          if (h >= g.H) break;
+          const int k = h / sh;
+          if (k != blk) { flush(); blk = k; }
+          const Tap ty = tap_of(h, rsh, g.A_h);
+          // ty.i0 / ty.i1 are in {k-1, k, k+1} (clamped at the borders: both weights may land on the same anchor row)
+          const float w_lo = 1.f - ty.lam, w_hi = ty.lam;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float x = v[u][q];
+            if (ty.i0 == k - 1) a_prev[q] += w_lo * x; else if (ty.i0 == k) a_cur[q] += w_lo * x; else a_next[q] += w_lo * x;
+            if (ty.i1 == k - 1) a_prev[q] += w_hi * x; else if (ty.i1 == k) a_cur[q] += w_hi * x; else a_next[q] += w_hi * x;
+          }
+        }
+      }
+      flush();
+    } else
     for (int w = lane; w < g.W; w += 32) {
 #pragma unroll 4
       for (int h = 0; h < g.H; ++h) {
@@ -297,15 +355,17 @@ extern "C" int dsf_upsample_add_fwd(const dsf_geom* g, const float* y, const voi
   Ptr3 fin{{img, lidar, radar}};
   MPtr3 fout{{out_img, out_lidar, out_radar}};
   if (g->layout == DSF_NCHW) {
-    dim3 grid(g->B * slots, cdiv(g->C, UP_CT));
-    const size_t smem = (size_t)cells * (UP_CT + 1) * sizeof(float);
-    if (g->feat_dtype == DSF_F32) {
-      if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_add_fwd_nchw_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      upsample_add_fwd_nchw_kernel<float><<<grid, UP_THREADS, smem, st>>>(*g, y, fin, fout);
-    } else {
-      if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_add_fwd_nchw_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      upsample_add_fwd_nchw_kernel<__nv_bfloat16><<<grid, UP_THREADS, smem, st>>>(*g, y, fin, fout);
-    }
+    const int ct = nchw_channel_tile(g);
+    dim3 grid(g->B * slots, cdiv(g->C, ct));
+    const size_t smem = (size_t)cells * (ct + 1) * sizeof(float);
+#define DSF_UP_FWD(FT, CT_)                                                                                                              \
+  do {                                                                                                                                   \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_add_fwd_nchw_kernel<FT, CT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    upsample_add_fwd_nchw_kernel<FT, CT_><<<grid, UP_THREADS, smem, st>>>(*g, y, fin, fout);                                              \
+  } while (0)
+    if (g->feat_dtype == DSF_F32) { if (ct == 8) DSF_UP_FWD(float, 8); else DSF_UP_FWD(float, 32); }
+    else { if (ct == 8) DSF_UP_FWD(__nv_bfloat16, 8); else DSF_UP_FWD(__nv_bfloat16, 32); }
+#undef DSF_UP_FWD
   } else {
     const int64_t total = (int64_t)g->B * slots * g->H * g->W * (g->C / 4);
     const int blocks = (int)std::min<int64_t>(cdiv64(total, 256), (int64_t)num_sms() * 16);
@@ -325,16 +385,18 @@ extern "C" int dsf_upsample_add_bwd(const dsf_geom* g, const void* dout_img, con
   const int cells = g->A_h * g->A_w, slots = (g->V + 2) * g->S;
   Ptr3 din{{dout_img, dout_lidar, dout_radar}};
   if (g->layout == DSF_NCHW) {
-    dim3 grid(g->B * slots + g->B, cdiv(g->C, UP_CT));
-    const size_t smem = ((size_t)cells * (UP_CT + 1) + (size_t)UP_WARPS * g->A_h * g->W) * sizeof(float);
+    const int ct = nchw_channel_tile(g);
+    dim3 grid(g->B * slots + g->B, cdiv(g->C, ct));
+    const size_t smem = ((size_t)cells * (ct + 1) + (size_t)UP_WARPS * g->A_h * g->W) * sizeof(float);
     DSF_REQUIRE(smem <= 227 * 1024, "upsample_add_bwd: tile does not fit shared memory (%zu B)", smem);
-    if (g->feat_dtype == DSF_F32) {
-      if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_add_bwd_nchw_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      upsample_add_bwd_nchw_kernel<float><<<grid, UP_THREADS, smem, st>>>(*g, din, dgps_out, dy);
-    } else {
-      if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_add_bwd_nchw_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      upsample_add_bwd_nchw_kernel<__nv_bfloat16><<<grid, UP_THREADS, smem, st>>>(*g, din, dgps_out, dy);
-    }
+#define DSF_UP_BWD(FT, CT_)                                                                                                              \
+  do {                                                                                                                                   \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_add_bwd_nchw_kernel<FT, CT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    upsample_add_bwd_nchw_kernel<FT, CT_><<<grid, UP_THREADS, smem, st>>>(*g, din, dgps_out, dy);                                         \
+  } while (0)
+    if (g->feat_dtype == DSF_F32) { if (ct == 8) DSF_UP_BWD(float, 8); else DSF_UP_BWD(float, 32); }
+    else { if (ct == 8) DSF_UP_BWD(__nv_bfloat16, 8); else DSF_UP_BWD(__nv_bfloat16, 32); }
+#undef DSF_UP_BWD
   } else {
     const int64_t total = (int64_t)g->B * (slots * cells + 2) * (g->C / 4);
     const int blocks = (int)std::min<int64_t>(cdiv64(total, 256), (int64_t)num_sms() * 16);

@@ -152,7 +152,48 @@ class GPT(nn.Module):
         return dict(dropout=dropout, seq_len=self.seq_len, n_views=self.config.n_views, vert_anchors=self.vert_anchors,
                     horz_anchors=self.horz_anchors, n_head=self.n_head, n_layer=self.n_layer,
                     compute_dtype=getattr(self.config, "fusion_dtype", torch.bfloat16), residual=residual,
-                    grad_hook=getattr(self, "_grad_reducer", None))
+                    grad_hook=getattr(self, "_grad_reducer", None), shadows=self._shadow_cfg())
+
+    # ---------------------------------------------------------------- persistent bf16 weight shadows (optim.FusedAdamWEMA)
+    def enable_persistent_shadows(self):
+        """Keep the bf16 weight shadows of every block (plain + transposed, q/k/v fused; see ``functional._forward_bf16``) in
+        buffers owned by this module instead of re-packing them at the start of every forward.  The forward re-packs only when
+        a parameter changed behind the shadows' back (``_shadow_key``); ``optim.FusedAdamWEMA`` writes them as part of its
+        update and calls ``mark_shadows_fresh``."""
+        if getattr(self, "_shadow_bufs", None) is None:
+            self._shadow_bufs = [None] * self.n_layer
+            self._shadow_fresh_key = None
+
+    def shadow_views(self, i):
+        C = self.n_embd
+        F = self.blocks[i].mlp[0].weight.shape[0]
+        dev = self.pos_emb.device
+        b = self._shadow_bufs[i]
+        if b is None or b["flat"].device != dev:
+            sizes = [3 * C * C, 3 * C * C, C * C, C * C, F * C, F * C, C * F, C * F]
+            flat = torch.empty(sum(sizes), device=dev, dtype=torch.bfloat16)
+            v, off = [], 0
+            for n in sizes:
+                v.append(flat[off:off + n])
+                off += n
+            b = dict(flat=flat, wqkv=v[0].view(3 * C, C), wqkv_t=v[1].view(C, 3 * C), wp=v[2].view(C, C), wp_t=v[3].view(C, C),
+                     w1=v[4].view(F, C), w1_t=v[5].view(C, F), w2=v[6].view(C, F), w2_t=v[7].view(F, C),
+                     bqkv=torch.empty(3 * C, device=dev, dtype=torch.float32))
+            self._shadow_bufs[i] = b
+            self._shadow_fresh_key = None
+        return {k: t for k, t in b.items() if k != "flat"}
+
+    def _shadow_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self._flat_params())
+
+    def mark_shadows_fresh(self):
+        self._shadow_fresh_key = self._shadow_key()
+
+    def _shadow_cfg(self):
+        if getattr(self, "_shadow_bufs", None) is None or getattr(self.config, "fusion_dtype", torch.bfloat16) != torch.bfloat16:
+            return None
+        views = [self.shadow_views(i) for i in range(self.n_layer)]
+        return dict(views=views, fresh=self._shadow_fresh_key is not None and self._shadow_fresh_key == self._shadow_key(), owner=self)
 
     def set_grad_reducer(self, reducer):
         """Data-parallel training: a ``dist.OverlappedGradReducer`` that averages this GPT's gradients block by block

@@ -50,6 +50,9 @@ class EMA:
         self.shadow = {n: p.data.clone() for n, p in self._named()}
 
     def update(self):
+        if getattr(self, "_fused_updates", 0) > 0:   # optim.FusedAdamWEMA.step() has already folded this update into its launch
+            self._fused_updates -= 1
+            return
         named = self._named()
         if not named:
             return

@@ -125,9 +125,9 @@ int dsf_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const fl
  * 97-99,109,122,124) and its autograd.
  *   NT:  C[M,N] = A[M,K] . B[N,K]^T  (+bias)(relu)(+residual)      A, B bf16 row-major (K contiguous)
  *        C is c_dtype (bf16 or fp32) with leading dimension ldc; residual is fp32 with ldc.
- *   TN:  C[N',K'] (+)= A[M,N']^T . B[M,K']   (weight gradient; contraction over the M rows)
- *        A, B bf16 row-major; C fp32.  With DSF_EPI_ACCUM the result is atomically added to C
- *        (split over M across CTAs); without it C must be zero-filled by the caller.              */
+ *   TN:  C[N',K'] += A[M,N']^T . B[M,K']   (weight gradient; contraction over the M rows)
+ *        A, B bf16 row-major; C fp32.  The contraction is split over CTAs and the partial products are ADDED to C with
+ *        fp32 vector reductions: C must be zero-filled (or hold a running sum) before the call.   */
 /*        `drop` (nullable): dropout applied after bias/ReLU and BEFORE the residual add, element index m*N + n
  *        (resid_drop of the proj / mlp.2 outputs, model2_seq.py:109,125).                              */
 /*        `relu_src` (nullable): bf16 (M,N) with leading dimension ldc; the result is zeroed where relu_src <= 0
@@ -138,17 +138,8 @@ int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32_t ldb, voi
                      void* stream);
 int dsf_gemm_bf16_tn(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc,
                      int32_t M, int32_t Nout, int32_t Kout, void* stream);
-/* NT GEMM + residual + the FOLLOWING LayerNorm in one launch (N = 512 only; a CTA pair owns full rows):
- *   C[M,512] (fp32) = A W^T + bias (dropout) + residual     -- proj / mlp.2 + residual add (model2_seq.py:109,124-126,131-132)
- *   H[M,512] (bf16) = LayerNorm(C) * gamma + beta, mean / rstd (fp32, M) saved for the backward  (:118-119, eps as given)
- * Replaces dsf_gemm_bf16_nt(..., residual) followed by dsf_layernorm_fwd on its output.                        */
-int dsf_gemm_bf16_nt_ln(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc,
-                        const float* bias, const float* residual, void* H, int32_t ldh, const float* gamma,
-                        const float* beta, float* mean, float* rstd, float eps, int32_t M, int32_t N, int32_t K,
-                        const dsf_dropout* drop, void* stream);
-/* Selects the tensor-core GEMM implementation (process-wide; tests and A/B timing): 0 = default (= 3),
- * 1 = v1 (one CTA per 128x128 tile), 2 = v2 (persistent, 128x256 tiles, double-buffered TMEM),
- * 3 = v3 (NT: CTA pairs, tcgen05.mma.cta_group::2 on 256x256 tiles where N % 256 == 0; otherwise v2). */
+/* Selects the NT tile schedule (process-wide, atomic; tests and A/B timing): 0 = default (CTA pairs, tcgen05.mma.cta_group::2 on
+ * 256 x 256 / 256 x 128 tiles where N % 128 == 0 and M > 128, single-CTA persistent tiles otherwise), 2 = single-CTA tiles only. */
 int dsf_gemm_set_impl(int32_t impl);
 
 /* fp32 parity path: generic strided, two-level batched SIMT GEMM (FFMA).
@@ -207,12 +198,8 @@ int dsf_attn_bwd(const void* qkv, const void* y, const void* dy, const float* ls
 int dsf_attn_bwd_parts(const void* qkv, const void* y, const void* dy, const float* lse, float* delta,
                        void* dqkv, int32_t B, int32_t T, int32_t C, int32_t nh, const dsf_dropout* drop,
                        const uint32_t* drop_bits, int32_t parts, void* stream);
-/* Selects the attention implementation (process-wide; for tests and A/B timing): 0 = default (= 4),
- * 1 = v1 (simple synchronous kernels), 2 = v2 (warp-specialised, TMA-fed, pipelined),
- * 3 = v3 (v2 + per-warpgroup double-buffered S/P in the forward), 4 = v4 (v3 schedule, the bf16 P / dS tiles
- * stay in tensor memory and feed tcgen05.mma as its A operand instead of going through shared memory),
- * 5 = v4 with the four-warpgroup forward, 6 / 7 = v4 with the forward forced to 128-row CTAs (two per SM) /
- * 256-row CTAs (one per SM); by default v4 picks whichever grid fills the SMs better. */
+/* Selects the forward CTA shape (process-wide, atomic; tests and A/B timing): 0 = default (128-row CTAs, two per SM),
+ * 1 = force 128-row CTAs, 2 = force 256-row CTAs (one per SM, two softmax warpgroups sharing each K/V tile). */
 int dsf_attn_set_impl(int32_t impl);
 
 /* K7 forward.  Replaces slice/view/permute/contiguous (model2_seq.py:275-286) + F.interpolate
@@ -225,6 +212,38 @@ int dsf_upsample_add_fwd(const dsf_geom* g, const float* y, const void* img, con
  * rows are copied from dgps_out (B,2,C) (zero when NULL).                                          */
 int dsf_upsample_add_bwd(const dsf_geom* g, const void* dout_img, const void* dout_lidar,
                          const void* dout_radar, const float* dgps_out, float* dy, void* stream);
+
+/* Optimizer step as one multi-tensor launch: torch.optim.AdamW.step() (train2_seq.py:131, 539: decoupled weight decay,
+ * bias-corrected moments, eps added to sqrt(v / bc2)) + EMA.update() (train2_seq.py:133-134, 315-320: shadow = decay * shadow +
+ * (1 - decay) * param, taken AFTER the parameter update) + the fp32 -> bf16 repack of GPT weights (what
+ * dsf_pack_block_weights does at the start of a forward), in a single pass over the parameters.
+ * One dsf_opt_tensor per parameter tensor (a dense blob of rows * cols fp32 elements; all pointers DEVICE pointers):
+ *   p, g, m, v : parameter (updated in place), gradient, AdamW first / second moment (updated in place)
+ *   ema        : nullable EMA shadow (updated in place)
+ *   shadow     : nullable bf16 copy of the updated parameter: element (r, c) at shadow[(row_off + r) * cols + c]
+ *   shadow_t   : nullable transposed bf16 copy: element (r, c) at shadow_t[c * ld_t + row_off + r]; needs rows, cols % 32 == 0
+ *   copy_f32   : nullable fp32 copy of the updated parameter (q/k/v biases concatenated into one [3C] vector)
+ * `tensors_dev` (n_tensors entries) and `tile0_dev` (first CTA of each tensor: prefix sums of dsf_opt_tiles(rows, cols,
+ * shadow_t != NULL), n_tiles in total) live in device memory, so one launch covers any number of tensors.
+ * `step_dev`: device int64 holding the 1-based step count t (the caller increments it on the device, which keeps the call
+ * CUDA-graph capturable); gradients are multiplied by `grad_scale` first (1 = as they are).                        */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  float* ema;
+  void* shadow;
+  void* shadow_t;
+  float* copy_f32;
+  int32_t rows, cols, row_off, ld_t;
+  float weight_decay;
+  int32_t reserved;
+} dsf_opt_tensor;
+int32_t dsf_opt_tiles(int32_t rows, int32_t cols, int32_t transposed_shadow);
+int dsf_adamw_ema_pack(const dsf_opt_tensor* tensors_dev, const int32_t* tile0_dev, int32_t n_tensors, int32_t n_tiles, float lr,
+                       float beta1, float beta2, float eps, float ema_decay, const int64_t* step_dev, float grad_scale,
+                       void* stream);
 
 /* fp32 -> bf16 conversion (weight shadow refresh), n elements. */
 int dsf_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);

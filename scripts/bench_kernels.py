@@ -36,7 +36,7 @@ if "attn" in what or "attn512" in what or "attnq" in what:
         delta = torch.empty(B, nh, T, device=dev)
         dqkv = torch.empty_like(qkv)
         fl = 4.0 * T * T * C * B
-        for impl in ((4, 5) if "attn" in what else ((7, 6) if "attnq" in what else (3,))):  # 7 / 6: forward with 256- / 128-row CTAs
+        for impl in (0, 2):  # forward with 128-row CTAs (two per SM, default) / 256-row CTAs
             K.attn_set_impl(impl)
             tf = timeit(lambda: K.attn_fwd(qkv, y, lse, B, T, C, nh))
             tb = timeit(lambda: K.attn_bwd(qkv, y, dy, lse, delta, dqkv, B, T, C, nh))
@@ -56,7 +56,7 @@ if "gemm" in what:
         dw = torch.zeros(N, Kd, device=dev)
         fl = 2.0 * M * N * Kd
         line = "gemm M=%d N=%d K=%d: cublas %.4f ms (%.0f TF/s)" % (M, N, Kd, tt, fl / tt / 1e9)
-        for impl in (2, 3):
+        for impl in (2, 0):  # single-CTA tiles / CTA pairs (default)
             K.gemm_set_impl(impl)
             t = timeit(lambda: K.gemm_bf16_nt(a, w, out, bias=bias))
             line += " | v%d nt %.4f ms (%.0f TF/s)" % (impl, t, fl / t / 1e9)
@@ -136,23 +136,3 @@ if "ln" in what:
     t = timeit(runc, iters=40, warm=8)
     print("colsum bf16 M x 1536 (HBM-resident): %.4f ms (%.0f GB/s)" % (t, M * 3 * C * 2 / t / 1e6))
 
-if "lnfuse" in what:
-    # proj / mlp.2 + residual followed by LayerNorm: separate launches vs the fused full-row epilogue (dsf_gemm_bf16_nt_ln)
-    M, N = 11544, 512
-    for Kd in (512, 2048):
-        a = torch.randn(M, Kd, device=dev).to(torch.bfloat16)
-        w = torch.randn(N, Kd, device=dev).to(torch.bfloat16)
-        bias = torch.randn(N, device=dev)
-        res = torch.randn(M, N, device=dev)
-        g = torch.ones(N, device=dev)
-        b = torch.zeros(N, device=dev)
-        x = torch.empty(M, N, device=dev)
-        h = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
-
-        def sep():
-            K.gemm_bf16_nt(a, w, x, bias=bias, residual=res)
-            K.layernorm_fwd(x, g, b, h, mean, rstd)
-        t1 = timeit(sep)
-        t2 = timeit(lambda: K.gemm_bf16_nt_ln(a, w, x, bias, res, h, g, b, mean, rstd))
-        print("N=512 K=%d fp32+bias+residual then LayerNorm: separate %.4f ms, fused %.4f ms" % (Kd, t1, t2))

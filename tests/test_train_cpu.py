@@ -82,3 +82,13 @@ def test_synthetic_batch_shapes_and_value_ranges():
         assert abs(float(soft[b, beam[b]]) - peak) < 1e-5
         far = (torch.arange(64) - beam[b]).abs() > 5
         assert float(soft[b][far].abs().max()) == 0.0
+
+
+def test_fused_optimizer_refuses_cpu_parameters():
+    """No CPU fallback on the optimizer side either (SURVEY.md §8(f)1 kernel lives in libdsfuse.so)."""
+    import pytest
+    from deepsense6g_tii_b200.optim import FusedAdamWEMA
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        FusedAdamWEMA([p]).step()
