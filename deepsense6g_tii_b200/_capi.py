@@ -7,7 +7,7 @@ PyTorch is used only for device memory and streams; every pointer handed to the 
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
 
 import torch
 
@@ -23,7 +23,7 @@ SYMBOLS = [
     "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_set_pdl", "dsf_set_sm_margin", "dsf_dropout_inplace", "dsf_tokens_fwd", "dsf_tokens_bwd",
     "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_set_impl", "dsf_gemm_f32",
     "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_bwd_parts", "dsf_attn_set_impl", "dsf_attn_drop_words",
-    "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16", "dsf_opt_tiles", "dsf_adamw_ema_pack",
+    "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16", "dsf_opt_tiles", "dsf_adamw_ema_pack", "dsf_chain_fwd",
 ]
 
 
@@ -97,8 +97,9 @@ def lib():
             "dsf_upsample_add_fwd": [POINTER(Geom), P, P, P, P, P, P, P, P],
             "dsf_upsample_add_bwd": [POINTER(Geom), P, P, P, P, P, P],
             "dsf_cast_f32_bf16": [P, P, c_int64, P],
+            "dsf_chain_fwd": [P] * 25 + [c_int32, c_int32, c_float, P],
             "dsf_opt_tiles": [c_int32, c_int32, c_int32],
-            "dsf_adamw_ema_pack": [P, P, c_int32, c_int32, c_float, c_float, c_float, c_float, c_float, P, c_float, P],
+            "dsf_adamw_ema_pack": [P, P, c_int32, c_int32, c_double, c_double, c_double, c_double, c_double, P, c_double, P],
         }
         for name, argtypes in sig.items():
             fn = getattr(L, name)
@@ -289,3 +290,13 @@ def adamw_ema_pack(table_dev, tile0_dev, n_tensors, n_tiles, lr, beta1, beta2, e
     """One launch: AdamW update + EMA lerp + bf16 repack over every tensor of the device-resident table (see include/dsfuse.h)."""
     _chk(lib().dsf_adamw_ema_pack(_p(table_dev), _p(tile0_dev), n_tensors, n_tiles, lr, beta1, beta2, eps, ema_decay, _p(step_dev),
                                   grad_scale, _stream()), "dsf_adamw_ema_pack")
+
+
+def chain_fwd(y, x_in, wp, w1, w2, wqkv_next, bp, b1, b2, bqkv_next, ln2_g, ln2_b, lnn_g, lnn_b, x_mid, x_out, h2, a, h_next, qkv_next, yf,
+              mean2, rstd2, mean_next, rstd_next, eps=1e-5):
+    """n_embd 64 / 128: proj + residual -> ln2 -> mlp.0 -> ReLU -> mlp.2 + residual -> (next block's ln1 -> fused QKV | ln_f) for
+    all rows in ONE launch (model2_seq.py:109, 121-126, 131-132 and :97-99 / :274 of what follows).  wqkv_next None = last block."""
+    M, C = y.shape
+    _chk(lib().dsf_chain_fwd(_p(y), _p(x_in), _p(wp), _p(w1), _p(w2), _p(wqkv_next), _p(bp), _p(b1), _p(b2), _p(bqkv_next), _p(ln2_g), _p(ln2_b),
+                             _p(lnn_g), _p(lnn_b), _p(x_mid), _p(x_out), _p(h2), _p(a), _p(h_next), _p(qkv_next), _p(yf), _p(mean2), _p(rstd2),
+                             _p(mean_next), _p(rstd_next), M, C, eps, _stream()), "dsf_chain_fwd")

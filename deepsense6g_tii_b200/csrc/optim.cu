@@ -15,7 +15,8 @@ namespace dsf {
 // shared memory), everything else in chunks of 1024 contiguous elements.
 __global__ void __launch_bounds__(256)
 adamw_ema_pack_kernel(const dsf_opt_tensor* __restrict__ tab, const int32_t* __restrict__ tile0, int n_tensors, float lr, float beta1,
-                      float beta2, float eps, float ema_decay, const int64_t* __restrict__ step_dev, float grad_scale) {
+                      float beta2, float eps, float ema_decay, const int64_t* __restrict__ step_dev, float grad_scale, float om_beta1,
+                      float om_beta2, float om_decay) {   // om_* = 1 - x rounded from double on the host, as torch computes them
   __shared__ float tile[32][33];
   __shared__ int s_ti;
   __shared__ float s_bc[2];
@@ -43,13 +44,13 @@ adamw_ema_pack_kernel(const dsf_opt_tensor* __restrict__ tab, const int32_t* __r
   auto update = [&](int64_t i) -> float {
     const float g = T.g[i] * grad_scale;
     float p = T.p[i] * decay_mul;
-    const float m = beta1 * T.m[i] + (1.f - beta1) * g;
-    const float v = beta2 * T.v[i] + (1.f - beta2) * g * g;
+    const float m = beta1 * T.m[i] + om_beta1 * g;
+    const float v = beta2 * T.v[i] + om_beta2 * g * g;
     p -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
     T.p[i] = p;
     T.m[i] = m;
     T.v[i] = v;
-    if (T.ema) T.ema[i] = ema_decay * T.ema[i] + (1.f - ema_decay) * p;
+    if (T.ema) T.ema[i] = ema_decay * T.ema[i] + om_decay * p;
     return p;
   };
 
@@ -95,14 +96,15 @@ extern "C" int32_t dsf_opt_tiles(int32_t rows, int32_t cols, int32_t transposed_
   return (int32_t)(((int64_t)rows * cols + 1023) / 1024);
 }
 
-extern "C" int dsf_adamw_ema_pack(const dsf_opt_tensor* tensors_dev, const int32_t* tile0_dev, int32_t n_tensors, int32_t n_tiles, float lr,
-                                  float beta1, float beta2, float eps, float ema_decay, const int64_t* step_dev, float grad_scale,
+extern "C" int dsf_adamw_ema_pack(const dsf_opt_tensor* tensors_dev, const int32_t* tile0_dev, int32_t n_tensors, int32_t n_tiles, double lr,
+                                  double beta1, double beta2, double eps, double ema_decay, const int64_t* step_dev, double grad_scale,
                                   void* stream) {
   DSF_REQUIRE(tensors_dev && tile0_dev && step_dev, "adamw_ema_pack: NULL table / step pointer");
   DSF_REQUIRE(n_tensors > 0 && n_tiles > 0, "adamw_ema_pack: empty launch (n_tensors=%d n_tiles=%d)", n_tensors, n_tiles);
-  DSF_REQUIRE(lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps > 0.f && ema_decay >= 0.f && ema_decay <= 1.f,
+  DSF_REQUIRE(lr >= 0. && beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps > 0. && ema_decay >= 0. && ema_decay <= 1.,
               "adamw_ema_pack: bad hyper-parameters");
-  dsf::launch_pdl(dsf::adamw_ema_pack_kernel, dim3(n_tiles), dim3(256), 0, (cudaStream_t)stream, tensors_dev, tile0_dev, (int)n_tensors, lr, beta1,
-                  beta2, eps, ema_decay, step_dev, grad_scale);
+  dsf::launch_pdl(dsf::adamw_ema_pack_kernel, dim3(n_tiles), dim3(256), 0, (cudaStream_t)stream, tensors_dev, tile0_dev, (int)n_tensors, (float)lr,
+                  (float)beta1, (float)beta2, (float)eps, (float)ema_decay, step_dev, (float)grad_scale, (float)(1.0 - beta1), (float)(1.0 - beta2),
+                  (float)(1.0 - ema_decay));
   return dsf::check_launch("adamw_ema_pack");
 }

@@ -201,7 +201,7 @@ upsample_add_bwd_nchw_kernel(dsf_geom g, Ptr3 dout, const float* __restrict__ dg
     __syncwarp();
     const FT* pl = src + (size_t)cl * HW;
     const int W4 = g.W / 4, sh = g.H / g.A_h;
-    if (g.W % 4 == 0 && (W4 == 1 || W4 == 2 || W4 == 4 || W4 == 8 || W4 == 16 || W4 == 32)) {
+    if (g.W % 4 == 0 && (W4 == 8 || W4 == 16 || W4 == 32) && sh >= 2 * (32 / W4)) {   // >= 2 rows per lane and anchor block
       // Rows of the plane are streamed with 16-byte loads: lane = (row phase, 16-byte chunk), npar = 32 / W4 rows per load
       // instruction.  Source rows of anchor block k (k*sh .. k*sh+sh-1) touch anchor rows k-1, k, k+1 only, so a lane keeps
       // three register accumulators per column and adds them to the shared [A_h][W] tile (shared-memory atomics: lanes of

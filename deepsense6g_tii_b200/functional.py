@@ -275,22 +275,36 @@ class _Runner:
         K.tokens_fwd(self.geom, feats[0], feats[1], feats[2], gps_emb, params[0], x)
         if self._drop("embd") is not None:
             K.dropout_inplace(x, self._drop("embd"))
-        for i in range(L):
-            (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[1 + 16 * i: 17 + 16 * i]
+        def take(i):
             if side is not None:
                 st = packed[i]
                 main.wait_event(st.packed_ev)
                 st.packed_ev = None
-            else:
-                st = pack(i)
+                return st
+            return pack(i)
+
+        # Narrow stages (n_embd 64 / 128, no dropout): everything between two attention calls is row-local and runs as ONE launch
+        # (csrc/chain.cu): per block = flash attention + dsf_chain_fwd instead of seven launches.  DSF_CHAIN=0 keeps the separate kernels.
+        chain = C in (64, 128) and F == 4 * C and L > 0 and self.dropout is None and os.environ.get("DSF_CHAIN", "1") == "1"
+        yf = torch.empty(M, C, device=dev, dtype=f32)
+        saved.mean_f = torch.empty(M, device=dev, dtype=f32)
+        saved.rstd_f = torch.empty(M, device=dev, dtype=f32)
+        nxt = None  # chain mode: (st, h1, qkv, mean1, rstd1) of block i, produced by block i-1's chain launch
+        for i in range(L):
+            (ln1w, ln1b, ln2w, ln2b, kw, kb, qw, qb, vw, vb, pw, pb, w1, b1, w2, b2) = params[1 + 16 * i: 17 + 16 * i]
+            st = take(i) if nxt is None else nxt
+            nxt = None
             bqkv = st.bqkv
             st.x_in = x
-            stats = torch.empty(4, M, device=dev, dtype=f32)
-            st.mean1, st.rstd1, st.mean2, st.rstd2 = stats[0], stats[1], stats[2], stats[3]
-            st.h1 = torch.empty(M, C, device=dev, dtype=bf)
-            K.layernorm_fwd(x, ln1w, ln1b, st.h1, st.mean1, st.rstd1)
-            st.qkv = torch.empty(M, 3 * C, device=dev, dtype=bf)
-            K.gemm_bf16_nt(st.h1, st.wqkv, st.qkv, bias=bqkv)
+            if not hasattr(st, "h1"):
+                stats = torch.empty(2, M, device=dev, dtype=f32)
+                st.mean1, st.rstd1 = stats[0], stats[1]
+                st.h1 = torch.empty(M, C, device=dev, dtype=bf)
+                K.layernorm_fwd(x, ln1w, ln1b, st.h1, st.mean1, st.rstd1)
+                st.qkv = torch.empty(M, 3 * C, device=dev, dtype=bf)
+                K.gemm_bf16_nt(st.h1, st.wqkv, st.qkv, bias=bqkv)
+            stats2 = torch.empty(2, M, device=dev, dtype=f32)
+            st.mean2, st.rstd2 = stats2[0], stats2[1]
             st.y = torch.empty(M, C, device=dev, dtype=bf)
             st.lse = torch.empty(self.B, self.nh, self.T, device=dev, dtype=f32)
             st.drop_bits = None
@@ -301,20 +315,33 @@ class _Runner:
             K.attn_fwd(st.qkv, st.y, st.lse, self.B, self.T, C, self.nh, self._drop("attn", i), st.drop_bits)
             st.x_mid = torch.empty(M, C, device=dev, dtype=f32)
             st.h2 = torch.empty(M, C, device=dev, dtype=bf)
-            K.gemm_bf16_nt(st.y, st.wp, st.x_mid, bias=pb, residual=x, drop=self._drop("proj", i))
-            K.layernorm_fwd(st.x_mid, ln2w, ln2b, st.h2, st.mean2, st.rstd2)
             st.a = torch.empty(M, F, device=dev, dtype=bf)
-            K.gemm_bf16_nt(st.h2, st.w1, st.a, bias=b1, relu=True)
+            x_new = torch.empty(M, C, device=dev, dtype=f32)
+            if chain:
+                if i + 1 < L:
+                    sn = take(i + 1)
+                    statn = torch.empty(2, M, device=dev, dtype=f32)
+                    sn.mean1, sn.rstd1 = statn[0], statn[1]
+                    sn.h1 = torch.empty(M, C, device=dev, dtype=bf)
+                    sn.qkv = torch.empty(M, 3 * C, device=dev, dtype=bf)
+                    K.chain_fwd(st.y, x, st.wp, st.w1, st.w2, sn.wqkv, pb, b1, b2, sn.bqkv, ln2w, ln2b, params[1 + 16 * (i + 1)],
+                                params[2 + 16 * (i + 1)], st.x_mid, x_new, st.h2, st.a, sn.h1, sn.qkv, None, st.mean2, st.rstd2, sn.mean1, sn.rstd1)
+                    nxt = sn
+                else:   # last block: the chain ends with ln_f
+                    K.chain_fwd(st.y, x, st.wp, st.w1, st.w2, None, pb, b1, b2, None, ln2w, ln2b, params[-2], params[-1], st.x_mid, x_new,
+                                st.h2, st.a, None, None, yf, st.mean2, st.rstd2, saved.mean_f, saved.rstd_f)
+            else:
+                K.gemm_bf16_nt(st.y, st.wp, st.x_mid, bias=pb, residual=x, drop=self._drop("proj", i))
+                K.layernorm_fwd(st.x_mid, ln2w, ln2b, st.h2, st.mean2, st.rstd2)
+                K.gemm_bf16_nt(st.h2, st.w1, st.a, bias=b1, relu=True)
+                K.gemm_bf16_nt(st.a, st.w2, x_new, bias=b2, residual=st.x_mid, drop=self._drop("mlp", i))
             if self.capture is not None:
                 self.capture["relu.%d" % i] = st.a
-            x = torch.empty(M, C, device=dev, dtype=f32)
-            K.gemm_bf16_nt(st.a, st.w2, x, bias=b2, residual=st.x_mid, drop=self._drop("mlp", i))
+            x = x_new
             saved.layers.append(st)
         saved.x_last = x
-        saved.mean_f = torch.empty(M, device=dev, dtype=f32)
-        saved.rstd_f = torch.empty(M, device=dev, dtype=f32)
-        yf = torch.empty(M, C, device=dev, dtype=f32)
-        K.layernorm_fwd(x, params[-2], params[-1], yf, saved.mean_f, saved.rstd_f)
+        if not chain:
+            K.layernorm_fwd(x, params[-2], params[-1], yf, saved.mean_f, saved.rstd_f)
         outs = [torch.empty_like(f) for f in feats]
         K.upsample_add_fwd(self.geom, yf, feats if residual else [torch.zeros_like(f) for f in feats], outs)
         gps_out = yf.view(self.B, self.T, C)[:, self.Tm:, :].contiguous()

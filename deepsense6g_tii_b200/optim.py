@@ -79,10 +79,11 @@ class FusedAdamWEMA(torch.optim.Optimizer):
                 tile0.append(tiles)
                 tiles += K.opt_tiles(rows, cols, sh_t is not None)
             dev = items[0][0].device
-            tab_h = torch.empty(ctypes.sizeof(tab), dtype=torch.uint8).pin_memory()
+            # two pinned host mirrors, used alternately: the one being rewritten was last read by the upload of two steps ago
+            tab_h = [torch.empty(ctypes.sizeof(tab), dtype=torch.uint8).pin_memory() for _ in range(2)]
             t0_d = torch.tensor(tile0, dtype=torch.int32).to(dev)
-            self._tables.append(dict(tab=tab, tab_h=tab_h, tab_d=torch.empty(tab_h.numel(), dtype=torch.uint8, device=dev), t0_d=t0_d,
-                                     n=len(items), tiles=tiles, uploaded=None, dirty=True))
+            self._tables.append(dict(tab=tab, tab_h=tab_h, tab_d=torch.empty(tab_h[0].numel(), dtype=torch.uint8, device=dev), t0_d=t0_d,
+                                     n=len(items), tiles=tiles, uploaded=[None, None], cur=0, dirty=True))
 
     def _refresh_grad_pointers(self, work):
         """Eager training allocates new gradient tensors every step: only the ``g`` column of the tables changes."""
@@ -130,6 +131,9 @@ class FusedAdamWEMA(torch.optim.Optimizer):
             ema_sig = None if self.ema is None else tuple(t.data_ptr() for t in self.ema.shadow.values())
             sig = (tuple(x[0] for x in sig), ema_sig, tuple(tuple(v.data_ptr() for v in g.shadow_views(0).values()) for g in self.gpts))
             if sig != self._sig:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("FusedAdamWEMA: the tensor table must be built before a CUDA-graph capture — run one eager "
+                                       "training step first (it allocates the moments and pins the host tables)")
                 self._build(work)
                 self._sig = sig
             else:
@@ -139,16 +143,19 @@ class FusedAdamWEMA(torch.optim.Optimizer):
             for group, tb in zip(self.param_groups, self._tables):
                 if tb is None:
                     continue
+                capturing = torch.cuda.is_current_stream_capturing()
                 if tb["dirty"]:
-                    if tb["uploaded"] is not None:
-                        tb["uploaded"].synchronize()   # the previous upload has long finished; never rewrite a buffer in flight
-                    ctypes.memmove(tb["tab_h"].data_ptr(), tb["tab"], ctypes.sizeof(tb["tab"]))
+                    tb["cur"] ^= 1
+                    ev = tb["uploaded"][tb["cur"]]
+                    if ev is not None and not capturing:   # (host synchronisation is illegal while a stream is being captured)
+                        ev.synchronize()                   # never rewrite a host table an upload may still be reading
+                    ctypes.memmove(tb["tab_h"][tb["cur"]].data_ptr(), tb["tab"], ctypes.sizeof(tb["tab"]))
                     tb["dirty"] = False
                 # 30-60 KB from pinned memory: a memcpy node under graph capture (replays re-read the unchanged host table)
-                tb["tab_d"].copy_(tb["tab_h"], non_blocking=True)
-                if not torch.cuda.is_current_stream_capturing():
-                    tb["uploaded"] = torch.cuda.Event()
-                    tb["uploaded"].record()
+                tb["tab_d"].copy_(tb["tab_h"][tb["cur"]], non_blocking=True)
+                if not capturing:
+                    tb["uploaded"][tb["cur"]] = torch.cuda.Event()
+                    tb["uploaded"][tb["cur"]].record()
                 b1, b2 = group["betas"]
                 K.adamw_ema_pack(tb["tab_d"], tb["t0_d"], tb["n"], tb["tiles"], float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                                  float(self.ema.decay) if self.ema is not None else 0.0, self._step_dev)

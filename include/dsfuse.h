@@ -213,6 +213,20 @@ int dsf_upsample_add_fwd(const dsf_geom* g, const float* y, const void* img, con
 int dsf_upsample_add_bwd(const dsf_geom* g, const void* dout_img, const void* dout_lidar,
                          const void* dout_radar, const float* dgps_out, float* dy, void* stream);
 
+/* Narrow stages (n_embd = 64 or 128): the row-local chain between two attention calls as ONE launch —
+ *   x_mid = x_in + y Wp^T + bp                      proj + residual                (model2_seq.py:109, 131)
+ *   h2 = LayerNorm(x_mid; ln2), a = ReLU(h2 W1^T + b1), x_out = x_mid + a W2^T + b2   (:119, 121-126, 132)
+ *   then either (wqkv_next != NULL)  h_next = LayerNorm(x_out; ln1 of the next block), qkv_next = h_next Wqkv^T + bqkv  (:118, 97-99)
+ *   or     (last block)              yf = LayerNorm(x_out; ln_f) in fp32                                                (:274)
+ * y (M,C) bf16; x_in, x_mid, x_out, yf (M,C) fp32; wp (C,C), w1 (4C,C), w2 (C,4C), wqkv_next (3C,C) bf16 weight shadows as packed
+ * by dsf_pack_block_weights; h2, h_next (M,C), a (M,4C), qkv_next (M,3C) bf16 and the four statistics vectors (M) are the
+ * tensors the backward reads.  No dropout on this path (the caller keeps the separate kernels when p > 0). */
+int dsf_chain_fwd(const void* y, const float* x_in, const void* wp, const void* w1, const void* w2, const void* wqkv_next,
+                  const float* bp, const float* b1, const float* b2, const float* bqkv_next, const float* ln2_g,
+                  const float* ln2_b, const float* lnn_g, const float* lnn_b, float* x_mid, float* x_out, void* h2, void* a,
+                  void* h_next, void* qkv_next, float* yf, float* mean2, float* rstd2, float* mean_next, float* rstd_next,
+                  int32_t M, int32_t C, float eps, void* stream);
+
 /* Optimizer step as one multi-tensor launch: torch.optim.AdamW.step() (train2_seq.py:131, 539: decoupled weight decay,
  * bias-corrected moments, eps added to sqrt(v / bc2)) + EMA.update() (train2_seq.py:133-134, 315-320: shadow = decay * shadow +
  * (1 - decay) * param, taken AFTER the parameter update) + the fp32 -> bf16 repack of GPT weights (what
@@ -226,7 +240,8 @@ int dsf_upsample_add_bwd(const dsf_geom* g, const void* dout_img, const void* do
  * `tensors_dev` (n_tensors entries) and `tile0_dev` (first CTA of each tensor: prefix sums of dsf_opt_tiles(rows, cols,
  * shadow_t != NULL), n_tiles in total) live in device memory, so one launch covers any number of tensors.
  * `step_dev`: device int64 holding the 1-based step count t (the caller increments it on the device, which keeps the call
- * CUDA-graph capturable); gradients are multiplied by `grad_scale` first (1 = as they are).                        */
+ * CUDA-graph capturable); gradients are multiplied by `grad_scale` first (1 = as they are).  Hyper-parameters are doubles, as
+ * torch holds them: 1 - beta and 1 - decay are formed in double before rounding to fp32, like torch's own kernels do.  */
 typedef struct {
   float* p;
   const float* g;
@@ -241,8 +256,8 @@ typedef struct {
   int32_t reserved;
 } dsf_opt_tensor;
 int32_t dsf_opt_tiles(int32_t rows, int32_t cols, int32_t transposed_shadow);
-int dsf_adamw_ema_pack(const dsf_opt_tensor* tensors_dev, const int32_t* tile0_dev, int32_t n_tensors, int32_t n_tiles, float lr,
-                       float beta1, float beta2, float eps, float ema_decay, const int64_t* step_dev, float grad_scale,
+int dsf_adamw_ema_pack(const dsf_opt_tensor* tensors_dev, const int32_t* tile0_dev, int32_t n_tensors, int32_t n_tiles, double lr,
+                       double beta1, double beta2, double eps, double ema_decay, const int64_t* step_dev, double grad_scale,
                        void* stream);
 
 /* fp32 -> bf16 conversion (weight shadow refresh), n elements. */

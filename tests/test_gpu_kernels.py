@@ -495,3 +495,44 @@ def _attention_dropout_case(K, cuda_dev, B, T, C, nh):
     assert not torch.equal(bits, bits2)
     K.attn_fwd(qkv, y, lse, B, T, C, nh, d, bits2)
     assert torch.equal(bits, bits2)
+
+
+@pytest.mark.parametrize("M,C,last", [(11544, 64, False), (11544, 128, False), (300, 64, True), (130, 128, True), (5, 64, False), (1924, 128, False)])
+def test_chain_fwd_matches_the_separate_operators(K, cuda_dev, M, C, last):
+    """dsf_chain_fwd (n_embd 64 / 128): proj + residual -> ln2 -> mlp.0 -> ReLU -> mlp.2 + residual -> next ln1 -> QKV (or ln_f) in one
+    launch, against the same operators in plain torch on the same bf16-rounded operands (model2_seq.py:109, 118-126, 131-132, 274)."""
+    g = _gen(31)
+    F = 4 * C
+    bf = torch.bfloat16
+    rnd = lambda *s, sc=1.0: (sc * torch.randn(*s, generator=g)).to(cuda_dev)
+    y = rnd(M, C).to(bf)
+    x_in = rnd(M, C, sc=2.0) + 0.3
+    wp, w1, w2, wq = rnd(C, C, sc=0.1).to(bf), rnd(F, C, sc=0.1).to(bf), rnd(C, F, sc=0.1).to(bf), rnd(3 * C, C, sc=0.1).to(bf)
+    bp, b1, b2, bq = rnd(C, sc=0.1), rnd(F, sc=0.1), rnd(C, sc=0.1), rnd(3 * C, sc=0.1)
+    g2, be2, gn, ben = 1 + rnd(C, sc=0.1), rnd(C, sc=0.1), 1 + rnd(C, sc=0.1), rnd(C, sc=0.1)
+    nan = lambda *s, dt=torch.float32: torch.full(s, float("nan"), device=cuda_dev, dtype=dt)
+    x_mid, x_out, yf = nan(M, C), nan(M, C), nan(M, C)
+    h2, a, hn, qkv = nan(M, C, dt=bf), nan(M, F, dt=bf), nan(M, C, dt=bf), nan(M, 3 * C, dt=bf)
+    st = [nan(M) for _ in range(4)]
+    K.chain_fwd(y, x_in, wp, w1, w2, None if last else wq, bp, b1, b2, None if last else bq, g2, be2, gn, ben, x_mid, x_out, h2, a,
+                None if last else hn, None if last else qkv, yf if last else None, st[0], st[1], st[2], st[3])
+    torch.cuda.synchronize()
+    r_mid = y.float() @ wp.float().t() + bp + x_in
+    assert_close(x_mid, r_mid, 1e-5, 1e-5, "x_mid")
+    mu, var = x_mid.mean(-1), x_mid.var(-1, unbiased=False)
+    assert_close(st[0], mu, 1e-4, 1e-5, "mean2")
+    assert_close(st[1], torch.rsqrt(var + 1e-5), 1e-4, 1e-5, "rstd2")
+    r_h2 = R.layer_norm(x_mid, g2, be2)
+    assert_close(h2.float(), r_h2, 6e-3, 1e-3, "h2 (bf16)")
+    r_a = torch.relu(h2.float() @ w1.float().t() + b1)          # from the kernel's own bf16 h2: isolates this GEMM
+    assert_close(a.float(), r_a, 6e-3, 1e-3, "a (bf16)")
+    r_out = a.float() @ w2.float().t() + b2 + x_mid
+    assert_close(x_out, r_out, 1e-5, 1e-5, "x_out")
+    r_n = R.layer_norm(x_out, gn, ben)
+    assert_close(st[2], x_out.mean(-1), 1e-4, 1e-5, "mean_next")
+    assert_close(st[3], torch.rsqrt(x_out.var(-1, unbiased=False) + 1e-5), 1e-4, 1e-5, "rstd_next")
+    if last:
+        assert_close(yf, r_n, 1e-5, 1e-5, "ln_f output")
+    else:
+        assert_close(hn.float(), r_n, 6e-3, 1e-3, "h_next (bf16)")
+        assert_close(qkv.float(), hn.float() @ wq.float().t() + bq, 6e-3, 1e-3, "qkv_next (bf16)")

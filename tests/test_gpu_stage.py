@@ -402,3 +402,36 @@ def test_dropout_is_graph_safe_fresh_masks_per_replay(cuda_dev):
     sum(o.float().square().sum() for o in eo).backward()
     assert torch.equal(eo[0], res[2][0])
     assert_close(pk[0].grad, res[2][1], 1e-4, 1e-6, "pos_emb grad of the replay = eager with the effective seed")
+
+
+@pytest.mark.parametrize("C,H", [(64, 64), (128, 32)])
+def test_chained_forward_matches_the_separate_kernels(cuda_dev, monkeypatch, C, H):
+    """Narrow stages run the row-local chain of every block as one launch (DSF_CHAIN=1, default).  Same math as the separate
+    LayerNorm / GEMM kernels (DSF_CHAIN=0) up to the fp32 summation order inside the GEMMs."""
+    from deepsense6g_tii_b200 import _capi as K
+    from deepsense6g_tii_b200.functional import fusion_stage, param_names
+    S, A, nh, L, B = 5, 8, 4, 3, 2
+    T = 3 * S * A * A + 2
+    gen = torch.Generator().manual_seed(80 + C)
+    p0 = {k: v.to(cuda_dev) for k, v in R.init_gpt_params(C, nh, 4, L, T, generator=gen, pos_std=0.02).items()}
+    feats = [torch.randn(B * S, C, H, H, generator=gen).to(cuda_dev) for _ in range(3)]
+    gps = torch.randn(B, 2, C, generator=gen).to(cuda_dev)
+    names = param_names(L)
+    cfg = dict(seq_len=S, n_views=1, vert_anchors=A, horz_anchors=A, n_head=nh, n_layer=L, compute_dtype=torch.bfloat16)
+    res, launches = [], []
+    for chain in ("0", "1"):
+        monkeypatch.setenv("DSF_CHAIN", chain)
+        pk = [p0[n].clone().requires_grad_(True) for n in names]
+        n0 = K.launch_count()
+        outs = fusion_stage(cfg, feats[0], feats[1], feats[2], gps, pk)
+        launches.append(K.launch_count() - n0)
+        sum(o.float().square().sum() for o in outs).backward()
+        torch.cuda.synchronize()
+        res.append(([o.detach().clone() for o in outs], [p.grad.clone() for p in pk]))
+    assert launches[0] - launches[1] == 5 * L - 1, launches     # 7 L + 1 (ln_f) launches become 2 L + 2 (first block: ln1 + QKV)
+    for a, b in zip(res[1][0], res[0][0]):
+        assert_close(a, b, 2e-3, 1e-5, "stage output")
+    for a, b, n in zip(res[1][1], res[0][1], names):
+        if n.endswith("attn.key.bias"):
+            continue
+        assert_close(a, b, 3e-2, 1e-5, n)
