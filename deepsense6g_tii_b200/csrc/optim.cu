@@ -39,14 +39,14 @@ adamw_ema_pack_kernel(const dsf_opt_tensor* __restrict__ tab, const int32_t* __r
   const dsf_opt_tensor T = tab[s_ti];
   const int lt = t - tile0[s_ti];
   const float bc1 = s_bc[0], bc2 = s_bc[1];
-  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay_mul = 1.f - lr * T.weight_decay;
+  const float step_size = lr / bc1, sqrt_bc2 = sqrtf(bc2), decay_mul = 1.f - lr * T.weight_decay;
 
   auto update = [&](int64_t i) -> float {
     const float g = T.g[i] * grad_scale;
     float p = T.p[i] * decay_mul;
     const float m = beta1 * T.m[i] + om_beta1 * g;
     const float v = beta2 * T.v[i] + om_beta2 * g * g;
-    p -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
+    p -= step_size * (m / (sqrtf(v) / sqrt_bc2 + eps));   // torch: addcdiv_(exp_avg, sqrt(v) / sqrt(bc2) + eps, -step_size)
     T.p[i] = p;
     T.m[i] = m;
     T.v[i] = v;

@@ -78,7 +78,7 @@ def test_graph_captured_step_as_bench_times_it_vs_oracle(cuda_dev, B, C, H, L, A
         return outs
 
     graph, outs, n_launch = bench.capture_step(step)
-    assert n_launch > 20 * L
+    assert n_launch > 10 * L
     for t in list(p.values()) + i:      # the replay must produce everything itself
         t.grad.zero_()
     graph.replay()
