@@ -195,29 +195,42 @@ upsample_add_bwd_nchw_kernel(dsf_geom g, Ptr3 dout, const float* __restrict__ dg
 #pragma unroll
       for (int k = 0; k < 4; ++k) outT[(cell + k) * (UP_CT + 1) + cl] = v[k];
     }
-  } else
+  } else {
+  const int W4 = g.W / 4, sh = g.H / g.A_h;
+  // stage-1-like planes (column scale a multiple of 8, >= 2 rows per lane and anchor block): fold both axes in registers
+  const bool direct = g.W % 4 == 0 && (W4 == 8 || W4 == 16 || W4 == 32) && sw % 8 == 0 && sh >= 2 * (32 / W4);
+  if (direct) {
+    for (int i = tid; i < cells * (UP_CT + 1); i += UP_THREADS) outT[i] = 0.f;
+    __syncthreads();
+  }
   for (int cl = warp; cl < nct; cl += UP_WARPS) {
-    for (int i = lane; i < g.A_h * g.W; i += 32) tmp[i] = 0.f;
-    __syncwarp();
     const FT* pl = src + (size_t)cl * HW;
-    const int W4 = g.W / 4, sh = g.H / g.A_h;
-    if (g.W % 4 == 0 && (W4 == 8 || W4 == 16 || W4 == 32) && sh >= 2 * (32 / W4)) {   // >= 2 rows per lane and anchor block
+    if (!direct) {
+      for (int i = lane; i < g.A_h * g.W; i += 32) tmp[i] = 0.f;
+      __syncwarp();
+    }
+    if (direct) {
       // Rows of the plane are streamed with 16-byte loads: lane = (row phase, 16-byte chunk), npar = 32 / W4 rows per load
-      // instruction.  Source rows of anchor block k (k*sh .. k*sh+sh-1) touch anchor rows k-1, k, k+1 only, so a lane keeps
-      // three register accumulators per column and adds them to the shared [A_h][W] tile (shared-memory atomics: lanes of
-      // other row phases own the same columns) whenever its next row belongs to another block.
+      // instruction.  With a column scale that is a multiple of 8 the four columns of a chunk share one pair of anchor columns
+      // (ix0, ix1), so a row's chunk folds to two values; source rows of anchor block k (k*sh .. k*sh+sh-1) touch anchor rows
+      // k-1, k, k+1 only, so a lane keeps 3 x 2 register accumulators and adds them to the (cell, channel) tile in shared memory
+      // (atomics: lanes of other row phases / chunks hit the same cells) whenever its next row belongs to another block.
       const int npar = 32 / W4, par = lane / W4, w0 = (lane % W4) * 4;
-      float a_prev[4] = {0.f, 0.f, 0.f, 0.f}, a_cur[4] = {0.f, 0.f, 0.f, 0.f}, a_next[4] = {0.f, 0.f, 0.f, 0.f};
+      const Tap tx0 = tap_of(w0, rsw, g.A_w);
+      float lx[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lx[k] = tap_of(w0 + k, rsw, g.A_w).lam;
+      float a_prev[2] = {0.f, 0.f}, a_cur[2] = {0.f, 0.f}, a_next[2] = {0.f, 0.f};
       int blk = -1;
       auto flush = [&]() {
         if (blk < 0) return;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (blk > 0) atomicAdd(tmp + (blk - 1) * g.W + w0 + k, a_prev[k]);
-          atomicAdd(tmp + blk * g.W + w0 + k, a_cur[k]);
-          if (blk + 1 < g.A_h) atomicAdd(tmp + (blk + 1) * g.W + w0 + k, a_next[k]);
-          a_prev[k] = a_cur[k] = a_next[k] = 0.f;
-        }
+        float* o0 = outT + (size_t)(blk * g.A_w + tx0.i0) * (UP_CT + 1) + cl;
+        float* o1 = outT + (size_t)(blk * g.A_w + tx0.i1) * (UP_CT + 1) + cl;
+        const int up = g.A_w * (UP_CT + 1);
+        if (blk > 0) { atomicAdd(o0 - up, a_prev[0]); atomicAdd(o1 - up, a_prev[1]); }
+        atomicAdd(o0, a_cur[0]); atomicAdd(o1, a_cur[1]);
+        if (blk + 1 < g.A_h) { atomicAdd(o0 + up, a_next[0]); atomicAdd(o1 + up, a_next[1]); }
+        a_prev[0] = a_prev[1] = a_cur[0] = a_cur[1] = a_next[0] = a_next[1] = 0.f;
       };
       constexpr int U = 4;
       for (int h0 = par; h0 < g.H; h0 += U * npar) {
@@ -234,17 +247,17 @@ upsample_add_bwd_nchw_kernel(dsf_geom g, Ptr3 dout, const float* __restrict__ dg
           const int k = h / sh;
           if (k != blk) { flush(); blk = k; }
           const Tap ty = tap_of(h, rsh, g.A_h);
-          // ty.i0 / ty.i1 are in {k-1, k, k+1} (clamped at the borders: both weights may land on the same anchor row)
-          const float w_lo = 1.f - ty.lam, w_hi = ty.lam;
+          float c0 = 0.f, c1 = 0.f;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float x = v[u][q];
-            if (ty.i0 == k - 1) a_prev[q] += w_lo * x; else if (ty.i0 == k) a_cur[q] += w_lo * x; else a_next[q] += w_lo * x;
-            if (ty.i1 == k - 1) a_prev[q] += w_hi * x; else if (ty.i1 == k) a_cur[q] += w_hi * x; else a_next[q] += w_hi * x;
-          }
+          for (int q = 0; q < 4; ++q) { c0 += (1.f - lx[q]) * v[u][q]; c1 += lx[q] * v[u][q]; }
+          // ty.i0 is k-1 or k, ty.i1 is k or k+1 (both k at a clamped border)
+          const float w_lo = 1.f - ty.lam, w_hi = ty.lam;
+          if (ty.i0 == k) { a_cur[0] += w_lo * c0; a_cur[1] += w_lo * c1; } else { a_prev[0] += w_lo * c0; a_prev[1] += w_lo * c1; }
+          if (ty.i1 == k) { a_cur[0] += w_hi * c0; a_cur[1] += w_hi * c1; } else { a_next[0] += w_hi * c0; a_next[1] += w_hi * c1; }
         }
       }
       flush();
+      continue;   // the (cell, channel) tile is complete for this plane: no separate fold along W
     } else
     for (int w = lane; w < g.W; w += 32) {
 #pragma unroll 4
@@ -270,6 +283,7 @@ upsample_add_bwd_nchw_kernel(dsf_geom g, Ptr3 dout, const float* __restrict__ dg
       outT[cell * (UP_CT + 1) + cl] = acc;
     }
     __syncwarp();
+  }
   }
   __syncthreads();
   if (nct == UP_CT && g.C % 4 == 0) {  // 16-byte stores
