@@ -429,14 +429,21 @@ def run_ours(args, rank, world, local_rank):
     gen = torch.Generator().manual_seed(rank)  # data generator seed 0 + rank
     works = [StageWork(c, scale, dev, gen, optimizer=args.optimizer) for c, scale in SPEC]
     n_params = sum(p.numel() for w in works for p in w.gpt.parameters())
+    reducer = None
     if world > 1:
+        # gradients are averaged bucket-by-bucket (one bucket per transformer block) while the backward is still running; ONE
+        # reducer serves all stages and the stream only waits for the outstanding collectives at the end of the step, so a
+        # stage's last all-reduce runs behind the next stage's kernels (DSF_DEFER_REDUCE=0: wait at the end of every stage)
+        reducer = D.OverlappedGradReducer(defer=os.environ.get("DSF_DEFER_REDUCE", "1") == "1")
         for w in works:
             D.broadcast_params(w.gpt.parameters())   # same initial weights on every rank
-            # gradients are averaged bucket-by-bucket (one bucket per transformer block) while backward is still running
-            w.gpt.set_grad_reducer(D.OverlappedGradReducer())
+            w.gpt.set_grad_reducer(reducer)
 
     def step_eager():
-        return one_step(works)
+        out = one_step(works)
+        if reducer is not None:
+            reducer.wait_all()
+        return out
 
     loss_h = torch.empty((), pin_memory=True)
     graph, graph_loss, graph_launches, graph_note = None, None, 0, "eager launches"
@@ -554,11 +561,15 @@ def run_ours(args, rank, world, local_rank):
         sustained = {"seconds": round(ms_s * 1e-3, 2), "steps": n_s, "ms_per_step": ms_s / n_s, "value": BATCH * world * n_s / (ms_s * 1e-3), "clocks": clk_s}
 
     synced = None
-    if world > 1:  # the replayed / eager steps really exchanged gradients: every rank holds the same averaged pos_emb gradient
-        g = works[-1].gpt.pos_emb.grad.detach().reshape(-1)[:4096].contiguous()
-        gs = [torch.empty_like(g) for _ in range(world)]
-        dist.all_gather(gs, g)
-        synced = all(torch.equal(gs[0], t) for t in gs[1:]) and bool(torch.isfinite(g).all()) and float(g.abs().sum()) > 0
+    if world > 1:  # the replayed / eager steps really exchanged gradients: every rank holds the same averaged gradients
+        synced = True
+        for w in (works[0], works[-1]):
+            blk = w.gpt.blocks
+            for t in (w.gpt.pos_emb, w.gpt.ln_f.weight, blk[0].mlp[0].weight, blk[0].attn.query.bias, blk[len(blk) - 1].attn.proj.weight):
+                g = t.grad.detach().reshape(-1)[:4096].contiguous()
+                gs = [torch.empty_like(g) for _ in range(world)]
+                dist.all_gather(gs, g)
+                synced = synced and all(torch.equal(gs[0], x) for x in gs[1:]) and bool(torch.isfinite(g).all()) and float(g.abs().sum()) > 0
     if rank != 0:
         return
     pk = peaks()

@@ -53,13 +53,19 @@ class OverlappedGradReducer:
     ``FusionStageFn`` keeps all gradients of one transformer block in ONE flat fp32 buffer and calls
     ``block_ready(i, flat)`` as soon as the kernels producing block i's gradients are enqueued; the reducer
     starts an asynchronous NCCL all-reduce (average) of that bucket, which runs while the backward of blocks
-    i-1 ... 0 is still computing.  ``finish(tensors)`` reduces the few remaining tensors (pos_emb, ln_f) and
+    i-1 ... 0 is still computing.  ``finish(tensors)`` reduces the few remaining tensors (pos_emb) and
     makes the compute stream wait for every outstanding collective, so the gradients autograd receives are
     already averaged.  With world_size 1 (or no process group) it is a no-op.
+
+    ``defer=True``: ``finish`` only STARTS the remaining collectives; the caller calls ``wait_all()`` once, before the
+    gradients are consumed (optimizer step / end of the training step).  One reducer shared by the four fusion stages of
+    a model then lets the tail all-reduce of a stage run behind the kernels that follow it instead of stalling the stream
+    at the end of every stage's backward.
     """
 
-    def __init__(self):
+    def __init__(self, defer=False):
         self.active = dist.is_initialized() and dist.get_world_size() > 1
+        self.defer = defer
         self._works = []
 
     def _start(self, t):
@@ -77,6 +83,13 @@ class OverlappedGradReducer:
             return
         for t in tensors:
             self._start(t)
+        if not self.defer:
+            self.wait_all()
+
+    def wait_all(self):
+        """The current stream waits for every collective started so far (gloo: and the sums are turned into means)."""
+        if not self.active:
+            return
         world = dist.get_world_size()
         for w, t in self._works:
             w.wait()

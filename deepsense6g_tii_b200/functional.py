@@ -383,6 +383,11 @@ class _Runner:
                 off += n
             return out
 
+        def bucket(i):
+            """All-reduce bucket of block i; the last block's bucket carries the ln_f gradients that follow it in the buffer (they
+            are final before any block's backward has started, so they must not wait for the tail of the backward)."""
+            return gbuf[i * per_block:(i + 1) * per_block + (2 * C if i == L - 1 else 0)]
+
         # The four weight-gradient GEMMs of a block only feed the optimizer, so they run on a second stream next to the
         # data-gradient chain: their CTAs fill the SMs that chain leaves idle (second, partly filled rounds of the
         # N = n_embd GEMMs and of the attention kernels, tails of the short HBM-bound kernels).  fork() orders a wgrad
@@ -426,7 +431,7 @@ class _Runner:
                 main.wait_event(ev)
                 pending = None
                 if self.grad_hook is not None:  # data parallel: average this block's bucket while the other blocks compute
-                    self.grad_hook.block_ready(blk, gbuf[blk * per_block:(blk + 1) * per_block])
+                    self.grad_hook.block_ready(blk, bucket(blk))
 
         dgf, dbf = gbuf[L * per_block:L * per_block + C], gbuf[L * per_block + C:]
         # The fc1 / QKV data-gradient GEMMs hand dL/d(LayerNorm output) to the LayerNorm backward kernels in bf16 (what stock
@@ -501,7 +506,7 @@ class _Runner:
                                       dwp, dbp, dw1, db1, dw2, db2]
             saved.layers[i] = None  # release this block's activations early (with the side stream: once `pending` lets go)
             if side is None and self.grad_hook is not None:  # data parallel: average this block's bucket while blocks i-1..0 compute
-                self.grad_hook.block_ready(i, gbuf[i * per_block:(i + 1) * per_block])
+                self.grad_hook.block_ready(i, bucket(i))
         join_pending()
         dfeats = [torch.empty_like(d) for d in douts]
         dgps = torch.empty(self.B, 2, C, device=dev, dtype=f32)
@@ -511,7 +516,7 @@ class _Runner:
         K.tokens_bwd(self.geom, dx, douts if residual else None, dfeats, dgps, dpos)
         grads[0] = dpos
         if self.grad_hook is not None:
-            self.grad_hook.finish([dpos, gbuf[L * per_block:]])
+            self.grad_hook.finish([dpos])
         return dfeats, dgps, grads
 
     def _backward_bf16_chain(self, saved, params, douts, dgps_out, residual):
@@ -535,6 +540,11 @@ class _Runner:
                 out.append(gbuf[off:off + n])
                 off += n
             return out
+
+        def bucket(i):
+            """All-reduce bucket of block i; the last block's bucket carries the ln_f gradients that follow it in the buffer (they
+            are final before any block's backward has started, so they must not wait for the tail of the backward)."""
+            return gbuf[i * per_block:(i + 1) * per_block + (2 * C if i == L - 1 else 0)]
 
         env = os.environ.get("DSF_WGRAD_STREAM")
         use_side = (env == "1") if env in ("0", "1") else torch.cuda.is_current_stream_capturing()
@@ -568,7 +578,7 @@ class _Runner:
                 main.wait_event(ev)
                 pending = None
                 if self.grad_hook is not None:
-                    self.grad_hook.block_ready(blk, gbuf[blk * per_block:(blk + 1) * per_block])
+                    self.grad_hook.block_ready(blk, bucket(blk))
 
         def half_b(i, dxa):
             """Operands / destinations of half B for block i (its MLP + proj backward)."""
@@ -632,7 +642,7 @@ class _Runner:
                                       dwp, dbp, dw1, db1, dw2, db2]
             saved.layers[i] = None
             if side is None and self.grad_hook is not None:
-                self.grad_hook.block_ready(i, gbuf[i * per_block:(i + 1) * per_block])
+                self.grad_hook.block_ready(i, bucket(i))
             cur = nxt
         join_pending()
         dfeats = [torch.empty_like(d_) for d_ in douts]
@@ -641,7 +651,7 @@ class _Runner:
         K.tokens_bwd(self.geom, dx0, douts if residual else None, dfeats, dgps, dpos)
         grads[0] = dpos
         if self.grad_hook is not None:
-            self.grad_hook.finish([dpos, gbuf[L * per_block:]])
+            self.grad_hook.finish([dpos])
         return dfeats, dgps, grads
 
     def backward(self, saved, params, douts, dgps_out, residual=True):

@@ -1,5 +1,5 @@
 """BASELINE.json configs[3]: missing-modality inference throughput sweep — eval mode, LiDAR and radar inputs replaced by
-zeros ahead of conv1 (mambafuser_seq.py:361-391, 418-420), batch 1 ... 256, bf16 fusion + bf16 autocast trunks.
+zeros ahead of conv1 (mambafuser_seq.py:361-391, 418-420), batch 1 ... 1024, bf16 fusion + bf16 autocast trunks.
 Batches <= 16 replay the forward as one CUDA graph (they are launch-bound otherwise).  Prints samples/s with the zeroed-stem cache (deepsense6g_tii_b200.modules.Encoder._stem) on and off."""
 import os
 import sys
@@ -19,7 +19,7 @@ cfg = types.SimpleNamespace(seq_len=5, pred_len=4, n_views=1, vert_anchors=8, ho
                             modality_missing="lidar_radar", modality_missing_type="zerolike")
 torch.manual_seed(100)
 model = TransFuser(cfg, dev).to(memory_format=torch.channels_last).eval()
-batches = [int(b) for b in sys.argv[1:]] or [1, 4, 16, 64, 128, 256]
+batches = [int(b) for b in sys.argv[1:]] or [1, 4, 16, 64, 128, 256, 512, 1024]
 for B in batches:
     imgs, lids, rads, gps, _, _ = synthetic_batch(B, 5, 256, generator=torch.Generator().manual_seed(B), device=dev)
     imgs = [t.contiguous(memory_format=torch.channels_last) for t in imgs]

@@ -64,7 +64,15 @@ def _reducer_worker(rank, world, port, q):
     for i in reversed(range(3)):
         red.block_ready(i, buckets[i])
     red.finish(tail)
-    q.put((rank, [b.numpy().copy() for b in buckets], [t.numpy().copy() for t in tail], red.active))
+    # deferred mode (one reducer shared by several stages): finish() only starts the collectives, wait_all() completes them
+    red2 = D.OverlappedGradReducer(defer=True)
+    stage_a, stage_b = torch.full((8,), float(rank + 1)), torch.full((8,), float(10 * (rank + 1)))
+    red2.block_ready(0, stage_a)
+    red2.finish([])
+    red2.block_ready(0, stage_b)
+    red2.finish([])
+    red2.wait_all()
+    q.put((rank, [b.numpy().copy() for b in buckets], [t.numpy().copy() for t in tail], red.active, stage_a.numpy().copy(), stage_b.numpy().copy()))
     dist.destroy_process_group()
 
 
@@ -82,8 +90,9 @@ def test_overlapped_grad_reducer_averages_block_buckets_world2():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, buckets, tail, active in res:
+    for rank, buckets, tail, active, stage_a, stage_b in res:
         assert active
+        assert np.allclose(stage_a, 1.5) and np.allclose(stage_b, 15.0)
         for i, b in enumerate(buckets):
             assert np.allclose(b, 10 * i + 1.5)          # mean of (10i + 1) and (10i + 2)
         assert np.allclose(tail[0], 100.5) and np.allclose(tail[1], 200.5)

@@ -84,6 +84,8 @@ def test_transfuser_forward_backward_vs_oracle(cuda_dev, mode):
     tol = 1e-3 if mode == torch.float32 else 2e-2
     assert_close(out.float(), ref, tol, 1e-5, "logits")
     assert torch.equal(out.argmax(-1), ref.argmax(-1)), "top-1 beam index"
+    # bf16: 2e-2 + 1.25 * sqrt(fraction of flipped ReLU decisions) ~ 6e-2 for the mlp.0 / LayerNorm gradients of ANY bf16 evaluation
+    # (tests/parity_util.py, profiles/r02_bf16_error_model.txt); the decision-matched 2e-2 check per tensor lives in test_gpu_parity.py
     gtol = 2e-3 if mode == torch.float32 else 6e-2
     for n in WATCH:
         r = ref_g[n].grad
@@ -165,6 +167,10 @@ def test_missing_modality_fast_path_caches_the_zeroed_stems(cuda_dev):
         got = m(*ins)
         assert set(k[0] for k in m.encoder._stem_cache) == {"lidar", "radar"}
         assert rel_err(got, ref) < 1e-6
+        # and against the oracle restatement of Encoder.forward fed with zeroed lidar / radar inputs (mambafuser_seq.py:418-420)
+        zl, zr = [torch.zeros_like(t) for t in ins[1]], [torch.zeros_like(t) for t in ins[2]]
+        orc = model_ref.transfuser_forward(m, ins[0], zl, zr, ins[3])
+        assert rel_err(got, orc) < 1e-3, rel_err(got, orc)
         again = m(*ins)
         assert torch.equal(again, got)
         # an in-place parameter update invalidates the cached stem

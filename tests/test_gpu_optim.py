@@ -150,5 +150,7 @@ def test_fused_training_step_replays_as_a_cuda_graph(cuda_dev):
     torch.cuda.synchronize()
     assert opt_g.steps_done == 5 and opt_e.steps_done == 5
     for (n, pa), (_, pb) in zip(net.gpt.named_parameters(), ref.gpt.named_parameters()):
+        if n.endswith("attn.key.bias"):   # mathematically zero gradient: Adam normalises pure atomics-order noise
+            continue
         assert rel_err(pa, pb) < 1e-3, n
         assert rel_err(ema_g.shadow[n], ema_e.shadow[n]) < 1e-3, n
