@@ -68,6 +68,15 @@ def _side_stream(device, which=0):
     return _SIDE_STREAMS[key]
 
 
+def _chain_mode(C, env, default):
+    """Whether the row-local chain kernels (csrc/chain.cu) serve n_embd = C: env value 0 = never, 1 = n_embd 64, 2 = 64 and 128."""
+    try:
+        m = int(os.environ.get(env, default))
+    except ValueError:
+        m = default
+    return (m >= 1 and C == 64) or (m >= 2 and C == 128)
+
+
 def drop_site(kind, block=0):
     """Site id of an nn.Dropout layer inside one GPT: 'embd' (:272), per block 'attn' (:104), 'proj' (:109), 'mlp' (:125)."""
     return 0 if kind == "embd" else 1 + 3 * block + ("attn", "proj", "mlp").index(kind)
@@ -283,9 +292,12 @@ class _Runner:
                 return st
             return pack(i)
 
-        # Narrow stages (n_embd 64 / 128, no dropout): everything between two attention calls is row-local and runs as ONE launch
-        # (csrc/chain.cu): per block = flash attention + dsf_chain_fwd instead of seven launches.  DSF_CHAIN=0 keeps the separate kernels.
-        chain = C in (64, 128) and F == 4 * C and L > 0 and self.dropout is None and os.environ.get("DSF_CHAIN", "1") == "1"
+        # Narrow stages (no dropout): everything between two attention calls is row-local and can run as ONE launch (csrc/chain.cu):
+        # per block = flash attention + dsf_chain_fwd instead of seven launches.  Measured on B200 (batch 12, profiles/r02e_*):
+        # n_embd 64: 24 us per chain launch against ~35 us for the five launches it replaces (stage step 1.85 -> 1.79 ms) -> ON;
+        # n_embd 128: 52 us (register-fragment mma.sync + ldmatrix at 5 warps per SM are latency-bound) against ~45 us -> OFF.
+        # DSF_CHAIN=0: never, 1 (default): n_embd 64, 2: n_embd 64 and 128.
+        chain = _chain_mode(C, "DSF_CHAIN", 1) and F == 4 * C and L > 0 and self.dropout is None
         yf = torch.empty(M, C, device=dev, dtype=f32)
         saved.mean_f = torch.empty(M, device=dev, dtype=f32)
         saved.rstd_f = torch.empty(M, device=dev, dtype=f32)
@@ -656,8 +668,11 @@ class _Runner:
 
     def backward(self, saved, params, douts, dgps_out, residual=True):
         if self.bf16:
-            if (self.C in (64, 128) and self.nh == 4 and self.L > 0 and self.dropout is None and params[13].shape[0] == 4 * self.C
-                    and os.environ.get("DSF_CHAIN", "1") == "1" and os.environ.get("DSF_CHAIN_BWD", "1") == "1"):
+            # backward chain launches (csrc/chain.cu): measured 38 us (n_embd 64) / 87 us (128) per launch against ~8 separate
+            # launches of 7-8 us: no gain at 64 (stage step 1.82 vs 1.79 ms), a loss at 128 -> OFF by default.
+            # DSF_CHAIN_BWD=1: n_embd 64, 2: n_embd 64 and 128.
+            if (_chain_mode(self.C, "DSF_CHAIN_BWD", 0) and self.nh == 4 and self.L > 0 and self.dropout is None
+                    and params[13].shape[0] == 4 * self.C):
                 return self._backward_bf16_chain(saved, params, douts, dgps_out, residual)
             return self._backward_bf16(saved, params, douts, dgps_out, residual)
         dev = douts[0].device
