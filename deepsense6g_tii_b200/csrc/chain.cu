@@ -122,6 +122,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(ChainFwdArgs p
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(smem_raw);             // [NS][CHUNK]
   __nv_bfloat16* ybuf = ring + NS * CHUNK;                                       // [CH_WARPS][16][LDW]
+  // Every operand an epilogue needs is staged in shared memory by the same cp.async group as the first weight chunk: with five
+  // warps per SM nothing hides a global-load round trip inside the dependent chain (ncu: 52 % of the stall samples of the first
+  // version sat on the FADDs consuming bias / residual loads).
+  constexpr int LDX = C + 8;
+  float* xbuf = reinterpret_cast<float*>(ybuf + CH_WARPS * 16 * LDW);           // [CH_WARPS][16][LDX]: x_in, then x_mid in place
+  float* vec = xbuf + CH_WARPS * 16 * LDX;                                       // bp | b2 | g2 | be2 | gn | ben | b1 | bqkv
+  const float *v_bp = vec, *v_b2 = vec + C, *v_g2 = vec + 2 * C, *v_be2 = vec + 3 * C, *v_gn = vec + 4 * C, *v_ben = vec + 5 * C,
+              *v_b1 = vec + 6 * C, *v_bqkv = vec + 6 * C + F;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int row0 = blockIdx.x * CH_ROWS + warp * 16;
   const int r_lo = row0 + g, r_hi = r_lo + 8;
@@ -156,7 +164,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(ChainFwdArgs p
     if (s + NS < n_steps) __syncthreads();
   };
 
-  // this warp's 16 rows of y -> shared memory (same cp.async group as the first weight chunk)
+  // this warp's 16 rows of y and x_in and the bias / LayerNorm vectors -> shared memory (same cp.async group as the first weight chunk)
+  {
+    float* xb = xbuf + warp * 16 * LDX;
+    for (int i = lane; i < 16 * (C / 4); i += 32) {
+      const int r = i / (C / 4), c4 = i % (C / 4);
+      if (row0 + r < p.M) cp_async16(xb + r * LDX + c4 * 4, p.x_in + (size_t)(row0 + r) * C + c4 * 4);
+      else *reinterpret_cast<float4*>(xb + r * LDX + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float* srcs[6] = {p.bp, p.b2, p.g2, p.be2, p.gn, p.ben};
+    for (int i = tid; i < 6 * (C / 4); i += CH_THREADS) cp_async16(vec + i * 4, srcs[i / (C / 4)] + (i % (C / 4)) * 4);
+    for (int i = tid; i < F / 4; i += CH_THREADS) cp_async16(vec + 6 * C + i * 4, p.b1 + i * 4);
+    if (p.wqkv) { for (int i = tid; i < 3 * C / 4; i += CH_THREADS) cp_async16(vec + 6 * C + F + i * 4, p.bqkv + i * 4); }
+  }
   {
     __nv_bfloat16* yb = ybuf + warp * 16 * LDW;
     for (int i = lane; i < 16 * (C / 8); i += 32) {
@@ -182,16 +202,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(ChainFwdArgs p
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const int n = j * 8 + 2 * t;
-      const float2 b = *reinterpret_cast<const float2*>(p.bp + n);
-      float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
-      if (ok_lo) x0 = *reinterpret_cast<const float2*>(p.x_in + (size_t)r_lo * C + n);
-      if (ok_hi) x1 = *reinterpret_cast<const float2*>(p.x_in + (size_t)r_hi * C + n);
+      const float2 b = *reinterpret_cast<const float2*>(v_bp + n);
+      float* xs_lo = xbuf + (warp * 16 + g) * LDX + n;
+      float* xs_hi = xs_lo + 8 * LDX;
+      const float2 x0 = *reinterpret_cast<const float2*>(xs_lo), x1 = *reinterpret_cast<const float2*>(xs_hi);
       xm[j][0] += b.x + x0.x; xm[j][1] += b.y + x0.y; xm[j][2] += b.x + x1.x; xm[j][3] += b.y + x1.y;
+      *reinterpret_cast<float2*>(xs_lo) = make_float2(xm[j][0], xm[j][1]);   // x_mid stays on chip for the mlp.2 epilogue
+      *reinterpret_cast<float2*>(xs_hi) = make_float2(xm[j][2], xm[j][3]);
       if (ok_lo) *reinterpret_cast<float2*>(p.x_mid + (size_t)r_lo * C + n) = make_float2(xm[j][0], xm[j][1]);
       if (ok_hi) *reinterpret_cast<float2*>(p.x_mid + (size_t)r_hi * C + n) = make_float2(xm[j][2], xm[j][3]);
     }
     float m_lo, s_lo, m_hi, s_hi;
-    warp_layernorm<NT>(xm, p.g2, p.be2, t, p.eps, m_lo, s_lo, m_hi, s_hi);
+    warp_layernorm<NT>(xm, v_g2, v_be2, t, p.eps, m_lo, s_lo, m_hi, s_hi);
     if (t == 0) {
       if (ok_lo) { p.mean2[r_lo] = m_lo; p.rstd2[r_lo] = s_lo; }
       if (ok_hi) { p.mean2[r_hi] = m_hi; p.rstd2[r_hi] = s_hi; }
@@ -225,7 +247,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(ChainFwdArgs p
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int n = hc * 64 + j * 8 + 2 * t;
-      const float2 b = *reinterpret_cast<const float2*>(p.b1 + n);
+      const float2 b = *reinterpret_cast<const float2*>(v_b1 + n);
       const uint32_t lo = pack2(fmaxf(aa[j][0] + b.x, 0.f), fmaxf(aa[j][1] + b.y, 0.f));
       const uint32_t hi = pack2(fmaxf(aa[j][2] + b.x, 0.f), fmaxf(aa[j][3] + b.y, 0.f));
       afr[j >> 1][(j & 1) * 2] = lo;
@@ -242,15 +264,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(ChainFwdArgs p
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     const int n = j * 8 + 2 * t;
-    const float2 b = *reinterpret_cast<const float2*>(p.b2 + n);
-    float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
-    if (ok_lo) x0 = *reinterpret_cast<const float2*>(p.x_mid + (size_t)r_lo * C + n);   // written by this thread above
-    if (ok_hi) x1 = *reinterpret_cast<const float2*>(p.x_mid + (size_t)r_hi * C + n);
+    const float2 b = *reinterpret_cast<const float2*>(v_b2 + n);
+    const float* xs_lo = xbuf + (warp * 16 + g) * LDX + n;   // x_mid, written by this thread above
+    const float2 x0 = *reinterpret_cast<const float2*>(xs_lo), x1 = *reinterpret_cast<const float2*>(xs_lo + 8 * LDX);
     acc2[j][0] += b.x + x0.x; acc2[j][1] += b.y + x0.y; acc2[j][2] += b.x + x1.x; acc2[j][3] += b.y + x1.y;
     if (ok_lo) *reinterpret_cast<float2*>(p.x_out + (size_t)r_lo * C + n) = make_float2(acc2[j][0], acc2[j][1]);
     if (ok_hi) *reinterpret_cast<float2*>(p.x_out + (size_t)r_hi * C + n) = make_float2(acc2[j][2], acc2[j][3]);
   }
-  warp_layernorm<NT>(acc2, p.gn, p.ben, t, p.eps, m_lo, s_lo, m_hi, s_hi);
+  warp_layernorm<NT>(acc2, v_gn, v_ben, t, p.eps, m_lo, s_lo, m_hi, s_hi);
   if (t == 0) {
     if (ok_lo) { p.meann[r_lo] = m_lo; p.rstdn[r_lo] = s_lo; }
     if (ok_hi) { p.meann[r_hi] = m_hi; p.rstdn[r_hi] = s_hi; }
@@ -285,7 +306,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(ChainFwdArgs p
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int n = qc * 64 + j * 8 + 2 * t;
-      const float2 b = *reinterpret_cast<const float2*>(p.bqkv + n);
+      const float2 b = *reinterpret_cast<const float2*>(v_bqkv + n);
       if (ok_lo) *reinterpret_cast<uint32_t*>(p.qkv + (size_t)r_lo * (3 * C) + n) = pack2(qa[j][0] + b.x, qa[j][1] + b.y);
       if (ok_hi) *reinterpret_cast<uint32_t*>(p.qkv + (size_t)r_hi * (3 * C) + n) = pack2(qa[j][2] + b.x, qa[j][3] + b.y);
     }
@@ -297,7 +318,7 @@ template <int C>
 static int launch_chain_fwd(const ChainFwdArgs& a, cudaStream_t st) {
   constexpr int LDW = C + 8, LDW2 = 72;
   constexpr int CHUNK = (C * LDW > 64 * LDW + C * LDW2) ? C * LDW : 64 * LDW + C * LDW2;
-  constexpr int SMEM = (ChainCfg<C>::NS_FWD * CHUNK + CH_WARPS * 16 * LDW) * 2;
+  constexpr int SMEM = (ChainCfg<C>::NS_FWD * CHUNK + CH_WARPS * 16 * LDW) * 2 + (CH_WARPS * 16 * (C + 8) + 13 * C) * 4;
   static_assert(SMEM <= 232448, "shared memory budget");
   static bool configured_on[64] = {};
   bool& configured = per_device_flag(configured_on);
