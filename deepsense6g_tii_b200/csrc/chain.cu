@@ -109,7 +109,10 @@ __device__ __forceinline__ void warp_layernorm(float (&v)[NT][4], const float* _
 // The weight chunks ride in a ring of NS slots filled NS - 1 steps ahead (cp.async groups): at n_embd = 64 the ring holds the whole
 // block (the weights are fetched once, up front), at 128 it runs four 36 KB chunks deep, so a step never waits for L2 latency.
 constexpr int CH_WARPS = 5, CH_THREADS = CH_WARPS * 32, CH_ROWS = CH_WARPS * 16;
-template <int C> struct ChainCfg { static constexpr int NS_FWD = C == 64 ? 8 : 4, NS_BWD = C == 64 ? 6 : 4; };
+template <int C> struct ChainCfg {
+  static constexpr int NS_FWD = C == 64 ? 8 : 4, NS_BWD = 4;
+  static constexpr bool STAGE_BWD = C == 64;   // backward: fp32 row tiles (dx_mid / x_in / x_mid / dx_in) and y staged in shared memory (fits at 64 only)
+};
 
 template <int C>
 __global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(ChainFwdArgs p) {
@@ -377,8 +380,8 @@ __device__ __forceinline__ void warp_colsum(const float (&v)[NTL][4], float* red
 // LayerNorm backward of the 16 rows a warp holds: dh (gradient of the LayerNorm output, accumulator layout) is replaced by
 // dx = add + rstd * (g*dh - mean(g*dh) - xhat * mean(g*dh*xhat)); dgamma += dh * xhat and dbeta += dh go to red_g / red_b.
 template <int NT>
-__device__ __forceinline__ void warp_layernorm_bwd(float (&dh)[NT][4], const float (&add)[NT][4], const float* __restrict__ x, const float* __restrict__ gamma,
-                                                   float mean_lo, float rstd_lo, float mean_hi, float rstd_hi, int r_lo, int r_hi, bool ok_lo, bool ok_hi,
+__device__ __forceinline__ void warp_layernorm_bwd(float (&dh)[NT][4], const float (&add)[NT][4], const float* x_lo, const float* x_hi, const float* gamma,
+                                                   float mean_lo, float rstd_lo, float mean_hi, float rstd_hi, bool ok_lo, bool ok_hi,
                                                    int t, int lane, float* red_g, float* red_b) {
   constexpr int C = NT * 8;
   constexpr float inv_c = 1.0f / (float)C;
@@ -388,8 +391,8 @@ __device__ __forceinline__ void warp_layernorm_bwd(float (&dh)[NT][4], const flo
   for (int j = 0; j < NT; ++j) {
     const int n = j * 8 + 2 * t;
     float2 x0 = make_float2(mean_lo, mean_lo), x1 = make_float2(mean_hi, mean_hi);
-    if (ok_lo) x0 = *reinterpret_cast<const float2*>(x + (size_t)r_lo * C + n);
-    if (ok_hi) x1 = *reinterpret_cast<const float2*>(x + (size_t)r_hi * C + n);
+    if (ok_lo) x0 = *reinterpret_cast<const float2*>(x_lo + n);
+    if (ok_hi) x1 = *reinterpret_cast<const float2*>(x_hi + n);
     xh[j][0] = (x0.x - mean_lo) * rstd_lo; xh[j][1] = (x0.y - mean_lo) * rstd_lo;
     xh[j][2] = (x1.x - mean_hi) * rstd_hi; xh[j][3] = (x1.y - mean_hi) * rstd_hi;
   }
@@ -439,6 +442,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(ChainBwdArgs p
   float* red = reinterpret_cast<float*>(ring + NS * CHUNK);            // column accumulators: [7][C] + [3C] + [F]
   float *red_g1 = red, *red_b1 = red + C, *red_b2p = red + 2 * C, *red_g2 = red + 3 * C, *red_be2 = red + 4 * C, *red_bp = red + 5 * C;
   float *red_bqkv = red + 6 * C, *red_db1 = red + 9 * C;
+  // n_embd 64: the row tiles the epilogues read (dx_mid_in | dx_in, x_in, x_mid: fp32; y: bf16) are staged per warp by the first
+  // cp.async group, like the forward kernel does (at 128 they do not fit next to the ring and are read from global memory)
+  constexpr bool STG = ChainCfg<C>::STAGE_BWD;
+  constexpr int LDX = C + 8;
+  float* vec = red + 9 * C + F;                                          // g1 | g2
+  float* st_add = vec + 2 * C;                                           // [CH_WARPS][16][LDX] dx_mid_in (half A) or dx_in (no half A)
+  float* st_x1 = st_add + (STG ? CH_WARPS * 16 * LDX : 0);               // x_in
+  float* st_x2 = st_x1 + (STG ? CH_WARPS * 16 * LDX : 0);                // x_mid
+  __nv_bfloat16* st_y = reinterpret_cast<__nv_bfloat16*>(st_x2 + (STG ? CH_WARPS * 16 * LDX : 0));   // [CH_WARPS][16][LDW]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int row0 = blockIdx.x * CH_ROWS + warp * 16;
   const int r_lo = row0 + g, r_hi = r_lo + 8;
@@ -465,6 +477,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(ChainBwdArgs p
       for (int i = tid; i < 64 * (C / 8); i += CH_THREADS) { const int r = i / (C / 8), c8 = i % (C / 8); cp_async16(dst + r * LDW + c8 * 8, p.w2_t + (size_t)(hc * 64 + r) * C + c8 * 8); }
       __nv_bfloat16* d2 = dst + 64 * LDW;
       for (int i = tid; i < C * 8; i += CH_THREADS) { const int r = i >> 3, c8 = i & 7; cp_async16(d2 + r * LDW2 + c8 * 8, p.w1_t + (size_t)r * F + hc * 64 + c8 * 8); }
+      __nv_bfloat16* act = dst + WCH + warp * 16 * LDW2;   // this warp's 64 columns of the saved mlp.0 output (ReLU decisions)
+      for (int i = lane; i < 16 * 8; i += 32) {
+        const int r = i >> 3, c8 = i & 7;
+        if (row0 + r < p.M) cp_async16(act + r * LDW2 + c8 * 8, p.a + (size_t)(row0 + r) * F + hc * 64 + c8 * 8);
+        else *reinterpret_cast<uint4*>(act + r * LDW2 + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
+      }
     } else {   // proj data gradient: wp_t (C, C)
       for (int i = tid; i < C * (C / 8); i += CH_THREADS) { const int r = i / (C / 8), c8 = i % (C / 8); cp_async16(dst + r * LDW + c8 * 8, p.wp_t + (size_t)r * C + c8 * 8); }
     }
@@ -478,7 +496,40 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(ChainBwdArgs p
   auto release = [&](int s) {
     if (s + NS < n_steps) __syncthreads();
   };
+  // row statistics: four scalars per thread, loaded now and consumed many steps later
+  const float m1_lo = half_a && ok_lo ? p.mean1[r_lo] : 0.f, s1_lo = half_a && ok_lo ? p.rstd1[r_lo] : 0.f;
+  const float m1_hi = half_a && ok_hi ? p.mean1[r_hi] : 0.f, s1_hi = half_a && ok_hi ? p.rstd1[r_hi] : 0.f;
+  const float m2_lo = half_b && ok_lo ? p.mean2[r_lo] : 0.f, s2_lo = half_b && ok_lo ? p.rstd2[r_lo] : 0.f;
+  const float m2_hi = half_b && ok_hi ? p.mean2[r_hi] : 0.f, s2_hi = half_b && ok_hi ? p.rstd2[r_hi] : 0.f;
+  {   // first cp.async group: LayerNorm gains and (n_embd 64) the row tiles
+    if (half_a) { for (int i = tid; i < C / 4; i += CH_THREADS) cp_async16(vec + i * 4, p.g1 + i * 4); }
+    if (half_b) { for (int i = tid; i < C / 4; i += CH_THREADS) cp_async16(vec + C + i * 4, p.g2 + i * 4); }
+    if (STG) {
+      auto stage_f32 = [&](float* dstw, const float* src) {
+        for (int i = lane; i < 16 * (C / 4); i += 32) {
+          const int r = i / (C / 4), c4 = i % (C / 4);
+          if (row0 + r < p.M) cp_async16(dstw + r * LDX + c4 * 4, src + (size_t)(row0 + r) * C + c4 * 4);
+          else *reinterpret_cast<float4*>(dstw + r * LDX + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      stage_f32(st_add + warp * 16 * LDX, half_a ? p.dx_mid_in : p.dx_in);
+      if (half_a) stage_f32(st_x1 + warp * 16 * LDX, p.x_in);
+      if (half_b) {
+        stage_f32(st_x2 + warp * 16 * LDX, p.x_mid);
+        __nv_bfloat16* yb = st_y + warp * 16 * LDW;
+        for (int i = lane; i < 16 * (C / 8); i += 32) {
+          const int r = i / (C / 8), c8 = i % (C / 8);
+          if (row0 + r < p.M) cp_async16(yb + r * LDW + c8 * 8, p.y + (size_t)(row0 + r) * C + c8 * 8);
+          else *reinterpret_cast<uint4*>(yb + r * LDW + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
+  }
   for (int q = 0; q < NS - 1; ++q) { if (q < n_steps) prefetch(q); else cp_async_commit(); }
+  // row pointers of this thread's two rows in the staged tiles (n_embd 64) or in global memory
+  const float* add_lo = STG ? st_add + (warp * 16 + g) * LDX : (half_a ? p.dx_mid_in : p.dx_in) + (size_t)r_lo * C;
+  const float* add_hi = STG ? add_lo + 8 * LDX : (half_a ? p.dx_mid_in : p.dx_in) + (size_t)r_hi * C;
+  const bool rd_lo = STG || ok_lo, rd_hi = STG || ok_hi;   // staged tiles are zero-filled past M
 
   float dx[NT][4];   // gradient of the residual stream between the two halves
   int s = 0;
@@ -515,13 +566,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(ChainBwdArgs p
     for (int j = 0; j < NT; ++j) {
       const int n = j * 8 + 2 * t;
       float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
-      if (ok_lo) a0 = *reinterpret_cast<const float2*>(p.dx_mid_in + (size_t)r_lo * C + n);
-      if (ok_hi) a1 = *reinterpret_cast<const float2*>(p.dx_mid_in + (size_t)r_hi * C + n);
+      if (rd_lo) a0 = *reinterpret_cast<const float2*>(add_lo + n);
+      if (rd_hi) a1 = *reinterpret_cast<const float2*>(add_hi + n);
       add[j][0] = a0.x; add[j][1] = a0.y; add[j][2] = a1.x; add[j][3] = a1.y;
     }
-    const float m_lo = ok_lo ? p.mean1[r_lo] : 0.f, s_lo = ok_lo ? p.rstd1[r_lo] : 0.f;
-    const float m_hi = ok_hi ? p.mean1[r_hi] : 0.f, s_hi = ok_hi ? p.rstd1[r_hi] : 0.f;
-    warp_layernorm_bwd<NT>(dx, add, p.x_in, p.g1, m_lo, s_lo, m_hi, s_hi, r_lo, r_hi, ok_lo, ok_hi, t, lane, red_g1, red_b1);
+    const float* x1_lo = STG ? st_x1 + (warp * 16 + g) * LDX : p.x_in + (size_t)r_lo * C;
+    const float* x1_hi = STG ? x1_lo + 8 * LDX : p.x_in + (size_t)r_hi * C;
+    warp_layernorm_bwd<NT>(dx, add, x1_lo, x1_hi, vec, m1_lo, s1_lo, m1_hi, s1_hi, rd_lo, rd_hi, t, lane, red_g1, red_b1);
     if (p.db2_prev) warp_colsum<NT>(dx, red_b2p, 0, lane);
     if (!half_b) {
 #pragma unroll
@@ -532,12 +583,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(ChainBwdArgs p
       }
     }
   } else {
+    if (STG) { cp_async_wait<NS - 2>(); __syncwarp(); }   // the first group (with this warp's own staged rows) has landed
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const int n = j * 8 + 2 * t;
       float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
-      if (ok_lo) a0 = *reinterpret_cast<const float2*>(p.dx_in + (size_t)r_lo * C + n);
-      if (ok_hi) a1 = *reinterpret_cast<const float2*>(p.dx_in + (size_t)r_hi * C + n);
+      if (rd_lo) a0 = *reinterpret_cast<const float2*>(add_lo + n);
+      if (rd_hi) a1 = *reinterpret_cast<const float2*>(add_hi + n);
       dx[j][0] = a0.x; dx[j][1] = a0.y; dx[j][2] = a1.x; dx[j][3] = a1.y;
     }
   }
@@ -563,6 +615,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(ChainBwdArgs p
       acquire(s);
       const __nv_bfloat16* w2c = ring + (s % NS) * CHUNK;
       const __nv_bfloat16* w1c = w2c + 64 * LDW;
+      const __nv_bfloat16* am_lo = w2c + WCH + (warp * 16 + g) * LDW2;   // saved mlp.0 outputs of this thread's two rows, this chunk
+      const __nv_bfloat16* am_hi = am_lo + 8 * LDW2;
       float dd[8][4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) { dd[j][0] = dd[j][1] = dd[j][2] = dd[j][3] = 0.f; }
@@ -571,9 +625,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(ChainBwdArgs p
 #pragma unroll
       for (int j = 0; j < 8; ++j) {   // ReLU backward with the saved activations (model2_seq.py:123)
         const int n = hc * 64 + j * 8 + 2 * t;
-        uint32_t m0 = 0u, m1 = 0u;
-        if (ok_lo) m0 = *reinterpret_cast<const uint32_t*>(p.a + (size_t)r_lo * F + n);
-        if (ok_hi) m1 = *reinterpret_cast<const uint32_t*>(p.a + (size_t)r_hi * F + n);
+        const uint32_t m0 = *reinterpret_cast<const uint32_t*>(am_lo + j * 8 + 2 * t);
+        const uint32_t m1 = *reinterpret_cast<const uint32_t*>(am_hi + j * 8 + 2 * t);
         const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m0));
         const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m1));
         dd[j][0] = a0.x > 0.f ? dd[j][0] : 0.f; dd[j][1] = a0.y > 0.f ? dd[j][1] : 0.f;
@@ -592,9 +645,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(ChainBwdArgs p
       warp_gemm<NT, 4>(dh2, dfr, w1c, LDW2, lane);
       release(s);
     }
-    const float m_lo = ok_lo ? p.mean2[r_lo] : 0.f, s_lo = ok_lo ? p.rstd2[r_lo] : 0.f;
-    const float m_hi = ok_hi ? p.mean2[r_hi] : 0.f, s_hi = ok_hi ? p.rstd2[r_hi] : 0.f;
-    warp_layernorm_bwd<NT>(dh2, dx, p.x_mid, p.g2, m_lo, s_lo, m_hi, s_hi, r_lo, r_hi, ok_lo, ok_hi, t, lane, red_g2, red_be2);
+    const float* x2_lo = STG ? st_x2 + (warp * 16 + g) * LDX : p.x_mid + (size_t)r_lo * C;
+    const float* x2_hi = STG ? x2_lo + 8 * LDX : p.x_mid + (size_t)r_hi * C;
+    warp_layernorm_bwd<NT>(dh2, dx, x2_lo, x2_hi, vec + C, m2_lo, s2_lo, m2_hi, s2_hi, rd_lo, rd_hi, t, lane, red_g2, red_be2);
     warp_colsum<NT>(dh2, red_bp, 0, lane);   // dh2 now holds dx_mid: bias gradient of proj
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -621,8 +674,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(ChainBwdArgs p
       const int n = j * 8 + 2 * t;
       const uint32_t lo = pack2(dyv[j][0], dyv[j][1]), hi = pack2(dyv[j][2], dyv[j][3]);
       uint32_t y0 = 0u, y1 = 0u;
-      if (ok_lo) { *reinterpret_cast<uint32_t*>(p.dy + (size_t)r_lo * C + n) = lo; y0 = *reinterpret_cast<const uint32_t*>(p.y + (size_t)r_lo * C + n); }
-      if (ok_hi) { *reinterpret_cast<uint32_t*>(p.dy + (size_t)r_hi * C + n) = hi; y1 = *reinterpret_cast<const uint32_t*>(p.y + (size_t)r_hi * C + n); }
+      if (ok_lo) *reinterpret_cast<uint32_t*>(p.dy + (size_t)r_lo * C + n) = lo;
+      if (ok_hi) *reinterpret_cast<uint32_t*>(p.dy + (size_t)r_hi * C + n) = hi;
+      if (STG) {
+        y0 = *reinterpret_cast<const uint32_t*>(st_y + (warp * 16 + g) * LDW + n);
+        y1 = *reinterpret_cast<const uint32_t*>(st_y + (warp * 16 + g + 8) * LDW + n);
+      } else {
+        if (ok_lo) y0 = *reinterpret_cast<const uint32_t*>(p.y + (size_t)r_lo * C + n);
+        if (ok_hi) y1 = *reinterpret_cast<const uint32_t*>(p.y + (size_t)r_hi * C + n);
+      }
       const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lo)), d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi));
       const float2 v0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&y0)), v1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&y1));
       dl_lo[j / (NT / NH)] += d0.x * v0.x + d0.y * v0.y;
@@ -665,7 +725,8 @@ static int launch_chain_bwd(const ChainBwdArgs& a, cudaStream_t st) {
   constexpr int F = 4 * C, LDW = C + 8, LDW2 = 72;
   constexpr int ACT = CH_WARPS * 16 * LDW2;
   constexpr int WCH = (64 * LDW + C * LDW2 > C * LDW) ? 64 * LDW + C * LDW2 : C * LDW;
-  constexpr int SMEM = ChainCfg<C>::NS_BWD * (WCH + ACT) * 2 + (9 * C + F) * 4;
+  constexpr int STAGE = ChainCfg<C>::STAGE_BWD ? 3 * CH_WARPS * 16 * (C + 8) * 4 + CH_WARPS * 16 * LDW * 2 : 0;
+  constexpr int SMEM = ChainCfg<C>::NS_BWD * (WCH + ACT) * 2 + (9 * C + F + 2 * C) * 4 + STAGE;
   static_assert(SMEM <= 232448, "shared memory budget");
   static bool configured_on[64] = {};
   bool& configured = per_device_flag(configured_on);

@@ -108,7 +108,7 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// ---------------------------------------------------------------- counter-based dropout (Philox4x32-10)
+// ---------------------------------------------------------------- counter-based dropout (Philox4x32, 7 rounds)
 // nn.Dropout sites of the path (model2_seq.py:104,109,125,272).  The mask of element e of a site is a pure function of
 // (seed, site, step, e): 16-bit lane e%8 of philox(key = seed, counter = (e/8, site, step)); keep iff lane >= t16 with
 // t16 = round(p * 65536), kept values are scaled by 65536 / (65536 - t16) (= 1/(1-p) to 1.5e-5).  One Philox call

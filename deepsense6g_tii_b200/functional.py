@@ -292,12 +292,11 @@ class _Runner:
                 return st
             return pack(i)
 
-        # Narrow stages (no dropout): everything between two attention calls is row-local and can run as ONE launch (csrc/chain.cu):
-        # per block = flash attention + dsf_chain_fwd instead of seven launches.  Measured on B200 (batch 12, profiles/r02e_*):
-        # n_embd 64: 24 us per chain launch against ~35 us for the five launches it replaces (stage step 1.85 -> 1.79 ms) -> ON;
-        # n_embd 128: 52 us (register-fragment mma.sync + ldmatrix at 5 warps per SM are latency-bound) against ~45 us -> OFF.
-        # DSF_CHAIN=0: never, 1 (default): n_embd 64, 2: n_embd 64 and 128.
-        chain = _chain_mode(C, "DSF_CHAIN", 1) and F == 4 * C and L > 0 and self.dropout is None
+        # Narrow stages (no dropout): everything between two attention calls is row-local and runs as ONE launch (csrc/chain.cu):
+        # per block = flash attention + dsf_chain_fwd instead of seven launches.  Measured on B200 (batch 12, graph-replayed stage
+        # step, profiles/r02f_*): n_embd 64: 13.6 us per chain launch, step 1.82 -> 1.68 ms; n_embd 128: 34 us, 2.17 -> 2.09 ms.
+        # DSF_CHAIN=0: never, 1: n_embd 64 only, 2 (default): n_embd 64 and 128.
+        chain = _chain_mode(C, "DSF_CHAIN", 2) and F == 4 * C and L > 0 and self.dropout is None
         yf = torch.empty(M, C, device=dev, dtype=f32)
         saved.mean_f = torch.empty(M, device=dev, dtype=f32)
         saved.rstd_f = torch.empty(M, device=dev, dtype=f32)

@@ -45,7 +45,7 @@ enum {
   DSF_EPI_BIAS = 1,      /* + bias[n]                      (nn.Linear bias, model2_seq.py:83-90,122,124) */
   DSF_EPI_RELU = 2,      /* max(.,0)                       (nn.ReLU(True), :123) */
   DSF_EPI_RESIDUAL = 4,  /* + residual[m,n] (fp32)          (x + attn / x + mlp, :131-132) */
-  DSF_EPI_ACCUM = 8      /* C += result (fp32 outputs only; used by weight-grad accumulation) */
+  DSF_EPI_ACCUM = 8      /* C += result: dsf_gemm_f32 only (fp32 parity path); the bf16 NT GEMM rejects it, the TN GEMM always accumulates */
 };
 
 int dsf_version(void);

@@ -84,7 +84,62 @@ def traffic(path, tag):
     print(json.dumps(res, indent=1))
 
 
+def families(path, tag):
+    """Launch list with several metrics per launch (scripts/r02_profile_final.sh) -> per kernel: launches, time, DRAM bytes, tensor-pipe
+    activity, executed bf16 tensor math ops; writes profiles/<tag>_traffic.json for the NT GEMM family (read by bench.py)."""
+    import json
+    import os
+    rows = list(csv.reader(open(path)))
+    hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[hi]
+    ki, ni, vi, ui, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("ID")
+    per = collections.OrderedDict()
+    for r in rows[hi + 1:]:
+        if len(r) <= vi:
+            continue
+        name = re.sub(r"^void ", "", re.sub(r"\(.*", "", r[ki]))
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        u = r[ui]
+        mult = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+        per.setdefault((r[ii], name), {})[r[ni]] = v * mult
+    agg = collections.OrderedDict()
+    for (_, name), m in per.items():
+        a = agg.setdefault(name, collections.Counter())
+        a["n"] += 1
+        a["us"] += m.get("gpu__time_duration.sum", 0.0)
+        a["dram"] += m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
+        a["ops"] += m.get("sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32.sum", 0.0)
+        t = m.get("gpu__time_duration.sum", 0.0)
+        a["pipe_w"] += t * m.get("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", 0.0)
+        a["hmma_w"] += t * m.get("sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", 0.0)
+        a["memt_w"] += t * m.get("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0)
+    tot = sum(a["us"] for a in agg.values())
+    print("# %s : %d launches, %.1f us total (ncu: cold cache, serialised launches -> compare SHARES, not absolutes)" % (path, sum(a["n"] for a in agg.values()), tot))
+    print("# tensor = sm__pipe_tensor_cycles_active_realtime %% of peak (time-weighted), hmma = ..._subpipe_hmma_..., memT = sm__mem_tensor_cycles_active %%;")
+    print("# TF/s = sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32 (executed tensor math ops, FMA = 2) / kernel time")
+    print("%-62s %5s %10s %7s %9s %7s %7s %7s %8s" % ("kernel", "n", "us", "share", "MB/launch", "tensor", "hmma", "memT", "TF/s"))
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+        us = max(a["us"], 1e-9)
+        print("%-62s %5d %10.1f %6.2f%% %9.2f %6.1f%% %6.1f%% %6.1f%% %8.1f" % (k[:62], a["n"], a["us"], 100 * a["us"] / tot, a["dram"] / a["n"] / 1e6,
+                                                                     a["pipe_w"] / us, a["hmma_w"] / us, a["memt_w"] / us, a["ops"] / us / 1e6))
+    nt = [a for k, a in agg.items() if "gemm_nt" in k]
+    if nt:
+        n = sum(a["n"] for a in nt)
+        res = {"family": "gemm_bf16_nt", "kernels": [k for k in agg if "gemm_nt" in k], "launches": int(n),
+               "avg_dram_bytes_per_launch": int(sum(a["dram"] for a in nt) / n),
+               "source": "profiles/%s_launches_metrics.txt (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over every launch of one eager step of the "
+                         "default workload; cold cache; writes that stay in the 126 MB L2 are not counted)" % tag}
+        dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "%s_traffic.json" % tag)
+        json.dump(res, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "families":
+        families(sys.argv[2], sys.argv[3])
+        sys.exit(0)
     if sys.argv[1] == "traffic":
         traffic(sys.argv[2], sys.argv[3])
     else:
