@@ -667,9 +667,9 @@ class _Runner:
 
     def backward(self, saved, params, douts, dgps_out, residual=True):
         if self.bf16:
-            # backward chain launches (csrc/chain.cu): measured 38 us (n_embd 64) / 87 us (128) per launch against ~8 separate
-            # launches of 7-8 us: no gain at 64 (stage step 1.82 vs 1.79 ms), a loss at 128 -> OFF by default.
-            # DSF_CHAIN_BWD=1: n_embd 64, 2: n_embd 64 and 128.
+            # backward chain launches (csrc/chain.cu): measured on B200 34 us (n_embd 64) / 79 us (128) per launch against the ~8
+            # separate launches of 7-8 us they replace: stage step 1.683 -> 1.668 ms at 64, 2.09 -> 2.36 ms at 128 (profiles/r02g_*)
+            # -> OFF by default.  DSF_CHAIN_BWD=1: n_embd 64, 2: n_embd 64 and 128.
             if (_chain_mode(self.C, "DSF_CHAIN_BWD", 0) and self.nh == 4 and self.L > 0 and self.dropout is None
                     and params[13].shape[0] == 4 * self.C):
                 return self._backward_bf16_chain(saved, params, douts, dgps_out, residual)
