@@ -417,6 +417,28 @@ def family_rooflines(fam, pk):
     return out
 
 
+def check_grads_synced(works, world, dist):
+    """N > 1: the replayed / eager steps really exchanged gradients — every rank holds the same averaged gradient for a sample of
+    parameters of the first and the last stage (ranks see different data, so un-reduced gradients would differ).  Returns
+    (all identical, names that are not)."""
+    if world <= 1:
+        return None, []
+    bad = []
+    for w in (works[0], works[-1]):
+        blk = w.gpt.blocks
+        named = {"pos_emb": w.gpt.pos_emb, "ln_f.weight": w.gpt.ln_f.weight, "blocks.0.mlp.0.weight": blk[0].mlp[0].weight,
+                 "blocks.0.attn.query.bias": blk[0].attn.query.bias, "blocks.%d.attn.proj.weight" % (len(blk) - 1): blk[len(blk) - 1].attn.proj.weight,
+                 "blocks.%d.mlp.2.bias" % (len(blk) - 1): blk[len(blk) - 1].mlp[2].bias}
+        for n, t in named.items():
+            g = t.grad.detach().reshape(-1)[:4096].contiguous()
+            gs = [torch.empty_like(g) for _ in range(world)]
+            dist.all_gather(gs, g)
+            ok = all(torch.equal(gs[0], x) for x in gs[1:]) and bool(torch.isfinite(g).all()) and float(g.abs().sum()) > 0
+            if not ok:
+                bad.append("C%d.%s (max |diff| %.3e, |g| %.3e)" % (w.c, n, max(float((gs[0] - x).abs().max()) for x in gs[1:]), float(g.abs().max())))
+    return len(bad) == 0, bad
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from deepsense6g_tii_b200 import _capi
@@ -546,8 +568,10 @@ def run_ours(args, rank, world, local_rank):
     ms, launches, clocks = timed(step_resident, steps, warmup, ClockSampler(local_rank) if rank == 0 else None)
     value = BATCH * world * steps / (ms * 1e-3)
     if args.quick:
+        synced, sync_bad = check_grads_synced(works, world, dist)
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": ms / steps, "value": value, "gpu_launches": launches}))
+            print(json.dumps({"quick": True, "ms_per_step": ms / steps, "value": value, "gpu_launches": launches,
+                              "grads_identical_across_ranks": synced, "not_identical": sync_bad}))
         return
     # the K-th prefetch issued inside the region must also complete inside it: K steps <-> K host-to-device batch copies
     ms_e2e, _, _ = timed(step_e2e, steps, 2, finalize=lambda: torch.cuda.current_stream().wait_event(ev_ready[e2e_k[0] & 1]))
@@ -560,16 +584,7 @@ def run_ours(args, rank, world, local_rank):
         ms_s, _, clk_s = timed(step_resident, n_s, 1, smp)
         sustained = {"seconds": round(ms_s * 1e-3, 2), "steps": n_s, "ms_per_step": ms_s / n_s, "value": BATCH * world * n_s / (ms_s * 1e-3), "clocks": clk_s}
 
-    synced = None
-    if world > 1:  # the replayed / eager steps really exchanged gradients: every rank holds the same averaged gradients
-        synced = True
-        for w in (works[0], works[-1]):
-            blk = w.gpt.blocks
-            for t in (w.gpt.pos_emb, w.gpt.ln_f.weight, blk[0].mlp[0].weight, blk[0].attn.query.bias, blk[len(blk) - 1].attn.proj.weight):
-                g = t.grad.detach().reshape(-1)[:4096].contiguous()
-                gs = [torch.empty_like(g) for _ in range(world)]
-                dist.all_gather(gs, g)
-                synced = synced and all(torch.equal(gs[0], x) for x in gs[1:]) and bool(torch.isfinite(g).all()) and float(g.abs().sum()) > 0
+    synced, sync_bad = check_grads_synced(works, world, dist)
     if rank != 0:
         return
     pk = peaks()
@@ -666,7 +681,7 @@ def run_ours(args, rank, world, local_rank):
                 if args.optimizer else "none (fwd+bwd only; bf16 weight shadows re-packed at the start of every forward)",
                 "l2": "per-step working set (saved activations of 8 blocks per stage, > 1 GB) > 126 MB L2; no explicit flush",
                 "grad_allreduce": ("NCCL all-reduce (avg) of %.1f M fp32 grads per step, one bucket per transformer block, overlapped with backward" % (n_params / 1e6)) if world > 1 else "none (1 GPU)",
-                "grads_identical_across_ranks": synced})
+                "grads_identical_across_ranks": synced, "grads_not_identical": sync_bad or None})
     out = {
         "metric": "train samples/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -702,10 +717,23 @@ def run_model(args, rank, world, local_rank):
     torch.manual_seed(100)
     model = TransFuser(cfg, dev).to(memory_format=torch.channels_last).train()
     net = model
+    enc = model.encoder
+    gpts = [enc.transformer1, enc.transformer2, enc.transformer3, enc.transformer4]
+    grad_sync, ddp_note = None, "none (1 GPU)"
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+        from deepsense6g_tii_b200 import dist as D
+        D.broadcast_params(model.parameters())
+        for b_ in model.buffers():   # BatchNorm statistics start equal on every rank, then stay per replica (as under nn.DataParallel)
+            dist.broadcast(b_, 0)
+        if args.ddp:   # stock DistributedDataParallel: its reducer hooks cannot be captured -> eager launches
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+            ddp_note = "torch DistributedDataParallel (NCCL, bucketed, overlapped) of %.1f M fp32 gradients; eager launches"
+        else:
+            grad_sync = D.DataParallelGrads(model, gpts)
+            ddp_note = ("dist.DataParallelGrads: GPT gradients all-reduced per transformer block inside the backward, the other "
+                        "parameters through one flat fp32 bucket after it (%.1f M gradients in total), all inside the captured CUDA graph")
     crit = FocalLoss()
-    use_graph = args.graph and world == 1
+    use_graph = args.graph and (world == 1 or not args.ddp)
     ema = EMA(model, 0.999)
     ema.register()
     if args.torch_optimizer:
@@ -713,8 +741,7 @@ def run_model(args, rank, world, local_rank):
         opt_note = "torch.optim.AdamW(fused, capturable) + multi-tensor EMA lerp"
     else:   # AdamW + EMA + the bf16 repack of the four GPTs' weights in one dsfuse launch (train2_seq.py:131-134, 315-320, 539)
         from deepsense6g_tii_b200.optim import FusedAdamWEMA
-        enc = model.encoder
-        opt = FusedAdamWEMA(model.parameters(), lr=1e-4, ema=ema, gpts=[enc.transformer1, enc.transformer2, enc.transformer3, enc.transformer4])
+        opt = FusedAdamWEMA(model.parameters(), lr=1e-4, ema=ema, gpts=gpts)
         opt_note = "dsf_adamw_ema_pack: AdamW + EMA + bf16 weight repack of the 4 GPTs in one launch"
     gen = torch.Generator().manual_seed(rank)
     host = synthetic_batch(BATCH, S, 256, generator=gen, pin=True)
@@ -729,7 +756,7 @@ def run_model(args, rank, world, local_rank):
     loss_h = torch.empty((), pin_memory=True)
 
     def step_eager(b=None):
-        return train_step(net, resident if b is None else b, crit, opt, ema, autocast_dtype=torch.bfloat16)
+        return train_step(net, resident if b is None else b, crit, opt, ema, autocast_dtype=torch.bfloat16, grad_sync=grad_sync)
 
     # N = 1: the whole training step (trunks, 4 fusion stages with graph-safe dropout, loss, backward, capturable fused
     # AdamW, multi-tensor EMA) is captured in one CUDA graph on static input tensors and replayed.
@@ -825,6 +852,15 @@ def run_model(args, rank, world, local_rank):
     clocks = sampler.stop() if sampler else None
     ms_e2e, _ = timed(step_e2e, steps, 2, finalize=lambda: torch.cuda.current_stream().wait_event(ev_ready[e2e_k[0] & 1]))
     loss_val = float(loss_h)
+    params_synced = None
+    if world > 1:   # same start + averaged gradients every step -> the replicas' parameters stay identical
+        params_synced = True
+        for t in (model.join[0].weight, enc.image_encoder.features.conv1.weight, enc.transformer4.blocks[0].mlp[0].weight, enc.transformer1.pos_emb,
+                  enc.vel_emb1.weight):
+            v = t.detach().reshape(-1)[:4096].float().contiguous()
+            vs = [torch.empty_like(v) for _ in range(world)]
+            dist.all_gather(vs, v)
+            params_synced = params_synced and all(torch.equal(vs[0], x) for x in vs[1:]) and bool(torch.isfinite(v).all())
     if rank != 0:
         return
     h2d = sum(t.numel() * t.element_size() for t in host[0] + host[1] + host[2]) + sum(t.numel() * t.element_size() for t in host[3:])
@@ -839,7 +875,8 @@ def run_model(args, rank, world, local_rank):
                    "global_batch": BATCH * world, "seq_len": S, "parallelism": "dp%d" % world, "launch": launch_note + ", PDL " + ("on" if args.pdl else "off"),
                    "optimizer": opt_note,
                    "l2": "per-step working set (activations of 3 ResNets + 4 fusion stages) >> 126 MB L2; no explicit flush",
-                   "grad_allreduce": "torch DistributedDataParallel (NCCL, bucketed, overlapped) of %.1f M fp32 gradients" % (n_params / 1e6) if world > 1 else "none (1 GPU)"},
+                   "grad_allreduce": (ddp_note % (n_params / 1e6)) if world > 1 else ddp_note,
+                   "params_identical_across_ranks": params_synced},
         "e2e": {"value": BATCH * world * steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / steps, "pipeline": "next batch copied pinned-host -> device on a copy stream during the current step"},
         "gpu_launches": launches, "clocks": clocks, "final_loss": loss_val,
@@ -862,6 +899,7 @@ def main():
     ap.add_argument("--no-gpu-baseline", dest="gpu_baseline", action="store_false", help="skip the stock-PyTorch-autocast leg on the GPU")
     ap.add_argument("--sustained", type=float, default=2.0, help="seconds of back-to-back replays for the `sustained` sub-record (0 = skip)")
     ap.add_argument("--optimizer", action="store_true", help="stage workloads: add the fused AdamW + EMA + weight-repack launch to every step")
+    ap.add_argument("--ddp", action="store_true", help="model workload, N > 1: stock DistributedDataParallel (eager launches) instead of dist.DataParallelGrads")
     ap.add_argument("--torch-optimizer", action="store_true", help="model workload: stock torch AdamW(fused) + multi-tensor EMA instead of dsf_adamw_ema_pack")
     ap.add_argument("--dropout", type=float, default=0.0,
                     help="embd/attn/resid dropout probability (default 0 = the parity configuration; the reference trains with 0.1)")

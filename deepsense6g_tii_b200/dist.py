@@ -96,3 +96,50 @@ class OverlappedGradReducer:
             if t is not None:
                 t.div_(world)
         self._works = []
+
+
+class DataParallelGrads:
+    """Gradient exchange of a whole drop-in model under one-process-per-GPU data parallelism, capturable in a CUDA graph
+    (replaces nn.DataParallel's gather / reduce, train2_seq.py:538, and stock DistributedDataParallel, whose reducer hooks
+    force eager launches):
+
+      * the GPT fusion stages average their own gradients bucket by bucket inside their backward (``OverlappedGradReducer``,
+        one shared instance, waits deferred to ``sync()``);
+      * every other trainable parameter (ResNet trunks, GPS MLP, join head) owns a fixed view of ONE flat fp32 buffer as its
+        ``.grad`` (autograd accumulates into it in place), which ``sync()`` averages with a single all-reduce.
+
+    Usage per step: ``zero_grad()`` -> forward / loss / backward -> ``sync()`` -> optimizer step.  BatchNorm statistics stay
+    per replica, as under nn.DataParallel."""
+
+    def __init__(self, model, gpts=()):
+        self.gpts = list(gpts)
+        self.reducer = OverlappedGradReducer(defer=True)
+        for g in self.gpts:
+            g.set_grad_reducer(self.reducer)
+        own = set(id(p) for g in self.gpts for p in g.parameters())
+        self.params = [p for p in model.parameters() if p.requires_grad and id(p) not in own]
+        self.flat = None
+        if self.params:
+            dev = self.params[0].device
+            self.flat = torch.zeros(flat_size(self.params), device=dev, dtype=torch.float32)
+            off = 0
+            for p in self.params:   # same strides as the parameter (channels_last conv weights are dense but permuted)
+                p.grad = torch.as_strided(self.flat, p.shape, p.stride(), off)
+                off += p.numel()
+
+    def zero_grad(self):
+        if self.flat is not None:
+            self.flat.zero_()
+        for g in self.gpts:
+            for p in g.parameters():
+                p.grad = None
+
+    def sync(self):
+        self.reducer.wait_all()
+        if self.flat is None or not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(self.flat)
+            self.flat.div_(dist.get_world_size())

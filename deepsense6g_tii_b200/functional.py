@@ -527,7 +527,9 @@ class _Runner:
         K.tokens_bwd(self.geom, dx, douts if residual else None, dfeats, dgps, dpos)
         grads[0] = dpos
         if self.grad_hook is not None:
-            self.grad_hook.finish([dpos])
+            # (a VIEW goes to the reducer: the collective keeps its argument alive, and autograd copies a gradient tensor somebody else
+            # still references instead of adopting it — with deferred waits that copy would be taken before the all-reduce has run)
+            self.grad_hook.finish([dpos.view(-1)])
         return dfeats, dgps, grads
 
     def _backward_bf16_chain(self, saved, params, douts, dgps_out, residual):
@@ -662,7 +664,9 @@ class _Runner:
         K.tokens_bwd(self.geom, dx0, douts if residual else None, dfeats, dgps, dpos)
         grads[0] = dpos
         if self.grad_hook is not None:
-            self.grad_hook.finish([dpos])
+            # (a VIEW goes to the reducer: the collective keeps its argument alive, and autograd copies a gradient tensor somebody else
+            # still references instead of adopting it — with deferred waits that copy would be taken before the all-reduce has run)
+            self.grad_hook.finish([dpos.view(-1)])
         return dfeats, dgps, grads
 
     def backward(self, saved, params, douts, dgps_out, residual=True):

@@ -106,13 +106,17 @@ def synthetic_batch(batch, seq_len=5, size=256, generator=None, device="cpu", pi
     return [mv(t) for t in imgs], [mv(t) for t in lids], [mv(t) for t in rads], mv(gps), mv(soft), mv(beam)
 
 
-def train_step(model, batch, criterion, optimizer, ema=None, autocast_dtype=None):
+def train_step(model, batch, criterion, optimizer, ema=None, autocast_dtype=None, grad_sync=None):
     """One iteration of ``Engine.train`` (train2_seq.py:105-134): zero_grad(set_to_none) -> forward -> focal loss on the
     soft target -> backward -> optimizer.step -> ema.update.  ``autocast_dtype`` (e.g. torch.bfloat16) runs the stock
-    trunks / MLPs under ``torch.autocast``; the fusion stages use ``config.fusion_dtype`` regardless.  Returns the loss
-    tensor (no host sync)."""
+    trunks / MLPs under ``torch.autocast``; the fusion stages use ``config.fusion_dtype`` regardless.  ``grad_sync``: a
+    ``dist.DataParallelGrads`` (one process per GPU): gradients are averaged over ranks before the optimizer step.  Returns
+    the loss tensor (no host sync)."""
     imgs, lids, rads, gps, soft, _ = batch
-    optimizer.zero_grad(set_to_none=True)
+    if grad_sync is not None:   # dist.DataParallelGrads: fixed gradient views of one flat bucket instead of fresh tensors
+        grad_sync.zero_grad()
+    else:
+        optimizer.zero_grad(set_to_none=True)
     if autocast_dtype is not None:
         with torch.autocast("cuda", dtype=autocast_dtype):
             pred = model(imgs, lids, rads, gps)
@@ -120,6 +124,8 @@ def train_step(model, batch, criterion, optimizer, ema=None, autocast_dtype=None
         pred = model(imgs, lids, rads, gps)
     loss = criterion(pred.float(), soft)
     loss.backward()
+    if grad_sync is not None:
+        grad_sync.sync()
     optimizer.step()
     if ema is not None:
         ema.update()

@@ -96,3 +96,46 @@ def test_overlapped_grad_reducer_averages_block_buckets_world2():
         for i, b in enumerate(buckets):
             assert np.allclose(b, 10 * i + 1.5)          # mean of (10i + 1) and (10i + 2)
         assert np.allclose(tail[0], 100.5) and np.allclose(tail[1], 200.5)
+
+
+def _dpgrads_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deepsense6g_tii_b200 import dist as D
+    torch.manual_seed(7)
+    m = torch.nn.Sequential(torch.nn.Conv2d(2, 4, 3), torch.nn.Flatten(), torch.nn.Linear(4 * 4 * 4, 3)).to(memory_format=torch.channels_last)
+    dp = D.DataParallelGrads(m)           # no GPT stages: everything rides in the flat bucket
+    views = [p.grad for p in m.parameters()]
+    out = []
+    for step in range(2):                 # the gradient views are reused: zero_grad() must clear the previous step
+        dp.zero_grad()
+        x = torch.full((2, 2, 6, 6), float(rank + 1 + step))
+        m(x).sum().backward()
+        local = [p.grad.clone() for p in m.parameters()]
+        dp.sync()
+        out.append(([g.numpy() for g in local], [p.grad.numpy().copy() for p in m.parameters()]))
+    same_views = all(p.grad is v for p, v in zip(m.parameters(), views))
+    strides_ok = all(p.grad.stride() == p.stride() for p in m.parameters())
+    q.put((rank, out, same_views, strides_ok))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_grads_flat_bucket_world2():
+    """dist.DataParallelGrads (bench.py --workload model at N > 1): parameters keep fixed gradient views of one flat buffer with the
+    parameter's own strides, and sync() leaves the mean over ranks in them."""
+    import numpy as np
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dpgrads_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (_, out_a, views_a, strides_a), (_, out_b, views_b, strides_b) = res
+    assert views_a and views_b and strides_a and strides_b
+    for step in range(2):
+        for la, lb, ra, rb in zip(out_a[step][0], out_b[step][0], out_a[step][1], out_b[step][1]):
+            assert np.allclose(ra, (la + lb) / 2, atol=1e-5) and np.array_equal(ra, rb)
