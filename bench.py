@@ -854,13 +854,18 @@ def run_model(args, rank, world, local_rank):
     loss_val = float(loss_h)
     params_synced = None
     if world > 1:   # same start + averaged gradients every step -> the replicas' parameters stay identical
-        params_synced = True
-        for t in (model.join[0].weight, enc.image_encoder.features.conv1.weight, enc.transformer4.blocks[0].mlp[0].weight, enc.transformer1.pos_emb,
-                  enc.vel_emb1.weight):
+        params_synced, not_synced = True, []
+        for n, t in (("join.0.weight", model.join[0].weight), ("image conv1.weight", enc.image_encoder.features.conv1.weight),
+                     ("transformer4.blocks.0.mlp.0.weight", enc.transformer4.blocks[0].mlp[0].weight), ("transformer1.pos_emb", enc.transformer1.pos_emb),
+                     ("transformer2.ln_f.weight", enc.transformer2.ln_f.weight), ("vel_emb1.weight", enc.vel_emb1.weight),
+                     ("lidar bn1.weight", enc.lidar_encoder._model.bn1.weight)):
             v = t.detach().reshape(-1)[:4096].float().contiguous()
             vs = [torch.empty_like(v) for _ in range(world)]
             dist.all_gather(vs, v)
-            params_synced = params_synced and all(torch.equal(vs[0], x) for x in vs[1:]) and bool(torch.isfinite(v).all())
+            ok = all(torch.equal(vs[0], x) for x in vs[1:]) and bool(torch.isfinite(v).all())
+            if not ok:
+                not_synced.append("%s (max |diff| %.3e)" % (n, max(float((vs[0] - x).abs().max()) for x in vs[1:])))
+            params_synced = params_synced and ok
     if rank != 0:
         return
     h2d = sum(t.numel() * t.element_size() for t in host[0] + host[1] + host[2]) + sum(t.numel() * t.element_size() for t in host[3:])
@@ -876,7 +881,7 @@ def run_model(args, rank, world, local_rank):
                    "optimizer": opt_note,
                    "l2": "per-step working set (activations of 3 ResNets + 4 fusion stages) >> 126 MB L2; no explicit flush",
                    "grad_allreduce": (ddp_note % (n_params / 1e6)) if world > 1 else ddp_note,
-                   "params_identical_across_ranks": params_synced},
+                   "params_identical_across_ranks": params_synced, "params_not_identical": (not_synced or None) if world > 1 else None},
         "e2e": {"value": BATCH * world * steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / steps, "pipeline": "next batch copied pinned-host -> device on a copy stream during the current step"},
         "gpu_launches": launches, "clocks": clocks, "final_loss": loss_val,

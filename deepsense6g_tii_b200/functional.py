@@ -385,7 +385,7 @@ class _Runner:
         # flat zero-filled gradient buffer per block: [dWqkv | dWp | dW1 | dW2 | dbqkv | dbp | db1 | db2 | dg1 | db1ln | dg2 | db2ln]
         sizes = [3 * C * C, C * C, F * C, C * F, 3 * C, C, F, C, C, C, C, C]
         per_block = sum(sizes)
-        gbuf = torch.zeros(L * per_block + 2 * C, device=dev, dtype=f32)
+        gbuf = torch.zeros(L * per_block + 2 * C + self.T * C, device=dev, dtype=f32)   # blocks | ln_f | pos_emb
 
         def block_views(i):
             out, off = [], i * per_block
@@ -444,7 +444,7 @@ class _Runner:
                 if self.grad_hook is not None:  # data parallel: average this block's bucket while the other blocks compute
                     self.grad_hook.block_ready(blk, bucket(blk))
 
-        dgf, dbf = gbuf[L * per_block:L * per_block + C], gbuf[L * per_block + C:]
+        dgf, dbf = gbuf[L * per_block:L * per_block + C], gbuf[L * per_block + C:L * per_block + 2 * C]
         # The fc1 / QKV data-gradient GEMMs hand dL/d(LayerNorm output) to the LayerNorm backward kernels in bf16 (what stock
         # autocast does; halves that tensor's traffic, -0.06 ms per step).  DSF_LN_DY_BF16=0 keeps it in fp32: measured on B200 at
         # all four stage shapes it changes no gradient tensor's error beyond the 3rd digit (profiles/r02a_error_tables.txt).
@@ -521,15 +521,15 @@ class _Runner:
         join_pending()
         dfeats = [torch.empty_like(d) for d in douts]
         dgps = torch.empty(self.B, 2, C, device=dev, dtype=f32)
-        dpos = torch.empty(1, self.T, C, device=dev, dtype=f32)
+        # pos_emb's gradient lives at the end of the flat buffer, like every other gradient of the stage: autograd adopts such views
+        # without copying them, which a deferred all-reduce relies on (a copy would be taken before the collective has run)
+        dpos = gbuf[L * per_block + 2 * C:].view(1, self.T, C)
         if self._drop("embd") is not None:
             K.dropout_inplace(dx, self._drop("embd"))
         K.tokens_bwd(self.geom, dx, douts if residual else None, dfeats, dgps, dpos)
         grads[0] = dpos
         if self.grad_hook is not None:
-            # (a VIEW goes to the reducer: the collective keeps its argument alive, and autograd copies a gradient tensor somebody else
-            # still references instead of adopting it — with deferred waits that copy would be taken before the all-reduce has run)
-            self.grad_hook.finish([dpos.view(-1)])
+            self.grad_hook.finish([gbuf[L * per_block + 2 * C:]])
         return dfeats, dgps, grads
 
     def _backward_bf16_chain(self, saved, params, douts, dgps_out, residual):
@@ -545,7 +545,7 @@ class _Runner:
         K.upsample_add_bwd(self.geom, douts, dgps_out, dyf)
         sizes = [3 * C * C, C * C, F * C, C * F, 3 * C, C, F, C, C, C, C, C]
         per_block = sum(sizes)
-        gbuf = torch.zeros(L * per_block + 2 * C, device=dev, dtype=f32)
+        gbuf = torch.zeros(L * per_block + 2 * C + self.T * C, device=dev, dtype=f32)   # blocks | ln_f | pos_emb
 
         def block_views(i):
             out, off = [], i * per_block
@@ -607,7 +607,7 @@ class _Runner:
                      wp_t=st.wp_t, dxa=dxa, da=o.da, dxm=o.dxm, dy=o.dy, dx_mid_out=o.dx_mid, delta=o.delta, db1=v[6], dg2=v[10], dbe2=v[11], dbp=v[5])
             return o, d
 
-        dgf, dbf = gbuf[L * per_block:L * per_block + C], gbuf[L * per_block + C:]
+        dgf, dbf = gbuf[L * per_block:L * per_block + C], gbuf[L * per_block + C:L * per_block + 2 * C]
         dx = torch.empty(M, C, device=dev, dtype=f32)
         dxa_bufs = [torch.empty(M, C, device=dev, dtype=bf), torch.empty(M, C, device=dev, dtype=bf)]   # block i reads [i & 1]
         K.layernorm_bwd(dyf, saved.x_last, params[-2], saved.mean_f, saved.rstd_f, None, dx, dgf, dbf, dx_bf16=dxa_bufs[(L - 1) & 1],
@@ -660,13 +660,13 @@ class _Runner:
         join_pending()
         dfeats = [torch.empty_like(d_) for d_ in douts]
         dgps = torch.empty(self.B, 2, C, device=dev, dtype=f32)
-        dpos = torch.empty(1, T, C, device=dev, dtype=f32)
+        # pos_emb's gradient lives at the end of the flat buffer, like every other gradient of the stage: autograd adopts such views
+        # without copying them, which a deferred all-reduce relies on (a copy would be taken before the collective has run)
+        dpos = gbuf[L * per_block + 2 * C:].view(1, self.T, C)
         K.tokens_bwd(self.geom, dx0, douts if residual else None, dfeats, dgps, dpos)
         grads[0] = dpos
         if self.grad_hook is not None:
-            # (a VIEW goes to the reducer: the collective keeps its argument alive, and autograd copies a gradient tensor somebody else
-            # still references instead of adopting it — with deferred waits that copy would be taken before the all-reduce has run)
-            self.grad_hook.finish([dpos.view(-1)])
+            self.grad_hook.finish([gbuf[L * per_block + 2 * C:]])
         return dfeats, dgps, grads
 
     def backward(self, saved, params, douts, dgps_out, residual=True):
