@@ -43,16 +43,26 @@ def main():
     cfg = types.SimpleNamespace(seq_len=5, pred_len=4, n_views=1, vert_anchors=8, horz_anchors=8, n_embd=512, block_exp=4, n_layer=8,
                                 n_head=4, embd_pdrop=0.1, attn_pdrop=0.1, resid_pdrop=0.1, add_velocity=1, fusion_dtype=torch.bfloat16)
     model = TransFuser(cfg, dev).to(memory_format=torch.channels_last).train()
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True) if world > 1 else model
-    optimizer = torch.optim.AdamW(model.parameters(), lr=args.lr, fused=True)   # train2_seq.py:539
+    net = model
+    enc = model.encoder
+    gpts = [enc.transformer1, enc.transformer2, enc.transformer3, enc.transformer4]
+    grad_sync = None
+    if world > 1:   # one process per GPU replaces nn.DataParallel (train2_seq.py:538): same start, gradients averaged every step
+        from deepsense6g_tii_b200 import dist as D
+        D.broadcast_params(model.parameters())
+        grad_sync = D.DataParallelGrads(model, gpts)
     criterion = FocalLoss()
     ema = EMA(model, 0.999) if args.ema else None
     if ema:
         ema.register()
+    # optim.AdamW(model.parameters(), lr) + ema.update() (train2_seq.py:131-134, 539) as one dsfuse launch that also keeps the GPTs' bf16
+    # weight shadows up to date
+    from deepsense6g_tii_b200.optim import FusedAdamWEMA
+    optimizer = FusedAdamWEMA(model.parameters(), lr=args.lr, ema=ema, gpts=gpts)
     gen = torch.Generator().manual_seed(rank)
     for step in range(args.steps):
         batch = synthetic_batch(args.batch_size, 5, 256, generator=gen, device=dev)
-        loss = train_step(net, batch, criterion, optimizer, ema, autocast_dtype=torch.bfloat16)
+        loss = train_step(net, batch, criterion, optimizer, ema, autocast_dtype=torch.bfloat16, grad_sync=grad_sync)
         if rank == 0 and (step % 5 == 0 or step == args.steps - 1):
             print("step %3d  loss %.5f" % (step, float(loss.detach())))
     if ema:  # validate with the shadow weights as Engine.validate does (train2_seq.py:159-160, 220-221)
