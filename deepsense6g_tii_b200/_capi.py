@@ -23,7 +23,7 @@ SYMBOLS = [
     "dsf_version", "dsf_last_error", "dsf_launch_count", "dsf_check_device", "dsf_set_pdl", "dsf_set_sm_margin", "dsf_dropout_inplace", "dsf_tokens_fwd", "dsf_tokens_bwd",
     "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_set_impl", "dsf_gemm_f32",
     "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_bwd_parts", "dsf_attn_set_impl", "dsf_attn_drop_words",
-    "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16", "dsf_opt_tiles", "dsf_adamw_ema_pack", "dsf_chain_fwd", "dsf_chain_bwd",
+    "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16", "dsf_opt_tiles", "dsf_adamw_ema_pack", "dsf_opt_upload_table", "dsf_chain_fwd", "dsf_chain_bwd",
 ]
 
 
@@ -100,6 +100,7 @@ def lib():
             "dsf_chain_fwd": [P] * 25 + [c_int32, c_int32, c_float, P],
             "dsf_chain_bwd": [P] * 32 + [c_int32, c_int32, c_int32, c_int32, P],
             "dsf_opt_tiles": [c_int32, c_int32, c_int32],
+            "dsf_opt_upload_table": [P, P, c_int64, P],
             "dsf_adamw_ema_pack": [P, P, c_int32, c_int32, c_double, c_double, c_double, c_double, c_double, P, c_double, P],
         }
         for name, argtypes in sig.items():
@@ -314,3 +315,11 @@ def chain_bwd(M, C, T, nh, half_a=None, half_b=None, dx_in=None, dx_f32=None):
                              ga("dbqkv"), ga("db2_prev"), _p(dx_f32), _p(dx_in), gb("a"), gb("y"), gb("x_mid"), gb("mean2"), gb("rstd2"), gb("g2"),
                              gb("w2_t"), gb("w1_t"), gb("wp_t"), gb("dxa"), gb("da"), gb("dxm"), gb("dy"), gb("dx_mid_out"), gb("delta"), gb("db1"),
                              gb("dg2"), gb("dbe2"), gb("dbp"), M, C, T, nh, _stream()), "dsf_chain_bwd")
+
+
+def opt_upload_table(dst_dev, src_pinned):
+    """Device copy of the (pinned-host) tensor table of the fused optimizer, done by a kernel (no copy-engine transfer)."""
+    if not src_pinned.is_pinned():
+        raise RuntimeError("opt_upload_table: the host table must be pinned memory")
+    _chk(lib().dsf_opt_upload_table(_p(dst_dev), c_void_p(src_pinned.data_ptr()), src_pinned.numel() * src_pinned.element_size(), _stream()),
+         "dsf_opt_upload_table")

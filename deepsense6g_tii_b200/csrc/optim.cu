@@ -88,7 +88,24 @@ adamw_ema_pack_kernel(const dsf_opt_tensor* __restrict__ tab, const int32_t* __r
   }
 }
 
+// 16-byte copy of the tensor table from PINNED HOST memory (device-accessible under unified addressing) into device memory by a
+// kernel: unlike a host-to-device memcpy node it does not queue behind whatever large input prefetch occupies the copy engine.
+__global__ void __launch_bounds__(256) opt_table_upload_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src_host, int n16) {
+  pdl_trigger();
+  pdl_wait();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src_host[i];
+}
+
 }  // namespace dsf
+
+extern "C" int dsf_opt_upload_table(void* dst_dev, const void* src_pinned_host, int64_t nbytes, void* stream) {
+  DSF_REQUIRE(dst_dev && src_pinned_host && nbytes > 0 && nbytes % 16 == 0, "opt_upload_table: bad arguments (nbytes must be a positive multiple of 16)");
+  DSF_REQUIRE(dsf::aligned16(dst_dev) && dsf::aligned16(src_pinned_host), "opt_upload_table: 16-byte alignment required");
+  const int n16 = (int)(nbytes / 16);
+  dsf::launch_pdl(dsf::opt_table_upload_kernel, dim3(std::min(dsf::cdiv(n16, 256), 32)), dim3(256), 0, (cudaStream_t)stream, (uint4*)dst_dev,
+                  (const uint4*)src_pinned_host, n16);
+  return dsf::check_launch("opt_upload_table");
+}
 
 extern "C" int32_t dsf_opt_tiles(int32_t rows, int32_t cols, int32_t transposed_shadow) {
   if (rows <= 0 || cols <= 0) return 0;

@@ -80,7 +80,7 @@ class FusedAdamWEMA(torch.optim.Optimizer):
                 tiles += K.opt_tiles(rows, cols, sh_t is not None)
             dev = items[0][0].device
             # two pinned host mirrors, used alternately: the one being rewritten was last read by the upload of two steps ago
-            tab_h = [torch.empty(ctypes.sizeof(tab), dtype=torch.uint8).pin_memory() for _ in range(2)]
+            tab_h = [torch.empty((ctypes.sizeof(tab) + 15) // 16 * 16, dtype=torch.uint8).pin_memory() for _ in range(2)]
             t0_d = torch.tensor(tile0, dtype=torch.int32).to(dev)
             self._tables.append(dict(tab=tab, tab_h=tab_h, tab_d=torch.empty(tab_h[0].numel(), dtype=torch.uint8, device=dev), t0_d=t0_d,
                                      n=len(items), tiles=tiles, uploaded=[None, None], cur=0, dirty=True))
@@ -151,8 +151,9 @@ class FusedAdamWEMA(torch.optim.Optimizer):
                         ev.synchronize()                   # never rewrite a host table an upload may still be reading
                     ctypes.memmove(tb["tab_h"][tb["cur"]].data_ptr(), tb["tab"], ctypes.sizeof(tb["tab"]))
                     tb["dirty"] = False
-                # 30-60 KB from pinned memory: a memcpy node under graph capture (replays re-read the unchanged host table)
-                tb["tab_d"].copy_(tb["tab_h"][tb["cur"]], non_blocking=True)
+                # 30-60 KB read straight from pinned host memory by a small kernel (a kernel node under graph capture: replays re-read the
+                # unchanged host table).  A host-to-device memcpy would queue behind the data loader's input prefetch on the copy engine.
+                K.opt_upload_table(tb["tab_d"], tb["tab_h"][tb["cur"]])
                 if not capturing:
                     tb["uploaded"][tb["cur"]] = torch.cuda.Event()
                     tb["uploaded"][tb["cur"]].record()

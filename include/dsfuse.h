@@ -272,6 +272,10 @@ typedef struct {
   int32_t reserved;
 } dsf_opt_tensor;
 int32_t dsf_opt_tiles(int32_t rows, int32_t cols, int32_t transposed_shadow);
+/* Copies the tensor table from PINNED host memory (cudaHostAlloc / torch pin_memory: device-accessible under unified addressing)
+ * into device memory with a kernel instead of a copy-engine transfer; nbytes a multiple of 16.  Graph-capturable: a replay
+ * re-reads the host table. */
+int dsf_opt_upload_table(void* dst_dev, const void* src_pinned_host, int64_t nbytes, void* stream);
 int dsf_adamw_ema_pack(const dsf_opt_tensor* tensors_dev, const int32_t* tile0_dev, int32_t n_tensors, int32_t n_tiles, double lr,
                        double beta1, double beta2, double eps, double ema_decay, const int64_t* step_dev, double grad_scale,
                        void* stream);
