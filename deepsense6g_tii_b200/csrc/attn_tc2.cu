@@ -209,39 +209,43 @@ __device__ __forceinline__ void store_row16_bf16(__nv_bfloat16* dst, const uint3
 // =============================================================================================== backward: dK, dV
 // CTA = 128 keys (K, V resident); loop over BQ-query tiles.  Threads own key rows:
 //   S^T = K Q^T, dP^T = V dO^T -> P^T = exp2(S^T*c - lse), dS^T = P^T (dP^T - delta) * scale -> dV += P^T dO, dK += dS^T Q
-template <int HS, int BQ, int ST>
+// P^T / dS^T are written back (bf16, two per column) over the S^T / dP^T tiles in tensor memory and feed the dV / dK MMAs as
+// TS-mode A operands; per-query statistics (lse, delta) are staged per WARP in shared memory (each lane fetches one pair a
+// tile ahead, a __syncwarp publishes them), so the math warps never meet at a CTA-wide barrier inside the loop.
+//
+// NP = math warpgroup PAIRS.  A pair (2 x 128 threads) splits a tile's 64 query columns in two halves.  The in-kernel timeline
+// (profiles/r01v_attn_timeline.txt) shows the math warps as the critical path at every head size: ~2200 cycles per tile for
+// ~180 instructions per warp, i.e. latency (tcgen05.ld -> MUFU -> tcgen05.st -> wait::st -> mbarrier) with only two warps
+// per SM sub-partition to hide it.  NP = 2: pair p owns the tiles i = p (mod 2) — which is TMEM buffer p — so every tile has
+// two tile periods of math time and four warps per sub-partition overlap each other's latencies; the MMA / TMA schedule and
+// every mbarrier count are unchanged (ds_full[bf] still collects 256 arrivals, all from pair bf).
+template <int HS, int BQ, int ST, int NP>
 struct BwdKV2 {
-  static constexpr int KV_BYTES = 128 * HS * 2, Q_BYTES = BQ * HS * 2, P_BYTES = 128 * BQ * 2;
+  static constexpr int KV_BYTES = 128 * HS * 2, Q_BYTES = BQ * HS * 2;
   static constexpr int K_OFF = 0, V_OFF = KV_BYTES, Q_OFF = 2 * KV_BYTES, DO_OFF = Q_OFF + ST * Q_BYTES;
-  static constexpr int PT_OFF = DO_OFF + ST * Q_BYTES, DST_OFF = PT_OFF + 2 * P_BYTES;
-  static constexpr int STAT_OFF = DST_OFF + 2 * P_BYTES;  // [2 buffers][lse | delta][BQ] floats
-  static constexpr int BAR_OFF = STAT_OFF + 2 * 2 * BQ * 4;
+  static constexpr int STAT_OFF = DO_OFF + ST * Q_BYTES;  // [math warp][2 buffers][lse 32 | delta 32] floats
+  static constexpr int BAR_OFF = STAT_OFF + 8 * NP * 2 * 64 * 4;
   static constexpr int NBAR = 2 + 2 * ST + 6;
   static constexpr int DYN = BAR_OFF + NBAR * 8 + 16 + 1024;
+  static constexpr int THREADS = 256 * NP + 64;
   static_assert(4 * BQ + 2 * HS <= 512, "TMEM budget");
   static_assert(DYN <= 232448, "shared memory budget");
 };
 
-// DS = true (experiment, measured slower, off): the math warps read the per-query statistics (lse, delta) of a tile straight
-// from global memory (broadcast 8-byte loads, L1 / L2 hits) instead of staging them in shared memory behind a 128-thread
-// named barrier per iteration.  The in-kernel timeline shows the math warps as the critical path of this kernel (~450 of
-// their ~2200 cycles per iteration in staging + barrier, the MMA warp waiting ~650 cycles for dS), but the loads cost more.
-// WS = true (needs PT: the staging lives in the then unused P^T region of shared memory): every math WARP stages the 32 lse +
-// 32 delta values of its warpgroup's query columns for itself (each lane fetches one pair a tile ahead) and only needs a
-// __syncwarp — the four warps of a warpgroup no longer rendezvous at a named barrier every iteration.
-template <int HS, int BQ, int ST, bool PT, bool DS = false, bool WS = false>
-__global__ void __launch_bounds__(320, 1)
+template <int HS, int BQ, int ST, int NP, bool DROP>
+__global__ void __launch_bounds__(256 * NP + 64, 1)
 attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
                     float scale, AttnDrop ad) {
-  using L = BwdKV2<HS, BQ, ST>;
+  using L = BwdKV2<HS, BQ, ST, NP>;
+  constexpr int MMAW = 8 * NP, TMAW = 8 * NP + 1;  // warp roles: 0 .. 8*NP-1 math, then MMA issuer, TMA producer
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t bar0 = sbase + L::BAR_OFF;
   const uint32_t kv_full = bar0, acc_done = bar0 + 8, q_full = bar0 + 16, q_empty = q_full + 8 * ST, s_full = q_empty + 8 * ST,
                  ds_full = s_full + 16, ds_empty = ds_full + 16, tmem_slot = ds_empty + 16;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int n_q = (T + BQ - 1) / BQ;
 
@@ -253,8 +257,8 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256); mbar_init(ds_empty + 8 * w, 1); }
     fence_barrier_init();
   }
-  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  if (warp == 9 && lane == 0) { tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); }
+  if (warp == MMAW) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == TMAW && lane == 0) { tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -263,7 +267,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
   pdl_wait();  // set-up above overlaps the previous kernel's tail
   const uint32_t tm_dv = tmem_base + 4 * BQ, tm_dk = tm_dv + HS;
 
-  if (warp == 9) {
+  if (warp == TMAW) {
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * L::KV_BYTES);
       tma_tile<HS>(sbase + L::K_OFF, &tmKV, kv_full, C + h * HS, kv0, b, 128);
@@ -276,7 +280,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         tma_tile<HS>(sbase + L::DO_OFF + st * L::Q_BYTES, &tmDO, q_full + 8 * st, h * HS, i * BQ, b, BQ);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == MMAW) {
     {  // MMA issuer: all 32 lanes walk the schedule (uniform control flow); single lanes are elected per instruction
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BQ, 0, 0);
       constexpr uint32_t idesc_g = make_idesc_bf16(128, HS, 0, 1);
@@ -290,6 +294,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         const int bf = i & 1, st = i % ST;
         TRACE(2, i, 0);
         if (i + 1 < n_q) {
+          // buffer bn is free: dV / dK (i-1) were issued after its math warps arrived at ds_full, and the tensor pipe runs in order
           const int sn = (i + 1) % ST, bn = (i + 1) & 1;
           mbar_wait(q_full + 8 * sn, ((i + 1) / ST) & 1);
           TRACE(2, i, 1);
@@ -302,13 +307,8 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         mbar_wait(ds_full + 8 * bf, (i >> 1) & 1);
         TRACE(2, i, 3);
         tc_fence_after();
-        if (PT) {  // P^T / dS^T were written back over the S^T / dP^T tiles in tensor memory
-          mma_over_rows_ts<HS, BQ, true>(tm_dv, tmem_base + bf * 2 * BQ, sbase + L::DO_OFF + st * L::Q_BYTES, idesc_g, i > 0);
-          mma_over_rows_ts<HS, BQ, true>(tm_dk, tmem_base + bf * 2 * BQ + BQ, sbase + L::Q_OFF + st * L::Q_BYTES, idesc_g, i > 0);
-        } else {
-          mma_over_rows<HS, BQ>(tm_dv, sbase + L::PT_OFF + bf * L::P_BYTES, sbase + L::DO_OFF + st * L::Q_BYTES, idesc_g, i > 0);
-          mma_over_rows<HS, BQ>(tm_dk, sbase + L::DST_OFF + bf * L::P_BYTES, sbase + L::Q_OFF + st * L::Q_BYTES, idesc_g, i > 0);
-        }
+        mma_over_rows_ts<HS, BQ, true>(tm_dv, tmem_base + bf * 2 * BQ, sbase + L::DO_OFF + st * L::Q_BYTES, idesc_g, i > 0);
+        mma_over_rows_ts<HS, BQ, true>(tm_dk, tmem_base + bf * 2 * BQ + BQ, sbase + L::Q_OFF + st * L::Q_BYTES, idesc_g, i > 0);
         tc_commit_elect(q_empty + 8 * st);
         tc_commit_elect(ds_empty + 8 * bf);
         TRACE(2, i, 4);
@@ -316,7 +316,8 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       tc_commit_elect(acc_done);
     }
   } else {
-    const int wg = warp >> 2;  // two compute warpgroups split the tile's columns
+    const int pair = warp >> 3;      // NP = 2: pair p owns the tiles i = p (mod 2)
+    const int wg = (warp >> 2) & 1;  // the two warpgroups of a pair split the tile's columns
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const bool key_ok = (kv0 + row) < T;
@@ -326,97 +327,50 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     static_assert(BQ == 64, "the math warps split a 64-query tile in two 32-column halves");
     const size_t bh = (size_t)b * nh + h;
     const int kw = kv0 / 32 + (warp & 3);  // bitmap word holding this warp's 32 keys
-    // per-query statistics of this warpgroup's 32 query columns (thread t of the warpgroup: t < 32 lse, 32 <= t < 64
-    // delta) and, for attn-dropout, the keep word of query (wg*32 + lane); both are fetched one tile ahead so their
-    // global-memory latency hides behind the current tile.  Each warpgroup stages and synchronises on its own half.
-    const int tw = threadIdx.x & 127;
-    auto fetch = [&](int it, float& sv, uint32_t& wv) {
-      const int qq = it * BQ + wg * 32 + (tw & 31);
-      sv = tw < 32 ? (qq < T ? lse_g[qq] * 1.4426950408889634f : INFINITY) : (tw < 64 && qq < T ? delta_g[qq] : 0.f);
-      wv = 0xFFFFFFFFu;
-      if (ad.thresh8) {
-        const int qd = it * BQ + wg * 32 + lane;
-        wv = qd < T ? ad.bits[(bh * T + qd) * ad.Tw + kw] : 0u;
-      }
-    };
-    static_assert(!WS || (PT && !DS), "warp-local statistics staging lives in the P^T region, which only PT leaves unused");
-    float sv;
-    uint32_t wv;
-    fetch(0, sv, wv);
-    float wl = 0.f, wd = 0.f;  // WS: this lane's lse (log2 units) / delta of query (tile * BQ + wg * 32 + lane), one tile ahead
+    // this lane's lse (log2 units) / delta of query (tile * BQ + wg * 32 + lane) and, for attn-dropout, the keep word of that
+    // query over this warp's 32 keys; fetched one own tile ahead so the global-memory latency hides behind the current tile
+    float wl = 0.f, wd = 0.f;
+    uint32_t wv = 0xFFFFFFFFu;
     auto fetch_w = [&](int it) {
       const int qq = it * BQ + wg * 32 + lane;
       wl = qq < T ? lse_g[qq] * 1.4426950408889634f : INFINITY;
       wd = qq < T ? delta_g[qq] : 0.f;
+      if (DROP) wv = qq < T ? ad.bits[(bh * T + qq) * ad.Tw + kw] : 0u;
     };
-    if (WS) fetch_w(0);
-    for (int i = 0; i < n_q; ++i) {
+    const int i0 = NP == 2 ? pair : 0;
+    if (i0 < n_q) fetch_w(i0);
+    float* wst0 = reinterpret_cast<float*>(smem + L::STAT_OFF) + warp * 2 * 64;
+    int own = 0;
+    for (int i = i0; i < n_q; i += NP, own ^= 1) {
       const int bf = i & 1;
-      float* st_lse = reinterpret_cast<float*>(smem + L::STAT_OFF) + bf * 2 * BQ;
-      float* st_delta = st_lse + BQ;
-      if (WS) {  // per-warp buffers [warp][bf][lse 32 | delta 32]; indexed below with the warpgroup's column offset removed
-        float* wst = reinterpret_cast<float*>(smem + L::PT_OFF) + (warp * 2 + bf) * 64;
-        wst[lane] = wl;
-        wst[32 + lane] = wd;
-        st_lse = wst - wg * 32;
-        st_delta = wst + 32 - wg * 32;
-      }
-      // the stats buffer bf was last read two iterations ago; every thread of the warpgroup has passed the barrier below since
-      if (!DS && !WS) {
-        if (tw < 32) st_lse[wg * 32 + tw] = sv;
-        else if (tw < 64) st_delta[wg * 32 + tw - 32] = sv;
-      }
+      // per-warp statistics buffers [own][lse 32 | delta 32]; buffer `own` was last read two own tiles (two __syncwarps) ago
+      float* wst = wst0 + own * 64;
+      wst[lane] = wl;
+      wst[32 + lane] = wd;
       const uint32_t myw = wv;
       if ((warp & 3) == 0) TRACE(wg, i, 0);
-      if ((!DS && !WS) || ad.thresh8) {
-        if (i + 1 < n_q) fetch(i + 1, sv, wv);
-      }
-      if (WS) {
-        if (i + 1 < n_q) fetch_w(i + 1);
-        __syncwarp();  // this warp's staging is visible to its lanes; buffer bf was last read two iterations (two __syncwarps) ago
-      }
-      if (!DS && !WS) named_bar_sync(1 + wg, 128);
+      if (i + NP < n_q) fetch_w(i + NP);
+      __syncwarp();
       if ((warp & 3) == 0) TRACE(wg, i, 1);
       mbar_wait(s_full + 8 * bf, (i >> 1) & 1);
       if ((warp & 3) == 0) TRACE(wg, i, 2);
       tc_fence_after();
       if (i >= 2) mbar_wait(ds_empty + 8 * bf, ((i >> 1) - 1) & 1);
       if ((warp & 3) == 0) TRACE(wg, i, 3);
-      uint8_t* pt = smem + L::PT_OFF + bf * L::P_BYTES;
-      uint8_t* dst = smem + L::DST_OFF + bf * L::P_BYTES;
-      const uint32_t tm_s = tmem_base + bf * 2 * BQ + lane_off, tm_dp = tm_s + BQ;
-#pragma unroll 1
-      for (int c = wg * (BQ / 2); c < (wg + 1) * (BQ / 2); c += 32) {
-        uint32_t rs[32], rp[32];
-        tmem_ld32(tm_s + c, rs);
-        tmem_ld32(tm_dp + c, rp);
+      const uint32_t tm_s = tmem_base + bf * 2 * BQ + lane_off + wg * 32, tm_dp = tm_s + BQ;
+      // two 16-column sub-chunks keep the live registers (2 x 16 loaded + 2 x 8 packed) within the 576-thread budget
+#pragma unroll
+      for (int c = 0; c < 32; c += 16) {
+        uint32_t rs[16], rp[16];
+        tmem_ld16(tm_s + c, rs);
+        tmem_ld16(tm_dp + c, rp);
         tmem_wait_ld();
-        uint32_t pk[16], dk[16];
-        const int qc = i * BQ + c;  // first query of this chunk
-        const bool q_full_chunk = qc + 32 <= T && (T & 1) == 0;  // even T: every head's vectors start 8-byte aligned
+        uint32_t pk[8], dk[8];
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          float ls[4], dl[4];
-          if (DS) {
-            if (q_full_chunk) {  // T and the chunk start are even: 8-byte aligned pairs
-              const float2 la = __ldg(reinterpret_cast<const float2*>(lse_g + qc + e)), lb = __ldg(reinterpret_cast<const float2*>(lse_g + qc + e + 2));
-              const float2 da = __ldg(reinterpret_cast<const float2*>(delta_g + qc + e)), db = __ldg(reinterpret_cast<const float2*>(delta_g + qc + e + 2));
-              ls[0] = la.x * 1.4426950408889634f; ls[1] = la.y * 1.4426950408889634f; ls[2] = lb.x * 1.4426950408889634f; ls[3] = lb.y * 1.4426950408889634f;
-              dl[0] = da.x; dl[1] = da.y; dl[2] = db.x; dl[3] = db.y;
-            } else {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int qq = qc + e + u;
-                ls[u] = qq < T ? __ldg(lse_g + qq) * 1.4426950408889634f : INFINITY;
-                dl[u] = qq < T ? __ldg(delta_g + qq) : 0.f;
-              }
-            }
-          } else {
-            const float4 l4 = *reinterpret_cast<const float4*>(st_lse + c + e);
-            const float4 d4 = *reinterpret_cast<const float4*>(st_delta + c + e);
-            ls[0] = l4.x; ls[1] = l4.y; ls[2] = l4.z; ls[3] = l4.w;
-            dl[0] = d4.x; dl[1] = d4.y; dl[2] = d4.z; dl[3] = d4.w;
-          }
+        for (int e = 0; e < 16; e += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(wst + c + e);
+          const float4 d4 = *reinterpret_cast<const float4*>(wst + 32 + c + e);
+          const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
           float p[4], d[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -424,8 +378,8 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
             // keys, which are never stored.  The 1/sqrt(hs) factor of dS is applied once when dK is drained.
             p[u] = ex2_approx(fmaf(__uint_as_float(rs[e + u]), scale_log2, -ls[u]));
             float dp = __uint_as_float(rp[e + u]);
-            if (ad.thresh8) {  // attn_drop: dV sees P*mask/(1-p); dP = dP_drop*mask/(1-p)
-              const float m = (__shfl_sync(0xffffffffu, myw, e + u) >> lane) & 1u ? ad.scale : 0.f;
+            if (DROP) {  // attn_drop: dV sees P*mask/(1-p); dP = dP_drop*mask/(1-p)
+              const float m = (__shfl_sync(0xffffffffu, myw, c + e + u) >> lane) & 1u ? ad.scale : 0.f;
               dp *= m;
               d[u] = p[u] * (dp - dl[u]);
               p[u] *= m;
@@ -438,16 +392,11 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           dk[e / 2] = pack_bf16x2(d[0], d[1]);
           dk[e / 2 + 1] = pack_bf16x2(d[2], d[3]);
         }
-        if (PT) {
-          tmem_st16(tm_s + c, pk);
-          tmem_st16(tm_dp + c, dk);
-        } else {
-          store_p32<BQ>(pt, row, c, pk);
-          store_p32<BQ>(dst, row, c, dk);
-        }
+        // packed pairs of columns c .. c+15 -> 8 columns at c/2 of this warpgroup's 32-column region (mma_over_rows_ts SPLIT layout)
+        tmem_st8(tm_s + c / 2, pk);
+        tmem_st8(tm_dp + c / 2, dk);
       }
-      if (PT) tmem_wait_st();
-      else fence_proxy_async();
+      tmem_wait_st();
       tc_fence_before();
       mbar_arrive(ds_full + 8 * bf);
       if ((warp & 3) == 0) TRACE(wg, i, 4);
@@ -457,28 +406,34 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     const int ld = 3 * C;
     __nv_bfloat16* dk_row = dqkv + ((size_t)b * T + kv0 + row) * ld + C + h * HS;
     __nv_bfloat16* dv_row = dk_row + C;
+    // warpgroup 0 of a pair drains dK, warpgroup 1 dV; with two pairs each takes half of the head's columns (hs = 16: pair 0 only)
+    constexpr int NSPLIT = (NP == 2 && HS >= 32) ? 2 : 1;
+    constexpr int CH = HS / NSPLIT;
+    if (pair < NSPLIT) {
 #pragma unroll 1
-    for (int c = 0; c < HS; c += 16) {  // warpgroup 0 drains dK, warpgroup 1 drains dV
-      uint32_t a[16];
-      tmem_ld16((wg == 0 ? tm_dk : tm_dv) + lane_off + c, a);
-      tmem_wait_ld();
-      if (key_ok) store_row16_bf16((wg == 0 ? dk_row : dv_row) + c, a, wg == 0 ? scale : 1.0f);
+      for (int c = pair * CH; c < (pair + 1) * CH; c += 16) {
+        uint32_t a[16];
+        tmem_ld16((wg == 0 ? tm_dk : tm_dv) + lane_off + c, a);
+        tmem_wait_ld();
+        if (key_ok) store_row16_bf16((wg == 0 ? dk_row : dv_row) + c, a, wg == 0 ? scale : 1.0f);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == MMAW) tmem_dealloc(tmem_base, 512);
 }
 
 // =============================================================================================== backward: dQ
 // CTA = 128 queries (Q, dO resident); loop over 64-key tiles.  Threads own query rows:
 //   S = Q K^T, dP = dO V^T -> dS = exp2(S*c - lse) (dP - delta) * scale -> dQ += dS K
+// dS (bf16) is written back over the dP tile in tensor memory and feeds dQ += dS K as a TS-mode A operand.
 template <int HS, int ST>
 struct BwdQ2 {
   static constexpr int BKV = 64;
-  static constexpr int Q_BYTES = 128 * HS * 2, KV_BYTES = BKV * HS * 2, DS_BYTES = 128 * BKV * 2;
-  static constexpr int Q_OFF = 0, DO_OFF = Q_BYTES, K_OFF = 2 * Q_BYTES, V_OFF = K_OFF + ST * KV_BYTES, DS_OFF = V_OFF + ST * KV_BYTES;
-  static constexpr int BAR_OFF = DS_OFF + 2 * DS_BYTES;
+  static constexpr int Q_BYTES = 128 * HS * 2, KV_BYTES = BKV * HS * 2;
+  static constexpr int Q_OFF = 0, DO_OFF = Q_BYTES, K_OFF = 2 * Q_BYTES, V_OFF = K_OFF + ST * KV_BYTES;
+  static constexpr int BAR_OFF = V_OFF + ST * KV_BYTES;
   static constexpr int NBAR = 2 + 2 * ST + 6;
   static constexpr int DYN = BAR_OFF + NBAR * 8 + 16 + 1024;
   static_assert(4 * BKV + HS <= 512, "TMEM budget");
@@ -488,20 +443,21 @@ struct BwdQ2 {
 // (written once by the math warps straight from global memory) and feed the S = Q K^T and dP = dO V^T MMAs as TS-mode A
 // operands.  A tcgen05.mma whose A operand comes from shared memory spends ~128 cycles fetching its 128 x 16 slice whatever
 // N is, so the 64-wide S / dP MMAs ran at a quarter of the tensor pipe's rate; from tensor memory they are N-bound.
-template <int HS, int ST, bool PT, bool AT>
-__global__ void __launch_bounds__(320, 1)
+// NP = math warpgroup pairs, as in the dK/dV kernel: pair p owns the key tiles j = p (mod 2).
+template <int HS, int ST, bool AT, int NP, bool DROP>
+__global__ void __launch_bounds__(256 * NP + 64, 1)
 attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmKV,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
                    float scale, AttnDrop ad, const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dy) {
   using L = BwdQ2<HS, ST>;
   constexpr int BKV = L::BKV;
+  constexpr int MMAW = 8 * NP, TMAW = 8 * NP + 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t bar0 = sbase + L::BAR_OFF;
   const uint32_t q_full = bar0, acc_done = bar0 + 8, kv_full = bar0 + 16, kv_empty = kv_full + 8 * ST, s_full = kv_empty + 8 * ST,
                  ds_full = s_full + 16, ds_empty = ds_full + 16, tmem_slot = ds_empty + 16;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (T + BKV - 1) / BKV;
   constexpr uint32_t TMEM_COLS = (4 * BKV + HS + (AT ? (HS >= 32 ? HS : 32) : 0)) <= 256 ? 256 : 512;
@@ -515,8 +471,8 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256); mbar_init(ds_empty + 8 * w, 1); }
     fence_barrier_init();
   }
-  if (warp == 8) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  if (warp == 9 && lane == 0) { tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); }
+  if (warp == MMAW) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  if (warp == TMAW && lane == 0) { tma_prefetch_desc(&tmKV); tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -526,7 +482,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tm_dq = tmem_base + 4 * BKV;
   const uint32_t tm_q = tm_dq + HS, tm_do = tm_q + (HS >= 32 ? HS / 2 : 16);  // AT: packed Q / dO rows (HS/2 columns each, >= 16 apart)
 
-  if (warp == 9) {
+  if (warp == TMAW) {
     if (lane == 0) {
       if (!AT) {
         mbar_expect_tx(q_full, 2 * L::Q_BYTES);
@@ -541,7 +497,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_tile<HS>(sbase + L::V_OFF + st * L::KV_BYTES, &tmKV, kv_full + 8 * st, 2 * C + h * HS, j * BKV, b, BKV);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == MMAW) {
     {  // MMA issuer: all 32 lanes walk the schedule (uniform control flow); single lanes are elected per instruction
       constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
       constexpr uint32_t idesc_q = make_idesc_bf16(128, HS, 0, 1);
@@ -573,15 +529,15 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         mbar_wait(ds_full + 8 * bf, (j >> 1) & 1);
         tc_fence_after();
-        if (PT) mma_over_rows_ts<HS, BKV, true>(tm_dq, tmem_base + bf * 2 * BKV + BKV, sbase + L::K_OFF + st * L::KV_BYTES, idesc_q, j > 0);
-        else mma_over_rows<HS, BKV>(tm_dq, sbase + L::DS_OFF + bf * L::DS_BYTES, sbase + L::K_OFF + st * L::KV_BYTES, idesc_q, j > 0);
+        mma_over_rows_ts<HS, BKV, true>(tm_dq, tmem_base + bf * 2 * BKV + BKV, sbase + L::K_OFF + st * L::KV_BYTES, idesc_q, j > 0);
         tc_commit_elect(kv_empty + 8 * st);
         tc_commit_elect(ds_empty + 8 * bf);
       }
       tc_commit_elect(acc_done);
     }
   } else {
-    const int wg = warp >> 2;  // two compute warpgroups split the tile's columns
+    const int pair = warp >> 3;      // NP = 2: pair p owns the key tiles j = p (mod 2)
+    const int wg = (warp >> 2) & 1;  // the two warpgroups of a pair split the tile's columns
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const int q = q0 + row;
@@ -589,7 +545,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float scale_log2 = scale * 1.4426950408889634f;
     const float my_lse = q_ok ? lse[((size_t)b * nh + h) * T + q] * 1.4426950408889634f : INFINITY;
     const float my_delta = q_ok ? delta[((size_t)b * nh + h) * T + q] : 0.f;
-    if (AT) {  // warpgroup 0 parks the Q row of its query in tensor memory, warpgroup 1 the dO row (two bf16 per column)
+    if (AT && pair == 0) {  // warpgroup 0 parks the Q row of its query in tensor memory, warpgroup 1 the dO row (two bf16 per column)
       const __nv_bfloat16* src = wg == 0 ? qkv + ((size_t)b * T + q) * (3 * C) + h * HS : dy + ((size_t)b * T + q) * C + h * HS;
       const uint32_t dst = (wg == 0 ? tm_q : tm_do) + lane_off;
 #pragma unroll 1
@@ -608,71 +564,74 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_arrive(q_full);
     }
     static_assert(BKV == 64, "the math warps split a 64-key tile in two 32-column halves");
-    // attn-dropout keep word of (my query row, keys 32*(2j + wg) ..), fetched one tile ahead
-    const uint32_t* my_bits = (ad.thresh8 && q_ok) ? ad.bits + (((size_t)b * nh + h) * T + q) * ad.Tw + wg : nullptr;
-    uint32_t wnext = my_bits ? my_bits[0] : 0xFFFFFFFFu;
-    for (int j = 0; j < n_kv; ++j) {
+    // attn-dropout keep word of (my query row, keys 32*(2j + wg) ..), fetched one own tile ahead
+    const int j0 = NP == 2 ? pair : 0;
+    const uint32_t* my_bits = (DROP && q_ok) ? ad.bits + (((size_t)b * nh + h) * T + q) * ad.Tw + wg : nullptr;
+    uint32_t wnext = (my_bits && j0 < n_kv) ? my_bits[2 * j0] : 0xFFFFFFFFu;
+    for (int j = j0; j < n_kv; j += NP) {
       const int bf = j & 1, kv0 = j * BKV;
       const uint32_t keepw = wnext;
-      if (my_bits && j + 1 < n_kv) wnext = my_bits[2 * (j + 1)];
+      if (my_bits && j + NP < n_kv) wnext = my_bits[2 * (j + NP)];
       mbar_wait(s_full + 8 * bf, (j >> 1) & 1);
       tc_fence_after();
       if (j >= 2) mbar_wait(ds_empty + 8 * bf, ((j >> 1) - 1) & 1);
-      uint8_t* ds = smem + L::DS_OFF + bf * L::DS_BYTES;
-      const uint32_t tm_s = tmem_base + bf * 2 * BKV + lane_off, tm_dp = tm_s + BKV;
-#pragma unroll 1
-      for (int c = wg * (BKV / 2); c < (wg + 1) * (BKV / 2); c += 32) {
-        uint32_t rs[32], rp[32];
-        tmem_ld32(tm_s + c, rs);
-        tmem_ld32(tm_dp + c, rp);
-        tmem_wait_ld();
-        uint32_t dk[16];
-        // the 1/sqrt(hs) factor of dS is applied once when dQ is drained; only the last key tile needs the column mask
-        if (kv0 + BKV <= T && !ad.thresh8) {
+      const uint32_t tm_s = tmem_base + bf * 2 * BKV + lane_off + wg * 32, tm_dp = tm_s + BKV;
+      const bool full = kv0 + BKV <= T;  // only the last key tile needs the column mask
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
+      for (int c = 0; c < 32; c += 16) {
+        uint32_t rs[16], rp[16];
+        tmem_ld16(tm_s + c, rs);
+        tmem_ld16(tm_dp + c, rp);
+        tmem_wait_ld();
+        uint32_t dk[8];
+        // the 1/sqrt(hs) factor of dS is applied once when dQ is drained
+        if (full && !DROP) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
             const float p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), scale_log2, -my_lse));
             const float p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), scale_log2, -my_lse));
             dk[e / 2] = pack_bf16x2(p0 * (__uint_as_float(rp[e]) - my_delta), p1 * (__uint_as_float(rp[e + 1]) - my_delta));
           }
         } else {
+          const int k0 = kv0 + wg * 32 + c;  // first key of this sub-chunk
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float p0 = (kv0 + c + e < T) ? ex2_approx(fmaf(__uint_as_float(rs[e]), scale_log2, -my_lse)) : 0.f;
-            float p1 = (kv0 + c + e + 1 < T) ? ex2_approx(fmaf(__uint_as_float(rs[e + 1]), scale_log2, -my_lse)) : 0.f;
+          for (int e = 0; e < 16; e += 2) {
+            float p0 = (k0 + e < T) ? ex2_approx(fmaf(__uint_as_float(rs[e]), scale_log2, -my_lse)) : 0.f;
+            float p1 = (k0 + e + 1 < T) ? ex2_approx(fmaf(__uint_as_float(rs[e + 1]), scale_log2, -my_lse)) : 0.f;
             float dp0 = __uint_as_float(rp[e]), dp1 = __uint_as_float(rp[e + 1]);
-            if (ad.thresh8) {  // dP = dP_drop * mask/(1-p)
-              dp0 *= (keepw >> e) & 1u ? ad.scale : 0.f;
-              dp1 *= (keepw >> (e + 1)) & 1u ? ad.scale : 0.f;
+            if (DROP) {  // dP = dP_drop * mask/(1-p)
+              dp0 *= (keepw >> (c + e)) & 1u ? ad.scale : 0.f;
+              dp1 *= (keepw >> (c + e + 1)) & 1u ? ad.scale : 0.f;
             }
             dk[e / 2] = pack_bf16x2(p0 * (dp0 - my_delta), p1 * (dp1 - my_delta));
           }
         }
-        if (PT) tmem_st16(tm_dp + c, dk);  // dS over the dP tile it came from
-        else store_p32<BKV>(ds, row, c, dk);
+        tmem_st8(tm_dp + c / 2, dk);  // dS over the dP tile it came from (mma_over_rows_ts SPLIT layout)
       }
-      if (PT) tmem_wait_st();
-      else fence_proxy_async();
+      tmem_wait_st();
       tc_fence_before();
       mbar_arrive(ds_full + 8 * bf);
     }
     mbar_wait(acc_done, 0);
     tc_fence_after();
     __nv_bfloat16* dq_row = dqkv + ((size_t)b * T + q) * (3 * C) + h * HS;
-    constexpr int CH = HS >= 32 ? HS / 2 : HS;  // columns drained by each warpgroup (hs = 16: warpgroup 0 only)
-    const int c_lo = HS >= 32 ? wg * CH : 0;
-    const int c_hi = (HS >= 32 || wg == 0) ? c_lo + CH : c_lo;
+    // the head's columns are drained in 16-column groups by as many warpgroups as there are groups (at most 2 * NP)
+    constexpr int NG = (HS / 16) < 2 * NP ? (HS / 16) : 2 * NP;
+    constexpr int CH = HS / NG;
+    const int g = pair * 2 + wg;
+    if (g < NG) {
 #pragma unroll 1
-    for (int c = c_lo; c < c_hi; c += 16) {
-      uint32_t a[16];
-      tmem_ld16(tm_dq + lane_off + c, a);
-      tmem_wait_ld();
-      if (q_ok) store_row16_bf16(dq_row + c, a, scale);
+      for (int c = g * CH; c < (g + 1) * CH; c += 16) {
+        uint32_t a[16];
+        tmem_ld16(tm_dq + lane_off + c, a);
+        tmem_wait_ld();
+        if (q_ok) store_row16_bf16(dq_row + c, a, scale);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == MMAW) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // =============================================================================================== forward (v3 schedule)
@@ -718,7 +677,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t bar0 = sbase + L::BAR_OFF;
   const uint32_t q_full = bar0, k_full = bar0 + 8, k_empty = k_full + 8 * KST, v_full = k_empty + 8 * KST, v_empty = v_full + 8 * VST,
                  s_full = v_empty + 8 * VST, p_full = s_full + 32, p_empty = p_full + 32, tmem_slot = p_empty + 32;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   const int q0 = blockIdx.x * (128 * NWG), h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (T + BKV - 1) / BKV;
 
@@ -970,48 +929,71 @@ int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, in
 
 // Q / dO rows of the dQ kernel parked in tensor memory as TS-mode A operands (default on: +-0 at T = 962, +6 % at T = 3842)
 static const bool g_attn_a_in_tmem = getenv("DSF_ATTN_A_TMEM") ? atoi(getenv("DSF_ATTN_A_TMEM")) != 0 : true;
+// math warpgroup pairs of the two backward kernels (see attn_bwd_kv2_kernel): 2 (default) or 1
+static const int g_attn_bwd_pairs = getenv("DSF_ATTN_BWD_PAIRS") ? (atoi(getenv("DSF_ATTN_BWD_PAIRS")) == 1 ? 1 : 2) : 2;
+
+template <int HS, int BQ, int STA, int NP, bool DROP>
+static int launch_bwd_kv(const CUtensorMap& tmKV128, const CUtensorMap& tmQs, const CUtensorMap& tmDOs, const float* lse, const float* delta, void* dqkv,
+                         dim3 grid, int T, int C, int nh, float scale, const AttnDrop& ad, cudaStream_t st) {
+  using LA = BwdKV2<HS, BQ, STA, NP>;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, NP, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess)
+      return check_launch("attn_bwd2/kv/attr");
+    configured = true;
+  }
+  launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, NP, DROP>, grid, dim3(LA::THREADS), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, delta, (__nv_bfloat16*)dqkv, T, C,
+             nh, scale, ad);
+  return check_launch("attn_bwd2/kv");
+}
+
+template <int HS, int STB, bool AT, int NP, bool DROP>
+static int launch_bwd_q(const CUtensorMap& tmQ128, const CUtensorMap& tmDO128, const CUtensorMap& tmKV64, const float* lse, const float* delta, void* dqkv,
+                        dim3 grid, int T, int C, int nh, float scale, const AttnDrop& ad, const void* qkv, const void* dy, cudaStream_t st) {
+  using LB = BwdQ2<HS, STB>;
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, AT, NP, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
+      return check_launch("attn_bwd2/q/attr");
+    configured = true;
+  }
+  launch_pdl(attn_bwd_q2_kernel<HS, STB, AT, NP, DROP>, grid, dim3(256 * NP + 64), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, delta, (__nv_bfloat16*)dqkv, T,
+             C, nh, scale, ad, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dy);
+  return check_launch("attn_bwd2/q");
+}
 
 template <int HS, int BQ, int STA, int STB>
 static int launch_bwd2(const void* qkv, const void* y, const void* dy, const float* lse, float* delta, void* dqkv, int B, int T, int C, int nh,
                        const AttnDrop& ad, int parts, cudaStream_t st) {
-  using LA = BwdKV2<HS, BQ, STA>;
-  using LB = BwdQ2<HS, STB>;
   using H = HeadCfg<HS>;
-  static bool configured_on[64] = {};
-  bool& configured = per_device_flag(configured_on);
-  if (!configured) {
-    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
-      return check_launch("attn_bwd2/attr");
-    configured = true;
-  }
   const float scale = 1.0f / sqrtf((float)HS);
   if (parts & 1) {
     if (int e = run_attn_delta(y, dy, delta, B, T, C, nh, st)) return e;
   }
-  CUtensorMap tmKV128, tmQs, tmDOs, tmQ128, tmDO128, tmKV64;
-  if (int e = make_tmap3(&tmKV128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
-  if (int e = make_tmap3(&tmQs, qkv, 3 * C, T, B, H::BOXC, BQ)) return e;
-  if (int e = make_tmap3(&tmDOs, dy, C, T, B, H::BOXC, BQ)) return e;
-  if (int e = make_tmap3(&tmQ128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
-  if (int e = make_tmap3(&tmDO128, dy, C, T, B, H::BOXC, 128)) return e;
-  if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
-  dim3 grid(cdiv(T, 128), nh, B);
+  const dim3 grid(cdiv(T, 128), nh, B);
+  const bool drop = ad.thresh8 != 0, two = g_attn_bwd_pairs == 2;
   if (parts & 2) {
-    // dK/dV kernel: P^T / dS^T stay in tensor memory, lse / delta staged per warp (no named barrier per iteration)
-    launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, true, false, true>, grid, dim3(320), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, (const float*)delta,
-               (__nv_bfloat16*)dqkv, T, C, nh, scale, ad);
-    if (int e = check_launch("attn_bwd2/kv")) return e;
+    CUtensorMap tmKV128, tmQs, tmDOs;
+    if (int e = make_tmap3(&tmKV128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
+    if (int e = make_tmap3(&tmQs, qkv, 3 * C, T, B, H::BOXC, BQ)) return e;
+    if (int e = make_tmap3(&tmDOs, dy, C, T, B, H::BOXC, BQ)) return e;
+#define DSF_KV(NP, DROP) launch_bwd_kv<HS, BQ, STA, NP, DROP>(tmKV128, tmQs, tmDOs, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, st)
+    if (int e = two ? (drop ? DSF_KV(2, true) : DSF_KV(2, false)) : (drop ? DSF_KV(1, true) : DSF_KV(1, false))) return e;
+#undef DSF_KV
   }
   if (parts & 4) {
-    if (g_attn_a_in_tmem)
-      launch_pdl(attn_bwd_q2_kernel<HS, STB, true, true>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta, (__nv_bfloat16*)dqkv,
-                 T, C, nh, scale, ad, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dy);
-    else
-      launch_pdl(attn_bwd_q2_kernel<HS, STB, true, false>, grid, dim3(320), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, (const float*)delta,
-                 (__nv_bfloat16*)dqkv, T, C, nh, scale, ad, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dy);
-    if (int e = check_launch("attn_bwd2/q")) return e;
+    CUtensorMap tmQ128, tmDO128, tmKV64;
+    if (int e = make_tmap3(&tmQ128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
+    if (int e = make_tmap3(&tmDO128, dy, C, T, B, H::BOXC, 128)) return e;
+    if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
+#define DSF_Q(AT, NP, DROP) launch_bwd_q<HS, STB, AT, NP, DROP>(tmQ128, tmDO128, tmKV64, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, qkv, dy, st)
+    int e;
+    if (g_attn_a_in_tmem) e = two ? (drop ? DSF_Q(true, 2, true) : DSF_Q(true, 2, false)) : (drop ? DSF_Q(true, 1, true) : DSF_Q(true, 1, false));
+    else e = two ? (drop ? DSF_Q(false, 2, true) : DSF_Q(false, 2, false)) : (drop ? DSF_Q(false, 1, true) : DSF_Q(false, 1, false));
+#undef DSF_Q
+    if (e) return e;
   }
   return DSF_OK;
 }

@@ -141,7 +141,7 @@ gemm_nt2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = base + L::BAR_OFF, bar_empty = bar_full + STAGES * 8, acc_full = bar_empty + STAGES * 8,
                  acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   const int num_k = K / G2_BK;
   const int total = m_tiles * n_tiles;
   pdl_trigger();
@@ -377,7 +377,7 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = base + L::BAR_OFF, bar_empty = bar_full + STAGES * 8, acc_full = bar_empty + STAGES * 8,
                  acc_empty = acc_full + 16, tmem_slot = acc_empty + 16;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int num_k = K / G2_BK;
@@ -654,7 +654,7 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = base + L::BAR_OFF, bar_empty = bar_full + STAGES * 8, bar_acc = bar_empty + STAGES * 8, tmem_slot = bar_acc + 8 * 4;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   const int n0 = blockIdx.y * G2_BM;  // rows of C (N' index)
   const int k0 = blockIdx.x * BN;     // cols of C (K' index)
   const int m_lo = blockIdx.z * m_chunk, m_hi = min(M, m_lo + m_chunk);
