@@ -223,13 +223,13 @@ template <int HS, int BQ, int ST, int NP>
 struct BwdKV2 {
   static constexpr int KV_BYTES = 128 * HS * 2, Q_BYTES = BQ * HS * 2;
   static constexpr int K_OFF = 0, V_OFF = KV_BYTES, Q_OFF = 2 * KV_BYTES, DO_OFF = Q_OFF + ST * Q_BYTES;
-  static constexpr int STAT_OFF = DO_OFF + ST * Q_BYTES;  // [math warp][2 buffers][lse 32 | delta 32] floats
-  static constexpr int BAR_OFF = STAT_OFF + 8 * NP * 2 * 64 * 4;
-  static constexpr int NBAR = 2 + 2 * ST + 6;
-  static constexpr int DYN = BAR_OFF + NBAR * 8 + 16 + 1024;
+  static constexpr int BAR_OFF = DO_OFF + ST * Q_BYTES;
+  static constexpr int NBAR = 2 + 2 * ST + 4;
+  static constexpr int STAT_OFF = BAR_OFF + NBAR * 8 + 16;  // lse (log2 units) | delta of ALL queries of this (batch, head), padded to tiles
   static constexpr int THREADS = 256 * NP + 64;
   static_assert(4 * BQ + 2 * HS <= 512, "TMEM budget");
-  static_assert(DYN <= 232448, "shared memory budget");
+  static_assert(STAT_OFF % 16 == 0, "float4 reads of the statistics");
+  static int dyn_bytes(int T) { return STAT_OFF + 2 * cdiv(T, BQ) * BQ * 4 + 1024; }
 };
 
 template <int HS, int BQ, int ST, int NP, bool DROP>
@@ -244,7 +244,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
   uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t bar0 = sbase + L::BAR_OFF;
   const uint32_t kv_full = bar0, acc_done = bar0 + 8, q_full = bar0 + 16, q_empty = q_full + 8 * ST, s_full = q_empty + 8 * ST,
-                 ds_full = s_full + 16, ds_empty = ds_full + 16, tmem_slot = ds_empty + 16;
+                 ds_full = s_full + 16, tmem_slot = ds_full + 16;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int n_q = (T + BQ - 1) / BQ;
@@ -254,7 +254,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     mbar_init(kv_full, 1);
     mbar_init(acc_done, 1);
     for (int s = 0; s < ST; ++s) { mbar_init(q_full + 8 * s, 1); mbar_init(q_empty + 8 * s, 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256); mbar_init(ds_empty + 8 * w, 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256); }
     fence_barrier_init();
   }
   if (warp == MMAW) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -310,7 +310,6 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         mma_over_rows_ts<HS, BQ, true>(tm_dv, tmem_base + bf * 2 * BQ, sbase + L::DO_OFF + st * L::Q_BYTES, idesc_g, i > 0);
         mma_over_rows_ts<HS, BQ, true>(tm_dk, tmem_base + bf * 2 * BQ + BQ, sbase + L::Q_OFF + st * L::Q_BYTES, idesc_g, i > 0);
         tc_commit_elect(q_empty + 8 * st);
-        tc_commit_elect(ds_empty + 8 * bf);
         TRACE(2, i, 4);
       }
       tc_commit_elect(acc_done);
@@ -327,57 +326,58 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     static_assert(BQ == 64, "the math warps split a 64-query tile in two 32-column halves");
     const size_t bh = (size_t)b * nh + h;
     const int kw = kv0 / 32 + (warp & 3);  // bitmap word holding this warp's 32 keys
-    // this lane's lse (log2 units) / delta of query (tile * BQ + wg * 32 + lane) and, for attn-dropout, the keep word of that
-    // query over this warp's 32 keys; fetched one own tile ahead so the global-memory latency hides behind the current tile
-    float wl = 0.f, wd = 0.f;
+    // lse (log2 units) and delta of every query of this (batch, head) are copied to shared memory ONCE by the math warps
+    // (2 x 4 B x T: 7.7 KB at T = 962, 31 KB at T = 3842); tiles then read them with broadcast 16-byte loads.  (Staging them per
+    // tile and warp cost ~250 of the ~1200 cycles a math warp spends on a tile.)  Padding queries get lse = +inf -> P = 0.
+    float* s_lse = reinterpret_cast<float*>(smem + L::STAT_OFF);
+    float* s_delta = s_lse + n_q * BQ;
+    for (int idx = threadIdx.x; idx < n_q * BQ; idx += 256 * NP) {
+      s_lse[idx] = idx < T ? __ldg(lse_g + idx) * 1.4426950408889634f : INFINITY;
+      s_delta[idx] = idx < T ? __ldg(delta_g + idx) : 0.f;
+    }
+    // attn-dropout: keep word of query (tile * BQ + wg * 32 + lane) over this warp's 32 keys, fetched one own tile ahead
     uint32_t wv = 0xFFFFFFFFu;
     auto fetch_w = [&](int it) {
       const int qq = it * BQ + wg * 32 + lane;
-      wl = qq < T ? lse_g[qq] * 1.4426950408889634f : INFINITY;
-      wd = qq < T ? delta_g[qq] : 0.f;
-      if (DROP) wv = qq < T ? ad.bits[(bh * T + qq) * ad.Tw + kw] : 0u;
+      wv = qq < T ? ad.bits[(bh * T + qq) * ad.Tw + kw] : 0u;
     };
     const int i0 = NP == 2 ? pair : 0;
-    if (i0 < n_q) fetch_w(i0);
-    float* wst0 = reinterpret_cast<float*>(smem + L::STAT_OFF) + warp * 2 * 64;
-    int own = 0;
-    for (int i = i0; i < n_q; i += NP, own ^= 1) {
+    if (DROP && i0 < n_q) fetch_w(i0);
+    named_bar_sync(1, 256 * NP);  // statistics visible to all math warps
+    for (int i = i0; i < n_q; i += NP) {
       const int bf = i & 1;
-      // per-warp statistics buffers [own][lse 32 | delta 32]; buffer `own` was last read two own tiles (two __syncwarps) ago
-      float* wst = wst0 + own * 64;
-      wst[lane] = wl;
-      wst[32 + lane] = wd;
+      const float* wst = s_lse + i * BQ + wg * 32;
+      const float* wsd = s_delta + i * BQ + wg * 32;
       const uint32_t myw = wv;
       if ((warp & 3) == 0) TRACE(wg, i, 0);
-      if (i + NP < n_q) fetch_w(i + NP);
-      __syncwarp();
+      if (DROP && i + NP < n_q) fetch_w(i + NP);
       if ((warp & 3) == 0) TRACE(wg, i, 1);
+      // s_full(i) also says that buffer bf is free: S^T / dP^T (i) were issued after dV / dK (i-2), the MMAs of one thread
+      // complete in order, and the commit covers every MMA issued before it
       mbar_wait(s_full + 8 * bf, (i >> 1) & 1);
       if ((warp & 3) == 0) TRACE(wg, i, 2);
       tc_fence_after();
-      if (i >= 2) mbar_wait(ds_empty + 8 * bf, ((i >> 1) - 1) & 1);
       if ((warp & 3) == 0) TRACE(wg, i, 3);
       const uint32_t tm_s = tmem_base + bf * 2 * BQ + lane_off + wg * 32, tm_dp = tm_s + BQ;
-      // two 16-column sub-chunks keep the live registers (2 x 16 loaded + 2 x 8 packed) within the 576-thread budget
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tm_s, rs);
+      tmem_ld32(tm_dp, rp);
+      tmem_wait_ld();
 #pragma unroll
       for (int c = 0; c < 32; c += 16) {
-        uint32_t rs[16], rp[16];
-        tmem_ld16(tm_s + c, rs);
-        tmem_ld16(tm_dp + c, rp);
-        tmem_wait_ld();
         uint32_t pk[8], dk[8];
 #pragma unroll
         for (int e = 0; e < 16; e += 4) {
           const float4 l4 = *reinterpret_cast<const float4*>(wst + c + e);
-          const float4 d4 = *reinterpret_cast<const float4*>(wst + 32 + c + e);
+          const float4 d4 = *reinterpret_cast<const float4*>(wsd + c + e);
           const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
           float p[4], d[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             // rows of keys >= T hold finite garbage (K, V rows are zero-filled): they only reach the dK / dV rows of those
             // keys, which are never stored.  The 1/sqrt(hs) factor of dS is applied once when dK is drained.
-            p[u] = ex2_approx(fmaf(__uint_as_float(rs[e + u]), scale_log2, -ls[u]));
-            float dp = __uint_as_float(rp[e + u]);
+            p[u] = ex2_approx(fmaf(__uint_as_float(rs[c + e + u]), scale_log2, -ls[u]));
+            float dp = __uint_as_float(rp[c + e + u]);
             if (DROP) {  // attn_drop: dV sees P*mask/(1-p); dP = dP_drop*mask/(1-p)
               const float m = (__shfl_sync(0xffffffffu, myw, c + e + u) >> lane) & 1u ? ad.scale : 0.f;
               dp *= m;
@@ -392,7 +392,8 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           dk[e / 2] = pack_bf16x2(d[0], d[1]);
           dk[e / 2 + 1] = pack_bf16x2(d[2], d[3]);
         }
-        // packed pairs of columns c .. c+15 -> 8 columns at c/2 of this warpgroup's 32-column region (mma_over_rows_ts SPLIT layout)
+        // packed pairs of columns c .. c+15 -> 8 columns at c/2 of this warpgroup's 32-column region (mma_over_rows_ts SPLIT layout);
+        // the first store only overwrites columns whose values already sit in registers
         tmem_st8(tm_s + c / 2, pk);
         tmem_st8(tm_dp + c / 2, dk);
       }
@@ -434,7 +435,7 @@ struct BwdQ2 {
   static constexpr int Q_BYTES = 128 * HS * 2, KV_BYTES = BKV * HS * 2;
   static constexpr int Q_OFF = 0, DO_OFF = Q_BYTES, K_OFF = 2 * Q_BYTES, V_OFF = K_OFF + ST * KV_BYTES;
   static constexpr int BAR_OFF = V_OFF + ST * KV_BYTES;
-  static constexpr int NBAR = 2 + 2 * ST + 6;
+  static constexpr int NBAR = 2 + 2 * ST + 4;
   static constexpr int DYN = BAR_OFF + NBAR * 8 + 16 + 1024;
   static_assert(4 * BKV + HS <= 512, "TMEM budget");
 };
@@ -456,7 +457,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = sbase + L::BAR_OFF;
   const uint32_t q_full = bar0, acc_done = bar0 + 8, kv_full = bar0 + 16, kv_empty = kv_full + 8 * ST, s_full = kv_empty + 8 * ST,
-                 ds_full = s_full + 16, ds_empty = ds_full + 16, tmem_slot = ds_empty + 16;
+                 ds_full = s_full + 16, tmem_slot = ds_full + 16;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (T + BKV - 1) / BKV;
@@ -468,7 +469,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(q_full, AT ? 256 : 1);
     mbar_init(acc_done, 1);
     for (int s = 0; s < ST; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256); mbar_init(ds_empty + 8 * w, 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256); }
     fence_barrier_init();
   }
   if (warp == MMAW) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
@@ -531,7 +532,6 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
         mma_over_rows_ts<HS, BKV, true>(tm_dq, tmem_base + bf * 2 * BKV + BKV, sbase + L::K_OFF + st * L::KV_BYTES, idesc_q, j > 0);
         tc_commit_elect(kv_empty + 8 * st);
-        tc_commit_elect(ds_empty + 8 * bf);
       }
       tc_commit_elect(acc_done);
     }
@@ -572,33 +572,33 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int bf = j & 1, kv0 = j * BKV;
       const uint32_t keepw = wnext;
       if (my_bits && j + NP < n_kv) wnext = my_bits[2 * (j + NP)];
+      // s_full(j) also says that buffer bf is free: S / dP (j) were issued after dQ += dS K (j-2), one thread's MMAs complete in order
       mbar_wait(s_full + 8 * bf, (j >> 1) & 1);
       tc_fence_after();
-      if (j >= 2) mbar_wait(ds_empty + 8 * bf, ((j >> 1) - 1) & 1);
       const uint32_t tm_s = tmem_base + bf * 2 * BKV + lane_off + wg * 32, tm_dp = tm_s + BKV;
       const bool full = kv0 + BKV <= T;  // only the last key tile needs the column mask
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tm_s, rs);
+      tmem_ld32(tm_dp, rp);
+      tmem_wait_ld();
 #pragma unroll
       for (int c = 0; c < 32; c += 16) {
-        uint32_t rs[16], rp[16];
-        tmem_ld16(tm_s + c, rs);
-        tmem_ld16(tm_dp + c, rp);
-        tmem_wait_ld();
         uint32_t dk[8];
         // the 1/sqrt(hs) factor of dS is applied once when dQ is drained
         if (full && !DROP) {
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), scale_log2, -my_lse));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), scale_log2, -my_lse));
-            dk[e / 2] = pack_bf16x2(p0 * (__uint_as_float(rp[e]) - my_delta), p1 * (__uint_as_float(rp[e + 1]) - my_delta));
+            const float p0 = ex2_approx(fmaf(__uint_as_float(rs[c + e]), scale_log2, -my_lse));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(rs[c + e + 1]), scale_log2, -my_lse));
+            dk[e / 2] = pack_bf16x2(p0 * (__uint_as_float(rp[c + e]) - my_delta), p1 * (__uint_as_float(rp[c + e + 1]) - my_delta));
           }
         } else {
           const int k0 = kv0 + wg * 32 + c;  // first key of this sub-chunk
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
-            float p0 = (k0 + e < T) ? ex2_approx(fmaf(__uint_as_float(rs[e]), scale_log2, -my_lse)) : 0.f;
-            float p1 = (k0 + e + 1 < T) ? ex2_approx(fmaf(__uint_as_float(rs[e + 1]), scale_log2, -my_lse)) : 0.f;
-            float dp0 = __uint_as_float(rp[e]), dp1 = __uint_as_float(rp[e + 1]);
+            float p0 = (k0 + e < T) ? ex2_approx(fmaf(__uint_as_float(rs[c + e]), scale_log2, -my_lse)) : 0.f;
+            float p1 = (k0 + e + 1 < T) ? ex2_approx(fmaf(__uint_as_float(rs[c + e + 1]), scale_log2, -my_lse)) : 0.f;
+            float dp0 = __uint_as_float(rp[c + e]), dp1 = __uint_as_float(rp[c + e + 1]);
             if (DROP) {  // dP = dP_drop * mask/(1-p)
               dp0 *= (keepw >> (c + e)) & 1u ? ad.scale : 0.f;
               dp1 *= (keepw >> (c + e + 1)) & 1u ? ad.scale : 0.f;
@@ -781,8 +781,11 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if ((warp & 3) == 0) TRACE(w, j, 2);
       float p_max = -INFINITY;
       if (kv0 + BKV <= T) {
+        // four independent chains of 3-input maxima (one 32-long dependent chain cost ~250 cycles of every tile's critical path)
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) p_max = fmaxf(p_max, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+        for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+        p_max = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -813,7 +816,9 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         m_run = m_new;
       }
       if ((warp & 3) == 0) TRACE(w, j, 3);
-      if (j >= 2) mbar_wait(p_empty + 8 * sb, ((j >> 1) - 1) & 1);  // P.V(j-2) retired: this P buffer is free
+      // P in shared memory: wait until P.V(j-2) has retired its buffer.  P in tensor memory (PT): the buffer is the S tile itself,
+      // and s_full(j) already implies it — S(j) was issued after P.V(j-2) by the same thread, whose MMAs complete in order.
+      if (!PT && j >= 2) mbar_wait(p_empty + 8 * sb, ((j >> 1) - 1) & 1);
       if (PP) named_bar_sync(3 + w, 256);  // my turn on the exponential unit
       if ((warp & 3) == 0) TRACE(w, j, 4);
       float l_add = 0.f;
@@ -929,21 +934,27 @@ int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, in
 
 // Q / dO rows of the dQ kernel parked in tensor memory as TS-mode A operands (default on: +-0 at T = 962, +6 % at T = 3842)
 static const bool g_attn_a_in_tmem = getenv("DSF_ATTN_A_TMEM") ? atoi(getenv("DSF_ATTN_A_TMEM")) != 0 : true;
-// math warpgroup pairs of the two backward kernels (see attn_bwd_kv2_kernel): 2 (default) or 1
-static const int g_attn_bwd_pairs = getenv("DSF_ATTN_BWD_PAIRS") ? (atoi(getenv("DSF_ATTN_BWD_PAIRS")) == 1 ? 1 : 2) : 2;
+// Math warpgroup pairs of the two backward kernels (template parameter NP, see attn_bwd_kv2_kernel).  Only NP = 1 is built:
+// measured on B200 (scripts/bench_attn_parts.py, batch 12, T = 962; profiles/r02ac_attn_parts.txt) NP = 2 runs the dK/dV kernel in
+// 32.6 / 36.9 / 44.5 / 59.6 us against 29.7 / 33.4 / 41.9 / 59.9 us for NP = 1 (head size 16 / 32 / 64 / 128) and the dQ kernel in
+// 27.9 / 30.5 / 35.6 / 45.6 against 26.3 / 28.2 / 32.9 / 45.5 us: once the statistics staging and the redundant buffer wait were gone
+// the second pair only added contention.
+constexpr int kBwdPairs = 1;
 
 template <int HS, int BQ, int STA, int NP, bool DROP>
 static int launch_bwd_kv(const CUtensorMap& tmKV128, const CUtensorMap& tmQs, const CUtensorMap& tmDOs, const float* lse, const float* delta, void* dqkv,
                          dim3 grid, int T, int C, int nh, float scale, const AttnDrop& ad, cudaStream_t st) {
   using LA = BwdKV2<HS, BQ, STA, NP>;
+  const int dyn = LA::dyn_bytes(T);
+  if (dyn > 232448) { set_error("attn_bwd: T = %d needs %d bytes of shared memory for the per-query statistics (limit 232448)", T, dyn); return DSF_EUNSUPPORTED; }
   static bool configured_on[64] = {};
   bool& configured = per_device_flag(configured_on);
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, NP, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, LA::DYN) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, NP, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess)
       return check_launch("attn_bwd2/kv/attr");
     configured = true;
   }
-  launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, NP, DROP>, grid, dim3(LA::THREADS), LA::DYN, st, tmKV128, tmQs, tmDOs, lse, delta, (__nv_bfloat16*)dqkv, T, C,
+  launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, NP, DROP>, grid, dim3(LA::THREADS), dyn, st, tmKV128, tmQs, tmDOs, lse, delta, (__nv_bfloat16*)dqkv, T, C,
              nh, scale, ad);
   return check_launch("attn_bwd2/kv");
 }
@@ -973,14 +984,14 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
     if (int e = run_attn_delta(y, dy, delta, B, T, C, nh, st)) return e;
   }
   const dim3 grid(cdiv(T, 128), nh, B);
-  const bool drop = ad.thresh8 != 0, two = g_attn_bwd_pairs == 2;
+  const bool drop = ad.thresh8 != 0;
   if (parts & 2) {
     CUtensorMap tmKV128, tmQs, tmDOs;
     if (int e = make_tmap3(&tmKV128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
     if (int e = make_tmap3(&tmQs, qkv, 3 * C, T, B, H::BOXC, BQ)) return e;
     if (int e = make_tmap3(&tmDOs, dy, C, T, B, H::BOXC, BQ)) return e;
-#define DSF_KV(NP, DROP) launch_bwd_kv<HS, BQ, STA, NP, DROP>(tmKV128, tmQs, tmDOs, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, st)
-    if (int e = two ? (drop ? DSF_KV(2, true) : DSF_KV(2, false)) : (drop ? DSF_KV(1, true) : DSF_KV(1, false))) return e;
+#define DSF_KV(DROP) launch_bwd_kv<HS, BQ, STA, kBwdPairs, DROP>(tmKV128, tmQs, tmDOs, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, st)
+    if (int e = drop ? DSF_KV(true) : DSF_KV(false)) return e;
 #undef DSF_KV
   }
   if (parts & 4) {
@@ -988,10 +999,10 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
     if (int e = make_tmap3(&tmQ128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
     if (int e = make_tmap3(&tmDO128, dy, C, T, B, H::BOXC, 128)) return e;
     if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
-#define DSF_Q(AT, NP, DROP) launch_bwd_q<HS, STB, AT, NP, DROP>(tmQ128, tmDO128, tmKV64, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, qkv, dy, st)
+#define DSF_Q(AT, DROP) launch_bwd_q<HS, STB, AT, kBwdPairs, DROP>(tmQ128, tmDO128, tmKV64, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, qkv, dy, st)
     int e;
-    if (g_attn_a_in_tmem) e = two ? (drop ? DSF_Q(true, 2, true) : DSF_Q(true, 2, false)) : (drop ? DSF_Q(true, 1, true) : DSF_Q(true, 1, false));
-    else e = two ? (drop ? DSF_Q(false, 2, true) : DSF_Q(false, 2, false)) : (drop ? DSF_Q(false, 1, true) : DSF_Q(false, 1, false));
+    if (g_attn_a_in_tmem) e = drop ? DSF_Q(true, true) : DSF_Q(true, false);
+    else e = drop ? DSF_Q(false, true) : DSF_Q(false, false);
 #undef DSF_Q
     if (e) return e;
   }

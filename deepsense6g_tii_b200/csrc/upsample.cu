@@ -179,6 +179,7 @@ upsample_add_bwd_nchw_kernel(dsf_geom g, Ptr3 dout, const float* __restrict__ dg
   }
   float* outT = sm;                                   // [cells][UP_CT + 1]
   float* tmp = sm + cells * (UP_CT + 1) + warp * (g.A_h * g.W);  // [A_h][W] per warp
+  const int tab_off = (cells * (UP_CT + 1) + UP_WARPS * g.A_h * g.W + 3) & ~3;  // 16-byte aligned tap tables behind them
   const int b = f / slots, sl = f % slots;
   int which, n;
   slot_frame(g, b, sl, which, n);
@@ -197,12 +198,134 @@ upsample_add_bwd_nchw_kernel(dsf_geom g, Ptr3 dout, const float* __restrict__ dg
     }
   } else {
   const int W4 = g.W / 4, sh = g.H / g.A_h;
+  // Per-row / per-column adjoint taps, computed once per CTA (they are the same for every plane): entry i = {weight into anchor
+  // k-1, weight into anchor k, weight into anchor k+1, k} with k = i / scale.  A source row (column) of anchor block k only
+  // touches anchors k-1, k, k+1 (ty.i0 is k-1 or k, ty.i1 is k or k+1; both k at a clamped border).  Looking the taps up costs
+  // one broadcast 16-byte load per row where recomputing them (float index arithmetic + an integer division) made these
+  // kernels instruction-bound (ncu: 3000 warp instructions per 32 x 32 plane, 1.1 TB/s).
+  float4* rowtab = reinterpret_cast<float4*>(sm + tab_off);
+  float4* coltab = rowtab + g.H;
+  const bool tables = g.H % g.A_h == 0 && g.W % g.A_w == 0;
+  if (tables) {
+    for (int i = tid; i < g.H + g.W; i += UP_THREADS) {
+      const bool is_row = i < g.H;
+      const int idx = is_row ? i : i - g.H, scale = is_row ? sh : sw, A = is_row ? g.A_h : g.A_w;
+      const Tap t = tap_of(idx, is_row ? rsh : rsw, A);
+      const int k = idx / scale;
+      float4 e = make_float4(0.f, 0.f, 0.f, __int_as_float(k));
+      if (t.i0 == k) e.y += 1.f - t.lam; else e.x += 1.f - t.lam;
+      if (t.i1 == k) e.y += t.lam; else e.z += t.lam;
+      (is_row ? rowtab : coltab)[idx] = e;
+    }
+    __syncthreads();
+  }
   // stage-1-like planes (column scale a multiple of 8, >= 2 rows per lane and anchor block): fold both axes in registers
-  const bool direct = g.W % 4 == 0 && (W4 == 8 || W4 == 16 || W4 == 32) && sw % 8 == 0 && sh >= 2 * (32 / W4);
+  const bool direct = tables && g.W % 4 == 0 && (W4 == 8 || W4 == 16 || W4 == 32) && sw % 8 == 0 && sh >= 2 * (32 / W4);
+  // narrow planes (W = 8 / 16 / 32, stages 2-3): rows streamed with coalesced 4-byte loads, 32 / W rows per load instruction,
+  // folded along H in registers (same three-row argument as the direct path), then along W from shared memory
+  const bool narrow = !direct && tables && (g.W == 8 || g.W == 16 || g.W == 32) && sh % (32 / g.W) == 0;
   if (direct) {
     for (int i = tid; i < cells * (UP_CT + 1); i += UP_THREADS) outT[i] = 0.f;
     __syncthreads();
   }
+  if (narrow) {
+    const int rpl = 32 / g.W, par = lane / g.W, w = lane % g.W;
+    float a_prev = 0.f, a_cur = 0.f, a_next = 0.f;
+    int blk = -1;
+    // The row phases of one load instruction lie in the same anchor block (sh is a multiple of 32 / W), so a block change is
+    // warp-uniform: the phases are folded with shuffles and lane w alone updates column w (fixed summation order, no atomics).
+    auto flush = [&]() {
+      if (blk < 0) return;
+      for (int o = g.W; o < 32; o <<= 1) {
+        a_prev += __shfl_xor_sync(0xffffffffu, a_prev, o);
+        a_cur += __shfl_xor_sync(0xffffffffu, a_cur, o);
+        a_next += __shfl_xor_sync(0xffffffffu, a_next, o);
+      }
+      if (par == 0) {
+        if (blk > 0) tmp[(blk - 1) * g.W + w] += a_prev;
+        tmp[blk * g.W + w] += a_cur;
+        if (blk + 1 < g.A_h) tmp[(blk + 1) * g.W + w] += a_next;
+      }
+      a_prev = a_cur = a_next = 0.f;
+    };
+    constexpr int U = 8;  // independent loads in flight per lane and plane
+    auto begin_plane = [&]() {
+      for (int i = lane; i < g.A_h * g.W; i += 32) tmp[i] = 0.f;
+      __syncwarp();
+      blk = -1;
+    };
+    auto fold_rows = [&](int h0, const float (&v)[U]) {  // rows h0, h0 + rpl, ... of this lane's row phase
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int h = h0 + u * rpl;
+        if (h >= g.H) break;
+        const float4 t = rowtab[h];
+        const int k = __float_as_int(t.w);
+        if (k != blk) { flush(); blk = k; }
+        a_prev += t.x * v[u];
+        a_cur += t.y * v[u];
+        a_next += t.z * v[u];
+      }
+    };
+    auto end_plane = [&](int cl) {
+      flush();
+      __syncwarp();
+      // fold along W: cell (cy, cx) collects the columns of anchor blocks cx-1, cx, cx+1 with their tabulated weights
+      for (int cell = lane; cell < cells; cell += 32) {
+        const int cy = cell / g.A_w, cx = cell % g.A_w;
+        const float* trow = tmp + cy * g.W;
+        const int wc = cx * sw;
+        float acc = 0.f;
+        for (int j = 0; j < sw; ++j) acc += coltab[wc + j].y * trow[wc + j];
+        if (cx > 0)
+          for (int j = 0; j < sw; ++j) acc += coltab[wc - sw + j].z * trow[wc - sw + j];
+        if (cx + 1 < g.A_w)
+          for (int j = 0; j < sw; ++j) acc += coltab[wc + sw + j].x * trow[wc + sw + j];
+        outT[cell * (UP_CT + 1) + cl] = acc;
+      }
+      __syncwarp();
+    };
+    if (g.H <= U * rpl) {
+      // tiny planes (<= 256 pixels, one load round): the rows of FOUR of this warp's planes are requested before the first one
+      // is folded — with one 1 KB plane in flight per warp the kernel sat at 0.7 TB/s on DRAM latency
+      constexpr int PL = 4;
+      for (int cl = warp; cl < nct; cl += UP_WARPS * PL) {
+        float v[PL][U];
+#pragma unroll
+        for (int p = 0; p < PL; ++p) {
+          const int c = cl + p * UP_WARPS;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int h = par + u * rpl;
+            v[p][u] = (c < nct && h < g.H) ? to_f<FT>(src[(size_t)c * HW + (size_t)h * g.W + w]) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < PL; ++p) {
+          const int c = cl + p * UP_WARPS;
+          if (c >= nct) break;
+          begin_plane();
+          fold_rows(par, v[p]);
+          end_plane(c);
+        }
+      }
+    } else {
+      for (int cl = warp; cl < nct; cl += UP_WARPS) {
+        const FT* pl = src + (size_t)cl * HW;
+        begin_plane();
+        for (int h0 = par; h0 < g.H; h0 += U * rpl) {
+          float v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int h = h0 + u * rpl;
+            v[u] = h < g.H ? to_f<FT>(pl[(size_t)h * g.W + w]) : 0.f;
+          }
+          fold_rows(h0, v);
+        }
+        end_plane(cl);
+      }
+    }
+  } else
   for (int cl = warp; cl < nct; cl += UP_WARPS) {
     const FT* pl = src + (size_t)cl * HW;
     if (!direct) {
@@ -244,16 +367,15 @@ upsample_add_bwd_nchw_kernel(dsf_geom g, Ptr3 dout, const float* __restrict__ dg
         for (int u = 0; u < U; ++u) {
           const int h = h0 + u * npar;
           if (h >= g.H) break;
-          const int k = h / sh;
+          const float4 t = rowtab[h];
+          const int k = __float_as_int(t.w);
           if (k != blk) { flush(); blk = k; }
-          const Tap ty = tap_of(h, rsh, g.A_h);
           float c0 = 0.f, c1 = 0.f;
 #pragma unroll
           for (int q = 0; q < 4; ++q) { c0 += (1.f - lx[q]) * v[u][q]; c1 += lx[q] * v[u][q]; }
-          // ty.i0 is k-1 or k, ty.i1 is k or k+1 (both k at a clamped border)
-          const float w_lo = 1.f - ty.lam, w_hi = ty.lam;
-          if (ty.i0 == k) { a_cur[0] += w_lo * c0; a_cur[1] += w_lo * c1; } else { a_prev[0] += w_lo * c0; a_prev[1] += w_lo * c1; }
-          if (ty.i1 == k) { a_cur[0] += w_hi * c0; a_cur[1] += w_hi * c1; } else { a_next[0] += w_hi * c0; a_next[1] += w_hi * c1; }
+          a_prev[0] += t.x * c0; a_prev[1] += t.x * c1;
+          a_cur[0] += t.y * c0; a_cur[1] += t.y * c1;
+          a_next[0] += t.z * c0; a_next[1] += t.z * c1;
         }
       }
       flush();
@@ -401,7 +523,7 @@ extern "C" int dsf_upsample_add_bwd(const dsf_geom* g, const void* dout_img, con
   if (g->layout == DSF_NCHW) {
     const int ct = nchw_channel_tile(g);
     dim3 grid(g->B * slots + g->B, cdiv(g->C, ct));
-    const size_t smem = ((size_t)cells * (ct + 1) + (size_t)UP_WARPS * g->A_h * g->W) * sizeof(float);
+    const size_t smem = ((((size_t)cells * (ct + 1) + (size_t)UP_WARPS * g->A_h * g->W + 3) & ~(size_t)3) + 4 * (size_t)(g->H + g->W)) * sizeof(float);
     DSF_REQUIRE(smem <= 227 * 1024, "upsample_add_bwd: tile does not fit shared memory (%zu B)", smem);
 #define DSF_UP_BWD(FT, CT_)                                                                                                              \
   do {                                                                                                                                   \

@@ -39,6 +39,7 @@ STAGE_SHAPES = [  # (B, S, A, C, H)  H = A * scale
     (2, 5, 8, 64, 64), (2, 5, 8, 128, 32), (1, 5, 8, 256, 16), (2, 5, 8, 512, 8),
     (1, 2, 16, 64, 32),  # scaled config: 16x16 anchors
     (1, 3, 4, 8, 24),    # odd scale 6, tiny C
+    (1, 2, 2, 8, 8),     # 8-pixel rows: four rows per load instruction in the narrow-plane upsample backward
 ]
 
 
