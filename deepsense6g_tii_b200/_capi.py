@@ -24,6 +24,7 @@ SYMBOLS = [
     "dsf_layernorm_fwd", "dsf_layernorm_bwd", "dsf_gemm_bf16_nt", "dsf_gemm_bf16_tn", "dsf_gemm_set_impl", "dsf_gemm_f32",
     "dsf_colsum", "dsf_relu_bwd", "dsf_relu_bwd_colsum", "dsf_pack_block_weights", "dsf_softmax_fwd", "dsf_softmax_bwd", "dsf_attn_fwd", "dsf_attn_bwd", "dsf_attn_bwd_parts", "dsf_attn_set_impl", "dsf_attn_drop_words",
     "dsf_upsample_add_fwd", "dsf_upsample_add_bwd", "dsf_cast_f32_bf16", "dsf_opt_tiles", "dsf_adamw_ema_pack", "dsf_opt_upload_table", "dsf_chain_fwd", "dsf_chain_bwd",
+    "dsf_stem_pack", "dsf_tail_fwd", "dsf_tail_bwd",
 ]
 
 
@@ -99,6 +100,9 @@ def lib():
             "dsf_cast_f32_bf16": [P, P, c_int64, P],
             "dsf_chain_fwd": [P] * 25 + [c_int32, c_int32, c_float, P],
             "dsf_chain_bwd": [P] * 32 + [c_int32, c_int32, c_int32, c_int32, P],
+            "dsf_stem_pack": [P, c_int32, c_int32, c_int32, c_int32, c_int32, P, P, P, c_int32, c_int32, P],
+            "dsf_tail_fwd": [P, P, P, P, P] + [c_int32] * 9 + [P],
+            "dsf_tail_bwd": [P, P, P, P, P] + [c_int32] * 9 + [P],
             "dsf_opt_tiles": [c_int32, c_int32, c_int32],
             "dsf_opt_upload_table": [P, P, c_int64, P],
             "dsf_adamw_ema_pack": [P, P, c_int32, c_int32, c_double, c_double, c_double, c_double, c_double, P, c_double, P],
@@ -274,6 +278,36 @@ def upsample_add_fwd(g, y, feats, outs):
 
 def upsample_add_bwd(g, douts, dgps_out, dy):
     _chk(lib().dsf_upsample_add_bwd(ctypes.byref(g), _p(douts[0]), _p(douts[1]), _p(douts[2]), _p(dgps_out), _p(dy), _stream()), "dsf_upsample_add_bwd")
+
+
+def stem_pack(frames, out, scale=None, shift=None):
+    """frames: list of contiguous fp32 (B, C_in, H, W) CUDA tensors -> out (B*len(frames), C_in, H, W), bf16 / fp32, contiguous or
+    channels_last (taken from out's dtype and strides); out = x * scale[c] + shift[c]."""
+    n = len(frames)
+    B, Cin, H, W = frames[0].shape
+    ptrs = (c_void_p * n)(*[f.data_ptr() for f in frames])
+    sc = None if scale is None else (c_float * Cin)(*[float(v) for v in scale])
+    sh = None if shift is None else (c_float * Cin)(*[float(v) for v in shift])
+    nhwc = Cin > 1 and out.is_contiguous(memory_format=torch.channels_last) and not out.is_contiguous()
+    _chk(lib().dsf_stem_pack(ptrs, n, B, Cin, H, W, sc, sh, _p(out), _dt(out), DSF_NHWC if nhwc else DSF_NCHW, _stream()), "dsf_stem_pack")
+
+
+def _tail_layout(t):
+    return DSF_NHWC if (t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()) else DSF_NCHW
+
+
+def tail_fwd(maps, gps, fused, B):
+    C, H, W = maps[0].shape[1:]
+    fr = [m.shape[0] // B for m in maps]
+    _chk(lib().dsf_tail_fwd(_p(maps[0]), _p(maps[1]), _p(maps[2]), _p(gps), _p(fused), B, fr[0], fr[1], fr[2], C, H, W, _dt(maps[0]),
+                            _tail_layout(maps[0]), _stream()), "dsf_tail_fwd")
+
+
+def tail_bwd(dfused, dmaps, dgps, B):
+    C, H, W = dmaps[0].shape[1:]
+    fr = [m.shape[0] // B for m in dmaps]
+    _chk(lib().dsf_tail_bwd(_p(dfused), _p(dmaps[0]), _p(dmaps[1]), _p(dmaps[2]), _p(dgps), B, fr[0], fr[1], fr[2], C, H, W, _dt(dmaps[0]),
+                            _tail_layout(dmaps[0]), _stream()), "dsf_tail_bwd")
 
 
 def cast_f32_bf16(src, dst):

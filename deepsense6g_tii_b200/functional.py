@@ -860,3 +860,74 @@ def fusion_stage(cfg, img, lidar, radar, gps_emb, params):
     [, capture]).  ``capture`` (a dict, diagnostics / tests) receives ``relu.{i}``: the (B*T, 4C) mlp.0 output of block i, whose
     sign pattern is the set of ReLU decisions this evaluation took (see tests/tools/bf16_error_model.py)."""
     return FusionStageFn.apply(cfg, img, lidar, radar, gps_emb, *params)
+
+
+# ------------------------------------------------------------------------------------------------ stem / tail of Encoder.forward
+_IMAGENET_MEAN, _IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def stem_pack_supported(frames):
+    """The fused stem takes a list of equally shaped, contiguous fp32 CUDA frames (B, C_in <= 3, H, W) that carry no gradient."""
+    f0 = frames[0]
+    return (0 < len(frames) <= 16 and f0.is_cuda and f0.dim() == 4 and f0.shape[1] <= 3 and (f0.shape[2] * f0.shape[3]) % 4 == 0
+            and all(f.is_cuda and f.dtype == torch.float32 and f.shape == f0.shape and f.is_contiguous() and not f.requires_grad
+                    and f.device == f0.device for f in frames))
+
+
+def stem_pack(frames, normalize, dtype, channels_last):
+    """``normalize_imagenet`` (model2_seq.py:36-45, 481-482) + ``torch.stack(frames, dim=1).view(B*S, C, H, W)`` (:491-493) + the
+    cast / layout change conv1 needs, as one launch (``dsf_stem_pack``).  Returns the stacked (B*S, C, H, W) tensor in ``dtype``,
+    channels_last storage when asked for."""
+    f0 = frames[0]
+    B, Cin, H, W = f0.shape
+    with torch.cuda.device(f0.device):
+        out = torch.empty((B * len(frames), Cin, H, W), device=f0.device, dtype=dtype,
+                          memory_format=torch.channels_last if (channels_last and Cin > 1) else torch.contiguous_format)
+        if normalize:
+            if Cin != 3:
+                raise RuntimeError("normalize_imagenet expects 3-channel frames, got %d channels" % Cin)
+            scale = [1.0 / (255.0 * s) for s in _IMAGENET_STD]
+            shift = [-m / s for m, s in zip(_IMAGENET_MEAN, _IMAGENET_STD)]
+            K.stem_pack(frames, out, scale, shift)
+        else:
+            K.stem_pack(frames, out)
+    return out
+
+
+class PooledTailFn(torch.autograd.Function):
+    """``avgpool -> flatten -> view -> cat(gps) -> sum(dim=1)`` of Encoder.forward (model2_seq.py:581-595) as one launch per direction
+    (``dsf_tail_fwd`` / ``dsf_tail_bwd``): fused[b, c] = sum over maps and frames of the pixel mean + the two GPS tokens."""
+
+    @staticmethod
+    def forward(ctx, f_img, f_lid, f_rad, gps, B):
+        maps = (f_img, f_lid, f_rad)
+        ctx.B = B
+        ctx.like = maps
+        with torch.cuda.device(f_img.device):
+            fused = torch.empty((B, f_img.shape[1]), device=f_img.device, dtype=torch.float32)
+            K.tail_fwd(maps, gps, fused, B)
+        return fused
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dfused):
+        maps = ctx.like
+        dfused = dfused.contiguous().float()
+        with torch.cuda.device(dfused.device):
+            dmaps = [torch.empty_like(m) for m in maps]  # preserves dtype and (channels_last) strides
+            dgps = torch.empty((ctx.B, 2, maps[0].shape[1]), device=dfused.device, dtype=torch.float32)
+            K.tail_bwd(dfused, dmaps, dgps, ctx.B)
+        return dmaps[0], dmaps[1], dmaps[2], dgps, None
+
+
+def pooled_tail_supported(f_img, f_lid, f_rad, gps):
+    maps = (f_img, f_lid, f_rad)
+    lay = K._tail_layout(f_img)
+    return (all(m.is_cuda and m.dim() == 4 and m.dtype == f_img.dtype and m.dtype in (torch.float32, torch.bfloat16) and m.shape[1:] == f_img.shape[1:]
+                and K._tail_layout(m) == lay and (m.is_contiguous() or m.is_contiguous(memory_format=torch.channels_last)) for m in maps)
+            and f_img.shape[1] % 4 == 0 and (f_img.shape[2] * f_img.shape[3]) % 4 == 0
+            and gps.is_cuda and gps.dtype == torch.float32 and gps.is_contiguous() and gps.dim() == 3 and gps.shape[1] == 2)
+
+
+def pooled_tail(f_img, f_lid, f_rad, gps, B):
+    return PooledTailFn.apply(f_img, f_lid, f_rad, gps, B)

@@ -25,7 +25,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .functional import fusion_stage, param_names
+from .functional import fusion_stage, param_names, pooled_tail, pooled_tail_supported, stem_pack, stem_pack_supported
 
 
 class SelfAttention(nn.Module):
@@ -329,6 +329,23 @@ class Encoder(nn.Module):
         nhwc = one.is_contiguous(memory_format=torch.channels_last) and not one.is_contiguous()
         return one.expand(x.shape[0], *one.shape[1:]).contiguous(memory_format=torch.channels_last if nhwc else torch.contiguous_format)
 
+    def _stack(self, frames, conv1, normalize):
+        """The stacked input of one trunk (model2_seq.py:481-482, 491-493): ``normalize_imagenet`` per frame, ``torch.stack(dim=1)``,
+        ``.view(B*S, C, H, W)``.  For plain fp32 CUDA frames this is one ``dsf_stem_pack`` launch that also writes the dtype
+        (bf16 under autocast) and storage order (channels_last when conv1's weight is) cuDNN is about to ask for; any other input
+        takes the reference's op sequence."""
+        if getattr(self.config, "fused_stem_tail", True) and stem_pack_supported(frames):
+            dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
+            if dtype in (torch.float32, torch.bfloat16):
+                wt = conv1.weight
+                nhwc = wt.dim() == 4 and wt.is_contiguous(memory_format=torch.channels_last) and not wt.is_contiguous()
+                return stem_pack(list(frames), normalize, dtype, nhwc)
+        if normalize:
+            frames = [normalize_imagenet(t) for t in frames]
+        f0 = frames[0]
+        # (the reference uses .view here, :491-493; reshape also accepts channels_last frames)
+        return torch.stack(list(frames), dim=1).reshape(f0.shape[0] * len(frames), f0.shape[1], f0.shape[2], f0.shape[3])
+
     def _apply_missing(self, name, t):
         # semantics of mambafuser_seq.py:361-391, 418-420: replace the stacked input ahead of conv1
         if not _missing(self.config, name):
@@ -339,18 +356,14 @@ class Encoder(nn.Module):
 
     def forward(self, image_list, lidar_list, radar_list, gps, velocity=None, rebuild_modality_feat_list=None):
         cfg = self.config
-        if self.image_encoder.normalize:
-            image_list = [normalize_imagenet(t) for t in image_list]
         bz, _, h, w = lidar_list[0].shape
         cfg.n_views = len(image_list) // cfg.seq_len  # the reference mutates the shared config too (:489)
         S, V = cfg.seq_len, cfg.n_views
-        # (the reference uses .view here, :491-493; reshape also accepts channels_last frames)
-        img = torch.stack(image_list, dim=1).reshape(bz * V * S, image_list[0].shape[1], h, w)
-        lid = torch.stack(lidar_list, dim=1).reshape(bz * S, lidar_list[0].shape[1], h, w)
-        rad = torch.stack(radar_list, dim=1).reshape(bz * S, radar_list[0].shape[1], h, w)
-        img, lid, rad = self._apply_missing("image", img), self._apply_missing("lidar", lid), self._apply_missing("radar", rad)
-
         ie, le, re_ = self.image_encoder.features, self.lidar_encoder._model, self.radar_encoder._model
+        img = self._stack(image_list, ie.conv1, self.image_encoder.normalize)
+        lid = self._stack(lidar_list, le.conv1, False)
+        rad = self._stack(radar_list, re_.conv1, False)
+        img, lid, rad = self._apply_missing("image", img), self._apply_missing("lidar", lid), self._apply_missing("radar", rad)
 
         f_img, f_lid, f_rad = self._stem("image", ie, img), self._stem("lidar", le, lid), self._stem("radar", re_, rad)
         g = self.vel_emb1(gps)
@@ -365,6 +378,8 @@ class Encoder(nn.Module):
         g = self.vel_emb4(g)
         f_img, f_lid, f_rad, g = self.transformer4.fuse(f_img, f_lid, f_rad, g)
 
+        if getattr(cfg, "fused_stem_tail", True) and pooled_tail_supported(f_img, f_lid, f_rad, g):
+            return pooled_tail(f_img, f_lid, f_rad, g, bz)  # avgpool + flatten + cat + sum (:581-595) in one launch
         p_img = torch.flatten(ie.avgpool(f_img), 1).view(bz, V * S, -1)
         p_lid = torch.flatten(le.avgpool(f_lid), 1).view(bz, S, -1)
         p_rad = torch.flatten(re_.avgpool(f_rad), 1).view(bz, S, -1)

@@ -213,6 +213,29 @@ int dsf_upsample_add_fwd(const dsf_geom* g, const float* y, const void* img, con
 int dsf_upsample_add_bwd(const dsf_geom* g, const void* dout_img, const void* dout_lidar,
                          const void* dout_radar, const float* dgps_out, float* dy, void* stream);
 
+/* Input stem of one trunk.  Replaces, in ONE pass over the frames: normalize_imagenet
+ * (model2_seq.py:36-45, applied at :481-482), torch.stack(frames, dim=1).view(B*n_frames, C_in, H, W) (:491-493) and the
+ * dtype / layout change conv1 wants under autocast with channels_last weights.
+ *   frames   HOST array of n_frames (<= 16) DEVICE pointers, each a contiguous fp32 (B, C_in, H, W) tensor, C_in in 1..3
+ *   scale, shift   HOST arrays of C_in floats (NULL = 1 / 0): out = x * scale[c] + shift[c]
+ *                  (ImageNet: scale = 1 / (255 std), shift = -mean / std)
+ *   out      (B*n_frames, C_in, H, W) in out_dtype (DSF_F32 / DSF_BF16); out_layout DSF_NCHW = contiguous, DSF_NHWC =
+ *            channels_last storage; stacked frame index = b * n_frames + t                                                */
+int dsf_stem_pack(const void* const* frames, int32_t n_frames, int32_t B, int32_t C_in, int32_t H, int32_t W,
+                  const float* scale, const float* shift, void* out, int32_t out_dtype, int32_t out_layout, void* stream);
+
+/* Pooled tail of Encoder.forward (model2_seq.py:581-595): AdaptiveAvgPool2d((1,1)) of the three stage-4 maps + flatten + view +
+ * cat with the GPS tokens + sum over the rows, and its autograd (train2_seq.py:127).
+ *   img (B*frames_img, C, H, W), lidar (B*frames_lidar, ...), radar (B*frames_radar, ...)  [feat_dtype, layout]
+ *   gps (B, 2, C) fp32  ->  fused[b, c] = sum_maps sum_frames mean_px f[(b, t), c, :, :] + gps[b, 0, c] + gps[b, 1, c]   (B, C) fp32
+ *   backward: d f[(b, t), c, y, x] = dfused[b, c] / (H*W)  [feat_dtype, layout],  dgps[b, j, c] = dfused[b, c]              */
+int dsf_tail_fwd(const void* img, const void* lidar, const void* radar, const float* gps, float* fused, int32_t B,
+                 int32_t frames_img, int32_t frames_lidar, int32_t frames_radar, int32_t C, int32_t H, int32_t W,
+                 int32_t feat_dtype, int32_t layout, void* stream);
+int dsf_tail_bwd(const float* dfused, void* dimg, void* dlidar, void* dradar, float* dgps, int32_t B, int32_t frames_img,
+                 int32_t frames_lidar, int32_t frames_radar, int32_t C, int32_t H, int32_t W, int32_t feat_dtype,
+                 int32_t layout, void* stream);
+
 /* Narrow stages (n_embd = 64 or 128): the row-local chain between two attention calls as ONE launch —
  *   x_mid = x_in + y Wp^T + bp                      proj + residual                (model2_seq.py:109, 131)
  *   h2 = LayerNorm(x_mid; ln2), a = ReLU(h2 W1^T + b1), x_out = x_mid + a W2^T + b2   (:119, 121-126, 132)

@@ -537,3 +537,60 @@ def test_chain_fwd_matches_the_separate_operators(K, cuda_dev, M, C, last):
     else:
         assert_close(hn.float(), r_n, 6e-3, 1e-3, "h_next (bf16)")
         assert_close(qkv.float(), hn.float() @ wq.float().t() + bq, 6e-3, 1e-3, "qkv_next (bf16)")
+
+
+# ---------------------------------------------------------------------------------------------- stem / tail of Encoder.forward
+@pytest.mark.parametrize("cin,normalize", [(3, True), (1, False), (2, False), (3, False)])
+@pytest.mark.parametrize("out", ["f32_nchw", "f32_nhwc", "bf16_nhwc", "bf16_nchw"])
+def test_stem_pack_matches_normalize_stack_view(K, cuda_dev, cin, normalize, out):
+    """dsf_stem_pack vs the reference's op sequence (model2_seq.py:36-45, 481-482, 491-493) as restated in oracle/model_ref.py."""
+    from deepsense6g_tii_b200 import functional as Fn
+    from oracle import model_ref as MR
+    B, S, H, W = 3, 5, 24, 20
+    g = _gen(7)
+    frames = [(torch.rand(B, cin, H, W, generator=g) * 255.0).to(cuda_dev) for _ in range(S)]
+    ref_frames = [MR.normalize_imagenet(f) for f in frames] if normalize else frames
+    ref = torch.stack(ref_frames, dim=1).view(B * S, cin, H, W)
+    dtype = torch.bfloat16 if out.startswith("bf16") else torch.float32
+    assert Fn.stem_pack_supported(frames)
+    got = Fn.stem_pack(frames, normalize, dtype, out.endswith("nhwc"))
+    assert got.shape == ref.shape and got.dtype == dtype
+    if out.endswith("nhwc") and cin > 1:
+        assert got.is_contiguous(memory_format=torch.channels_last)
+    else:
+        assert got.is_contiguous()
+    if dtype == torch.float32:
+        assert_close(got, ref, 2e-6, msg="stem_pack fp32")     # x*a + b against (x/255 - mean)/std: a few ulp
+    else:
+        assert torch.equal(got, got.float().to(torch.bfloat16))
+        assert_close(got.float(), ref, 4e-3, msg="stem_pack bf16")  # one bf16 rounding
+    assert not Fn.stem_pack_supported([f.requires_grad_(True) for f in frames[:1]])
+
+
+@pytest.mark.parametrize("variant", ["nchw_f32", "nhwc_f32", "nchw_bf16", "nhwc_bf16"])
+@pytest.mark.parametrize("shape", [(2, 5, 1, 512, 8), (3, 2, 2, 64, 6), (1, 5, 1, 40, 4)])
+def test_pooled_tail_fwd_bwd(K, cuda_dev, variant, shape):
+    """dsf_tail_fwd / dsf_tail_bwd vs avgpool -> flatten -> view -> cat(gps) -> sum (model2_seq.py:581-595) and its autograd."""
+    from deepsense6g_tii_b200 import functional as Fn
+    B, S, V, C, H = shape
+    g = _gen(11)
+    nhwc, dt = variant.startswith("nhwc"), torch.bfloat16 if variant.endswith("bf16") else torch.float32
+    maps = [_feat(B * n, C, H, H, g, cuda_dev, dt, nhwc).requires_grad_(True) for n in (V * S, S, S)]
+    gps = torch.randn(B, 2, C, generator=g).to(cuda_dev).requires_grad_(True)
+    assert Fn.pooled_tail_supported(maps[0], maps[1], maps[2], gps)
+    fused = Fn.pooled_tail(maps[0], maps[1], maps[2], gps, B)
+    dfused = torch.randn(B, C, generator=g).to(cuda_dev)
+    fused.backward(dfused)
+    got = [fused.detach()] + [m.grad.float() for m in maps] + [gps.grad]
+    for m in maps:
+        assert m.grad.dtype == dt and m.grad.stride() == m.stride()
+    ref_maps = [m.detach().double().requires_grad_(True) for m in maps]
+    ref_gps = gps.detach().double().requires_grad_(True)
+    pool = torch.nn.AdaptiveAvgPool2d((1, 1))
+    rows = [torch.flatten(pool(m), 1).view(B, -1, C) for m in ref_maps] + [ref_gps]
+    ref = torch.cat(rows, dim=1).sum(dim=1)
+    ref.backward(dfused.double())
+    want = [ref.detach()] + [m.grad for m in ref_maps] + [ref_gps.grad]
+    tol = 1e-5 if dt == torch.float32 else 4e-3  # bf16: the gradient maps are rounded to bf16 once
+    for name, a, b in zip(["fused", "dimg", "dlidar", "dradar", "dgps"], got, want):
+        assert_close(a.double(), b, 1e-5 if name in ("fused", "dgps") else tol, msg="pooled tail %s" % name)

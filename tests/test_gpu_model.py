@@ -207,3 +207,35 @@ def test_training_steps_with_dropout_reduce_the_focal_loss(cuda_dev):
     assert losses[-1] < 0.6 * losses[0], losses
     assert all(torch.isfinite(p).all() for p in m.parameters())
     assert all(torch.isfinite(t).all() for t in ema.shadow.values())
+
+
+@pytest.mark.parametrize("nhwc_bf16", [False, True], ids=["fp32_nchw", "autocast_channels_last"])
+def test_encoder_runs_the_fused_stem_and_tail(cuda_dev, nhwc_bf16):
+    """normalize_imagenet + stack + view (model2_seq.py:481-493) is one dsf_stem_pack launch per trunk and
+    avgpool + flatten + cat + sum (:581-595) one dsf_tail_fwd / dsf_tail_bwd launch; logits and the conv1 / vel_emb4 gradients
+    equal the op-by-op sequence (config.fused_stem_tail = False)."""
+    from deepsense6g_tii_b200 import _capi as K
+    m = _build(cuda_dev, torch.float32, n_layer=1).train()
+    if nhwc_bf16:
+        m = m.to(memory_format=torch.channels_last)
+    ins = _inputs(2, cuda_dev, seed=9)
+    watch = ["encoder.image_encoder.features.conv1.weight", "encoder.lidar_encoder._model.conv1.weight", "encoder.vel_emb4.weight",
+             "encoder.radar_encoder._model.layer4.1.conv2.weight"]
+    res = {}
+    for fused in (True, False):
+        m.config.fused_stem_tail = fused
+        m.zero_grad(set_to_none=True)
+        n0 = K.launch_count()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=nhwc_bf16):
+            out = m(*ins)
+        n_fwd = K.launch_count() - n0
+        out.float().square().mean().backward()
+        n_all = K.launch_count() - n0
+        p = dict(m.named_parameters())
+        res[fused] = (out.detach().float(), {k: p[k].grad.detach().float().clone() for k in watch}, n_fwd, n_all)
+    assert res[True][2] - res[False][2] == 4, "3 x dsf_stem_pack + dsf_tail_fwd in the forward"
+    assert res[True][3] - res[False][3] == 5, "+ dsf_tail_bwd in the backward"
+    tol = 3e-2 if nhwc_bf16 else 1e-4   # bf16 trunks: the two arms round the trunk inputs / pooled sums at different points
+    assert_close(res[True][0], res[False][0], tol, 1e-6, "logits fused vs op-by-op")
+    for k in watch:
+        assert_close(res[True][1][k], res[False][1][k], tol * (4 if nhwc_bf16 else 1), 1e-7, k)
