@@ -43,6 +43,52 @@ __device__ __forceinline__ float ex2_approx(float x) {  // 2^x, MUFU.EX2 without
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2: two lanes of fp32 per instruction, half the issue slots of the scalar forms)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// 2^x for a pair on the FMA / ALU pipes instead of MUFU.EX2 (the forward kernel's softmax is MUFU-bound: 64 exponentials per
+// row and tile against 16 per clock and SM).  Cody-Waite: n = round(x) via the 1.5 * 2^23 trick, f = x - n in [-0.5, 0.5],
+// 2^f by a cubic (max relative error 7.5e-5 — the result is rounded to bf16, 2e-3, right after), n added into the exponent field.
+__device__ __forceinline__ void ex2_poly2(uint64_t x, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  const uint64_t xc = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t t = add2(xc, pack2(12582912.f, 12582912.f));
+  const uint64_t r = add2(t, pack2(-12582912.f, -12582912.f));
+  const uint64_t f = fma2(r, pack2(-1.f, -1.f), xc);
+  uint64_t q = fma2(f, pack2(0.05517164617776871f, 0.05517164617776871f), pack2(0.2426111251115799f, 0.2426111251115799f));
+  q = fma2(q, f, pack2(0.6932609677314758f, 0.6932609677314758f));
+  q = fma2(q, f, pack2(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, t0, t1;
+  unpack2(q, q0, q1);
+  unpack2(t, t0, t1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
+// 2^x of a packed pair: pair number j of a tile goes to the polynomial when POLY > 0 and j % POLY == POLY - 1, else to MUFU.EX2
+template <int POLY>
+__device__ __forceinline__ uint64_t ex2_pair(uint64_t x, int j) {
+  float p0, p1;
+  if (POLY > 0 && (j % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+    ex2_poly2(x, p0, p1);
+  } else {
+    float x0, x1;
+    unpack2(x, x0, x1);
+    p0 = ex2_approx(x0);
+    p1 = ex2_approx(x1);
+  }
+  return pack2(p0, p1);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_pair(uint64_t v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+
 // Attention-probability dropout (attn_drop, model2_seq.py:104).  Decisions use 8-bit thresholds (p is quantised to
 // k/256, scale = 256/(256-k)) so that one Philox4x32 call yields 16 of them; the forward kernel writes the keep
 // bits of every (b, h, q) row to a bitmap (Tw 32-bit words per row) and the backward kernels read them back.
@@ -232,7 +278,8 @@ struct BwdKV2 {
   static int dyn_bytes(int T) { return STAT_OFF + 2 * cdiv(T, BQ) * BQ * 4 + 1024; }
 };
 
-template <int HS, int BQ, int ST, int NP, bool DROP>
+// POLY: every POLY-th pair of exponentials on the FMA pipe (ex2_poly2); the dropout-free math runs on packed fp32 pairs.
+template <int HS, int BQ, int ST, int NP, bool DROP, int POLY>
 __global__ void __launch_bounds__(256 * NP + 64, 1)
 attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
@@ -328,12 +375,12 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     const int kw = kv0 / 32 + (warp & 3);  // bitmap word holding this warp's 32 keys
     // lse (log2 units) and delta of every query of this (batch, head) are copied to shared memory ONCE by the math warps
     // (2 x 4 B x T: 7.7 KB at T = 962, 31 KB at T = 3842); tiles then read them with broadcast 16-byte loads.  (Staging them per
-    // tile and warp cost ~250 of the ~1200 cycles a math warp spends on a tile.)  Padding queries get lse = +inf -> P = 0.
+    // tile and warp cost ~250 of the ~1200 cycles a math warp spends on a tile.)  Padding queries get lse = +inf -> P = 0.  Both are stored negated.
     float* s_lse = reinterpret_cast<float*>(smem + L::STAT_OFF);
     float* s_delta = s_lse + n_q * BQ;
     for (int idx = threadIdx.x; idx < n_q * BQ; idx += 256 * NP) {
-      s_lse[idx] = idx < T ? __ldg(lse_g + idx) * 1.4426950408889634f : INFINITY;
-      s_delta[idx] = idx < T ? __ldg(delta_g + idx) : 0.f;
+      s_lse[idx] = idx < T ? __ldg(lse_g + idx) * -1.4426950408889634f : -INFINITY;  // NEGATED: x = s * c + (-lse), d = p * (dp + (-delta))
+      s_delta[idx] = idx < T ? -__ldg(delta_g + idx) : 0.f;
     }
     // attn-dropout: keep word of query (tile * BQ + wg * 32 + lane) over this warp's 32 keys, fetched one own tile ahead
     uint32_t wv = 0xFFFFFFFFu;
@@ -363,29 +410,40 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       tmem_ld32(tm_s, rs);
       tmem_ld32(tm_dp, rp);
       tmem_wait_ld();
+      const uint64_t sc2 = pack2(scale_log2, scale_log2);
 #pragma unroll
       for (int c = 0; c < 32; c += 16) {
         uint32_t pk[8], dk[8];
 #pragma unroll
         for (int e = 0; e < 16; e += 4) {
+          // rows of keys >= T hold finite garbage (K, V rows are zero-filled): they only reach the dK / dV rows of those
+          // keys, which are never stored.  The 1/sqrt(hs) factor of dS is applied once when dK is drained.
+          if (!DROP) {  // packed pairs: FFMA2 / FADD2 / FMUL2, two queries per instruction
+            const ulonglong2 nl = *reinterpret_cast<const ulonglong2*>(wst + c + e);  // -lse of queries c+e .. c+e+3
+            const ulonglong2 nd = *reinterpret_cast<const ulonglong2*>(wsd + c + e);  // -delta
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+              const uint64_t x = fma2(pack2(__uint_as_float(rs[c + e + u]), __uint_as_float(rs[c + e + u + 1])), sc2, u ? nl.y : nl.x);
+              const uint64_t p2 = ex2_pair<POLY>(x, (c + e + u) / 2);
+              const uint64_t t2 = add2(pack2(__uint_as_float(rp[c + e + u]), __uint_as_float(rp[c + e + u + 1])), u ? nd.y : nd.x);
+              pk[(e + u) / 2] = pack_bf16x2_pair(p2);
+              dk[(e + u) / 2] = pack_bf16x2_pair(mul2(p2, t2));
+            }
+            continue;
+          }
           const float4 l4 = *reinterpret_cast<const float4*>(wst + c + e);
           const float4 d4 = *reinterpret_cast<const float4*>(wsd + c + e);
           const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
           float p[4], d[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            // rows of keys >= T hold finite garbage (K, V rows are zero-filled): they only reach the dK / dV rows of those
-            // keys, which are never stored.  The 1/sqrt(hs) factor of dS is applied once when dK is drained.
-            p[u] = ex2_approx(fmaf(__uint_as_float(rs[c + e + u]), scale_log2, -ls[u]));
+            p[u] = ex2_approx(fmaf(__uint_as_float(rs[c + e + u]), scale_log2, ls[u]));
             float dp = __uint_as_float(rp[c + e + u]);
-            if (DROP) {  // attn_drop: dV sees P*mask/(1-p); dP = dP_drop*mask/(1-p)
-              const float m = (__shfl_sync(0xffffffffu, myw, c + e + u) >> lane) & 1u ? ad.scale : 0.f;
-              dp *= m;
-              d[u] = p[u] * (dp - dl[u]);
-              p[u] *= m;
-            } else {
-              d[u] = p[u] * (dp - dl[u]);
-            }
+            // attn_drop: dV sees P*mask/(1-p); dP = dP_drop*mask/(1-p)
+            const float m = (__shfl_sync(0xffffffffu, myw, c + e + u) >> lane) & 1u ? ad.scale : 0.f;
+            dp *= m;
+            d[u] = p[u] * (dp + dl[u]);
+            p[u] *= m;
           }
           pk[e / 2] = pack_bf16x2(p[0], p[1]);
           pk[e / 2 + 1] = pack_bf16x2(p[2], p[3]);
@@ -445,7 +503,7 @@ struct BwdQ2 {
 // operands.  A tcgen05.mma whose A operand comes from shared memory spends ~128 cycles fetching its 128 x 16 slice whatever
 // N is, so the 64-wide S / dP MMAs ran at a quarter of the tensor pipe's rate; from tensor memory they are N-bound.
 // NP = math warpgroup pairs, as in the dK/dV kernel: pair p owns the key tiles j = p (mod 2).
-template <int HS, int ST, bool AT, int NP, bool DROP>
+template <int HS, int ST, bool AT, int NP, bool DROP, int POLY>
 __global__ void __launch_bounds__(256 * NP + 64, 1)
 attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmKV,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int T, int C, int nh,
@@ -585,12 +643,14 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int c = 0; c < 32; c += 16) {
         uint32_t dk[8];
         // the 1/sqrt(hs) factor of dS is applied once when dQ is drained
-        if (full && !DROP) {
+        if (full && !DROP) {  // packed pairs: FFMA2 / FADD2 / FMUL2, two keys per instruction
+          const uint64_t sc2 = pack2(scale_log2, scale_log2), nl2 = pack2(-my_lse, -my_lse), nd2 = pack2(-my_delta, -my_delta);
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(rs[c + e]), scale_log2, -my_lse));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(rs[c + e + 1]), scale_log2, -my_lse));
-            dk[e / 2] = pack_bf16x2(p0 * (__uint_as_float(rp[c + e]) - my_delta), p1 * (__uint_as_float(rp[c + e + 1]) - my_delta));
+            const uint64_t x = fma2(pack2(__uint_as_float(rs[c + e]), __uint_as_float(rs[c + e + 1])), sc2, nl2);
+            const uint64_t p2 = ex2_pair<POLY>(x, (c + e) / 2);
+            const uint64_t t2 = add2(pack2(__uint_as_float(rp[c + e]), __uint_as_float(rp[c + e + 1])), nd2);
+            dk[e / 2] = pack_bf16x2_pair(mul2(p2, t2));
           }
         } else {
           const int k0 = kv0 + wg * 32 + c;  // first key of this sub-chunk
@@ -663,7 +723,8 @@ struct Fwd3 {
 // over the S tile they came from and P.V runs with its A operand in tensor memory (tcgen05.mma [d], [a], b-desc).
 // PP = true (experiment, DSF_ATTN_PINGPONG=1): the two softmax warpgroups take turns in the exponential phase (named
 // barriers 3 / 4) so that one warpgroup's MUFU.EX2 work runs under the other's max / rescale bookkeeping.
-template <int HS, int KST, int VST, bool PT, bool PP, int NWG = 2>
+// POLY > 0: every POLY-th pair of probabilities of a full, dropout-free tile is exponentiated by ex2_poly2 instead of MUFU.EX2.
+template <int HS, int KST, int VST, bool PT, bool PP, int NWG = 2, int POLY = 0>
 __global__ void __launch_bounds__(128 * NWG + 64, NWG == 1 ? 2 : 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, __nv_bfloat16* __restrict__ y,
                  float* __restrict__ lse, int T, int C, int nh, float scale_log2, AttnDrop ad) {
@@ -825,6 +886,35 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const bool full = kv0 + BKV <= T;
       const int qrow = q0 + 128 * w + row;
       const uint64_t rowid = ((uint64_t)b * nh + h) * T + qrow;
+      if (POLY > 0 && PT && full && !ad.thresh8) {
+        // packed fast path: x = s * scale - m as FFMA2, the row sum as FADD2, every POLY-th pair off the MUFU pipe
+        const uint64_t sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_run, -m_run);
+        uint64_t lsum = pack2(0.f, 0.f);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint32_t a0 = half ? r1[i] : r0[i], a1 = half ? r1[i + 1] : r0[i + 1];
+            const uint64_t x = fma2(pack2(__uint_as_float(a0), __uint_as_float(a1)), sc2, nm2);
+            float p0, p1;
+            if (((i / 2) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+              ex2_poly2(x, p0, p1);
+            } else {
+              float x0, x1;
+              unpack2(x, x0, x1);
+              p0 = ex2_approx(x0);
+              p1 = ex2_approx(x1);
+            }
+            lsum = add2(lsum, pack2(p0, p1));
+            pk[i / 2] = pack_bf16x2(p0, p1);
+          }
+          tmem_st16(tm_s + half * 16, pk);
+        }
+        float l0, l1;
+        unpack2(lsum, l0, l1);
+        l_add = l0 + l1;
+      } else
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t keepw = 0xFFFFFFFFu;
@@ -909,14 +999,20 @@ static int make_tmap3(CUtensorMap* m, const void* base, int ncols, int T, int B,
   return DSF_OK;
 }
 
-template <int HS, int KST, int VST, int NWG>
-static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const AttnDrop& ad, cudaStream_t st) {
+// Exponentials of the forward kernel moved from MUFU.EX2 to the FMA pipe (ex2_poly2): every 3rd pair at head sizes <= 64, every 4th
+// at 128.  Measured on B200 (scripts/bench_attn_parts.py, batch 12, T = 962; profiles/r02ah_attn_exp_poly.txt), none / every 4th / 3rd /
+// 2nd pair: hs 16: 28.1 / 25.2 / 24.4 / 25.3 us, hs 32: 28.6 / 25.5 / 24.8 / 25.5, hs 64: 30.3 / 27.0 / 27.1 / 27.8, hs 128: 35.4 / 34.8 /
+// 35.7 / 35.1 us; T = 3842, hs 128: 64.9 / 55.0 / 56.0 / 57.4 us (932 -> 1099 TF/s).  DSF_ATTN_EXP_POLY=0 keeps every exponential on MUFU.
+static const bool g_attn_exp_poly = getenv("DSF_ATTN_EXP_POLY") ? atoi(getenv("DSF_ATTN_EXP_POLY")) != 0 : true;
+
+template <int HS, int KST, int VST, int NWG, int POLY>
+static int launch_fwd3p(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const AttnDrop& ad, cudaStream_t st) {
   using L = Fwd3<HS, KST, VST, NWG, true>;
   using H = HeadCfg<HS>;
   static bool configured_on[64] = {};
   bool& configured = per_device_flag(configured_on);
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, true, false, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fwd3_kernel<HS, KST, VST, true, false, NWG, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN) != cudaSuccess)
       return check_launch("attn_fwd3/attr");
     configured = true;
   }
@@ -925,9 +1021,17 @@ static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C
   if (int e = make_tmap3(&tmKV, qkv, 3 * C, T, B, H::BOXC, L::BKV)) return e;
   const float scale_log2 = (1.0f / sqrtf((float)HS)) * 1.4426950408889634f;
   dim3 grid(cdiv(T, 128 * NWG), nh, B);
-  launch_pdl(attn_fwd3_kernel<HS, KST, VST, true, false, NWG>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh, scale_log2,
-             ad);
+  launch_pdl(attn_fwd3_kernel<HS, KST, VST, true, false, NWG, POLY>, grid, dim3(L::THREADS), L::DYN, st, tmQ, tmKV, (__nv_bfloat16*)y, lse, T, C, nh,
+             scale_log2, ad);
   return check_launch("attn_fwd3");
+}
+
+template <int HS, int KST, int VST, int NWG>
+static int launch_fwd3(const void* qkv, void* y, float* lse, int B, int T, int C, int nh, const AttnDrop& ad, cudaStream_t st) {
+  if constexpr (NWG == 1) {  // the default 128-row CTAs
+    if (g_attn_exp_poly) return launch_fwd3p<HS, KST, VST, NWG, (HS >= 128 ? 4 : 3)>(qkv, y, lse, B, T, C, nh, ad, st);
+  }
+  return launch_fwd3p<HS, KST, VST, NWG, 0>(qkv, y, lse, B, T, C, nh, ad, st);
 }
 
 int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, int C, int nh, cudaStream_t st);  // attn_api.cu
@@ -940,8 +1044,12 @@ static const bool g_attn_a_in_tmem = getenv("DSF_ATTN_A_TMEM") ? atoi(getenv("DS
 // 27.9 / 30.5 / 35.6 / 45.6 against 26.3 / 28.2 / 32.9 / 45.5 us: once the statistics staging and the redundant buffer wait were gone
 // the second pair only added contention.
 constexpr int kBwdPairs = 1;
+// The backward kernels keep every exponential on MUFU.EX2 (template parameter POLY = 0): they run 32 exponentials per thread and tile
+// against the forward's 64 and are bound by the per-tile latency chain, not by the MUFU pipe — with every 3rd pair on the FMA pipe the
+// dK/dV kernel measured 30.2 / 32.7 / 41.9 / 62.9 us against 28.4 / 31.6 / 41.4 / 60.3 us (head size 16 / 32 / 64 / 128, batch 12,
+// T = 962; profiles/r02ai_attn_bwd_poly.txt).  The packed-pair arithmetic (FFMA2 / FADD2 / FMUL2) stays: -1.3 / -1.8 us at 16 / 32.
 
-template <int HS, int BQ, int STA, int NP, bool DROP>
+template <int HS, int BQ, int STA, int NP, bool DROP, int POLY>
 static int launch_bwd_kv(const CUtensorMap& tmKV128, const CUtensorMap& tmQs, const CUtensorMap& tmDOs, const float* lse, const float* delta, void* dqkv,
                          dim3 grid, int T, int C, int nh, float scale, const AttnDrop& ad, cudaStream_t st) {
   using LA = BwdKV2<HS, BQ, STA, NP>;
@@ -950,27 +1058,27 @@ static int launch_bwd_kv(const CUtensorMap& tmKV128, const CUtensorMap& tmQs, co
   static bool configured_on[64] = {};
   bool& configured = per_device_flag(configured_on);
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, NP, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_bwd_kv2_kernel<HS, BQ, STA, NP, DROP, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448) != cudaSuccess)
       return check_launch("attn_bwd2/kv/attr");
     configured = true;
   }
-  launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, NP, DROP>, grid, dim3(LA::THREADS), dyn, st, tmKV128, tmQs, tmDOs, lse, delta, (__nv_bfloat16*)dqkv, T, C,
+  launch_pdl(attn_bwd_kv2_kernel<HS, BQ, STA, NP, DROP, POLY>, grid, dim3(LA::THREADS), dyn, st, tmKV128, tmQs, tmDOs, lse, delta, (__nv_bfloat16*)dqkv, T, C,
              nh, scale, ad);
   return check_launch("attn_bwd2/kv");
 }
 
-template <int HS, int STB, bool AT, int NP, bool DROP>
+template <int HS, int STB, bool AT, int NP, bool DROP, int POLY>
 static int launch_bwd_q(const CUtensorMap& tmQ128, const CUtensorMap& tmDO128, const CUtensorMap& tmKV64, const float* lse, const float* delta, void* dqkv,
                         dim3 grid, int T, int C, int nh, float scale, const AttnDrop& ad, const void* qkv, const void* dy, cudaStream_t st) {
   using LB = BwdQ2<HS, STB>;
   static bool configured_on[64] = {};
   bool& configured = per_device_flag(configured_on);
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, AT, NP, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_bwd_q2_kernel<HS, STB, AT, NP, DROP, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB::DYN) != cudaSuccess)
       return check_launch("attn_bwd2/q/attr");
     configured = true;
   }
-  launch_pdl(attn_bwd_q2_kernel<HS, STB, AT, NP, DROP>, grid, dim3(256 * NP + 64), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, delta, (__nv_bfloat16*)dqkv, T,
+  launch_pdl(attn_bwd_q2_kernel<HS, STB, AT, NP, DROP, POLY>, grid, dim3(256 * NP + 64), LB::DYN, st, tmQ128, tmDO128, tmKV64, lse, delta, (__nv_bfloat16*)dqkv, T,
              C, nh, scale, ad, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dy);
   return check_launch("attn_bwd2/q");
 }
@@ -990,8 +1098,8 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
     if (int e = make_tmap3(&tmKV128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
     if (int e = make_tmap3(&tmQs, qkv, 3 * C, T, B, H::BOXC, BQ)) return e;
     if (int e = make_tmap3(&tmDOs, dy, C, T, B, H::BOXC, BQ)) return e;
-#define DSF_KV(DROP) launch_bwd_kv<HS, BQ, STA, kBwdPairs, DROP>(tmKV128, tmQs, tmDOs, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, st)
-    if (int e = drop ? DSF_KV(true) : DSF_KV(false)) return e;
+#define DSF_KV(DROP, POLY) launch_bwd_kv<HS, BQ, STA, kBwdPairs, DROP, POLY>(tmKV128, tmQs, tmDOs, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, st)
+    if (int e = drop ? DSF_KV(true, 0) : DSF_KV(false, 0)) return e;
 #undef DSF_KV
   }
   if (parts & 4) {
@@ -999,10 +1107,10 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
     if (int e = make_tmap3(&tmQ128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
     if (int e = make_tmap3(&tmDO128, dy, C, T, B, H::BOXC, 128)) return e;
     if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
-#define DSF_Q(AT, DROP) launch_bwd_q<HS, STB, AT, kBwdPairs, DROP>(tmQ128, tmDO128, tmKV64, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, qkv, dy, st)
+#define DSF_Q(AT, DROP, POLY) launch_bwd_q<HS, STB, AT, kBwdPairs, DROP, POLY>(tmQ128, tmDO128, tmKV64, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, qkv, dy, st)
     int e;
-    if (g_attn_a_in_tmem) e = drop ? DSF_Q(true, true) : DSF_Q(true, false);
-    else e = drop ? DSF_Q(false, true) : DSF_Q(false, false);
+    if (g_attn_a_in_tmem) e = drop ? DSF_Q(true, true, 0) : DSF_Q(true, false, 0);
+    else e = drop ? DSF_Q(false, true, 0) : DSF_Q(false, false, 0);
 #undef DSF_Q
     if (e) return e;
   }
