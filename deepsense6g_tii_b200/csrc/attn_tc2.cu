@@ -191,10 +191,10 @@ __device__ __forceinline__ void mma_over_rows(uint32_t tmem_d, uint32_t p_tile, 
 }
 
 // D[128 x HS] (+)= P(tensor memory, [128 x KC] bf16 packed two per column at p_tmem) . B(tile with KC rows, MN-major)
-// SPLIT = false: the packed columns are contiguous (8 per K = 16 step).  SPLIT = true (backward kernels): the two math
-// warpgroups each overwrite the first 16 columns of their own 32-column region of the fp32 tile, so K-steps 0,1 sit at
-// columns 0 / 8 and K-steps 2,3 at columns 32 / 40.
-template <int HS, int KC, bool SPLIT = false>
+// CW = 0: the packed columns are contiguous (8 per K = 16 step).  CW = 32 / 16 (backward kernels): every math warpgroup owns CW
+// fp32 columns of the tile and overwrites the first CW / 2 of them with its packed values, so K-step kk (16 values = 8 packed
+// columns) sits at column (16 kk / CW) * CW + (16 kk % CW) / 2: 0, 8, 32, 40 for CW = 32 and 0, 16, 32, 48 for CW = 16.
+template <int HS, int KC, int CW = 0>
 __device__ __forceinline__ void mma_over_rows_ts(uint32_t tmem_d, uint32_t p_tmem, uint32_t b_tile, uint32_t idesc, bool accumulate) {
   using H = HeadCfg<HS>;
   const uint64_t db = make_smem_desc(b_tile, (uint32_t)KC * H::ROWB, 8 * H::ROWB, H::SWZ);
@@ -202,7 +202,7 @@ __device__ __forceinline__ void mma_over_rows_ts(uint32_t tmem_d, uint32_t p_tme
   if (elect_one()) {
 #pragma unroll
     for (int kk = 0; kk < KC / 16; ++kk) {
-      const uint32_t col = SPLIT ? (uint32_t)((kk / 2) * 32 + (kk % 2) * 8) : (uint32_t)(kk * 8);
+      const uint32_t col = CW > 0 ? (uint32_t)((kk * 16 / (CW > 0 ? CW : 1)) * CW + (kk * 16 % (CW > 0 ? CW : 1)) / 2) : (uint32_t)(kk * 8);
       tc_mma_bf16_ts(tmem_d, p_tmem + col, db + (uint32_t)((kk * 16 * H::ROWB) >> 4), idesc, kk == 0 ? acc : 1u);
     }
   }
@@ -259,12 +259,10 @@ __device__ __forceinline__ void store_row16_bf16(__nv_bfloat16* dst, const uint3
 // TS-mode A operands; per-query statistics (lse, delta) are staged per WARP in shared memory (each lane fetches one pair a
 // tile ahead, a __syncwarp publishes them), so the math warps never meet at a CTA-wide barrier inside the loop.
 //
-// NP = math warpgroup PAIRS.  A pair (2 x 128 threads) splits a tile's 64 query columns in two halves.  The in-kernel timeline
-// (profiles/r01v_attn_timeline.txt) shows the math warps as the critical path at every head size: ~2200 cycles per tile for
-// ~180 instructions per warp, i.e. latency (tcgen05.ld -> MUFU -> tcgen05.st -> wait::st -> mbarrier) with only two warps
-// per SM sub-partition to hide it.  NP = 2: pair p owns the tiles i = p (mod 2) — which is TMEM buffer p — so every tile has
-// two tile periods of math time and four warps per sub-partition overlap each other's latencies; the MMA / TMA schedule and
-// every mbarrier count are unchanged (ds_full[bf] still collects 256 arrivals, all from pair bf).
+// NP = math warpgroup PAIRS: 2 NP warpgroups of 128 threads split a tile's 64 query columns in 64 / (2 NP) = 32 or 16 columns
+// each (all of them work on EVERY tile).  The in-kernel timeline shows the math warps as the critical path at head sizes <= 64:
+// the same warps take tile after tile, so a tile costs their whole latency chain (tcgen05.ld -> MUFU -> tcgen05.st -> wait::st ->
+// mbarrier) — halving the columns per warp shortens that chain; the MMA / TMA schedule is unchanged (ds_full collects 256 NP arrivals).
 template <int HS, int BQ, int ST, int NP>
 struct BwdKV2 {
   static constexpr int KV_BYTES = 128 * HS * 2, Q_BYTES = BQ * HS * 2;
@@ -301,7 +299,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     mbar_init(kv_full, 1);
     mbar_init(acc_done, 1);
     for (int s = 0; s < ST; ++s) { mbar_init(q_full + 8 * s, 1); mbar_init(q_empty + 8 * s, 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256 * NP); }
     fence_barrier_init();
   }
   if (warp == MMAW) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -354,23 +352,23 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         mbar_wait(ds_full + 8 * bf, (i >> 1) & 1);
         TRACE(2, i, 3);
         tc_fence_after();
-        mma_over_rows_ts<HS, BQ, true>(tm_dv, tmem_base + bf * 2 * BQ, sbase + L::DO_OFF + st * L::Q_BYTES, idesc_g, i > 0);
-        mma_over_rows_ts<HS, BQ, true>(tm_dk, tmem_base + bf * 2 * BQ + BQ, sbase + L::Q_OFF + st * L::Q_BYTES, idesc_g, i > 0);
+        mma_over_rows_ts<HS, BQ, 32 / NP>(tm_dv, tmem_base + bf * 2 * BQ, sbase + L::DO_OFF + st * L::Q_BYTES, idesc_g, i > 0);
+        mma_over_rows_ts<HS, BQ, 32 / NP>(tm_dk, tmem_base + bf * 2 * BQ + BQ, sbase + L::Q_OFF + st * L::Q_BYTES, idesc_g, i > 0);
         tc_commit_elect(q_empty + 8 * st);
         TRACE(2, i, 4);
       }
       tc_commit_elect(acc_done);
     }
   } else {
-    const int pair = warp >> 3;      // NP = 2: pair p owns the tiles i = p (mod 2)
-    const int wg = (warp >> 2) & 1;  // the two warpgroups of a pair split the tile's columns
+    constexpr int CW = BQ / (2 * NP);  // query columns of a tile per warpgroup
+    const int wgi = warp >> 2;         // warpgroup 0 .. 2 NP - 1: columns wgi * CW ..
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const bool key_ok = (kv0 + row) < T;
     const float scale_log2 = scale * 1.4426950408889634f;
     const float* lse_g = lse + ((size_t)b * nh + h) * T;
     const float* delta_g = delta + ((size_t)b * nh + h) * T;
-    static_assert(BQ == 64, "the math warps split a 64-query tile in two 32-column halves");
+    static_assert(BQ == 64 && (CW == 32 || CW == 16), "a 64-query tile in 32- or 16-column shares");
     const size_t bh = (size_t)b * nh + h;
     const int kw = kv0 / 32 + (warp & 3);  // bitmap word holding this warp's 32 keys
     // lse (log2 units) and delta of every query of this (batch, head) are copied to shared memory ONCE by the math warps
@@ -382,37 +380,36 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       s_lse[idx] = idx < T ? __ldg(lse_g + idx) * -1.4426950408889634f : -INFINITY;  // NEGATED: x = s * c + (-lse), d = p * (dp + (-delta))
       s_delta[idx] = idx < T ? -__ldg(delta_g + idx) : 0.f;
     }
-    // attn-dropout: keep word of query (tile * BQ + wg * 32 + lane) over this warp's 32 keys, fetched one own tile ahead
+    // attn-dropout: keep word of query (tile * BQ + wgi * CW + lane % CW) over this warp's 32 keys, fetched one tile ahead
     uint32_t wv = 0xFFFFFFFFu;
     auto fetch_w = [&](int it) {
-      const int qq = it * BQ + wg * 32 + lane;
+      const int qq = it * BQ + wgi * CW + (lane % CW);
       wv = qq < T ? ad.bits[(bh * T + qq) * ad.Tw + kw] : 0u;
     };
-    const int i0 = NP == 2 ? pair : 0;
-    if (DROP && i0 < n_q) fetch_w(i0);
+    if (DROP) fetch_w(0);
     named_bar_sync(1, 256 * NP);  // statistics visible to all math warps
-    for (int i = i0; i < n_q; i += NP) {
+    for (int i = 0; i < n_q; ++i) {
       const int bf = i & 1;
-      const float* wst = s_lse + i * BQ + wg * 32;
-      const float* wsd = s_delta + i * BQ + wg * 32;
+      const float* wst = s_lse + i * BQ + wgi * CW;
+      const float* wsd = s_delta + i * BQ + wgi * CW;
       const uint32_t myw = wv;
-      if ((warp & 3) == 0) TRACE(wg, i, 0);
-      if (DROP && i + NP < n_q) fetch_w(i + NP);
-      if ((warp & 3) == 0) TRACE(wg, i, 1);
+      if ((warp & 3) == 0 && wgi < 2) TRACE(wgi, i, 0);
+      if (DROP && i + 1 < n_q) fetch_w(i + 1);
+      if ((warp & 3) == 0 && wgi < 2) TRACE(wgi, i, 1);
       // s_full(i) also says that buffer bf is free: S^T / dP^T (i) were issued after dV / dK (i-2), the MMAs of one thread
       // complete in order, and the commit covers every MMA issued before it
       mbar_wait(s_full + 8 * bf, (i >> 1) & 1);
-      if ((warp & 3) == 0) TRACE(wg, i, 2);
+      if ((warp & 3) == 0 && wgi < 2) TRACE(wgi, i, 2);
       tc_fence_after();
-      if ((warp & 3) == 0) TRACE(wg, i, 3);
-      const uint32_t tm_s = tmem_base + bf * 2 * BQ + lane_off + wg * 32, tm_dp = tm_s + BQ;
-      uint32_t rs[32], rp[32];
-      tmem_ld32(tm_s, rs);
-      tmem_ld32(tm_dp, rp);
+      if ((warp & 3) == 0 && wgi < 2) TRACE(wgi, i, 3);
+      const uint32_t tm_s = tmem_base + bf * 2 * BQ + lane_off + wgi * CW, tm_dp = tm_s + BQ;
+      uint32_t rs[CW], rp[CW];
+      if constexpr (CW == 32) { tmem_ld32(tm_s, rs); tmem_ld32(tm_dp, rp); }
+      else { tmem_ld16(tm_s, rs); tmem_ld16(tm_dp, rp); }
       tmem_wait_ld();
       const uint64_t sc2 = pack2(scale_log2, scale_log2);
 #pragma unroll
-      for (int c = 0; c < 32; c += 16) {
+      for (int c = 0; c < CW; c += 16) {
         uint32_t pk[8], dk[8];
 #pragma unroll
         for (int e = 0; e < 16; e += 4) {
@@ -450,7 +447,7 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           dk[e / 2] = pack_bf16x2(d[0], d[1]);
           dk[e / 2 + 1] = pack_bf16x2(d[2], d[3]);
         }
-        // packed pairs of columns c .. c+15 -> 8 columns at c/2 of this warpgroup's 32-column region (mma_over_rows_ts SPLIT layout);
+        // packed pairs of columns c .. c+15 -> 8 columns at c/2 of this warpgroup's CW-column region (mma_over_rows_ts CW layout);
         // the first store only overwrites columns whose values already sit in registers
         tmem_st8(tm_s + c / 2, pk);
         tmem_st8(tm_dp + c / 2, dk);
@@ -458,23 +455,24 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(ds_full + 8 * bf);
-      if ((warp & 3) == 0) TRACE(wg, i, 4);
+      if ((warp & 3) == 0 && wgi < 2) TRACE(wgi, i, 4);
     }
     mbar_wait(acc_done, 0);
     tc_fence_after();
     const int ld = 3 * C;
     __nv_bfloat16* dk_row = dqkv + ((size_t)b * T + kv0 + row) * ld + C + h * HS;
     __nv_bfloat16* dv_row = dk_row + C;
-    // warpgroup 0 of a pair drains dK, warpgroup 1 dV; with two pairs each takes half of the head's columns (hs = 16: pair 0 only)
+    // even warpgroups drain dK, odd ones dV; with two pairs each takes half of the head's columns (hs = 16: the first pair only)
     constexpr int NSPLIT = (NP == 2 && HS >= 32) ? 2 : 1;
     constexpr int CH = HS / NSPLIT;
-    if (pair < NSPLIT) {
+    const int which = wgi & 1, part = wgi >> 1;
+    if (part < NSPLIT) {
 #pragma unroll 1
-      for (int c = pair * CH; c < (pair + 1) * CH; c += 16) {
+      for (int c = part * CH; c < (part + 1) * CH; c += 16) {
         uint32_t a[16];
-        tmem_ld16((wg == 0 ? tm_dk : tm_dv) + lane_off + c, a);
+        tmem_ld16((which == 0 ? tm_dk : tm_dv) + lane_off + c, a);
         tmem_wait_ld();
-        if (key_ok) store_row16_bf16((wg == 0 ? dk_row : dv_row) + c, a, wg == 0 ? scale : 1.0f);
+        if (key_ok) store_row16_bf16((which == 0 ? dk_row : dv_row) + c, a, which == 0 ? scale : 1.0f);
       }
     }
   }
@@ -502,7 +500,7 @@ struct BwdQ2 {
 // (written once by the math warps straight from global memory) and feed the S = Q K^T and dP = dO V^T MMAs as TS-mode A
 // operands.  A tcgen05.mma whose A operand comes from shared memory spends ~128 cycles fetching its 128 x 16 slice whatever
 // N is, so the 64-wide S / dP MMAs ran at a quarter of the tensor pipe's rate; from tensor memory they are N-bound.
-// NP = math warpgroup pairs, as in the dK/dV kernel: pair p owns the key tiles j = p (mod 2).
+// NP = math warpgroup pairs, as in the dK/dV kernel: 2 NP warpgroups share every key tile (64 / (2 NP) columns each).
 template <int HS, int ST, bool AT, int NP, bool DROP, int POLY>
 __global__ void __launch_bounds__(256 * NP + 64, 1)
 attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmKV,
@@ -527,7 +525,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(q_full, AT ? 256 : 1);
     mbar_init(acc_done, 1);
     for (int s = 0; s < ST; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full + 8 * w, 1); mbar_init(ds_full + 8 * w, 256 * NP); }
     fence_barrier_init();
   }
   if (warp == MMAW) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
@@ -588,14 +586,15 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         mbar_wait(ds_full + 8 * bf, (j >> 1) & 1);
         tc_fence_after();
-        mma_over_rows_ts<HS, BKV, true>(tm_dq, tmem_base + bf * 2 * BKV + BKV, sbase + L::K_OFF + st * L::KV_BYTES, idesc_q, j > 0);
+        mma_over_rows_ts<HS, BKV, 32 / NP>(tm_dq, tmem_base + bf * 2 * BKV + BKV, sbase + L::K_OFF + st * L::KV_BYTES, idesc_q, j > 0);
         tc_commit_elect(kv_empty + 8 * st);
       }
       tc_commit_elect(acc_done);
     }
   } else {
-    const int pair = warp >> 3;      // NP = 2: pair p owns the key tiles j = p (mod 2)
-    const int wg = (warp >> 2) & 1;  // the two warpgroups of a pair split the tile's columns
+    constexpr int CW = BKV / (2 * NP);  // key columns of a tile per warpgroup
+    static_assert(BKV == 64 && (CW == 32 || CW == 16), "a 64-key tile in 32- or 16-column shares");
+    const int wgi = warp >> 2;          // warpgroup 0 .. 2 NP - 1: columns wgi * CW ..
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const int q = q0 + row;
@@ -603,9 +602,9 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float scale_log2 = scale * 1.4426950408889634f;
     const float my_lse = q_ok ? lse[((size_t)b * nh + h) * T + q] * 1.4426950408889634f : INFINITY;
     const float my_delta = q_ok ? delta[((size_t)b * nh + h) * T + q] : 0.f;
-    if (AT && pair == 0) {  // warpgroup 0 parks the Q row of its query in tensor memory, warpgroup 1 the dO row (two bf16 per column)
-      const __nv_bfloat16* src = wg == 0 ? qkv + ((size_t)b * T + q) * (3 * C) + h * HS : dy + ((size_t)b * T + q) * C + h * HS;
-      const uint32_t dst = (wg == 0 ? tm_q : tm_do) + lane_off;
+    if (AT && wgi < 2) {  // warpgroup 0 parks the Q row of its query in tensor memory, warpgroup 1 the dO row (two bf16 per column)
+      const __nv_bfloat16* src = wgi == 0 ? qkv + ((size_t)b * T + q) * (3 * C) + h * HS : dy + ((size_t)b * T + q) * C + h * HS;
+      const uint32_t dst = (wgi == 0 ? tm_q : tm_do) + lane_off;
 #pragma unroll 1
       for (int c = 0; c < HS; c += 32) {
         uint32_t wds[16];
@@ -621,26 +620,24 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       mbar_arrive(q_full);
     }
-    static_assert(BKV == 64, "the math warps split a 64-key tile in two 32-column halves");
-    // attn-dropout keep word of (my query row, keys 32*(2j + wg) ..), fetched one own tile ahead
-    const int j0 = NP == 2 ? pair : 0;
-    const uint32_t* my_bits = (DROP && q_ok) ? ad.bits + (((size_t)b * nh + h) * T + q) * ad.Tw + wg : nullptr;
-    uint32_t wnext = (my_bits && j0 < n_kv) ? my_bits[2 * j0] : 0xFFFFFFFFu;
-    for (int j = j0; j < n_kv; j += NP) {
+    // attn-dropout keep bits of (my query row, keys kv0 + wgi * CW ..): word 2j + wgi * CW / 32 of the row, fetched one tile ahead
+    const uint32_t* my_bits = (DROP && q_ok) ? ad.bits + (((size_t)b * nh + h) * T + q) * ad.Tw + (wgi * CW) / 32 : nullptr;
+    uint32_t wnext = my_bits ? my_bits[0] : 0xFFFFFFFFu;
+    for (int j = 0; j < n_kv; ++j) {
       const int bf = j & 1, kv0 = j * BKV;
-      const uint32_t keepw = wnext;
-      if (my_bits && j + NP < n_kv) wnext = my_bits[2 * (j + NP)];
+      const uint32_t keepw = wnext >> ((wgi * CW) % 32);
+      if (my_bits && j + 1 < n_kv) wnext = my_bits[2 * (j + 1)];
       // s_full(j) also says that buffer bf is free: S / dP (j) were issued after dQ += dS K (j-2), one thread's MMAs complete in order
       mbar_wait(s_full + 8 * bf, (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t tm_s = tmem_base + bf * 2 * BKV + lane_off + wg * 32, tm_dp = tm_s + BKV;
+      const uint32_t tm_s = tmem_base + bf * 2 * BKV + lane_off + wgi * CW, tm_dp = tm_s + BKV;
       const bool full = kv0 + BKV <= T;  // only the last key tile needs the column mask
-      uint32_t rs[32], rp[32];
-      tmem_ld32(tm_s, rs);
-      tmem_ld32(tm_dp, rp);
+      uint32_t rs[CW], rp[CW];
+      if constexpr (CW == 32) { tmem_ld32(tm_s, rs); tmem_ld32(tm_dp, rp); }
+      else { tmem_ld16(tm_s, rs); tmem_ld16(tm_dp, rp); }
       tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < 32; c += 16) {
+      for (int c = 0; c < CW; c += 16) {
         uint32_t dk[8];
         // the 1/sqrt(hs) factor of dS is applied once when dQ is drained
         if (full && !DROP) {  // packed pairs: FFMA2 / FADD2 / FMUL2, two keys per instruction
@@ -653,7 +650,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             dk[e / 2] = pack_bf16x2_pair(mul2(p2, t2));
           }
         } else {
-          const int k0 = kv0 + wg * 32 + c;  // first key of this sub-chunk
+          const int k0 = kv0 + wgi * CW + c;  // first key of this sub-chunk
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
             float p0 = (k0 + e < T) ? ex2_approx(fmaf(__uint_as_float(rs[c + e]), scale_log2, -my_lse)) : 0.f;
@@ -666,7 +663,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             dk[e / 2] = pack_bf16x2(p0 * (dp0 - my_delta), p1 * (dp1 - my_delta));
           }
         }
-        tmem_st8(tm_dp + c / 2, dk);  // dS over the dP tile it came from (mma_over_rows_ts SPLIT layout)
+        tmem_st8(tm_dp + c / 2, dk);  // dS over the dP tile it came from (mma_over_rows_ts CW layout)
       }
       tmem_wait_st();
       tc_fence_before();
@@ -678,7 +675,7 @@ attn_bwd_q2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // the head's columns are drained in 16-column groups by as many warpgroups as there are groups (at most 2 * NP)
     constexpr int NG = (HS / 16) < 2 * NP ? (HS / 16) : 2 * NP;
     constexpr int CH = HS / NG;
-    const int g = pair * 2 + wg;
+    const int g = wgi;
     if (g < NG) {
 #pragma unroll 1
       for (int c = g * CH; c < (g + 1) * CH; c += 16) {
@@ -1038,11 +1035,13 @@ int run_attn_delta(const void* y, const void* dy, float* delta, int B, int T, in
 
 // Q / dO rows of the dQ kernel parked in tensor memory as TS-mode A operands (default on: +-0 at T = 962, +6 % at T = 3842)
 static const bool g_attn_a_in_tmem = getenv("DSF_ATTN_A_TMEM") ? atoi(getenv("DSF_ATTN_A_TMEM")) != 0 : true;
-// Math warpgroup pairs of the two backward kernels (template parameter NP, see attn_bwd_kv2_kernel).  Only NP = 1 is built:
-// measured on B200 (scripts/bench_attn_parts.py, batch 12, T = 962; profiles/r02ac_attn_parts.txt) NP = 2 runs the dK/dV kernel in
-// 32.6 / 36.9 / 44.5 / 59.6 us against 29.7 / 33.4 / 41.9 / 59.9 us for NP = 1 (head size 16 / 32 / 64 / 128) and the dQ kernel in
-// 27.9 / 30.5 / 35.6 / 45.6 against 26.3 / 28.2 / 32.9 / 45.5 us: once the statistics staging and the redundant buffer wait were gone
-// the second pair only added contention.
+// Math warpgroup pairs of the two backward kernels (template parameter NP, see attn_bwd_kv2_kernel).  Only NP = 1 is built.  Measured on
+// B200 (scripts/bench_attn_parts.py, batch 12, T = 962, head size 16 / 32 / 64 / 128; profiles/r02aj_attn_pairs.txt): four warpgroups
+// sharing every tile (NP = 2) run the dK/dV kernel in 29.1 / 31.9 / 42.0 / 59.7 us against 28.7 / 31.7 / 41.2 / 59.3 us and the dQ kernel
+// in 25.3 / 27.8 / 33.0 / 44.8 against 25.9 / 27.7 / 32.1 / 44.6 us.  The in-kernel timeline (profiles/r02aj_attn_trace.txt) says why:
+// halving a warp's columns shortens its tile from ~740 to ~670 cycles only — the tile is a fixed latency chain (tcgen05.ld, wait::ld,
+// tcgen05.st, wait::st, fence, mbarrier), not arithmetic.  An earlier variant whose two pairs took alternate tiles (git history) lost
+// to NP = 1 as well: with two S^T/dP^T buffers the next tile of a pair cannot be issued before its previous one is consumed.
 constexpr int kBwdPairs = 1;
 // The backward kernels keep every exponential on MUFU.EX2 (template parameter POLY = 0): they run 32 exponentials per thread and tile
 // against the forward's 64 and are bound by the per-tile latency chain, not by the MUFU pipe — with every 3rd pair on the FMA pipe the
@@ -1098,8 +1097,8 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
     if (int e = make_tmap3(&tmKV128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
     if (int e = make_tmap3(&tmQs, qkv, 3 * C, T, B, H::BOXC, BQ)) return e;
     if (int e = make_tmap3(&tmDOs, dy, C, T, B, H::BOXC, BQ)) return e;
-#define DSF_KV(DROP, POLY) launch_bwd_kv<HS, BQ, STA, kBwdPairs, DROP, POLY>(tmKV128, tmQs, tmDOs, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, st)
-    if (int e = drop ? DSF_KV(true, 0) : DSF_KV(false, 0)) return e;
+#define DSF_KV(DROP) launch_bwd_kv<HS, BQ, STA, kBwdPairs, DROP, 0>(tmKV128, tmQs, tmDOs, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, st)
+    if (int e = drop ? DSF_KV(true) : DSF_KV(false)) return e;
 #undef DSF_KV
   }
   if (parts & 4) {
@@ -1107,10 +1106,10 @@ static int launch_bwd2(const void* qkv, const void* y, const void* dy, const flo
     if (int e = make_tmap3(&tmQ128, qkv, 3 * C, T, B, H::BOXC, 128)) return e;
     if (int e = make_tmap3(&tmDO128, dy, C, T, B, H::BOXC, 128)) return e;
     if (int e = make_tmap3(&tmKV64, qkv, 3 * C, T, B, H::BOXC, 64)) return e;
-#define DSF_Q(AT, DROP, POLY) launch_bwd_q<HS, STB, AT, kBwdPairs, DROP, POLY>(tmQ128, tmDO128, tmKV64, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, qkv, dy, st)
+#define DSF_Q(AT, DROP) launch_bwd_q<HS, STB, AT, kBwdPairs, DROP, 0>(tmQ128, tmDO128, tmKV64, lse, (const float*)delta, dqkv, grid, T, C, nh, scale, ad, qkv, dy, st)
     int e;
-    if (g_attn_a_in_tmem) e = drop ? DSF_Q(true, true, 0) : DSF_Q(true, false, 0);
-    else e = drop ? DSF_Q(false, true, 0) : DSF_Q(false, false, 0);
+    if (g_attn_a_in_tmem) e = drop ? DSF_Q(true, true) : DSF_Q(true, false);
+    else e = drop ? DSF_Q(false, true) : DSF_Q(false, false);
 #undef DSF_Q
     if (e) return e;
   }
