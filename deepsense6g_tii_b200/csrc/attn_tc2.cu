@@ -83,6 +83,8 @@ __device__ __forceinline__ uint64_t ex2_pair(uint64_t x, int j) {
   }
   return pack2(p0, p1);
 }
+// (Packing on the ALU pipe instead of cvt.rn.bf16x2 — bit pattern + 0x8000, then one byte permute per pair — measured slower in all
+// three kernels: forward 24.4 -> 25.7 us, dK/dV 28.7 -> 30.7 us at head size 16; profiles/r02al_attn_pack_alu.txt.)
 __device__ __forceinline__ uint32_t pack_bf16x2_pair(uint64_t v) {
   float lo, hi;
   unpack2(v, lo, hi);
@@ -401,12 +403,12 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       mbar_wait(s_full + 8 * bf, (i >> 1) & 1);
       if ((warp & 3) == 0 && wgi < 2) TRACE(wgi, i, 2);
       tc_fence_after();
-      if ((warp & 3) == 0 && wgi < 2) TRACE(wgi, i, 3);
       const uint32_t tm_s = tmem_base + bf * 2 * BQ + lane_off + wgi * CW, tm_dp = tm_s + BQ;
       uint32_t rs[CW], rp[CW];
       if constexpr (CW == 32) { tmem_ld32(tm_s, rs); tmem_ld32(tm_dp, rp); }
       else { tmem_ld16(tm_s, rs); tmem_ld16(tm_dp, rp); }
       tmem_wait_ld();
+      if ((warp & 3) == 0 && wgi < 2) TRACE(wgi, i, 3);
       const uint64_t sc2 = pack2(scale_log2, scale_log2);
 #pragma unroll
       for (int c = 0; c < CW; c += 16) {
@@ -452,10 +454,11 @@ attn_bwd_kv2_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         tmem_st8(tm_s + c / 2, pk);
         tmem_st8(tm_dp + c / 2, dk);
       }
+      if ((warp & 3) == 0 && wgi < 2) TRACE(wgi, i, 4);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(ds_full + 8 * bf);
-      if ((warp & 3) == 0 && wgi < 2) TRACE(wgi, i, 4);
+      if ((warp & 3) == 0 && wgi < 2) TRACE(wgi, i, 5);
     }
     mbar_wait(acc_done, 0);
     tc_fence_after();

@@ -51,7 +51,7 @@ assert fn(buf) == 0
 t = torch.tensor(list(buf), dtype=torch.int64).view(3, 64, 6)
 n_q = (T + 63) // 64
 print("dK/dV kernel, head size %d: per-iteration cycles of CTA (0,0,0)" % (C // nh))
-print("iter | MMA warp: wait Q/dO(i+1), issue S/dP(i+1), wait dS(i), issue dV/dK | math wg0: stats+bar, wait S, wait dS buf, exp/dS/store | wg1 same | iter total")
+print("iter | MMA warp: wait Q/dO(i+1), issue S/dP(i+1), wait dS(i), issue dV/dK | math wg0: prefetch, wait S, tcgen05.ld + wait::ld, exp/dS + tcgen05.st issue, wait::st + fence + arrive | wg1 same | iter total")
 for i in range(n_q):
     m = t[2, i]
     nxt = int(t[2, i + 1, 0]) if i + 1 < n_q else None
@@ -61,7 +61,7 @@ for i in range(n_q):
         row = "%4d | %6s %6s %6d %6d |" % (i, "-", "-", int(m[3] - m[2]), int(m[4] - m[3]))
     for w in (0, 1):
         a = t[w, i]
-        row += " %6d %6d %6d %6d |" % (int(a[1] - a[0]), int(a[2] - a[1]), int(a[3] - a[2]), int(a[4] - a[3]))
+        row += " %6d %6d %6d %6d %6d |" % (int(a[1] - a[0]), int(a[2] - a[1]), int(a[3] - a[2]), int(a[4] - a[3]), int(a[5] - a[4]))
     row += " %s" % ("%6d" % (nxt - int(m[0])) if nxt else "")
     print(row)
 
