@@ -82,7 +82,7 @@ def lib():
             "dsf_relu_bwd_colsum": [P, P, P, c_int32, c_int32, P],
             "dsf_pack_block_weights": [P] * 9 + [c_int32, c_int32] + [P] * 10,
             "dsf_gemm_bf16_nt": [P, c_int32, P, c_int32, P, c_int32, c_int32, P, P, c_int32, c_int32, c_int32, c_int32, POINTER(Dropout), P, P],
-            "dsf_gemm_bf16_tn": [P, c_int32, P, c_int32, P, c_int32, c_int32, c_int32, c_int32, P],
+            "dsf_gemm_bf16_tn": [P, c_int32, P, c_int32, P, c_int32, c_int32, c_int32, c_int32, P, P],
             "dsf_gemm_f32": [POINTER(GemmF32Desc), P, P, P, P, P, P],
             "dsf_colsum": [P, c_int32, c_int32, P, c_int32, c_int32, P],
             "dsf_relu_bwd": [P, P, c_int32, c_int64, P],
@@ -208,11 +208,13 @@ def gemm_bf16_nt(A, B, C, bias=None, residual=None, relu=False, drop=None, relu_
                                 M, N, K, flags, _dp(drop), _p(relu_src), _stream()), "dsf_gemm_bf16_nt")
 
 
-def gemm_bf16_tn(A, B, C):
-    """C[N',K'] += A[M,N']^T @ B[M,K'] (fp32 atomics; C must be pre-zeroed or hold a running sum)."""
+def gemm_bf16_tn(A, B, C, colsum=None):
+    """C[N',K'] += A[M,N']^T @ B[M,K'] (fp32 atomics; C must be pre-zeroed or hold a running sum).  colsum (N') fp32, optional:
+    colsum[n'] += sum_m A[m, n'] in the same launch (the bias gradient next to the weight gradient)."""
     M, Nout = A.shape
     Kout = B.shape[1]
-    _chk(lib().dsf_gemm_bf16_tn(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, Nout, Kout, _stream()), "dsf_gemm_bf16_tn")
+    _chk(lib().dsf_gemm_bf16_tn(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, Nout, Kout, _p(colsum), _stream()),
+         "dsf_gemm_bf16_tn")
 
 
 def gemm_f32(desc, A, B, C, bias=None, residual=None):

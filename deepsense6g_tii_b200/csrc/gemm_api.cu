@@ -65,7 +65,7 @@ namespace dsf {
 // persistent kernels (double-buffered TMEM accumulators; CTA pairs with cta_group::2 where the shape allows), gemm_tc2.cu
 int gemm_nt_run(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype, const float* bias, const float* residual, int M,
                 int N, int K, int flags, const dsf_dropout* drop, const void* relu_src, bool pairs, cudaStream_t st);
-int gemm_tn_run(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st);
+int gemm_tn_run(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int Nout, int Kout, float* colsum, cudaStream_t st);
 // 0 = default (NT on CTA pairs where N % 128 == 0 and M > 128, else single-CTA tiles), 2 = single-CTA tiles only.  Relaxed
 // atomic: calls are re-entrant, the selector is a tuning / test knob.
 static std::atomic<int> g_gemm_impl{0};
@@ -99,11 +99,11 @@ extern "C" int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32
 }
 
 extern "C" int dsf_gemm_bf16_tn(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc, int32_t M,
-                                int32_t Nout, int32_t Kout, void* stream) {
+                                int32_t Nout, int32_t Kout, float* colsum_a, void* stream) {
   DSF_REQUIRE(A && B && C, "gemm_bf16_tn: NULL pointer");
   DSF_REQUIRE(M > 0 && Nout > 0 && Kout > 0, "gemm_bf16_tn: non-positive extent");
   DSF_REQUIRE(Nout % 64 == 0 && Kout % 64 == 0, "gemm_bf16_tn: output extents (%d, %d) must be multiples of 64", Nout, Kout);
   DSF_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= Nout && ldb >= Kout && ldc >= Kout, "gemm_bf16_tn: bad leading dimensions");
   DSF_REQUIRE(aligned16(A) && aligned16(B) && aligned16(C), "gemm_bf16_tn: 16-byte alignment required");
-  return gemm_tn_run(A, lda, B, ldb, C, ldc, M, Nout, Kout, (cudaStream_t)stream);
+  return gemm_tn_run(A, lda, B, ldb, C, ldc, M, Nout, Kout, colsum_a, (cudaStream_t)stream);
 }

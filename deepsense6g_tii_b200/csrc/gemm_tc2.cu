@@ -646,11 +646,25 @@ gemm_nt3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 // ---------------------------------------------------------------------------------- TN (wgrad), split contraction
 
+// colsum (nullable): colsum[n'] += sum_m A[m, n'] — the bias gradient of the Linear whose weight gradient this GEMM computes
+// (model2_seq.py:97-99, 122).  It rides on the tensor core: the CTAs of the first K' tile issue one extra 128 x 16 MMA per k-step
+// whose B operand is a 2 KB shared-memory tile of ones, so an accumulator column next to the C tile collects the row sums of A^T.
+// (The separate column-sum kernel re-read dqkv / da: 16 launches and 0.12 - 0.19 ms of kernel time per stage.)
+template <int BN, int STAGES>
+struct TnSmem : G2Smem<BN, STAGES, false> {
+  using Base = G2Smem<BN, STAGES, false>;
+  static constexpr int ONES_OFF = (Base::BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1023) / 1024 * 1024;
+  static constexpr int ONES_BYTES = 16 * 128;  // 16 contraction rows x one 128-byte swizzle row, every element 1.0
+  static constexpr int DYN = ONES_OFF + ONES_BYTES + 1024;
+  static constexpr uint32_t TMEM_COLS = BN + 32 <= 128 ? 128 : (BN + 32 <= 256 ? 256 : 512);
+  static_assert(DYN <= 232448, "shared memory budget");
+};
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C, int ldc, int M, int Nout,
-                int Kout, int m_chunk) {
-  using L = G2Smem<BN, STAGES, false>;
+                int Kout, int m_chunk, float* __restrict__ colsum) {
+  using L = TnSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = base + L::BAR_OFF, bar_empty = bar_full + STAGES * 8, bar_acc = bar_empty + STAGES * 8, tmem_slot = bar_acc + 8 * 4;
@@ -659,9 +673,15 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int k0 = blockIdx.x * BN;     // cols of C (K' index)
   const int m_lo = blockIdx.z * m_chunk, m_hi = min(M, m_lo + m_chunk);
   const int num_it = (m_hi - m_lo + G2_BK - 1) / G2_BK;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = L::TMEM_COLS;
   constexpr int BOX_BYTES = G2_BK * 128;  // 64 rows x 128 B
+  const bool do_cs = colsum != nullptr && blockIdx.x == 0;
   pdl_trigger();
+  if (do_cs) {  // the ones tile (bf16 1.0 = 0x3F80), visible to the tensor core's operand reads after the barrier below
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + L::ONES_OFF);
+    for (int i = threadIdx.x; i < L::ONES_BYTES / 4; i += G2_THREADS) ones[i] = 0x3F803F80u;
+    fence_proxy_async();
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -695,6 +715,8 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     {  // MMA issuer: all 32 lanes walk the schedule (uniform control flow keeps descriptors in uniform registers)
       constexpr uint32_t idesc = make_idesc_bf16(G2_BM, BN, 1, 1);
+      constexpr uint32_t idesc_cs = make_idesc_bf16(G2_BM, 16, 1, 1);
+      const uint64_t d_ones = make_smem_desc(base + L::ONES_OFF, BOX_BYTES, 1024, SWZ_128B);  // the same 16 rows for every k-step
       for (int it = 0; it < num_it; ++it) {
         const int s = it % STAGES;
         mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
@@ -706,6 +728,10 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < G2_BK / 16; ++k) tc_mma_bf16(tmem_base, da + (uint32_t)(k * 128), db + (uint32_t)(k * 128), idesc, k == 0 ? first : 1u);
+          if (do_cs) {
+#pragma unroll
+            for (int k = 0; k < G2_BK / 16; ++k) tc_mma_bf16(tmem_base + BN, da + (uint32_t)(k * 128), d_ones, idesc_cs, k == 0 ? first : 1u);
+          }
           tc_commit(bar_empty + s * 8);
         }
         __syncwarp();
@@ -719,6 +745,12 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int q = warp & 3, ch = (warp - 2) >> 2;
     constexpr int HALF = BN / 2;
     const int row = n0 + q * 32 + lane;
+    if (do_cs && ch == 0) {  // every one of the 16 columns holds the row sum of A^T over this CTA's contraction chunk
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + BN, r);
+      tmem_wait_ld();
+      if (row < Nout) atomicAdd(colsum + row, __uint_as_float(r[0]));
+    }
 #pragma unroll 1
     for (int c = 0; c < HALF; c += 32) {
       uint32_t r[32];
@@ -761,8 +793,8 @@ static int launch_nt2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
 }
 
 template <int BN, int STAGES>
-static int launch_tn2(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st) {
-  using L = G2Smem<BN, STAGES, false>;
+static int launch_tn2(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int ldc, int M, int Nout, int Kout, float* colsum, cudaStream_t st) {
+  using L = TnSmem<BN, STAGES>;
   static bool configured_on[64] = {};
   bool& configured = per_device_flag(configured_on);
   if (!configured) {
@@ -776,7 +808,7 @@ static int launch_tn2(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, 
   int m_chunk = cdiv(cdiv(M, splits), G2_BK) * G2_BK;
   splits = cdiv(M, m_chunk);
   dim3 grid(cdiv(Kout, BN), cdiv(Nout, G2_BM), splits);
-  launch_pdl(gemm_tn2_kernel<BN, STAGES>, grid, dim3(G2_THREADS), L::DYN, st, tmA, tmB, C, ldc, M, Nout, Kout, m_chunk);
+  launch_pdl(gemm_tn2_kernel<BN, STAGES>, grid, dim3(G2_THREADS), L::DYN, st, tmA, tmB, C, ldc, M, Nout, Kout, m_chunk, colsum);
   return check_launch("gemm_tn2");
 }
 
@@ -881,14 +913,14 @@ int gemm_nt_run(const void* A, int lda, const void* B, int ldb, void* C, int ldc
   return launch_nt2<64, 5>(tmA, tmB, tmC, epi, M, N, K, st);
 }
 
-int gemm_tn_run(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int Nout, int Kout, cudaStream_t st) {
+int gemm_tn_run(const void* A, int lda, const void* B, int ldb, float* C, int ldc, int M, int Nout, int Kout, float* colsum, cudaStream_t st) {
   const int BN = (Kout % 256 == 0) ? 256 : ((Kout % 128 == 0) ? 128 : 64);
   CUtensorMap tmA, tmB;
   if (int e = make_tmap_bf16(&tmA, A, M, Nout, lda, G2_BK)) return e;
   if (int e = make_tmap_bf16(&tmB, B, M, Kout, ldb, G2_BK)) return e;
-  if (BN == 256) return launch_tn2<256, 4>(tmA, tmB, C, ldc, M, Nout, Kout, st);
-  if (BN == 128) return launch_tn2<128, 6>(tmA, tmB, C, ldc, M, Nout, Kout, st);
-  return launch_tn2<64, 8>(tmA, tmB, C, ldc, M, Nout, Kout, st);
+  if (BN == 256) return launch_tn2<256, 4>(tmA, tmB, C, ldc, M, Nout, Kout, colsum, st);
+  if (BN == 128) return launch_tn2<128, 6>(tmA, tmB, C, ldc, M, Nout, Kout, colsum, st);
+  return launch_tn2<64, 8>(tmA, tmB, C, ldc, M, Nout, Kout, colsum, st);
 }
 
 }  // namespace dsf

@@ -469,10 +469,7 @@ class _Runner:
             da = torch.empty(M, F, device=dev, dtype=bf)
             K.gemm_bf16_nt(dxa, st.w2_t, da, relu_src=st.a)  # ReLU backward fused in the epilogue
 
-            def mlp0_grads():
-                K.colsum(da, db1)
-                K.gemm_bf16_tn(da, st.h2, dw1)
-            fork(mlp0_grads)
+            fork(lambda: K.gemm_bf16_tn(da, st.h2, dw1, colsum=db1))  # mlp.0 weight and bias gradients in one launch
             dh2 = torch.empty(M, C, device=dev, dtype=dh_dt)  # feeds LayerNorm backward, not a GEMM
             K.gemm_bf16_nt(da, st.w1_t, dh2)
             dx_mid = torch.empty(M, C, device=dev, dtype=f32)
@@ -494,10 +491,7 @@ class _Runner:
                 K.attn_bwd(st.qkv, st.y, dy, st.lse, delta, dqkv, self.B, self.T, C, self.nh, adrop, st.drop_bits, parts=2)
                 join(side_q)
 
-            def qkv_grads():
-                K.colsum(dqkv, dbqkv)
-                K.gemm_bf16_tn(dqkv, st.h1, dwqkv)
-            fork(qkv_grads)
+            fork(lambda: K.gemm_bf16_tn(dqkv, st.h1, dwqkv, colsum=dbqkv))  # fused QKV weight and bias gradients in one launch
             dh1 = torch.empty(M, C, device=dev, dtype=dh_dt)
             K.gemm_bf16_nt(dqkv, st.wqkv_t, dh1)
             # block i+1's weight-gradient work must be complete now: the next kernel overwrites the bf16 buffer its first wgrad

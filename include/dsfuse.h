@@ -125,7 +125,9 @@ int dsf_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const fl
  * 97-99,109,122,124) and its autograd.
  *   NT:  C[M,N] = A[M,K] . B[N,K]^T  (+bias)(relu)(+residual)      A, B bf16 row-major (K contiguous)
  *        C is c_dtype (bf16 or fp32) with leading dimension ldc; residual is fp32 with ldc.
- *   TN:  C[N',K'] += A[M,N']^T . B[M,K']   (weight gradient; contraction over the M rows)
+ *   TN:  C[N',K'] += A[M,N']^T . B[M,K']   (weight gradient; contraction over the M rows);  colsum_a (N') fp32, nullable:
+ *        colsum_a[n'] += sum_m A[m,n'] in the same launch (the bias gradient of that Linear: one extra 128 x 16 MMA per k-step
+ *        against a shared-memory tile of ones)
  *        A, B bf16 row-major; C fp32.  The contraction is split over CTAs and the partial products are ADDED to C with
  *        fp32 vector reductions: C must be zero-filled (or hold a running sum) before the call.   */
 /*        `drop` (nullable): dropout applied after bias/ReLU and BEFORE the residual add, element index m*N + n
@@ -137,7 +139,7 @@ int dsf_gemm_bf16_nt(const void* A, int32_t lda, const void* B, int32_t ldb, voi
                      int32_t K, int32_t epi_flags, const dsf_dropout* drop, const void* relu_src,
                      void* stream);
 int dsf_gemm_bf16_tn(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc,
-                     int32_t M, int32_t Nout, int32_t Kout, void* stream);
+                     int32_t M, int32_t Nout, int32_t Kout, float* colsum_a, void* stream);
 /* Selects the NT tile schedule (process-wide, atomic; tests and A/B timing): 0 = default (CTA pairs, tcgen05.mma.cta_group::2 on
  * 256 x 256 / 256 x 128 tiles where N % 128 == 0 and M > 128, single-CTA persistent tiles otherwise), 2 = single-CTA tiles only. */
 int dsf_gemm_set_impl(int32_t impl);

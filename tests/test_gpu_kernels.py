@@ -297,6 +297,12 @@ def test_gemm_bf16_tn(K, cuda_dev, gemm_impl, M, No, Ko):
     assert_close(out, ref, 2e-5, 1e-5, "wgrad")
     K.gemm_bf16_tn(dy, x, out)
     assert_close(out, 2 * ref, 2e-5, 1e-5, "wgrad accumulates")
+    # bias gradient in the same launch (ones-tile MMA): colsum += sum_m dy[m, :], the weight gradient unchanged
+    out2 = torch.zeros(No, Ko, device=cuda_dev)
+    cs = torch.full((No,), 0.5, device=cuda_dev)
+    K.gemm_bf16_tn(dy, x, out2, colsum=cs)
+    assert_close(out2, ref, 2e-5, 1e-5, "wgrad next to the bias gradient")
+    assert_close(cs, 0.5 + dy.float().sum(0), 2e-5, 1e-5, "bias gradient (accumulated)")
 
 
 def _attn_ref(qkv, B, T, C, nh):
