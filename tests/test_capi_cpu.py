@@ -80,3 +80,14 @@ def test_transfuser_state_dict_matches_reference():
         assert a[k].shape == b[k].shape, k
     mine.load_state_dict(a, strict=True)
     assert sum(p.numel() for p in mine.parameters()) == 78422528
+
+
+def test_fused_stem_and_tail_are_declined_off_the_gpu():
+    """The fused stem / tail (dsf_stem_pack, dsf_tail_fwd) take CUDA tensors only; anything else makes the drop-in Encoder run the
+    reference's op sequence (model2_seq.py:481-493, 581-595) — the predicates must say so without touching the library."""
+    import torch
+    from deepsense6g_tii_b200 import functional as Fn
+    frames = [torch.rand(2, 3, 8, 8) for _ in range(5)]
+    assert not Fn.stem_pack_supported(frames)
+    maps = [torch.rand(10, 512, 8, 8) for _ in range(3)]
+    assert not Fn.pooled_tail_supported(maps[0], maps[1], maps[2], torch.rand(2, 2, 512))
