@@ -855,7 +855,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       p_max *= scale_log2;
-      const bool need = p_max > m_run + 8.f;  // lazy rescale (exact: m only has to bound the exponent)
+      // lazy rescale (exact: m only has to bound the exponent).  Measured and NOT kept: taking the exponentials speculatively against the
+      // running maximum and tracking the row maximum inside that loop (tile repeated when it moved by > 8) removes this maximum pass
+      // but lengthens the exponential loop: +1 .. 2.4 us per launch at every head size (profiles/r02sp_attn_fwd_speculative_tiles.txt).
+      const bool need = p_max > m_run + 8.f;
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = need ? p_max : m_run;
         const float alpha = ex2_approx(m_run - m_new);

@@ -439,8 +439,9 @@ template <typename TY, int VPT>
 int launch_ln_fwd2(const float* x, const float* gamma, const float* beta, TY* y, float* mean, float* rstd, int M, float eps, cudaStream_t st) {
   constexpr int ST = VPT <= 2 ? 8 : (VPT <= 4 ? 8 : 4);
   constexpr int SMEM = LN2_WARPS * ST * 128 * VPT * 4;
-  static bool ok = ln2_configure(layernorm_fwd2_kernel<TY, VPT, ST>, SMEM);
-  if (!ok) return check_launch("layernorm_fwd2/attr");
+  static bool configured_on[64] = {};
+  bool& configured = per_device_flag(configured_on);  // the attribute is per device (common.cuh)
+  if (!configured && !(configured = ln2_configure(layernorm_fwd2_kernel<TY, VPT, ST>, SMEM))) return check_launch("layernorm_fwd2/attr");
   const int blocks = std::min(cdiv(M, LN2_WARPS), num_sms());
   launch_pdl(layernorm_fwd2_kernel<TY, VPT, ST>, dim3(blocks), dim3(LN2_WARPS * 32), SMEM, st, x, gamma, beta, y, mean, rstd, M, eps);
   return check_launch("layernorm_fwd2");
@@ -452,13 +453,15 @@ int launch_ln_bwd2(const TY* dy, const float* x, const float* gamma, const float
   using L = Ln2Bwd<TY, VPT>;
   const int blocks = std::min(cdiv(M, LN2_WARPS), num_sms());
   if (EXTRA && drop.thresh != 0) {
-    static bool ok = ln2_configure(layernorm_bwd2_kernel<TY, VPT, EXTRA, EXTRA>, L::RING);
-    if (!ok) return check_launch("layernorm_bwd2/attr");
+    static bool configured_on[64] = {};
+    bool& configured = per_device_flag(configured_on);
+    if (!configured && !(configured = ln2_configure(layernorm_bwd2_kernel<TY, VPT, EXTRA, EXTRA>, L::RING))) return check_launch("layernorm_bwd2/attr");
     launch_pdl(layernorm_bwd2_kernel<TY, VPT, EXTRA, EXTRA>, dim3(blocks), dim3(LN2_WARPS * 32), L::RING, st, dy, x, gamma, mean, rstd, dx_add, dx,
                dgamma, dbeta, dx_bf16, dx_colsum, drop, M);
   } else {
-    static bool ok = ln2_configure(layernorm_bwd2_kernel<TY, VPT, EXTRA, false>, L::RING);
-    if (!ok) return check_launch("layernorm_bwd2/attr");
+    static bool configured_on[64] = {};
+    bool& configured = per_device_flag(configured_on);
+    if (!configured && !(configured = ln2_configure(layernorm_bwd2_kernel<TY, VPT, EXTRA, false>, L::RING))) return check_launch("layernorm_bwd2/attr");
     launch_pdl(layernorm_bwd2_kernel<TY, VPT, EXTRA, false>, dim3(blocks), dim3(LN2_WARPS * 32), L::RING, st, dy, x, gamma, mean, rstd, dx_add, dx,
                dgamma, dbeta, dx_bf16, dx_colsum, drop, M);
   }

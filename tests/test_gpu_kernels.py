@@ -346,6 +346,30 @@ def _attention_case(K, cuda_dev, B, T, C, nh):
         assert_close(dqkv[:, sl].float(), qr.grad[:, sl], 2e-2, 1e-4, nm)
 
 
+@pytest.mark.parametrize("B,T,C,nh", [(2, 962, 512, 4), (2, 962, 64, 4), (1, 1000, 128, 4), (1, 3842, 256, 4)])
+@pytest.mark.parametrize("impl", [0, 2], ids=["fwd_128row_ctas", "fwd_256row_ctas"])
+def test_attention_fwd_when_the_running_maximum_keeps_moving(K, cuda_dev, B, T, C, nh, impl):
+    """Keys grow along the sequence, so later key tiles raise a row's maximum by far more than the lazy-rescale threshold (2^8):
+    the forward kernel's speculative tiles (exponentials taken against the running maximum first) have to be repeated and the
+    output accumulator rescaled.  Same softmax, model2_seq.py:94-106."""
+    K.attn_set_impl(impl)
+    try:
+        g = _gen(21)
+        qkv = torch.randn(B, T, 3 * C, generator=g)
+        ramp = 0.25 + 5.0 * torch.arange(T, dtype=torch.float32).view(1, T, 1) / T
+        qkv[:, :, C:2 * C] *= ramp          # logits of key t scale with ramp[t]: standard deviation 0.25 .. 5.25
+        qkv = qkv.reshape(B * T, 3 * C).to(cuda_dev).to(torch.bfloat16)
+        y = torch.empty(B * T, C, device=cuda_dev, dtype=torch.bfloat16)
+        lse = torch.empty(B, nh, T, device=cuda_dev)
+        K.attn_fwd(qkv, y, lse, B, T, C, nh)
+        torch.cuda.synchronize()
+        ref, lse_ref = _attn_ref(qkv.float(), B, T, C, nh)
+        assert_close(lse, lse_ref, 1e-4, 1e-4, "lse")
+        assert_close(y.float(), ref, 1e-2, 1e-4, "attn fwd")
+    finally:
+        K.attn_set_impl(0)
+
+
 def test_error_paths(K, cuda_dev):
     x = torch.zeros(4, 6, device=cuda_dev)
     with pytest.raises(RuntimeError, match="multiple of 4"):
