@@ -1,7 +1,7 @@
 """Attention kernels timed one by one (GPU): forward, dK/dV (part 2), dQ (part 4), delta (part 1) at the four stage shapes and
 the 16x16-anchor shape.  CUDA events around back-to-back launches of one kernel; the working set of a shape (<= 75 MB) is
 L2-resident, as it is inside the step (qkv / dy were just written by the preceding kernels).
-Usage: [DSF_ATTN_BWD_PAIRS=1|2] [DSF_ATTN_SPEC=0|1] python scripts/bench_attn_parts.py [tag] [fwd]     (fwd: forward kernel only)"""
+Usage: [DSF_ATTN_BWD_PAIRS=1|2] python scripts/bench_attn_parts.py [tag] [fwd]     (fwd: forward kernel only)"""
 import os
 import sys
 
